@@ -1,0 +1,124 @@
+// Shared device helpers for the graphchem_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/graphchem_b200.h"
+
+#ifndef __CUDA_ARCH_FEAT_SM100_ALL
+#if defined(__CUDA_ARCH__)
+#error "graphchem_b200 kernels are written for sm_100a only (compile with -gencode arch=compute_100a,code=sm_100a)"
+#endif
+#endif
+
+namespace gcb {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_cuda_error(cudaError_t e, const char* file, int line);
+#define GCB_CUDA(expr)                                  \
+  do {                                                  \
+    cudaError_t _e = (expr);                            \
+    if (_e != cudaSuccess) {                            \
+      gcb::set_cuda_error(_e, __FILE__, __LINE__);      \
+      return GCB_ERR_CUDA;                              \
+    }                                                   \
+  } while (0)
+#define GCB_LAUNCH_CHECK() GCB_CUDA(cudaGetLastError())
+#define GCB_TRY(expr)          \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != GCB_OK) return _rc; \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- 16-byte vector access: VEC elements of T ---------------------------------------------------
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int N = 4; };
+template <> struct Vec<bf16> { static constexpr int N = 8; };
+
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[4]) {
+  float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load_vec(const bf16* __restrict__ p, float (&v)[8]) {
+  uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store_vec(bf16* __restrict__ p, const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+// Round-trip through the storage type (what a later reader of the stored value will see).
+__device__ __forceinline__ float round_to(float v, const float*) { return v; }
+__device__ __forceinline__ float round_to(float v, const bf16*) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_float<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- activations (gcn.py:42; tests/test_gcn.py:107-113) ----------------------------------------
+// Forward follows torch's CPU kernels: softplus(beta=1, threshold=20), sigmoid, relu, tanh,
+// leaky_relu(0.01).  The derivative is evaluated from the OUTPUT y = act(x) so that only the
+// activations themselves need to be kept for the backward pass.
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case GCB_ACT_SOFTPLUS: return x > 20.f ? x : log1pf(expf(x));
+    case GCB_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+    case GCB_ACT_RELU: return fmaxf(x, 0.f);
+    case GCB_ACT_TANH: return tanhf(x);
+    default: return x > 0.f ? x : 0.01f * x;
+  }
+}
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+  switch (act) {
+    case GCB_ACT_SOFTPLUS: return -expm1f(-y);  // sigmoid(x) = 1 - exp(-softplus(x))
+    case GCB_ACT_SIGMOID: return y * (1.f - y);
+    case GCB_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case GCB_ACT_TANH: return 1.f - y * y;
+    default: return y > 0.f ? 1.f : 0.01f;
+  }
+}
+
+// ---- counter-based RNG for dropout (Philox-4x32-10) --------------------------------------------
+// Keyed by (seed, tensor tag) and indexed by the element's linear index, so that the backward pass
+// regenerates the same keep-mask without storing it.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+// keep-mask for element `idx` of tensor `tag`: true with probability 1-p.
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t tag, uint64_t idx, float p) {
+  uint4 r = philox4x32(make_uint4((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), tag, 0u),
+                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  return (w >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
+}  // namespace gcb

@@ -1,0 +1,329 @@
+// Generic CUDA-core GEMMs (fp32 FFMA accumulation) with fused epilogues.
+//
+// These serve (a) the fp32 parity mode, where 1e-5 agreement with the reference rules out single
+// pass TF32/BF16 tensor-core math, (b) the tiny readout MLP (gcn.py:184-199) and
+// (c) every shape the tcgen05 kernels in gemm_tc.cuh do not cover.  All reductions have a fixed
+// order: results are bit-reproducible run to run.
+#pragma once
+#include "common.cuh"
+
+namespace gcb {
+
+// Epilogue of the row-major "NT" GEMM:  C[r,n] = f( acc[r,n] + w(r) * bias[n] + res[r,n] )
+//   w(r) = 1                         when rowptr == nullptr
+//        = deg(r)                    when rowptr != nullptr, aggr == ADD   (PyG adds the bias per edge)
+//        = deg(r) > 0                when rowptr != nullptr, aggr == MEAN
+//   f    = act (act >= 0), identity (act < 0); or, when actgrad_y != nullptr,
+//          C = acc * act'(y[r,n]) * dropout-factor   (backward through an activation)
+struct Epilogue {
+  const float* bias = nullptr;
+  const int32_t* rowptr = nullptr;
+  int aggr = GCB_AGGR_ADD;
+  const void* res = nullptr;  // same dtype as C, leading dimension ld_res
+  int ld_res = 0;
+  int act = -1;
+  const void* actgrad_y = nullptr;  // same dtype as C, leading dimension ld_y
+  int ld_y = 0;
+  // dropout applied to the tensor y was produced with (training only, p > 0)
+  float p_drop = 0.f;
+  uint64_t seed = 0;
+  uint32_t drop_tag = 0;
+};
+
+template <typename T, int CNT>
+__device__ __forceinline__ void load_seg(const T* __restrict__ row, int k0, int K, bool vec_ok, float (&out)[CNT]) {
+  // CNT contiguous elements row[k0 .. k0+CNT), zero-filled past K.
+  if (vec_ok && k0 + CNT <= K) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int i = 0; i < CNT; i += 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(row + k0 + i));
+        out[i] = t.x; out[i + 1] = t.y; out[i + 2] = t.z; out[i + 3] = t.w;
+      }
+    } else {
+      if constexpr (CNT == 8) {
+        uint4 t = __ldg(reinterpret_cast<const uint4*>(row + k0));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
+      } else {  // CNT == 4
+        uint2 t = __ldg(reinterpret_cast<const uint2*>(row + k0));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) out[i] = (k0 + i < K) ? to_float(row[k0 + i]) : 0.f;
+  }
+}
+
+// C[M,N] = epilogue( A[M,K] * W ), W given as [N,K] row-major (W_KN == false, y = x W^T like
+// nn.Linear) or as [K,N] row-major (W_KN == true).
+template <typename T, bool W_KN>
+__global__ void __launch_bounds__(256)
+gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw, T* __restrict__ C, int ldc,
+               int M, int N, int K, Epilogue ep) {
+  constexpr int BM = 128, BN = 64, BK = 16;
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Ws[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // A loader: row a_r (0..127), 8 contiguous k starting at a_k
+  const int a_r = tid & 127, a_k = (tid >> 7) * 8;
+  const bool a_vec = (lda % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool a_row_ok = (m0 + a_r) < M;
+  const T* a_row = A + (size_t)(a_row_ok ? m0 + a_r : 0) * lda;
+  // W loader
+  int w_n, w_k;
+  if (W_KN) { w_k = tid >> 4; w_n = (tid & 15) * 4; } else { w_n = tid & 63; w_k = (tid >> 6) * 4; }
+  const bool w_vec = (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+
+  float a_reg[8], w_reg[4];
+  auto fetch = [&](int k0) {
+    if (a_row_ok) load_seg<T, 8>(a_row, k0 + a_k, K, a_vec, a_reg);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a_reg[i] = 0.f;
+    }
+    if (W_KN) {
+      const int k = k0 + w_k;
+      if (k < K) load_seg<T, 4>(W + (size_t)k * ldw, n0 + w_n, N, w_vec, w_reg);
+      else { w_reg[0] = w_reg[1] = w_reg[2] = w_reg[3] = 0.f; }
+    } else {
+      const int n = n0 + w_n;
+      if (n < N) load_seg<T, 4>(W + (size_t)n * ldw, k0 + w_k, K, w_vec, w_reg);
+      else { w_reg[0] = w_reg[1] = w_reg[2] = w_reg[3] = 0.f; }
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[buf][a_k + i][a_r] = a_reg[i];
+    if (W_KN) {
+      *reinterpret_cast<float4*>(&Ws[buf][w_k][w_n]) = make_float4(w_reg[0], w_reg[1], w_reg[2], w_reg[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Ws[buf][w_k + i][w_n] = w_reg[i];
+    }
+  };
+
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = (K + BK - 1) / BK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) fetch((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      float4 w = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) stash(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  const T* res = reinterpret_cast<const T*>(ep.res);
+  const T* ygrad = reinterpret_cast<const T*>(ep.actgrad_y);
+  const float keep_scale = ep.p_drop > 0.f ? 1.f / (1.f - ep.p_drop) : 1.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = m0 + ty * 8 + i;
+    if (r >= M) continue;
+    float wrow = 1.f;
+    if (ep.rowptr) {
+      const int deg = ep.rowptr[r + 1] - ep.rowptr[r];
+      wrow = ep.aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (ygrad) {
+        float y = to_float(ygrad[(size_t)r * ep.ld_y + n]);
+        float f = 1.f;
+        if (ep.p_drop > 0.f) {
+          const bool keep = dropout_keep(ep.seed, ep.drop_tag, (uint64_t)r * (uint64_t)N + n, ep.p_drop);
+          f = keep ? keep_scale : 0.f;
+          y = y * (1.f - ep.p_drop);  // undo the 1/(1-p) scaling to recover act(x)
+        }
+        v = v * f * act_grad_from_out(y, ep.act);
+      } else {
+        if (ep.bias) v = fmaf(wrow, ep.bias[n], v);
+        if (res) v += to_float(res[(size_t)r * ep.ld_res + n]);
+        if (ep.act >= 0) v = act_fwd(v, ep.act);
+      }
+      C[(size_t)r * ldc + n] = from_float<T>(v);
+    }
+  }
+}
+
+template <typename T>
+inline int launch_gemm_nt(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
+                          const Epilogue& ep, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return GCB_OK;
+  dim3 grid((unsigned)ceil_div(M, 128), (unsigned)ceil_div(N, 64));
+  if (w_kn) gemm_nt_kernel<T, true><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep);
+  else gemm_nt_kernel<T, false><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep);
+  GCB_LAUNCH_CHECK();
+  return GCB_OK;
+}
+
+// ---- "TN" GEMM: weight gradients ----------------------------------------------------------------
+// partial[z][n][k] = sum_{r in split z} A[r,n] * B[r,k]      (A: [rows,Nn], B: [rows,Kk])
+// bias_partial[z][n] = sum_{r in split z} w(r) * A[r,n]       (optional, from the k-tile-0 CTAs)
+// Splits are contiguous row ranges; a second kernel adds the partials in split order.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemm_tn_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, float* __restrict__ partial,
+               float* __restrict__ bias_partial, const int32_t* __restrict__ rowptr, int aggr, int rows, int Nn,
+               int Kk, int rows_per_split) {
+  constexpr int BT = 64, BR = 16;
+  __shared__ __align__(16) float As[2][BR][BT + 4];
+  __shared__ __align__(16) float Bs[2][BR][BT + 4];
+  __shared__ float wrow_s[2][BR];
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * BT, n0 = blockIdx.y * BT, z = blockIdx.z;
+  const int r_begin = z * rows_per_split;
+  const int r_end = min(rows, r_begin + rows_per_split);
+  const int l_r = tid >> 4, l_c = (tid & 15) * 4;
+  const bool a_vec = (lda % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool b_vec = (ldb % 8 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  const bool want_bias = bias_partial != nullptr && blockIdx.x == 0;
+
+  float a_reg[4], b_reg[4], w_reg = 0.f;
+  auto fetch = [&](int r0) {
+    const int r = r0 + l_r;
+    if (r < r_end) {
+      load_seg<T, 4>(A + (size_t)r * lda, n0 + l_c, Nn, a_vec, a_reg);
+      load_seg<T, 4>(B + (size_t)r * ldb, k0 + l_c, Kk, b_vec, b_reg);
+      if (want_bias && l_c == 0) {
+        if (rowptr) {
+          const int deg = rowptr[r + 1] - rowptr[r];
+          w_reg = aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+        } else w_reg = 1.f;
+      }
+    } else {
+      a_reg[0] = a_reg[1] = a_reg[2] = a_reg[3] = 0.f;
+      b_reg[0] = b_reg[1] = b_reg[2] = b_reg[3] = 0.f;
+      w_reg = 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][l_r][l_c]) = make_float4(a_reg[0], a_reg[1], a_reg[2], a_reg[3]);
+    *reinterpret_cast<float4*>(&Bs[buf][l_r][l_c]) = make_float4(b_reg[0], b_reg[1], b_reg[2], b_reg[3]);
+    if (want_bias && l_c == 0) wrow_s[buf][l_r] = w_reg;
+  };
+
+  const int ty = tid >> 4, tx = tid & 15;  // n = n0 + ty*4 + i, k = k0 + tx*4 + j
+  float acc[4][4];
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nt = (r_end - r_begin + BR - 1) / BR;
+  if (nt > 0) {
+    fetch(r_begin);
+    stash(0);
+  }
+  __syncthreads();
+  for (int t = 0; t < nt; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nt) fetch(r_begin + (t + 1) * BR);
+#pragma unroll
+    for (int r = 0; r < BR; ++r) {
+      float4 a4 = *reinterpret_cast<const float4*>(&As[buf][r][ty * 4]);
+      float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][r][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (want_bias && tx == 0) {
+        const float w = wrow_s[buf][r];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bacc[i] = fmaf(w, a[i], bacc[i]);
+      }
+    }
+    if (t + 1 < nt) stash(buf ^ 1);
+    __syncthreads();
+  }
+  float* out = partial + (size_t)z * Nn * Kk;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= Nn) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < Kk) out[(size_t)n * Kk + k] = acc[i][j];
+    }
+    if (want_bias && tx == 0) bias_partial[(size_t)z * Nn + n] = bacc[i];
+  }
+}
+
+// out[i] (+)= sum_{z < splits} partial[z*count + i]   (fixed order)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, int64_t count,
+                                       float* __restrict__ out, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(size_t)z * count + i];
+  out[i] = accumulate ? out[i] + s : s;
+}
+
+inline int launch_reduce_partials(const float* partial, int splits, int64_t count, float* out, int accumulate,
+                                  cudaStream_t s) {
+  if (count <= 0) return GCB_OK;
+  reduce_partials_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, s>>>(partial, splits, count, out, accumulate);
+  GCB_LAUNCH_CHECK();
+  return GCB_OK;
+}
+
+inline int tn_splits(int rows) {
+  if (rows <= 0) return 0;
+  int s = (int)ceil_div(rows, 1024);
+  if (s > 64) s = 64;
+  return s;
+}
+
+// dW[Nn,Kk] (+)= A^T B ; db[Nn] (+)= sum_r w(r) A[r,:]  (db may be null).  partial needs
+// tn_splits(rows) * Nn * (Kk + 1) floats.
+template <typename T>
+inline int launch_gemm_tn(const T* A, int lda, const T* B, int ldb, int rows, int Nn, int Kk, float* partial,
+                          float* dW, float* db, const int32_t* rowptr, int aggr, int accumulate, cudaStream_t s) {
+  if (Nn <= 0 || Kk <= 0) return GCB_OK;
+  const int splits = tn_splits(rows);
+  float* bias_partial = db ? partial + (size_t)splits * Nn * Kk : nullptr;
+  if (splits > 0) {
+    const int rps = (int)align_up(ceil_div(rows, splits), 16);
+    dim3 grid((unsigned)ceil_div(Kk, 64), (unsigned)ceil_div(Nn, 64), (unsigned)splits);
+    gemm_tn_kernel<T><<<grid, 256, 0, s>>>(A, lda, B, ldb, partial, bias_partial, rowptr, aggr, rows, Nn, Kk, rps);
+    GCB_LAUNCH_CHECK();
+  }
+  GCB_TRY(launch_reduce_partials(partial, splits, (int64_t)Nn * Kk, dW, accumulate, s));
+  if (db) GCB_TRY(launch_reduce_partials(bias_partial, splits, Nn, db, accumulate, s));
+  return GCB_OK;
+}
+
+}  // namespace gcb

@@ -1,0 +1,575 @@
+// Orchestration of the MoleculeGCN hot path behind the C-ABI of include/graphchem_b200.h:
+// parameter layout, derived weights, workspace plan, forward, backward, loss and optimiser.
+//
+// Reference path being replaced: graphchem/nn/gcn.py:120-202 (forward), autograd through it
+// (examples/predict_cn.ipynb:250), F.mse_loss (:249) and torch.optim.Adam.step (:251).
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+
+namespace gcb {
+
+// ---- error string (thread-local; the only state the library keeps) ------------------------------
+static thread_local char g_err[512] = "";
+void set_cuda_error(cudaError_t e, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
+}
+
+// ---- parameter layout ---------------------------------------------------------------------------
+struct ParamLayout {
+  int n_tensors = 0;
+  int64_t off[GCB_MAX_PARAM_TENSORS + 1];
+  // named offsets
+  int64_t emb_atom, emb_bond, w_msg, b_msg, w_edge, b_edge, w_bond, b_bond;
+  int64_t r_w[32], r_b[32];
+  int r_in[32], r_out[32];
+  int n_lin = 0;  // number of readout Linear layers (n_readout + 1, or 0)
+  int64_t total = 0;
+};
+
+static int make_layout(const gcb_model_cfg& c, ParamLayout& p) {
+  if (c.D <= 0 || c.atom_vocab <= 0 || c.bond_vocab <= 0 || c.L < 0 || c.n_readout < 0) return GCB_ERR_INVALID_ARG;
+  if (c.n_readout > 30) return GCB_ERR_UNSUPPORTED;
+  if (c.n_readout > 0 && (c.R <= 0 || c.out_dim <= 0)) return GCB_ERR_INVALID_ARG;
+  const int64_t D = c.D;
+  int64_t o = 0;
+  int n = 0;
+  auto add = [&](int64_t& slot, int64_t count) { slot = o; p.off[n++] = o; o += count; };
+  add(p.emb_atom, (int64_t)c.atom_vocab * D);
+  add(p.emb_bond, (int64_t)c.bond_vocab * D);
+  add(p.w_msg, D * D); add(p.b_msg, D);
+  add(p.w_edge, D * D); add(p.b_edge, D);
+  add(p.w_bond, D * 2 * D); add(p.b_bond, D);
+  p.n_lin = c.n_readout > 0 ? c.n_readout + 1 : 0;
+  for (int k = 0; k < p.n_lin; ++k) {
+    p.r_in[k] = k == 0 ? c.D : c.R;
+    p.r_out[k] = k == p.n_lin - 1 ? c.out_dim : c.R;
+    add(p.r_w[k], (int64_t)p.r_in[k] * p.r_out[k]);
+    add(p.r_b[k], p.r_out[k]);
+  }
+  p.off[n] = o;
+  p.n_tensors = n;
+  p.total = o;
+  return GCB_OK;
+}
+
+static int check_cfg(const gcb_model_cfg& c) {
+  if (c.dtype != GCB_F32 && c.dtype != GCB_BF16) return GCB_ERR_INVALID_ARG;
+  if (c.act < 0 || c.act > GCB_ACT_LEAKY_RELU) return GCB_ERR_INVALID_ARG;
+  if (c.aggr != GCB_AGGR_ADD && c.aggr != GCB_AGGR_MEAN) return GCB_ERR_UNSUPPORTED;
+  if (c.D % 8 != 0) return GCB_ERR_UNSUPPORTED;  // 16-byte channel chunks in both dtypes
+  if (!(c.p_dropout >= 0.f && c.p_dropout < 1.f)) return GCB_ERR_UNSUPPORTED;
+  if (c.L > 250) return GCB_ERR_UNSUPPORTED;
+  return GCB_OK;
+}
+
+// ---- derived weights ----------------------------------------------------------------------------
+struct Derived {
+  char* base;
+  int64_t wpq, wat, watT, wpqT, bpq, bat, total;
+};
+static Derived derived_layout(const gcb_model_cfg& c, void* base) {
+  const int64_t D = c.D, es = c.dtype == GCB_BF16 ? 2 : 4;
+  Derived d;
+  d.base = (char*)base;
+  int64_t o = 0;
+  auto add = [&](int64_t& slot, int64_t bytes) { slot = o; o += align_up(bytes, 256); };
+  add(d.wpq, 2 * D * D * es); add(d.wat, 2 * D * D * es); add(d.watT, 2 * D * D * es); add(d.wpqT, 2 * D * D * es);
+  add(d.bpq, 2 * D * 4); add(d.bat, D * 4);
+  d.total = o;
+  return d;
+}
+
+template <typename T>
+__global__ void prepare_weights_kernel(const float* __restrict__ w_msg, const float* __restrict__ b_msg,
+                                       const float* __restrict__ w_edge, const float* __restrict__ b_edge,
+                                       const float* __restrict__ w_bond, const float* __restrict__ b_bond,
+                                       T* __restrict__ wpq, T* __restrict__ wat, T* __restrict__ watT,
+                                       T* __restrict__ wpqT, float* __restrict__ bpq, float* __restrict__ bat, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int DD2 = 2 * D * D;
+  if (idx < DD2) {
+    // Wpq[n][k], n in [0,2D), k in [0,D):  U = W1 - W2 (n < D), V = W2 (n >= D);  W_b = [W1 | W2], [D, 2D]
+    const int n = idx / D, k = idx % D;
+    const float pq = n < D ? w_bond[(size_t)n * 2 * D + k] - w_bond[(size_t)n * 2 * D + D + k]
+                           : w_bond[(size_t)(n - D) * 2 * D + D + k];
+    wpq[idx] = from_float<T>(pq);
+    wpqT[(size_t)k * 2 * D + n] = from_float<T>(pq);
+    // Wat[o][j], o in [0,D), j in [0,2D): [W_msg | W_edge]
+    const int o = idx / (2 * D), j = idx % (2 * D);
+    const float at = j < D ? w_msg[(size_t)o * D + j] : w_edge[(size_t)o * D + (j - D)];
+    wat[idx] = from_float<T>(at);
+    watT[(size_t)j * D + o] = from_float<T>(at);
+  }
+  if (idx < 2 * D) bpq[idx] = idx < D ? b_bond[idx] : 0.f;
+  if (idx < D) bat[idx] = b_msg[idx] + b_edge[idx];
+}
+
+// acc buffers -> flat gradient of the conv parameters.
+__global__ void finalize_conv_grads_kernel(const float* __restrict__ accWpq, const float* __restrict__ accBpq,
+                                           const float* __restrict__ accWat, const float* __restrict__ accBat,
+                                           float* __restrict__ g_wmsg, float* __restrict__ g_bmsg,
+                                           float* __restrict__ g_wedge, float* __restrict__ g_bedge,
+                                           float* __restrict__ g_wbond, float* __restrict__ g_bbond, int D,
+                                           int accumulate, int zero) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  auto put = [&](float* dst, float v) { *dst = accumulate ? *dst + v : v; };
+  if (idx < 2 * D * D) {
+    {  // bond weight [D, 2D]: dW1 = dU, dW2 = dV - dU
+      const int o = idx / (2 * D), j = idx % (2 * D);
+      float v = 0.f;
+      if (!zero) v = j < D ? accWpq[(size_t)o * D + j] : accWpq[(size_t)(D + o) * D + (j - D)] - accWpq[(size_t)o * D + (j - D)];
+      put(g_wbond + idx, v);
+    }
+    {  // [W_msg | W_edge] accumulated as [D, 2D]
+      const int o = idx / (2 * D), j = idx % (2 * D);
+      const float v = zero ? 0.f : accWat[idx];
+      if (j < D) put(g_wmsg + (size_t)o * D + j, v);
+      else put(g_wedge + (size_t)o * D + (j - D), v);
+    }
+  }
+  if (idx < D) {
+    const float vb = zero ? 0.f : accBat[idx];
+    put(g_bmsg + idx, vb);
+    put(g_bedge + idx, vb);
+    put(g_bbond + idx, zero ? 0.f : accBpq[idx]);
+  }
+}
+
+// ---- workspace plan -----------------------------------------------------------------------------
+constexpr int kMaxLayers = 256;
+constexpr int kEmbedSplits = 32;
+
+struct Plan {
+  int64_t total = 0;
+  char* base = nullptr;
+  // forward (saved) tensors
+  void* A[kMaxLayers];
+  void* B[kMaxLayers];
+  void* PQ[kMaxLayers];
+  void* S[kMaxLayers];
+  float* pooled = nullptr;
+  float* H[33];
+  // backward temporaries
+  void* dZA[2];
+  void* dS = nullptr;
+  void* dBn[2];
+  void* dPQ = nullptr;
+  void* mx = nullptr;
+  void* gsplit = nullptr;
+  float* dH[2];
+  float* dPool = nullptr;
+  float* partial = nullptr;
+  float *accWpq = nullptr, *accBpq = nullptr, *accWat = nullptr, *accBat = nullptr;
+};
+
+static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, int64_t E, int64_t G, int64_t M,
+                     int flags, void* base, Plan& p) {
+  const int64_t D = c.D, es = c.dtype == GCB_BF16 ? 2 : 4;
+  const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
+  const int L = c.L;
+  if (L + 1 > kMaxLayers) return GCB_ERR_UNSUPPORTED;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) -> void* {
+    void* ptr = base ? (char*)base + o : nullptr;
+    o += align_up(bytes > 0 ? bytes : 1, 256);
+    return ptr;
+  };
+  p.base = (char*)base;
+  if (save) {
+    for (int l = 0; l <= L; ++l) p.A[l] = take(N * D * es);
+    for (int l = 0; l <= L; ++l) p.B[l] = take(M * D * es);
+    for (int l = 1; l <= L; ++l) p.PQ[l] = take(M * 2 * D * es);
+    for (int l = 1; l <= L; ++l) p.S[l] = take(N * 2 * D * es);
+  } else {
+    void* a2[2] = {take(N * D * es), take(N * D * es)};
+    void* b2[2] = {take(M * D * es), take(M * D * es)};
+    void* pq = take(M * 2 * D * es);
+    void* s = take(N * 2 * D * es);
+    for (int l = 0; l <= L; ++l) { p.A[l] = a2[l & 1]; p.B[l] = b2[l & 1]; p.PQ[l] = pq; p.S[l] = s; }
+  }
+  p.pooled = (float*)take(G * D * 4);
+  const int64_t R = c.n_readout > 0 ? c.R : 0;
+  p.H[0] = p.pooled;
+  for (int k = 1; k <= c.n_readout; ++k) p.H[k] = (float*)take(G * R * 4);
+  if (save) {
+    p.dZA[0] = take(N * D * es); p.dZA[1] = take(N * D * es);
+    p.dS = take(N * 2 * D * es);
+    p.dBn[0] = take(M * D * es); p.dBn[1] = take(M * D * es);
+    p.dPQ = take(M * 2 * D * es);
+    p.mx = take(M * D * es);
+    p.gsplit = take(M * D * es);
+    const int64_t wmax = D > R ? D : R;
+    p.dH[0] = (float*)take(G * wmax * 4); p.dH[1] = (float*)take(G * wmax * 4);
+    p.dPool = (float*)take(G * D * 4);
+    // partial sums of the TN GEMMs / embedding gradients
+    int64_t pf = 64 * (2 * D * D + 2 * D);
+    for (int k = 0; k < pl.n_lin; ++k) {
+      const int64_t need = (int64_t)tn_splits((int)G) * pl.r_out[k] * (pl.r_in[k] + 1);
+      if (need > pf) pf = need;
+    }
+    const int64_t vmax = c.atom_vocab > c.bond_vocab ? c.atom_vocab : c.bond_vocab;
+    if (kEmbedSplits * vmax * D > pf) pf = kEmbedSplits * vmax * D;
+    p.partial = (float*)take(pf * 4);
+    p.accWpq = (float*)take(2 * D * D * 4);
+    p.accBpq = (float*)take(2 * D * 4);
+    p.accWat = (float*)take(2 * D * D * 4);
+    p.accBat = (float*)take(D * 4);
+  }
+  p.total = o;
+  return GCB_OK;
+}
+
+struct Graph {
+  int N, E, G, M;
+  const int32_t *x_tok, *e_tok, *src, *dst, *in_ptr, *in_eid, *in_src, *out_ptr, *out_eid, *out_dst, *graph_ptr,
+      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row;
+};
+static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32_t* h, Graph& g) {
+  if (!packed || !h || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
+  g.N = h[GCB_H_N]; g.E = h[GCB_H_E]; g.G = h[GCB_H_G]; g.M = h[GCB_H_M];
+  if (h[GCB_H_AV] != c.atom_vocab || h[GCB_H_BV] != c.bond_vocab) return GCB_ERR_INVALID_ARG;
+  const int expectM = c.L >= 1 ? (g.N < g.E ? g.N : g.E) : g.E;
+  if (g.M != expectM) return GCB_ERR_INVALID_ARG;
+  g.x_tok = packed + h[GCB_H_X_TOK]; g.e_tok = packed + h[GCB_H_E_TOK];
+  g.src = packed + h[GCB_H_SRC]; g.dst = packed + h[GCB_H_DST];
+  g.in_ptr = packed + h[GCB_H_IN_PTR]; g.in_eid = packed + h[GCB_H_IN_EID]; g.in_src = packed + h[GCB_H_IN_SRC];
+  g.out_ptr = packed + h[GCB_H_OUT_PTR]; g.out_eid = packed + h[GCB_H_OUT_EID]; g.out_dst = packed + h[GCB_H_OUT_DST];
+  g.graph_ptr = packed + h[GCB_H_GRAPH_PTR]; g.graph_node = packed + h[GCB_H_GRAPH_NODE];
+  g.atok_ptr = packed + h[GCB_H_ATOK_PTR]; g.atok_node = packed + h[GCB_H_ATOK_NODE];
+  g.btok_ptr = packed + h[GCB_H_BTOK_PTR]; g.btok_row = packed + h[GCB_H_BTOK_ROW];
+  return GCB_OK;
+}
+
+static inline Drop make_drop(const gcb_model_cfg& c, int flags, uint64_t seed, uint32_t tag) {
+  Drop d;
+  if ((flags & GCB_TRAINING) && c.p_dropout > 0.f) { d.p = c.p_dropout; d.seed = seed; d.tag = tag; }
+  return d;
+}
+static inline uint32_t tag_bond(int l) { return 4u * (uint32_t)l; }
+static inline uint32_t tag_atom(int l) { return 4u * (uint32_t)l + 1u; }
+static inline uint32_t tag_readout(int k) { return 100000u + (uint32_t)k; }
+
+// ---- forward ------------------------------------------------------------------------------------
+template <typename T>
+static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Graph& g, const float* params,
+                        const Derived& dv, const Plan& p, int flags, uint64_t seed, float* out, T* out_atom,
+                        T* out_bond, cudaStream_t s) {
+  constexpr int V = Vec<T>::N;
+  const int D = c.D, L = c.L, N = g.N, E = g.E, G = g.G, M = g.M;
+  const T* wpq = (const T*)(dv.base + dv.wpq);
+  const T* wat = (const T*)(dv.base + dv.wat);
+  const float* bpq = (const float*)(dv.base + dv.bpq);
+  const float* bat = (const float*)(dv.base + dv.bat);
+
+  if (N > 0) {
+    embed_act_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>(params + pl.emb_atom, g.x_tok, (T*)p.A[0], N, D, c.act);
+    GCB_LAUNCH_CHECK();
+  }
+  if (M > 0) {
+    embed_act_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(params + pl.emb_bond, g.e_tok, (T*)p.B[0], M, D, c.act);
+    GCB_LAUNCH_CHECK();
+  }
+  for (int l = 1; l <= L; ++l) {
+    const Drop db = make_drop(c, flags, seed, tag_bond(l));
+    const Drop da = make_drop(c, flags, seed, tag_atom(l));
+    if (M > 0) {
+      Epilogue ep;
+      ep.bias = bpq;
+      GCB_TRY(launch_gemm_nt<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
+      bond_update_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>((const T*)p.PQ[l], g.in_ptr, g.in_src, (T*)p.B[l],
+                                                                       M, D, c.act, db);
+      GCB_LAUNCH_CHECK();
+    }
+    if (N > 0) {
+      atom_gather_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr,
+                                                                       g.in_src, g.in_eid, (T*)p.S[l], N, M, D, c.act,
+                                                                       c.aggr, db);
+      GCB_LAUNCH_CHECK();
+      Epilogue ep;
+      ep.bias = bat; ep.rowptr = g.in_ptr; ep.aggr = c.aggr;
+      ep.res = p.A[l - 1]; ep.ld_res = D; ep.act = c.act;
+      GCB_TRY(launch_gemm_nt<T>((const T*)p.S[l], 2 * D, wat, 2 * D, false, (T*)p.A[l], D, N, D, 2 * D, ep, s));
+      if (da.p > 0.f) {
+        dropout_inplace_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((T*)p.A[l], N, D, da);
+        GCB_LAUNCH_CHECK();
+      }
+    }
+  }
+  // pooling + readout (fp32)
+  if (G > 0) {
+    pool_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>((const T*)p.A[L], g.graph_ptr, g.graph_node, p.pooled, G, D);
+    GCB_LAUNCH_CHECK();
+    if (pl.n_lin == 0) {
+      if (out) GCB_CUDA(cudaMemcpyAsync(out, p.pooled, (size_t)G * D * 4, cudaMemcpyDeviceToDevice, s));
+    } else {
+      for (int k = 0; k < pl.n_lin; ++k) {
+        const bool last = k == pl.n_lin - 1;
+        Epilogue ep;
+        ep.bias = params + pl.r_b[k];
+        ep.act = last ? -1 : c.act;
+        float* dst = last ? out : p.H[k + 1];
+        if (!dst) break;
+        GCB_TRY(launch_gemm_nt<float>(p.H[k], pl.r_in[k], params + pl.r_w[k], pl.r_in[k], false, dst, pl.r_out[k], G,
+                                      pl.r_out[k], pl.r_in[k], ep, s));
+        const Drop dr = make_drop(c, flags, seed, tag_readout(k + 1));
+        if (!last && dr.p > 0.f) {
+          const int64_t cnt = (int64_t)G * pl.r_out[k];
+          dropout_scalar_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, s>>>(dst, cnt, dr);
+          GCB_LAUNCH_CHECK();
+        }
+      }
+    }
+  }
+  if (out_atom && N > 0) GCB_CUDA(cudaMemcpyAsync(out_atom, p.A[L], (size_t)N * D * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  if (out_bond && E > 0) {
+    if (M > 0) GCB_CUDA(cudaMemcpyAsync(out_bond, p.B[L], (size_t)M * D * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (E > M) {
+      fill_const_rows_kernel<T><<<row_chunk_blocks(E - M, D, V), 256, 0, s>>>(out_bond, M, E - M, D, c.act,
+                                                                             make_drop(c, flags, seed, tag_bond(L)));
+      GCB_LAUNCH_CHECK();
+    }
+  }
+  return GCB_OK;
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+template <typename T>
+static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Graph& g, const float* params,
+                         const Derived& dv, const Plan& p, int flags, uint64_t seed, const float* d_out,
+                         const T* d_out_atom, const T* d_out_bond, float* grad, int accumulate, cudaStream_t s) {
+  constexpr int V = Vec<T>::N;
+  const int D = c.D, L = c.L, N = g.N, G = g.G, M = g.M;
+  const T* watT = (const T*)(dv.base + dv.watT);
+  const T* wpqT = (const T*)(dv.base + dv.wpqT);
+
+  // ---- readout ----
+  const float* dPool = nullptr;
+  if (d_out && G > 0) {
+    if (pl.n_lin == 0) {
+      dPool = d_out;
+    } else {
+      const float* dcur = d_out;
+      for (int k = pl.n_lin - 1; k >= 0; --k) {
+        GCB_TRY(launch_gemm_tn<float>(dcur, pl.r_out[k], p.H[k], pl.r_in[k], G, pl.r_out[k], pl.r_in[k], p.partial,
+                                      grad + pl.r_w[k], grad + pl.r_b[k], nullptr, GCB_AGGR_ADD, accumulate, s));
+        float* dnext = k > 0 ? p.dH[k & 1] : p.dPool;
+        Epilogue ep;
+        if (k > 0) {
+          ep.actgrad_y = p.H[k]; ep.ld_y = pl.r_in[k]; ep.act = c.act;
+          const Drop dr = make_drop(c, flags, seed, tag_readout(k));
+          ep.p_drop = dr.p; ep.seed = dr.seed; ep.drop_tag = dr.tag;
+        }
+        GCB_TRY(launch_gemm_nt<float>(dcur, pl.r_out[k], params + pl.r_w[k], pl.r_in[k], true, dnext, pl.r_in[k], G,
+                                      pl.r_in[k], pl.r_out[k], ep, s));
+        dcur = dnext;
+      }
+      dPool = p.dPool;
+    }
+  } else if (pl.n_lin > 0 && !accumulate) {
+    for (int k = 0; k < pl.n_lin; ++k) {
+      GCB_CUDA(cudaMemsetAsync(grad + pl.r_w[k], 0, sizeof(float) * (size_t)(pl.off[8 + 2 * k + 2] - pl.off[8 + 2 * k]), s));
+    }
+  }
+
+  // ---- pool backward -> dZA_L ----
+  int cur = 0;
+  if (N > 0) {
+    if (G > 0) {
+      pool_bwd_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>(
+          dPool, d_out_atom, (const T*)p.A[L], g.graph_ptr, g.graph_node, (T*)p.dZA[cur], G, D, c.act,
+          L >= 1 ? make_drop(c, flags, seed, tag_atom(L)) : Drop());
+      GCB_LAUNCH_CHECK();
+    } else {
+      GCB_CUDA(cudaMemsetAsync(p.dZA[cur], 0, (size_t)N * D * sizeof(T), s));
+    }
+  }
+  // ---- message-passing layers, last to first ----
+  const T* dBnext = nullptr;
+  int bcur = 0;
+  for (int l = L; l >= 1; --l) {
+    const int acc_w = l != L;
+    if (N > 0) {
+      Epilogue ep;
+      GCB_TRY(launch_gemm_nt<T>((const T*)p.dZA[cur], D, watT, D, false, (T*)p.dS, 2 * D, N, 2 * D, D, ep, s));
+    }
+    GCB_TRY(launch_gemm_tn<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
+                              p.accBat, g.in_ptr, c.aggr, acc_w, s));
+    if (N > 0) {
+      atom_bwd_gather_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>(
+          (const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.in_ptr, (const T*)p.A[l - 1], (T*)p.dZA[cur ^ 1],
+          N, D, c.act, c.aggr, l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop());
+      GCB_LAUNCH_CHECK();
+    }
+    if (M > 0) {
+      bond_bwd_tie_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(
+          (const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l], g.dst, g.in_ptr,
+          g.in_src, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit, M, D, c.act, c.aggr, make_drop(c, flags, seed, tag_bond(l)));
+      GCB_LAUNCH_CHECK();
+      bond_bwd_scatter_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(
+          (const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, (T*)p.dPQ, M, D);
+      GCB_LAUNCH_CHECK();
+    }
+    GCB_TRY(launch_gemm_tn<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
+                              p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s));
+    if (M > 0) {
+      Epilogue ep;
+      GCB_TRY(launch_gemm_nt<T>((const T*)p.dPQ, 2 * D, wpqT, 2 * D, false, (T*)p.dBn[bcur], D, M, D, 2 * D, ep, s));
+      dBnext = (const T*)p.dBn[bcur];
+      bcur ^= 1;
+    }
+    cur ^= 1;
+  }
+  // ---- embeddings ----
+  {
+    const int av = c.atom_vocab, bv = c.bond_vocab, CH = D / V;
+    if (N > 0) {
+      embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)av * kEmbedSplits * CH, 256), 256, 0, s>>>(
+          (const T*)p.dZA[cur], nullptr, g.atok_ptr, g.atok_node, p.partial, av, kEmbedSplits, D, c.act);
+      GCB_LAUNCH_CHECK();
+    }
+    GCB_TRY(launch_reduce_partials(p.partial, N > 0 ? kEmbedSplits : 0, (int64_t)av * D, grad + pl.emb_atom, accumulate, s));
+    const T* dB0 = L >= 1 ? dBnext : d_out_bond;
+    const bool have = dB0 != nullptr && M > 0;
+    if (have) {
+      embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)bv * kEmbedSplits * CH, 256), 256, 0, s>>>(
+          dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, p.partial, bv, kEmbedSplits, D, c.act);
+      GCB_LAUNCH_CHECK();
+    }
+    GCB_TRY(launch_reduce_partials(p.partial, have ? kEmbedSplits : 0, (int64_t)bv * D, grad + pl.emb_bond, accumulate, s));
+  }
+  // ---- conv parameters ----
+  finalize_conv_grads_kernel<<<(unsigned)ceil_div(2 * D * D, 256), 256, 0, s>>>(
+      p.accWpq, p.accBpq, p.accWat, p.accBat, grad + pl.w_msg, grad + pl.b_msg, grad + pl.w_edge, grad + pl.b_edge,
+      grad + pl.w_bond, grad + pl.b_bond, D, accumulate, L == 0);
+  GCB_LAUNCH_CHECK();
+  return GCB_OK;
+}
+
+}  // namespace gcb
+
+using namespace gcb;
+
+// =================================================================================================
+extern "C" int gcb_abi_version(void) { return GCB_ABI_VERSION; }
+extern "C" const char* gcb_last_cuda_error(void) { return g_err; }
+extern "C" const char* gcb_build_info(void) {
+  return "graphchem_b200 sm_100a; kernels: simt-gemm fp32/bf16, csr gather/reduce; built " __DATE__ " " __TIME__;
+}
+
+extern "C" int gcb_param_layout(const gcb_model_cfg* cfg, int64_t* offsets) {
+  if (!cfg) return GCB_ERR_INVALID_ARG;
+  ParamLayout pl;
+  int rc = make_layout(*cfg, pl);
+  if (rc != GCB_OK) return rc;
+  if (offsets) std::memcpy(offsets, pl.off, sizeof(int64_t) * (pl.n_tensors + 1));
+  return pl.n_tensors;
+}
+
+extern "C" int64_t gcb_derived_bytes(const gcb_model_cfg* cfg) {
+  if (!cfg || check_cfg(*cfg) != GCB_OK) return GCB_ERR_INVALID_ARG;
+  return derived_layout(*cfg, nullptr).total;
+}
+
+extern "C" int gcb_prepare_weights(const gcb_model_cfg* cfg, const float* params, void* derived, void* stream) {
+  if (!cfg || !params || !derived) return GCB_ERR_INVALID_ARG;
+  GCB_TRY(check_cfg(*cfg));
+  ParamLayout pl;
+  GCB_TRY(make_layout(*cfg, pl));
+  Derived d = derived_layout(*cfg, derived);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = cfg->D;
+  const unsigned blocks = (unsigned)ceil_div(2 * D * D, 256);
+  if (cfg->dtype == GCB_BF16) {
+    prepare_weights_kernel<bf16><<<blocks, 256, 0, s>>>(
+        params + pl.w_msg, params + pl.b_msg, params + pl.w_edge, params + pl.b_edge, params + pl.w_bond,
+        params + pl.b_bond, (bf16*)(d.base + d.wpq), (bf16*)(d.base + d.wat), (bf16*)(d.base + d.watT),
+        (bf16*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D);
+  } else {
+    prepare_weights_kernel<float><<<blocks, 256, 0, s>>>(
+        params + pl.w_msg, params + pl.b_msg, params + pl.w_edge, params + pl.b_edge, params + pl.w_bond,
+        params + pl.b_bond, (float*)(d.base + d.wpq), (float*)(d.base + d.wat), (float*)(d.base + d.watT),
+        (float*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D);
+  }
+  GCB_LAUNCH_CHECK();
+  return GCB_OK;
+}
+
+extern "C" int64_t gcb_workspace_bytes(const gcb_model_cfg* cfg, int32_t N, int32_t E, int32_t G, int32_t flags) {
+  if (!cfg || N < 0 || E < 0 || G < 0) return GCB_ERR_INVALID_ARG;
+  if (check_cfg(*cfg) != GCB_OK) return GCB_ERR_UNSUPPORTED;
+  ParamLayout pl;
+  if (make_layout(*cfg, pl) != GCB_OK) return GCB_ERR_INVALID_ARG;
+  const int64_t M = cfg->L >= 1 ? (N < E ? N : E) : E;
+  Plan p;
+  if (make_plan(*cfg, pl, N, E, G, M, flags, nullptr, p) != GCB_OK) return GCB_ERR_UNSUPPORTED;
+  return p.total;
+}
+
+extern "C" int gcb_forward(const gcb_model_cfg* cfg, const int32_t* packed, const int32_t* packed_header_host,
+                           const float* params, const void* derived, void* workspace, int64_t workspace_bytes,
+                           int32_t flags, uint64_t seed, float* out, void* out_atom, void* out_bond, void* stream) {
+  if (!cfg || !params || !derived || !workspace) return GCB_ERR_INVALID_ARG;
+  GCB_TRY(check_cfg(*cfg));
+  ParamLayout pl;
+  GCB_TRY(make_layout(*cfg, pl));
+  Graph g;
+  GCB_TRY(make_graph(*cfg, packed, packed_header_host, g));
+  Plan p;
+  GCB_TRY(make_plan(*cfg, pl, g.N, g.E, g.G, g.M, flags, workspace, p));
+  if (p.total > workspace_bytes) return GCB_ERR_WORKSPACE;
+  Derived dv = derived_layout(*cfg, const_cast<void*>(derived));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->dtype == GCB_BF16)
+    return forward_impl<bf16>(*cfg, pl, g, params, dv, p, flags, seed, out, (bf16*)out_atom, (bf16*)out_bond, s);
+  return forward_impl<float>(*cfg, pl, g, params, dv, p, flags, seed, out, (float*)out_atom, (float*)out_bond, s);
+}
+
+extern "C" int gcb_backward(const gcb_model_cfg* cfg, const int32_t* packed, const int32_t* packed_header_host,
+                            const float* params, const void* derived, void* workspace, int64_t workspace_bytes,
+                            int32_t flags, uint64_t seed, const float* d_out, const void* d_out_atom,
+                            const void* d_out_bond, float* grad, int32_t accumulate, void* stream) {
+  if (!cfg || !params || !derived || !workspace || !grad) return GCB_ERR_INVALID_ARG;
+  if (!(flags & GCB_SAVE_FOR_BWD)) return GCB_ERR_INVALID_ARG;
+  GCB_TRY(check_cfg(*cfg));
+  ParamLayout pl;
+  GCB_TRY(make_layout(*cfg, pl));
+  Graph g;
+  GCB_TRY(make_graph(*cfg, packed, packed_header_host, g));
+  Plan p;
+  GCB_TRY(make_plan(*cfg, pl, g.N, g.E, g.G, g.M, flags, workspace, p));
+  if (p.total > workspace_bytes) return GCB_ERR_WORKSPACE;
+  Derived dv = derived_layout(*cfg, const_cast<void*>(derived));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->dtype == GCB_BF16)
+    return backward_impl<bf16>(*cfg, pl, g, params, dv, p, flags, seed, d_out, (const bf16*)d_out_atom,
+                               (const bf16*)d_out_bond, grad, accumulate, s);
+  return backward_impl<float>(*cfg, pl, g, params, dv, p, flags, seed, d_out, (const float*)d_out_atom,
+                              (const float*)d_out_bond, grad, accumulate, s);
+}
+
+extern "C" int gcb_mse_loss(const float* pred, const float* y, int64_t n, float* loss, float* d_pred,
+                            float grad_scale, void* stream) {
+  if (!pred || !y || n <= 0) return GCB_ERR_INVALID_ARG;
+  mse_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, y, n, loss, d_pred, grad_scale);
+  GCB_LAUNCH_CHECK();
+  return GCB_OK;
+}
+
+extern "C" int gcb_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             const float* hyper, int32_t* step_count, float beta1, float beta2, float eps,
+                             void* stream) {
+  if (!params || !grad || !exp_avg || !exp_avg_sq || !hyper || !step_count || n < 0) return GCB_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n > 0) {
+    adam_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(params, grad, exp_avg, exp_avg_sq, n, hyper, step_count,
+                                                           beta1, beta2, eps);
+    GCB_LAUNCH_CHECK();
+  }
+  increment_kernel<<<1, 1, 0, s>>>(step_count);
+  GCB_LAUNCH_CHECK();
+  return GCB_OK;
+}

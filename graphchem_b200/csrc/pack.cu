@@ -1,0 +1,192 @@
+// Host-side packer: PyG-style Batch -> one int32 buffer with tokens, edge list, destination- and
+// source-sorted CSR, graph segments and token buckets.  Pure integer work; must match
+// oracle/csr_oracle.py (stable argsort) bit for bit.
+//
+// Reference semantics restated here (not code): PyG scatters messages in edge-id order over
+// edge_index[1], collate concatenates graphs with cumulative node offsets
+// (call site examples/predict_cn.ipynb:212,245), MoleculeEncoder.encode emits
+// int32 tokens and an int64 [2,e] connectivity (graphchem/preprocessing/features.py:294-319).
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gcb {
+
+static inline int64_t pad4(int64_t n) { return (n + 3) & ~int64_t(3); }
+
+static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, int32_t bv, int32_t* h) {
+  int64_t off = GCB_PACK_HEADER_INTS;
+  auto put = [&](int field, int64_t n) {
+    if (h) h[field] = (int32_t)off;
+    off += pad4(n);
+  };
+  if (h) {
+    std::memset(h, 0, sizeof(int32_t) * GCB_PACK_HEADER_INTS);
+    h[GCB_H_MAGIC] = GCB_PACK_MAGIC;
+    h[GCB_H_N] = N; h[GCB_H_E] = E; h[GCB_H_G] = G; h[GCB_H_M] = M; h[GCB_H_AV] = av; h[GCB_H_BV] = bv;
+  }
+  put(GCB_H_X_TOK, N); put(GCB_H_E_TOK, E); put(GCB_H_SRC, E); put(GCB_H_DST, E);
+  put(GCB_H_IN_PTR, (int64_t)N + 1); put(GCB_H_IN_EID, E); put(GCB_H_IN_SRC, E);
+  put(GCB_H_OUT_PTR, (int64_t)N + 1); put(GCB_H_OUT_EID, E); put(GCB_H_OUT_DST, E);
+  put(GCB_H_GRAPH_PTR, (int64_t)G + 1); put(GCB_H_GRAPH_NODE, N);
+  put(GCB_H_ATOK_PTR, (int64_t)av + 1); put(GCB_H_ATOK_NODE, N);
+  put(GCB_H_BTOK_PTR, (int64_t)bv + 1); put(GCB_H_BTOK_ROW, E);
+  if (off > INT32_MAX) return -1;
+  if (h) h[GCB_H_TOTAL_INTS] = (int32_t)off;
+  return off;
+}
+
+// Stable counting sort of ids 0..n-1 by key: ptr[nb+1], perm[n].
+static void bucket(const int32_t* key, int64_t n, int32_t nb, int32_t* ptr, int32_t* perm) {
+  std::memset(ptr, 0, sizeof(int32_t) * ((size_t)nb + 1));
+  for (int64_t i = 0; i < n; ++i) ptr[key[i] + 1]++;
+  for (int32_t b = 0; b < nb; ++b) ptr[b + 1] += ptr[b];
+  std::vector<int32_t> cur(ptr, ptr + nb);
+  for (int64_t i = 0; i < n; ++i) perm[cur[key[i]]++] = (int32_t)i;
+}
+
+static inline int64_t read_idx(const void* p, int32_t idx_bytes, int64_t i) {
+  return idx_bytes == 8 ? ((const int64_t*)p)[i] : (int64_t)((const int32_t*)p)[i];
+}
+
+// Fill every derived section from x_tok/e_tok/src/dst (already written) and a batch vector.
+static int finish_pack(int32_t* packed, const int32_t* h, const int32_t* batch_i32 /*[N] or null*/) {
+  const int32_t N = h[GCB_H_N], E = h[GCB_H_E], G = h[GCB_H_G], M = h[GCB_H_M];
+  const int32_t av = h[GCB_H_AV], bv = h[GCB_H_BV];
+  int32_t* x_tok = packed + h[GCB_H_X_TOK];
+  int32_t* e_tok = packed + h[GCB_H_E_TOK];
+  int32_t* src = packed + h[GCB_H_SRC];
+  int32_t* dst = packed + h[GCB_H_DST];
+  int32_t* in_ptr = packed + h[GCB_H_IN_PTR];
+  int32_t* in_eid = packed + h[GCB_H_IN_EID];
+  int32_t* in_src = packed + h[GCB_H_IN_SRC];
+  int32_t* out_ptr = packed + h[GCB_H_OUT_PTR];
+  int32_t* out_eid = packed + h[GCB_H_OUT_EID];
+  int32_t* out_dst = packed + h[GCB_H_OUT_DST];
+  bucket(dst, E, N, in_ptr, in_eid);
+  for (int64_t k = 0; k < E; ++k) in_src[k] = src[in_eid[k]];
+  bucket(src, E, N, out_ptr, out_eid);
+  for (int64_t k = 0; k < E; ++k) out_dst[k] = dst[out_eid[k]];
+  int32_t* graph_ptr = packed + h[GCB_H_GRAPH_PTR];
+  int32_t* graph_node = packed + h[GCB_H_GRAPH_NODE];
+  if (batch_i32) {
+    bucket(batch_i32, N, G, graph_ptr, graph_node);
+  } else {
+    graph_ptr[0] = 0;
+    for (int32_t g = 1; g <= G; ++g) graph_ptr[g] = N;
+    for (int32_t i = 0; i < N; ++i) graph_node[i] = i;
+  }
+  bucket(x_tok, N, av, packed + h[GCB_H_ATOK_PTR], packed + h[GCB_H_ATOK_NODE]);
+  bucket(e_tok, M, bv, packed + h[GCB_H_BTOK_PTR], packed + h[GCB_H_BTOK_ROW]);
+  return GCB_OK;
+}
+
+}  // namespace gcb
+
+using namespace gcb;
+
+extern "C" int64_t gcb_pack_ints(int32_t N, int32_t E, int32_t G, int32_t M, int32_t atom_vocab,
+                                 int32_t bond_vocab, int32_t* header) {
+  if (N < 0 || E < 0 || G < 0 || M < 0 || M > E || atom_vocab < 0 || bond_vocab < 0) return GCB_ERR_INVALID_ARG;
+  return layout(N, E, G, M, atom_vocab, bond_vocab, header);
+}
+
+extern "C" int gcb_pack_host(const void* x, const void* edge_attr, const void* edge_index, const void* batch,
+                             int32_t idx_bytes, int32_t N, int32_t E, int32_t G, int32_t M, int32_t atom_vocab,
+                             int32_t bond_vocab, int32_t check_bond_rows, int32_t* packed, int64_t packed_ints) {
+  if (idx_bytes != 4 && idx_bytes != 8) return GCB_ERR_INVALID_ARG;
+  if (!packed || (N > 0 && !x) || (E > 0 && (!edge_attr || !edge_index))) return GCB_ERR_INVALID_ARG;
+  int32_t h[GCB_PACK_HEADER_INTS];
+  int64_t total = gcb_pack_ints(N, E, G, M, atom_vocab, bond_vocab, h);
+  if (total < 0) return GCB_ERR_INVALID_ARG;
+  if (packed_ints < total) return GCB_ERR_WORKSPACE;
+  std::memset(packed, 0, sizeof(int32_t) * (size_t)total);
+  std::memcpy(packed, h, sizeof(h));
+  int32_t* x_tok = packed + h[GCB_H_X_TOK];
+  int32_t* e_tok = packed + h[GCB_H_E_TOK];
+  int32_t* src = packed + h[GCB_H_SRC];
+  int32_t* dst = packed + h[GCB_H_DST];
+  for (int64_t i = 0; i < N; ++i) {
+    int64_t t = read_idx(x, idx_bytes, i);
+    if (t < 0 || t >= atom_vocab) return GCB_ERR_INDEX;  // nn.Embedding: index out of range
+    x_tok[i] = (int32_t)t;
+  }
+  for (int64_t e = 0; e < E; ++e) {
+    int64_t t = read_idx(edge_attr, idx_bytes, e);
+    if (t < 0 || t >= bond_vocab) return GCB_ERR_INDEX;
+    e_tok[e] = (int32_t)t;
+  }
+  const int64_t lim = check_bond_rows ? (N < E ? N : E) : N;
+  for (int64_t e = 0; e < E; ++e) {
+    int64_t s = read_idx(edge_index, idx_bytes, e), d = read_idx(edge_index, idx_bytes, (int64_t)E + e);
+    if (s < 0 || d < 0 || s >= lim || d >= lim) return GCB_ERR_INDEX;  // PyG _lift IndexError
+    src[e] = (int32_t)s;
+    dst[e] = (int32_t)d;
+  }
+  std::vector<int32_t> b32;
+  if (batch) {
+    b32.resize((size_t)N);
+    for (int64_t i = 0; i < N; ++i) {
+      int64_t g = read_idx(batch, idx_bytes, i);
+      if (g < 0 || g >= G) return GCB_ERR_INDEX;
+      b32[(size_t)i] = (int32_t)g;
+    }
+  }
+  return finish_pack(packed, h, batch ? b32.data() : nullptr);
+}
+
+extern "C" int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t* n_atoms,
+                                     const int32_t* const* bonds, const int64_t* const* conn,
+                                     const int32_t* n_edges, const float* const* y, int32_t n_targets,
+                                     int32_t n_graphs, int32_t n_messages, int32_t atom_vocab,
+                                     int32_t bond_vocab, int32_t* packed, int64_t packed_ints, float* y_out) {
+  if (n_graphs < 0 || !packed || (n_graphs > 0 && (!atoms || !n_atoms || !bonds || !conn || !n_edges)))
+    return GCB_ERR_INVALID_ARG;
+  int64_t N64 = 0, E64 = 0;
+  for (int32_t g = 0; g < n_graphs; ++g) {
+    if (n_atoms[g] < 0 || n_edges[g] < 0) return GCB_ERR_INVALID_ARG;
+    N64 += n_atoms[g];
+    E64 += n_edges[g];
+  }
+  if (N64 > INT32_MAX || E64 > INT32_MAX) return GCB_ERR_INVALID_ARG;
+  const int32_t N = (int32_t)N64, E = (int32_t)E64, G = n_graphs;
+  const int32_t M = n_messages >= 1 ? (N < E ? N : E) : E;
+  int32_t h[GCB_PACK_HEADER_INTS];
+  int64_t total = gcb_pack_ints(N, E, G, M, atom_vocab, bond_vocab, h);
+  if (total < 0) return GCB_ERR_INVALID_ARG;
+  if (packed_ints < total) return GCB_ERR_WORKSPACE;
+  std::memset(packed, 0, sizeof(int32_t) * (size_t)total);
+  std::memcpy(packed, h, sizeof(h));
+  int32_t* x_tok = packed + h[GCB_H_X_TOK];
+  int32_t* e_tok = packed + h[GCB_H_E_TOK];
+  int32_t* src = packed + h[GCB_H_SRC];
+  int32_t* dst = packed + h[GCB_H_DST];
+  std::vector<int32_t> b32((size_t)N);
+  const int64_t lim = n_messages >= 1 ? M : N;
+  int64_t node_off = 0, edge_off = 0;
+  for (int32_t g = 0; g < G; ++g) {
+    const int32_t na = n_atoms[g], ne = n_edges[g];
+    for (int32_t i = 0; i < na; ++i) {
+      int32_t t = atoms[g][i];
+      if (t < 0 || t >= atom_vocab) return GCB_ERR_INDEX;
+      x_tok[node_off + i] = t;
+      b32[(size_t)(node_off + i)] = g;
+    }
+    for (int32_t e = 0; e < ne; ++e) {
+      int32_t t = bonds[g][e];
+      if (t < 0 || t >= bond_vocab) return GCB_ERR_INDEX;
+      e_tok[edge_off + e] = t;
+      int64_t s = conn[g][e] + node_off, d = conn[g][(int64_t)ne + e] + node_off;  // [2,e] row-major
+      if (conn[g][e] < 0 || conn[g][(int64_t)ne + e] < 0 || s >= lim || d >= lim) return GCB_ERR_INDEX;
+      src[edge_off + e] = (int32_t)s;
+      dst[edge_off + e] = (int32_t)d;
+    }
+    if (y_out) {
+      for (int32_t t = 0; t < n_targets; ++t) y_out[(int64_t)g * n_targets + t] = y && y[g] ? y[g][t] : 0.f;
+    }
+    node_off += na;
+    edge_off += ne;
+  }
+  return finish_pack(packed, h, b32.data());
+}

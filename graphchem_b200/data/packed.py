@@ -1,0 +1,184 @@
+"""Pre-packed batches: the host-side half of the hot path.
+
+A `PackedBatch` is ONE int32 buffer (tokens, edge list, destination- and source-sorted CSR, graph
+segments, token buckets; layout in include/graphchem_b200.h) plus the float targets.  It is built
+on host cores by the C-ABI packer (`gcb_pack_host` / `gcb_collate_pack_host`), normally into pinned
+memory, and shipped to HBM with a single copy.  This is the "RDKit featurisation stays on host
+cores, is prepacked into pinned CSR buffers" step of the north star; its index semantics restate
+PyG's collate and scatter order (reference call site
+examples/predict_cn.ipynb:212,245).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from .. import _lib
+
+
+def live_bond_rows(n_nodes: int, n_edges: int, n_messages: int) -> int:
+    """Rows of the bond matrix that carry information: min(N, E) once EdgeConv has run on the bond
+    matrix indexed by atom ids (reference gcn.py:163), all E rows otherwise."""
+    return min(n_nodes, n_edges) if n_messages >= 1 else n_edges
+
+
+class PackedBatch:
+    """Packed batch; `ints` lives on the host (optionally pinned) or on a CUDA device."""
+
+    __slots__ = ("ints", "header", "y", "N", "E", "G", "M")
+
+    def __init__(self, ints: Tensor, header: np.ndarray, y: Optional[Tensor]):
+        self.ints, self.header, self.y = ints, header, y
+        self.N, self.E, self.G, self.M = (int(header[_lib.H_N]), int(header[_lib.H_E]), int(header[_lib.H_G]),
+                                          int(header[_lib.H_M]))
+
+    @property
+    def device(self) -> torch.device:
+        return self.ints.device
+
+    @property
+    def nbytes(self) -> int:
+        return self.ints.numel() * 4 + (0 if self.y is None else self.y.numel() * self.y.element_size())
+
+    def to(self, device, non_blocking: bool = False) -> "PackedBatch":
+        y = None if self.y is None else self.y.to(device, non_blocking=non_blocking)
+        return PackedBatch(self.ints.to(device, non_blocking=non_blocking), self.header, y)
+
+    def section(self, field: int, count: int) -> Tensor:
+        off = int(self.header[field])
+        return self.ints[off:off + count]
+
+    def sections(self) -> dict:
+        """All index arrays as int32 tensors (views), for tests and debugging."""
+        N, E, G, M = self.N, self.E, self.G, self.M
+        av, bv = int(self.header[_lib.H_AV]), int(self.header[_lib.H_BV])
+        L = _lib
+        return dict(
+            x_tok=self.section(L.H_X_TOK, N), e_tok=self.section(L.H_E_TOK, E), src=self.section(L.H_SRC, E),
+            dst=self.section(L.H_DST, E), in_ptr=self.section(L.H_IN_PTR, N + 1), in_eid=self.section(L.H_IN_EID, E),
+            in_src=self.section(L.H_IN_SRC, E), out_ptr=self.section(L.H_OUT_PTR, N + 1),
+            out_eid=self.section(L.H_OUT_EID, E), out_dst=self.section(L.H_OUT_DST, E),
+            graph_ptr=self.section(L.H_GRAPH_PTR, G + 1), graph_node=self.section(L.H_GRAPH_NODE, N),
+            atok_ptr=self.section(L.H_ATOK_PTR, av + 1), atok_node=self.section(L.H_ATOK_NODE, N),
+            btok_ptr=self.section(L.H_BTOK_PTR, bv + 1), btok_row=self.section(L.H_BTOK_ROW, M))
+
+
+def _alloc_ints(n: int, pin: bool) -> Tensor:
+    pin = pin and torch.cuda.is_available()
+    return torch.empty(n, dtype=torch.int32, pin_memory=pin)
+
+
+def _header(N: int, E: int, G: int, M: int, av: int, bv: int):
+    header = np.zeros(_lib.PACK_HEADER_INTS, dtype=np.int32)
+    total = _lib.lib().gcb_pack_ints(N, E, G, M, av, bv, header.ctypes.data)
+    _lib.check(int(total), "gcb_pack_ints")
+    return header, int(total)
+
+
+def _host_index_tensor(t: Tensor, name: str) -> Tensor:
+    if t.dtype not in (torch.int64, torch.int32):
+        if t.dtype in (torch.int16, torch.int8, torch.uint8):
+            t = t.to(torch.int64)
+        else:
+            # nn.Embedding / PyG _check_input reject non-integer indices
+            raise (ValueError if name == "edge_index" else RuntimeError)(
+                f"Expected '{name}' to be of integer type (got '{t.dtype}')")
+    return t.detach().to("cpu").contiguous()
+
+
+def pack_batch(data, n_messages: int, atom_vocab: int, bond_vocab: int, pin: bool = True) -> PackedBatch:
+    """Pack a collated PyG-style Batch (or a single graph with `batch=None`)."""
+    x, edge_attr, edge_index = data.x, data.edge_attr, data.edge_index
+    batch = getattr(data, "batch", None)
+    if x is None:
+        # reference gcn.py:148-149 would feed float ones to nn.Embedding, which raises
+        raise RuntimeError("MoleculeGCN needs integer atom tokens in data.x (nn.Embedding indices)")
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError(f"Expected 'edge_index' to be of shape [2, num_edges] (got {list(edge_index.shape)})")
+    if x.dim() != 1 or edge_attr.dim() != 1:
+        raise ValueError("x and edge_attr must be 1-D integer token tensors")
+    N, E = int(x.size(0)), int(edge_index.size(1))
+    if int(edge_attr.size(0)) != E:
+        raise ValueError("edge_attr and edge_index disagree on the number of edges")
+    x_h = _host_index_tensor(x, "x").to(torch.int64)
+    ea_h = _host_index_tensor(edge_attr, "edge_attr").to(torch.int64)
+    ei_h = _host_index_tensor(edge_index, "edge_index").to(torch.int64)
+    b_h = None
+    if batch is not None:
+        b_h = _host_index_tensor(batch, "batch").to(torch.int64)
+        if b_h.numel() != N:
+            raise ValueError("batch must have one entry per node")
+        G = getattr(data, "num_graphs", None)
+        G = int(G) if isinstance(G, int) else (int(b_h.max()) + 1 if N > 0 else 0)
+    else:
+        G = 1
+    M = live_bond_rows(N, E, n_messages)
+    header, total = _header(N, E, G, M, atom_vocab, bond_vocab)
+    ints = _alloc_ints(total, pin)
+    rc = _lib.lib().gcb_pack_host(x_h.data_ptr(), ea_h.data_ptr(), ei_h.data_ptr(),
+                                  b_h.data_ptr() if b_h is not None else None, 8, N, E, G, M, atom_vocab, bond_vocab,
+                                  1 if n_messages >= 1 else 0, ints.data_ptr(), total)
+    _lib.check(rc, "gcb_pack_host")
+    y = getattr(data, "y", None)
+    y = None if y is None else y.detach().to("cpu", torch.float32).contiguous()
+    return PackedBatch(ints, header, y)
+
+
+class MoleculeStore:
+    """Flat host storage of many encoded molecules (int32 atoms / int32 bonds / int64 [2,e]
+    connectivity, i.e. the MoleculeEncoder.encode layout of reference features.py:263-321), laid
+    out so that the C-ABI collate can address any subset by pointer arithmetic."""
+
+    def __init__(self, atoms: Sequence[Tensor], bonds: Sequence[Tensor], conns: Sequence[Tensor],
+                 targets: Optional[Tensor] = None):
+        n = len(atoms)
+        self.n_atoms = np.array([int(a.numel()) for a in atoms], dtype=np.int32)
+        self.n_edges = np.array([int(b.numel()) for b in bonds], dtype=np.int32)
+        self.atoms = torch.cat([a.reshape(-1).to(torch.int32) for a in atoms]) if n else torch.zeros(0, dtype=torch.int32)
+        self.bonds = torch.cat([b.reshape(-1).to(torch.int32) for b in bonds]) if n else torch.zeros(0, dtype=torch.int32)
+        self.conn = torch.cat([c.to(torch.int64).contiguous().reshape(-1) for c in conns]) if n else torch.zeros(0, dtype=torch.int64)
+        self.atom_off = np.concatenate([[0], np.cumsum(self.n_atoms, dtype=np.int64)])
+        self.edge_off = np.concatenate([[0], np.cumsum(self.n_edges, dtype=np.int64)])
+        self.targets = None if targets is None else targets.to(torch.float32).reshape(n, -1).contiguous()
+
+    @classmethod
+    def from_graphs(cls, graphs: Sequence) -> "MoleculeStore":
+        ys = [g.y for g in graphs]
+        targets = torch.cat(ys, dim=0) if all(y is not None for y in ys) and len(ys) else None
+        return cls([g.x for g in graphs], [g.edge_attr for g in graphs], [g.edge_index for g in graphs], targets)
+
+    def __len__(self) -> int:
+        return int(self.n_atoms.shape[0])
+
+    def collate_pack(self, idx: Sequence[int], n_messages: int, atom_vocab: int, bond_vocab: int,
+                     pin: bool = True) -> PackedBatch:
+        """Collate molecules `idx` (in that order) and pack them: one C call, no Python per-graph loop."""
+        idx = np.asarray(idx, dtype=np.int64)
+        G = int(idx.shape[0])
+        na, ne = self.n_atoms[idx], self.n_edges[idx]
+        N, E = int(na.sum()), int(ne.sum())
+        M = live_bond_rows(N, E, n_messages)
+        header, total = _header(N, E, G, M, atom_vocab, bond_vocab)
+        ints = _alloc_ints(total, pin)
+        atoms_p = (self.atoms.data_ptr() + 4 * self.atom_off[idx]).astype(np.uint64)
+        bonds_p = (self.bonds.data_ptr() + 4 * self.edge_off[idx]).astype(np.uint64)
+        conn_p = (self.conn.data_ptr() + 16 * self.edge_off[idx]).astype(np.uint64)
+        nt = 0 if self.targets is None else int(self.targets.size(1))
+        y = None
+        y_p, yo_p, y_ptrs = None, None, None
+        if nt:
+            y = torch.empty(G, nt, dtype=torch.float32, pin_memory=pin and torch.cuda.is_available())
+            y_ptrs = (self.targets.data_ptr() + 4 * nt * idx).astype(np.uint64)  # kept alive across the call
+            y_p = y_ptrs.ctypes.data
+            yo_p = y.data_ptr()
+        na = np.ascontiguousarray(na)
+        ne = np.ascontiguousarray(ne)
+        rc = _lib.lib().gcb_collate_pack_host(atoms_p.ctypes.data, na.ctypes.data, bonds_p.ctypes.data,
+                                              conn_p.ctypes.data, ne.ctypes.data, y_p, nt, G, n_messages, atom_vocab,
+                                              bond_vocab, ints.data_ptr(), total, yo_p)
+        _lib.check(rc, "gcb_collate_pack_host")
+        return PackedBatch(ints, header, y)

@@ -1,0 +1,163 @@
+/*
+ * graphchem_b200 -- C-ABI of the B200-native MoleculeGCN hot path.
+ *
+ * The reference (ecrl/graphchem 2.3.3) is pure Python on PyTorch-Geometric and has no FFI of its
+ * own; the boundary it exposes to user code is the Python class API.  Every entry
+ * point below names the reference interface (file:line under /root/reference) whose work it
+ * replaces.  The Python host (graphchem_b200/_lib.py) binds these with ctypes; INTEGRATION.md
+ * shows the stub a graphchem maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every function returns GCB_OK or a
+ * negative error code and never throws; all device buffers are caller-allocated, 16-byte
+ * aligned; no hidden allocation, no hidden host synchronisation, no global mutable state; all
+ * kernels are deterministic (no floating-point atomics).  `stream` is a cudaStream_t passed as
+ * void* (0 = legacy default stream).
+ */
+#ifndef GRAPHCHEM_B200_H
+#define GRAPHCHEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCB_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------- */
+#define GCB_OK 0
+#define GCB_ERR_INVALID_ARG (-1) /* reference raises ValueError (PyG _check_input, bad shapes)   */
+#define GCB_ERR_INDEX (-2)       /* reference raises IndexError (edge_index/token out of range) */
+#define GCB_ERR_UNSUPPORTED (-3) /* configuration outside what the kernels implement            */
+#define GCB_ERR_CUDA (-4)        /* a CUDA runtime call failed; see gcb_last_cuda_error()       */
+#define GCB_ERR_WORKSPACE (-5)   /* caller-provided buffer too small                            */
+
+/* ---- enums ------------------------------------------------------------------------------- */
+/* act_fn of graphchem/nn/gcn.py:42,75 -- the five callables tests/test_gcn.py:107-113 exercise */
+enum gcb_act { GCB_ACT_SOFTPLUS = 0, GCB_ACT_SIGMOID = 1, GCB_ACT_RELU = 2, GCB_ACT_TANH = 3, GCB_ACT_LEAKY_RELU = 4 };
+/* aggr of GeneralConv, graphchem/nn/gcn.py:41,84-86 */
+enum gcb_aggr { GCB_AGGR_ADD = 0, GCB_AGGR_MEAN = 1 };
+/* storage type of activations (accumulation is always fp32) */
+enum gcb_dtype { GCB_F32 = 0, GCB_BF16 = 1 };
+
+/* Constructor arguments of MoleculeGCN, graphchem/nn/gcn.py:35-42. */
+typedef struct gcb_model_cfg {
+  int32_t atom_vocab;  /* atom_vocab_size                                  */
+  int32_t bond_vocab;  /* bond_vocab_size                                  */
+  int32_t out_dim;     /* output_dim (ignored when n_readout == 0)          */
+  int32_t D;           /* embedding_dim                                    */
+  int32_t L;           /* n_messages                                       */
+  int32_t n_readout;   /* n_readout                                        */
+  int32_t R;           /* readout_dim                                      */
+  int32_t act;         /* enum gcb_act                                     */
+  int32_t aggr;        /* enum gcb_aggr                                    */
+  int32_t dtype;       /* enum gcb_dtype                                   */
+  float p_dropout;     /* p_dropout (applied only when flags & GCB_TRAINING) */
+  int32_t reserved;
+} gcb_model_cfg;
+
+/* ---- packed batch ------------------------------------------------------------------------ */
+/*
+ * A PyG-style Batch (x, edge_index, edge_attr, batch; examples/predict_cn.ipynb:212,245 and
+ * graphchem/data/structs.py:61-66) pre-packed into ONE int32 buffer: tokens, the edge list, a
+ * destination-sorted and a source-sorted CSR (stable, i.e. edge-id order inside a row, which is
+ * the reference's scatter order), graph segments and token buckets.  GCB_PACK_HEADER_INTS header
+ * ints are followed by the sections; offsets (in ints, from the buffer start) live in the header.
+ */
+#define GCB_PACK_MAGIC 0x47434231 /* "GCB1" */
+#define GCB_PACK_HEADER_INTS 32
+enum gcb_pack_field {
+  GCB_H_MAGIC = 0, GCB_H_N, GCB_H_E, GCB_H_G, GCB_H_M, GCB_H_AV, GCB_H_BV, GCB_H_TOTAL_INTS,
+  GCB_H_X_TOK, GCB_H_E_TOK, GCB_H_SRC, GCB_H_DST,
+  GCB_H_IN_PTR, GCB_H_IN_EID, GCB_H_IN_SRC,
+  GCB_H_OUT_PTR, GCB_H_OUT_EID, GCB_H_OUT_DST,
+  GCB_H_GRAPH_PTR, GCB_H_GRAPH_NODE,
+  GCB_H_ATOK_PTR, GCB_H_ATOK_NODE, GCB_H_BTOK_PTR, GCB_H_BTOK_ROW,
+  GCB_H_FIELDS
+};
+
+/* Number of int32 elements a packed batch needs; fills header[GCB_PACK_HEADER_INTS] (host memory)
+ * with sizes and section offsets.  M = number of live bond rows = min(N,E) when n_messages >= 1,
+ * E when n_messages == 0. */
+int64_t gcb_pack_ints(int32_t N, int32_t E, int32_t G, int32_t M, int32_t atom_vocab, int32_t bond_vocab,
+                      int32_t* header);
+
+/* Host packer (replaces nothing in the reference: it is the "prepacked into pinned CSR buffers"
+ * step of the north star; the index semantics restate PyG's scatter order).
+ * x, edge_attr: int32 or int64 ([N], [E]); edge_index: int64 or int32 [2,E] row-major;
+ * batch: int64/int32 [N] or NULL (one graph, gcn.py:181 batch=None).  idx_bytes = 4 or 8 for all.
+ * check_bond_rows != 0 enforces max(edge_index) < E (the EdgeConv-on-bond-matrix precondition,
+ * gcn.py:163).  Returns GCB_ERR_INDEX as the reference would raise IndexError. */
+int gcb_pack_host(const void* x, const void* edge_attr, const void* edge_index, const void* batch,
+                  int32_t idx_bytes, int32_t N, int32_t E, int32_t G, int32_t M, int32_t atom_vocab,
+                  int32_t bond_vocab, int32_t check_bond_rows, int32_t* packed, int64_t packed_ints);
+
+/* Host collate + pack (replaces torch_geometric.loader.DataLoader's Collater ->
+ * Batch.from_data_list, examples/predict_cn.ipynb:212,245): concatenates n_graphs
+ * molecules (per-graph pointer arrays, MoleculeEncoder.encode layout of features.py:263-321:
+ * int32 atoms, int32 bonds, int64 [2,e] connectivity) with cumulative node offsets and packs the
+ * result.  y_out (float [n_graphs*n_targets]) receives the concatenated targets. */
+int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t* n_atoms, const int32_t* const* bonds,
+                          const int64_t* const* conn, const int32_t* n_edges, const float* const* y,
+                          int32_t n_targets, int32_t n_graphs, int32_t n_messages, int32_t atom_vocab,
+                          int32_t bond_vocab, int32_t* packed, int64_t packed_ints, float* y_out);
+
+/* ---- parameters -------------------------------------------------------------------------- */
+/* Flat fp32 parameter vector in the reference's state_dict order (gcn.py:78-114):
+ * emb_atom.weight, emb_bond.weight, atom_conv.lin_msg.{weight,bias}, atom_conv.lin_edge.{weight,
+ * bias}, bond_conv.nn.0.{weight,bias}, readout.k.0.{weight,bias} (k = 0..n_readout).
+ * offsets[] receives n_tensors+1 element offsets; returns n_tensors (8 + 2*(n_readout+1) or 8). */
+#define GCB_MAX_PARAM_TENSORS 64
+int gcb_param_layout(const gcb_model_cfg* cfg, int64_t* offsets);
+
+/* Derived (re-laid-out, dtype-converted) copies of the conv weights the kernels consume.  Must be
+ * refreshed after every parameter update. */
+int64_t gcb_derived_bytes(const gcb_model_cfg* cfg);
+int gcb_prepare_weights(const gcb_model_cfg* cfg, const float* params, void* derived, void* stream);
+
+/* ---- forward / backward ------------------------------------------------------------------ */
+#define GCB_TRAINING 1    /* nn.Module.training: dropout active (gcn.py:167-169,176-178,194-196) */
+#define GCB_SAVE_FOR_BWD 2 /* keep per-layer activations in the workspace for gcb_backward        */
+
+int64_t gcb_workspace_bytes(const gcb_model_cfg* cfg, int32_t N, int32_t E, int32_t G, int32_t flags);
+
+/* MoleculeGCN.forward, graphchem/nn/gcn.py:120-202 (embedding :152-157, EdgeConv :163-164,
+ * GeneralConv :172-173, dropout :167-178, global_add_pool :181, readout :184-199).
+ * packed: device packed batch.  out: float [G, out_dim] (or [G, D] when n_readout == 0);
+ * out_atom: dtype [N, D]; out_bond: dtype [E, D] (either may be NULL to skip materialising). */
+int gcb_forward(const gcb_model_cfg* cfg, const int32_t* packed, const int32_t* packed_header_host,
+                const float* params, const void* derived, void* workspace, int64_t workspace_bytes,
+                int32_t flags, uint64_t seed, float* out, void* out_atom, void* out_bond, void* stream);
+
+/* loss.backward() through the forward above (examples/predict_cn.ipynb:250).  Needs the workspace
+ * of a forward run with GCB_SAVE_FOR_BWD and the same flags/seed.  d_out: float [G, out_dim];
+ * d_out_atom (dtype [N,D]) and d_out_bond (dtype [E,D]) may be NULL.  grad: flat fp32 in the
+ * gcb_param_layout order, overwritten (accumulate == 0) or accumulated into (accumulate != 0). */
+int gcb_backward(const gcb_model_cfg* cfg, const int32_t* packed, const int32_t* packed_header_host,
+                 const float* params, const void* derived, void* workspace, int64_t workspace_bytes,
+                 int32_t flags, uint64_t seed, const float* d_out, const void* d_out_atom,
+                 const void* d_out_bond, float* grad, int32_t accumulate, void* stream);
+
+/* F.mse_loss(pred, y) mean-reduced and its gradient (examples/predict_cn.ipynb:249): loss[0] =
+ * mean((pred-y)^2); d_pred = 2 (pred-y) / n * grad_scale. */
+int gcb_mse_loss(const float* pred, const float* y, int64_t n, float* loss, float* d_pred, float grad_scale,
+                 void* stream);
+
+/* torch.optim.Adam.step (examples/predict_cn.ipynb:230-232,251): betas, eps, no weight decay,
+ * bias-corrected, one fused pass over the flat buffers.  hyper (device, float[2]) = {lr, grad_scale}
+ * so that the per-epoch lr rewrite (predict_cn.ipynb:241-242) survives CUDA-graph replay;
+ * step_count (device int32[1]) is incremented by the kernel. */
+int gcb_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  const float* hyper, int32_t* step_count, float beta1, float beta2, float eps,
+                  void* stream);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+int gcb_abi_version(void);
+const char* gcb_last_cuda_error(void);
+const char* gcb_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHCHEM_B200_H */

@@ -1,0 +1,46 @@
+"""TEST INFRASTRUCTURE ONLY -- integer restatement (numpy) of the index structures the CUDA path
+consumes.  Everything here must match the product's packer BIT FOR BIT.
+
+The reference has no CSR: PyG scatters in edge-id order (`scatter_add_` / `scatter_reduce_` over
+`edge_index[1]`).  A destination-sorted CSR that keeps edge-id order inside each
+row is the *stable* argsort of `edge_index[1]`; the source-sorted CSR (used by the backward pass)
+is the stable argsort of `edge_index[0]`; graph segments are the stable argsort of `batch`
+(`global_add_pool`, gcn.py:181); token buckets are the stable argsort of the token ids
+(`embedding_dense_backward` sums rows of equal token in row order).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def stable_buckets(keys: np.ndarray, n_buckets: int):
+    """Return (ptr[n_buckets+1], perm) with perm = argsort(keys, stable)."""
+    keys = np.asarray(keys, dtype=np.int64)
+    perm = np.argsort(keys, kind="stable").astype(np.int32)
+    counts = np.bincount(keys, minlength=n_buckets)[:n_buckets] if keys.size else np.zeros(n_buckets, np.int64)
+    ptr = np.zeros(n_buckets + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum(counts)
+    return ptr, perm
+
+
+def build_index(x_tok, e_tok, edge_index, batch, n_graphs, atom_vocab, bond_vocab, live_rows):
+    """All index arrays of a packed batch, as a dict of int32 numpy arrays."""
+    x_tok = np.asarray(x_tok).astype(np.int32)
+    e_tok = np.asarray(e_tok).astype(np.int32)
+    src = np.asarray(edge_index[0]).astype(np.int32)
+    dst = np.asarray(edge_index[1]).astype(np.int32)
+    N, E = x_tok.shape[0], e_tok.shape[0]
+    in_ptr, in_eid = stable_buckets(dst, N)
+    out_ptr, out_eid = stable_buckets(src, N)
+    if batch is None:
+        batch = np.zeros(N, dtype=np.int64)
+    graph_ptr, graph_node = stable_buckets(np.asarray(batch), n_graphs)
+    atok_ptr, atok_node = stable_buckets(x_tok, atom_vocab)
+    btok_ptr, btok_row = stable_buckets(e_tok[:live_rows], bond_vocab)
+    return dict(
+        x_tok=x_tok, e_tok=e_tok, src=src, dst=dst,
+        in_ptr=in_ptr, in_eid=in_eid, in_src=src[in_eid] if E else in_eid,
+        out_ptr=out_ptr, out_eid=out_eid, out_dst=dst[out_eid] if E else out_eid,
+        graph_ptr=graph_ptr, graph_node=graph_node,
+        atok_ptr=atok_ptr, atok_node=atok_node, btok_ptr=btok_ptr, btok_row=btok_row,
+    )

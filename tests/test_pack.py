@@ -1,0 +1,100 @@
+"""-m "not gpu": the host packer / collate (C-ABI, pure integer) against the numpy oracle, bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from graphchem_b200.data import Batch, Data, MoleculeGraph, MoleculeStore, pack_batch
+from oracle.csr_oracle import build_index
+from oracle.pyg_restated import collate as ocollate
+from tests.util import random_batch, random_graph_batch
+
+
+def _assert_matches_oracle(pb, data, G, av, bv):
+    batch = None if getattr(data, "batch", None) is None else data.batch.numpy()
+    ref = build_index(data.x.numpy(), data.edge_attr.numpy(), data.edge_index.numpy(), batch, G, av, bv, pb.M)
+    for k, v in pb.sections().items():
+        assert v.dtype == torch.int32
+        assert np.array_equal(v.numpy(), ref[k]), k
+
+
+@pytest.mark.parametrize("seed,G", [(0, 1), (1, 16), (2, 64)])
+def test_pack_molecule_batches_bit_exact(seed, G):
+    data, _ = random_batch(seed, G)
+    pb = pack_batch(data, 2, 12, 7, pin=False)
+    assert (pb.N, pb.E, pb.G) == (data.x.numel(), data.edge_index.size(1), G)
+    assert pb.M == min(pb.N, pb.E)
+    _assert_matches_oracle(pb, data, G, 12, 7)
+    pb0 = pack_batch(data, 0, 12, 7, pin=False)
+    assert pb0.M == pb0.E
+    _assert_matches_oracle(pb0, data, G, 12, 7)
+
+
+def test_pack_random_graph_with_duplicates_and_unsorted_batch():
+    data = random_graph_batch(seed=3, N=50, E=300, av=10, bv=5, G=1)
+    g = torch.Generator().manual_seed(0)
+    data.batch = torch.randint(0, 7, (50,), generator=g)  # unsorted on purpose
+    data.num_graphs = 7
+    pb = pack_batch(data, 3, 10, 5, pin=False)
+    _assert_matches_oracle(pb, data, 7, 10, 5)
+
+
+def test_pack_empty_edges_and_batch_none():
+    d = Data(x=torch.tensor([3], dtype=torch.int32), edge_index=torch.zeros(2, 0, dtype=torch.long),
+             edge_attr=torch.zeros(0, dtype=torch.int32))
+    pb = pack_batch(d, 2, 12, 7, pin=False)
+    assert (pb.N, pb.E, pb.G, pb.M) == (1, 0, 1, 0)
+    s = pb.sections()
+    assert s["in_ptr"].tolist() == [0, 0] and s["graph_ptr"].tolist() == [0, 1] and s["graph_node"].tolist() == [0]
+
+
+def test_pack_errors_follow_the_reference():
+    # atom index >= E with n_messages >= 1: IndexError (reference gcn.py:163 via PyG index_select)
+    d = Data(x=torch.tensor([2, 2, 2]), edge_index=torch.tensor([[1, 2], [2, 1]]), edge_attr=torch.tensor([2, 2]))
+    with pytest.raises(IndexError):
+        pack_batch(d, 2, 12, 7, pin=False)
+    pack_batch(d, 0, 12, 7, pin=False)  # n_messages == 0 never indexes the bond matrix
+    # token out of range: nn.Embedding IndexError
+    d = Data(x=torch.tensor([2, 12]), edge_index=torch.tensor([[0, 1], [1, 0]]), edge_attr=torch.tensor([2, 2]))
+    with pytest.raises(IndexError):
+        pack_batch(d, 2, 12, 7, pin=False)
+    # PyG _check_input: shape / dtype of edge_index -> ValueError
+    d = Data(x=torch.tensor([2, 3]), edge_index=torch.tensor([[0, 1, 1]]), edge_attr=torch.tensor([2, 2, 2]))
+    with pytest.raises(ValueError):
+        pack_batch(d, 2, 12, 7, pin=False)
+    d = Data(x=torch.tensor([2, 3]), edge_index=torch.tensor([[0., 1.], [1., 0.]]), edge_attr=torch.tensor([2, 2]))
+    with pytest.raises(ValueError):
+        pack_batch(d, 2, 12, 7, pin=False)
+
+
+def test_collate_matches_pyg_restatement_and_c_collate():
+    data, graphs = random_batch(seed=5, n_graphs=33)
+    mgs = [MoleculeGraph(g.x, g.edge_attr, g.edge_index, g.y) for g in graphs]
+    b = Batch.from_data_list(mgs)
+    for k in ("x", "edge_index", "edge_attr", "y", "batch", "ptr"):
+        assert torch.equal(getattr(b, k), getattr(data, k)), k
+        assert getattr(b, k).dtype == getattr(data, k).dtype
+    assert b.num_graphs == 33 and b.x.dtype == torch.int32 and b.edge_index.dtype == torch.int64
+    store = MoleculeStore.from_graphs(mgs)
+    pb = store.collate_pack(np.arange(33), 2, 12, 7, pin=False)
+    ref = pack_batch(b, 2, 12, 7, pin=False)
+    assert torch.equal(pb.ints, ref.ints) and torch.equal(pb.y, ref.y)
+    # a shuffled subset, as DataLoader(shuffle=True) would draw it
+    idx = np.random.default_rng(0).permutation(33)[:16]
+    pb = store.collate_pack(idx, 2, 12, 7, pin=False)
+    ref = pack_batch(Batch.from_data_list([mgs[i] for i in idx]), 2, 12, 7, pin=False)
+    assert torch.equal(pb.ints, ref.ints) and torch.equal(pb.y, ref.y)
+
+
+def test_synthetic_generator_is_encoder_shaped():
+    from graphchem_b200.synthetic import make_molecules
+    store = make_molecules(64, seed=1)
+    assert len(store) == 64 and (store.n_atoms == 23).all() and (store.n_edges == 50).all()
+    conn = store.conn[:100].view(2, 50)
+    assert (conn[0][1:] >= conn[0][:-1]).all(), "edges must be grouped by source atom (features.py:307-318)"
+    fwd = {(int(s), int(d)): int(t) for s, d, t in zip(conn[0], conn[1], store.bonds[:50])}
+    assert all(fwd[(d, s)] == t for (s, d), t in fwd.items()), "both directions of a bond share one token"
+    assert len(fwd) == 50
+    var = make_molecules(200, seed=2, variable=True)
+    assert var.n_atoms.min() >= 6 and var.n_atoms.max() <= 38
+    pb = var.collate_pack(np.arange(200), 4, 64, 32, pin=False)
+    assert pb.G == 200 and pb.E >= pb.N
