@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- MoleculeGCN train molecules/s on B200 (BASELINE.json metric), with the HBM roofline
+of the dominant kernel, the end-to-end number through the public API with host buffers, and the
+reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+N > 1 is launched by the driver with torchrun (one rank per GPU, NCCL); RANK / LOCAL_RANK /
+WORLD_SIZE / MASTER_* come from the environment.  Rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json configs[3] at 1..8 GPUs, configs[2] shape): synthetic ZINC-scale molecules,
+23 atoms / 50 directed edges each, 8192 molecules per GPU per step (weak scaling), embedding_dim
+128, n_messages 4, n_readout 2, readout_dim 64, bf16 storage / fp32 accumulate, MSE + Adam; 8
+distinct pre-packed batches per GPU resident in HBM are cycled (per-step working set ~1.3 GB,
+far above the 126 MB L2).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+ATOMS, EDGES = 23, 50
+CFG = dict(atom_vocab=64, bond_vocab=32, out_dim=1, D=128, L=4, n_readout=2, R=64)
+N_RESIDENT = 8
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes
+def fwd_bytes(N, E, D, L, s):
+    return s * D * (5 * N * L + E - 2 * N) + L * (8 * N + 16 * E) + 8 * N
+
+
+def train_step_bytes(N, E, D, L, s):
+    return 3 * fwd_bytes(N, E, D, L, s)
+
+
+def kernel_alg_bytes(name, N, E, M, G, D, s):
+    """Algorithmic HBM bytes of ONE launch of a kernel class (inputs read once + outputs written
+    once; weights / embedding tables are cache resident and not counted).  Several launch shapes
+    share a class name; the value is the per-layer message-passing shape, which dominates."""
+    i4 = 4
+    table = {
+        "embed_act_kernel": N * i4 + N * D * s,
+        "bond_update_kernel": M * 2 * D * s + (M + E) * i4 + M * D * s,
+        "atom_gather_kernel": (N + M) * D * s + (N + 2 * E) * i4 + N * 2 * D * s,
+        "pool_kernel": N * D * s + (G + N) * i4 + G * D * 4,
+        "pool_bwd_kernel": G * D * 4 + N * D * s + (G + N) * i4 + N * D * s,
+        "atom_bwd_gather_kernel": 2 * N * D * s + N * D * s + (N + E) * i4 + N * D * s,
+        "bond_bwd_tie_kernel": 4 * M * D * s + (2 * M + E) * i4 + 4 * M * D * s,
+        "bond_bwd_scatter_kernel": 3 * M * D * s + (M + E) * i4 + M * D * s,
+        # GEMMs: per-layer average of the two NT shapes ([M,D]x[D,2D] and [N,2D]x[2D,D]) fwd / bwd
+        "gemm_nt_kernel": (3 * M * D * s + 4 * N * D * s) / 2,
+        "gemm_tn_kernel": (3 * N * D * s + 3 * M * D * s) / 2,
+    }
+    return table.get(name)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        rows = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.2] or [ln for _, ln in self.lines]
+        for ln in rows:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_train_throughput(batch: int, steps: int, warmup: int, seed: int = 1234):
+    """Reference CPU path (oracle restatement of graphchem + PyG 2.6.1), all host threads."""
+    from graphchem_b200.synthetic import make_molecules
+    from oracle.gcn_oracle import OracleMoleculeGCN, train_step
+    from oracle.pyg_restated import Data as OData, collate
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    store = make_molecules(batch, seed=seed, atom_vocab=CFG["atom_vocab"], bond_vocab=CFG["bond_vocab"])
+    graphs = []
+    for i in range(batch):
+        a0, a1 = store.atom_off[i], store.atom_off[i + 1]
+        e0, e1 = store.edge_off[i], store.edge_off[i + 1]
+        graphs.append(OData(x=store.atoms[a0:a1], edge_attr=store.bonds[e0:e1],
+                            edge_index=store.conn[2 * e0:2 * e1].view(2, -1), y=store.targets[i:i + 1]))
+    data = collate(graphs)
+    torch.manual_seed(0)
+    model = OracleMoleculeGCN(CFG["atom_vocab"], CFG["bond_vocab"], CFG["out_dim"], embedding_dim=CFG["D"],
+                              n_messages=CFG["L"], n_readout=CFG["n_readout"], readout_dim=CFG["R"])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    model.train()
+    for _ in range(warmup):
+        train_step(model, opt, data)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_step(model, opt, data)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 1024
+    value, sec_per_step, cores = oracle_train_throughput(batch, max(1, args.steps), max(1, args.warmup))
+    sample = (f"{args.steps} train steps (fwd+MSE+bwd+Adam) of a {batch}-molecule batch of the same synthetic "
+              f"shape (fp32, torch CPU, {cores} threads)")
+    line = {
+        "impl": "reference", "metric": "MoleculeGCN train molecules/sec", "value": value, "unit": "molecules/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, ranks=1),
+        "cpu_baseline": {"value": value, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = CPU oracle (op-for-op restatement of graphchem 2.3.3 on PyG 2.6.1; PyG/RDKit are not "
+                "installable offline, see DESIGN.md)",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, ranks):
+    return {
+        "workload": f"synthetic ZINC-scale molecules ({ATOMS} atoms / {EDGES} directed edges), batch {args.batch} per GPU, "
+                    f"MoleculeGCN D={CFG['D']} n_messages={CFG['L']} n_readout={CFG['n_readout']} R={CFG['R']}, "
+                    "train step = fwd + MSE + bwd + Adam (BASELINE.json configs[3]; configs[2] shape)",
+        "global_batch": args.batch * ranks, "atoms_per_molecule": ATOMS, "edges_per_molecule": EDGES,
+        "parallelism": f"dp{ranks}", "resident_batches": N_RESIDENT,
+        "l2": "no flush needed: per-step working set (~1.3 GB of activations at batch 8192) exceeds the 126 MB L2 "
+              "and 8 distinct resident batches are cycled",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from graphchem_b200 import _lib
+    from graphchem_b200.nn import MoleculeGCN
+    from graphchem_b200.synthetic import make_molecules
+    from graphchem_b200.train import TrainStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+
+    B, K, W = args.batch, args.steps, args.warmup
+    N, E = ATOMS * B, EDGES * B
+    s_bytes = 2
+    torch.manual_seed(0)
+    model = MoleculeGCN(CFG["atom_vocab"], CFG["bond_vocab"], CFG["out_dim"], embedding_dim=CFG["D"],
+                        n_messages=CFG["L"], n_readout=CFG["n_readout"], readout_dim=CFG["R"],
+                        compute_dtype=torch.bfloat16).to(dev)
+    if world > 1:  # identical replicas
+        dist.broadcast(model.flat_parameters(), src=0)
+
+    # ---- host side: synthetic shard, prepacked into pinned CSR buffers (not timed as GPU work)
+    store = make_molecules(N_RESIDENT * B, seed=1234 + rank, atom_vocab=CFG["atom_vocab"], bond_vocab=CFG["bond_vocab"])
+    t_pack0 = time.perf_counter()
+    host_batches = [store.collate_pack(np.arange(i * B, (i + 1) * B), CFG["L"], CFG["atom_vocab"], CFG["bond_vocab"],
+                                       pin=True) for i in range(N_RESIDENT)]
+    pack_ms = (time.perf_counter() - t_pack0) * 1e3 / N_RESIDENT
+    dev_batches = [hb.to(dev) for hb in host_batches]
+    torch.cuda.synchronize()
+
+    step = TrainStep(model, lr=1e-3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- (1) device-resident throughput -------------------------------------------------------
+    for i in range(max(W, N_RESIDENT)):  # captures one CUDA graph per resident batch, then warms up
+        step(dev_batches[i % N_RESIDENT])
+    barrier()
+    launches0 = lib.gcb_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for i in range(K):
+        step(dev_batches[i % N_RESIDENT])
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    loss_resident = float(step.loss.item())
+    value = B * world * K / (ms * 1e-3)
+
+    # ---- (2) end to end through the public API with HOST buffers ---------------------------------
+    # per step: pinned packed batch -> HBM (copy stream, double buffered), step, loss -> pinned host
+    copy_stream = torch.cuda.Stream(dev)
+    n_ints = host_batches[0].ints.numel()
+    stage = [(torch.empty(n_ints, dtype=torch.int32, device=dev), torch.empty(B, 1, dtype=torch.float32, device=dev))
+             for _ in range(2)]
+    from graphchem_b200.data.packed import PackedBatch
+    staged = [PackedBatch(si, host_batches[0].header, sy) for si, sy in stage]
+    loss_host = torch.zeros(K + W + 2, dtype=torch.float32).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        hb, slot = host_batches[i % N_RESIDENT], i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            stage[slot][0].copy_(hb.ints, non_blocking=True)
+            stage[slot][1].copy_(hb.y, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n, base):
+        cur = torch.cuda.current_stream(dev)
+        upload(base)
+        for i in range(n):
+            slot = (base + i) % 2
+            if i + 1 < n:
+                upload(base + i + 1)
+            cur.wait_event(ready[slot])
+            loss = step(staged[slot])
+            consumed[slot].record(cur)
+            loss_host[base + i:base + i + 1].copy_(loss, non_blocking=True)
+
+    for ev in consumed:
+        ev.record(torch.cuda.current_stream(dev))
+    e2e_loop(max(W, 2) + (max(W, 2) % 2), 0)  # warm-up (captures the two staging graphs); even count keeps slots aligned
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(K, 0)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = B * world * K / (ms_e2e * 1e-3)
+    h2d = host_batches[0].ints.numel() * 4 + B * 4
+    launches_per_step = None
+
+    # ---- (3) per-kernel timing with CUDA events (un-graphed pass, rank 0, N == 1 only) -------------
+    roofline, kernels, cpu_baseline = None, None, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        plain = TrainStep(model, lr=1e-3, use_cuda_graph=False)
+        plain.exp_avg, plain.exp_avg_sq, plain.step_count = step.exp_avg, step.exp_avg_sq, step.step_count
+        for i in range(3):
+            plain(dev_batches[i % N_RESIDENT])
+        torch.cuda.synchronize()
+        l0 = lib.gcb_launch_count()
+        plain(dev_batches[0])
+        launches_per_step = int(lib.gcb_launch_count() - l0)
+        lib.gcb_timing_enable(1)
+        n_prof = 8
+        for i in range(n_prof):
+            plain(dev_batches[i % N_RESIDENT])
+        torch.cuda.synchronize()
+        buf = C.create_string_buffer(1 << 16)
+        lib.gcb_timing_report(buf, len(buf))
+        lib.gcb_timing_enable(0)
+        rep = json.loads(buf.value.decode())
+        total_ms = sum(r["ms"] for r in rep) or 1.0
+        kernels = []
+        M = min(N, E)
+        for r in sorted(rep, key=lambda r: -r["ms"]):
+            per = r["ms"] / r["launches"]
+            alg = kernel_alg_bytes(r["name"], N, E, M, B, CFG["D"], s_bytes)
+            kernels.append({"name": r["name"], "launches_per_step": r["launches"] / n_prof, "ms_per_launch": per,
+                            "share": r["ms"] / total_ms,
+                            "alg_GBps": (alg / (per * 1e-3) / 1e9) if alg else None})
+        top = kernels[0]
+        alg_top = kernel_alg_bytes(top["name"], N, E, M, B, CFG["D"], s_bytes)
+        roofline = {
+            "bound": "hbm", "kernel": top["name"], "achieved": top["alg_GBps"], "peak": peak_hbm, "unit": "GB/s",
+            "frac": (top["alg_GBps"] / peak_hbm) if top["alg_GBps"] else None, "traffic": None,
+            "alg_bytes_per_launch": alg_top, "ms_per_launch": top["ms_per_launch"], "share_of_step": top["share"],
+            "peak_source": peak_src,
+            "step": {"alg_bytes": train_step_bytes(N, E, CFG["D"], CFG["L"], s_bytes),
+                     "achieved": train_step_bytes(N, E, CFG["D"], CFG["L"], s_bytes) / (ms / K * 1e-3) / 1e9,
+                     "frac": train_step_bytes(N, E, CFG["D"], CFG["L"], s_bytes) / (ms / K * 1e-3) / 1e9 / peak_hbm},
+        }
+        # ---- (4) reference CPU path on this box's host cores, bounded sample -----------------------
+        if world == 1 and not args.no_cpu_baseline:
+            cb, cb_spb, cores = oracle_train_throughput(2048, 3, 1)
+            cpu_baseline = {"value": cb, "unit": "molecules/s", "cores": cores, "kind": "port",
+                            "sample": "3 train steps of a 2048-molecule batch of the same synthetic shape, fp32 torch "
+                                      f"CPU oracle, {cores} threads ({cb_spb:.2f} s/step)"}
+
+    if rank == 0:
+        line = {
+            "metric": "MoleculeGCN train molecules/sec", "value": value, "unit": "molecules/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": (launches_per_step or 0) * K,
+            "launches_per_step": launches_per_step,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
+            "loss": loss_resident, "host_pack_ms_per_batch": pack_ms,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=8192, help="molecules per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,24 @@ void set_cuda_error(cudaError_t e, const char* file, int line);
     if (_rc != GCB_OK) return _rc; \
   } while (0)
 
+// ---- optional per-kernel timing (debug/bench facility; thread-local, off by default) ------------
+// When enabled with gcb_timing_enable(1) every kernel launch is bracketed by two CUDA events on its
+// stream (so it must not be used under stream capture).  Launches are always counted.
+struct KernelTimer {
+  KernelTimer(const char* name, cudaStream_t s);
+  void stop();
+  const char* name_;
+  cudaStream_t s_;
+  int slot_;
+};
+#define GCB_KERNEL(NAME, STREAM, ...)          \
+  do {                                         \
+    gcb::KernelTimer _kt(NAME, STREAM);        \
+    __VA_ARGS__;                               \
+    _kt.stop();                                \
+    GCB_LAUNCH_CHECK();                        \
+  } while (0)
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

@@ -180,9 +180,11 @@ inline int launch_gemm_nt(const T* A, int lda, const T* W, int ldw, bool w_kn, T
                           const Epilogue& ep, cudaStream_t s) {
   if (M <= 0 || N <= 0) return GCB_OK;
   dim3 grid((unsigned)ceil_div(M, 128), (unsigned)ceil_div(N, 64));
-  if (w_kn) gemm_nt_kernel<T, true><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep);
-  else gemm_nt_kernel<T, false><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep);
-  GCB_LAUNCH_CHECK();
+  if (w_kn) {
+    GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_kernel<T, true><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+  } else {
+    GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_kernel<T, false><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+  }
   return GCB_OK;
 }
 
@@ -295,8 +297,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int sp
 inline int launch_reduce_partials(const float* partial, int splits, int64_t count, float* out, int accumulate,
                                   cudaStream_t s) {
   if (count <= 0) return GCB_OK;
-  reduce_partials_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, s>>>(partial, splits, count, out, accumulate);
-  GCB_LAUNCH_CHECK();
+  GCB_KERNEL("reduce_partials_kernel", s, reduce_partials_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, s>>>(partial, splits, count, out, accumulate));
   return GCB_OK;
 }
 
@@ -318,8 +319,7 @@ inline int launch_gemm_tn(const T* A, int lda, const T* B, int ldb, int rows, in
   if (splits > 0) {
     const int rps = (int)align_up(ceil_div(rows, splits), 16);
     dim3 grid((unsigned)ceil_div(Kk, 64), (unsigned)ceil_div(Nn, 64), (unsigned)splits);
-    gemm_tn_kernel<T><<<grid, 256, 0, s>>>(A, lda, B, ldb, partial, bias_partial, rowptr, aggr, rows, Nn, Kk, rps);
-    GCB_LAUNCH_CHECK();
+    GCB_KERNEL("gemm_tn_kernel", s, gemm_tn_kernel<T><<<grid, 256, 0, s>>>(A, lda, B, ldb, partial, bias_partial, rowptr, aggr, rows, Nn, Kk, rps));
   }
   GCB_TRY(launch_reduce_partials(partial, splits, (int64_t)Nn * Kk, dW, accumulate, s));
   if (db) GCB_TRY(launch_reduce_partials(bias_partial, splits, Nn, db, accumulate, s));

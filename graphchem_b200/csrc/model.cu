@@ -5,6 +5,9 @@
 // (examples/predict_cn.ipynb:250), F.mse_loss (:249) and torch.optim.Adam.step (:251).
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -16,6 +19,27 @@ namespace gcb {
 static thread_local char g_err[512] = "";
 void set_cuda_error(cudaError_t e, const char* file, int line) {
   snprintf(g_err, sizeof(g_err), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
+}
+
+// ---- kernel timing / launch counting (thread-local debug facility) -------------------------------
+struct TimingSlot { const char* name; cudaEvent_t e0, e1; };
+static thread_local bool g_timing = false;
+static thread_local int64_t g_launches = 0;
+static thread_local std::vector<TimingSlot>* g_slots = nullptr;
+KernelTimer::KernelTimer(const char* name, cudaStream_t s) : name_(name), s_(s), slot_(-1) {
+  ++g_launches;
+  if (g_timing) {
+    if (!g_slots) g_slots = new std::vector<TimingSlot>();
+    TimingSlot t{name, nullptr, nullptr};
+    if (cudaEventCreate(&t.e0) == cudaSuccess && cudaEventCreate(&t.e1) == cudaSuccess) {
+      cudaEventRecord(t.e0, s);
+      g_slots->push_back(t);
+      slot_ = (int)g_slots->size() - 1;
+    }
+  }
+}
+void KernelTimer::stop() {
+  if (slot_ >= 0) cudaEventRecord((*g_slots)[slot_].e1, s_);
 }
 
 // ---- parameter layout ---------------------------------------------------------------------------
@@ -266,12 +290,10 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
   const float* bat = (const float*)(dv.base + dv.bat);
 
   if (N > 0) {
-    embed_act_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>(params + pl.emb_atom, g.x_tok, (T*)p.A[0], N, D, c.act);
-    GCB_LAUNCH_CHECK();
+    GCB_KERNEL("embed_act_kernel", s, embed_act_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>(params + pl.emb_atom, g.x_tok, (T*)p.A[0], N, D, c.act));
   }
   if (M > 0) {
-    embed_act_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(params + pl.emb_bond, g.e_tok, (T*)p.B[0], M, D, c.act);
-    GCB_LAUNCH_CHECK();
+    GCB_KERNEL("embed_act_kernel", s, embed_act_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(params + pl.emb_bond, g.e_tok, (T*)p.B[0], M, D, c.act));
   }
   for (int l = 1; l <= L; ++l) {
     const Drop db = make_drop(c, flags, seed, tag_bond(l));
@@ -280,29 +302,25 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       Epilogue ep;
       ep.bias = bpq;
       GCB_TRY(launch_gemm_nt<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
-      bond_update_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>((const T*)p.PQ[l], g.in_ptr, g.in_src, (T*)p.B[l],
-                                                                       M, D, c.act, db);
-      GCB_LAUNCH_CHECK();
+      GCB_KERNEL("bond_update_kernel", s, bond_update_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>((const T*)p.PQ[l], g.in_ptr, g.in_src, (T*)p.B[l],
+                                                                       M, D, c.act, db));
     }
     if (N > 0) {
-      atom_gather_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr,
+      GCB_KERNEL("atom_gather_kernel", s, atom_gather_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr,
                                                                        g.in_src, g.in_eid, (T*)p.S[l], N, M, D, c.act,
-                                                                       c.aggr, db);
-      GCB_LAUNCH_CHECK();
+                                                                       c.aggr, db));
       Epilogue ep;
       ep.bias = bat; ep.rowptr = g.in_ptr; ep.aggr = c.aggr;
       ep.res = p.A[l - 1]; ep.ld_res = D; ep.act = c.act;
       GCB_TRY(launch_gemm_nt<T>((const T*)p.S[l], 2 * D, wat, 2 * D, false, (T*)p.A[l], D, N, D, 2 * D, ep, s));
       if (da.p > 0.f) {
-        dropout_inplace_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((T*)p.A[l], N, D, da);
-        GCB_LAUNCH_CHECK();
+        GCB_KERNEL("dropout_inplace_kernel", s, dropout_inplace_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((T*)p.A[l], N, D, da));
       }
     }
   }
   // pooling + readout (fp32)
   if (G > 0) {
-    pool_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>((const T*)p.A[L], g.graph_ptr, g.graph_node, p.pooled, G, D);
-    GCB_LAUNCH_CHECK();
+    GCB_KERNEL("pool_kernel", s, pool_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>((const T*)p.A[L], g.graph_ptr, g.graph_node, p.pooled, G, D));
     if (pl.n_lin == 0) {
       if (out) GCB_CUDA(cudaMemcpyAsync(out, p.pooled, (size_t)G * D * 4, cudaMemcpyDeviceToDevice, s));
     } else {
@@ -318,8 +336,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
         const Drop dr = make_drop(c, flags, seed, tag_readout(k + 1));
         if (!last && dr.p > 0.f) {
           const int64_t cnt = (int64_t)G * pl.r_out[k];
-          dropout_scalar_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, s>>>(dst, cnt, dr);
-          GCB_LAUNCH_CHECK();
+          GCB_KERNEL("dropout_scalar_kernel", s, dropout_scalar_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, s>>>(dst, cnt, dr));
         }
       }
     }
@@ -328,9 +345,8 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
   if (out_bond && E > 0) {
     if (M > 0) GCB_CUDA(cudaMemcpyAsync(out_bond, p.B[L], (size_t)M * D * sizeof(T), cudaMemcpyDeviceToDevice, s));
     if (E > M) {
-      fill_const_rows_kernel<T><<<row_chunk_blocks(E - M, D, V), 256, 0, s>>>(out_bond, M, E - M, D, c.act,
-                                                                             make_drop(c, flags, seed, tag_bond(L)));
-      GCB_LAUNCH_CHECK();
+      GCB_KERNEL("fill_const_rows_kernel", s, fill_const_rows_kernel<T><<<row_chunk_blocks(E - M, D, V), 256, 0, s>>>(out_bond, M, E - M, D, c.act,
+                                                                             make_drop(c, flags, seed, tag_bond(L))));
     }
   }
   return GCB_OK;
@@ -379,10 +395,9 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   int cur = 0;
   if (N > 0) {
     if (G > 0) {
-      pool_bwd_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>(
+      GCB_KERNEL("pool_bwd_kernel", s, pool_bwd_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>(
           dPool, d_out_atom, (const T*)p.A[L], g.graph_ptr, g.graph_node, (T*)p.dZA[cur], G, D, c.act,
-          L >= 1 ? make_drop(c, flags, seed, tag_atom(L)) : Drop());
-      GCB_LAUNCH_CHECK();
+          L >= 1 ? make_drop(c, flags, seed, tag_atom(L)) : Drop()));
     } else {
       GCB_CUDA(cudaMemsetAsync(p.dZA[cur], 0, (size_t)N * D * sizeof(T), s));
     }
@@ -399,19 +414,16 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     GCB_TRY(launch_gemm_tn<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
                               p.accBat, g.in_ptr, c.aggr, acc_w, s));
     if (N > 0) {
-      atom_bwd_gather_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>(
+      GCB_KERNEL("atom_bwd_gather_kernel", s, atom_bwd_gather_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>(
           (const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.in_ptr, (const T*)p.A[l - 1], (T*)p.dZA[cur ^ 1],
-          N, D, c.act, c.aggr, l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop());
-      GCB_LAUNCH_CHECK();
+          N, D, c.act, c.aggr, l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop()));
     }
     if (M > 0) {
-      bond_bwd_tie_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(
+      GCB_KERNEL("bond_bwd_tie_kernel", s, bond_bwd_tie_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(
           (const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l], g.dst, g.in_ptr,
-          g.in_src, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit, M, D, c.act, c.aggr, make_drop(c, flags, seed, tag_bond(l)));
-      GCB_LAUNCH_CHECK();
-      bond_bwd_scatter_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(
-          (const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, (T*)p.dPQ, M, D);
-      GCB_LAUNCH_CHECK();
+          g.in_src, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit, M, D, c.act, c.aggr, make_drop(c, flags, seed, tag_bond(l))));
+      GCB_KERNEL("bond_bwd_scatter_kernel", s, bond_bwd_scatter_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(
+          (const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, (T*)p.dPQ, M, D));
     }
     GCB_TRY(launch_gemm_tn<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
                               p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s));
@@ -427,25 +439,22 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   {
     const int av = c.atom_vocab, bv = c.bond_vocab, CH = D / V;
     if (N > 0) {
-      embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)av * kEmbedSplits * CH, 256), 256, 0, s>>>(
-          (const T*)p.dZA[cur], nullptr, g.atok_ptr, g.atok_node, p.partial, av, kEmbedSplits, D, c.act);
-      GCB_LAUNCH_CHECK();
+      GCB_KERNEL("embed_bwd_partial_kernel", s, embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)av * kEmbedSplits * CH, 256), 256, 0, s>>>(
+          (const T*)p.dZA[cur], nullptr, g.atok_ptr, g.atok_node, p.partial, av, kEmbedSplits, D, c.act));
     }
     GCB_TRY(launch_reduce_partials(p.partial, N > 0 ? kEmbedSplits : 0, (int64_t)av * D, grad + pl.emb_atom, accumulate, s));
     const T* dB0 = L >= 1 ? dBnext : d_out_bond;
     const bool have = dB0 != nullptr && M > 0;
     if (have) {
-      embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)bv * kEmbedSplits * CH, 256), 256, 0, s>>>(
-          dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, p.partial, bv, kEmbedSplits, D, c.act);
-      GCB_LAUNCH_CHECK();
+      GCB_KERNEL("embed_bwd_partial_kernel", s, embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)bv * kEmbedSplits * CH, 256), 256, 0, s>>>(
+          dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, p.partial, bv, kEmbedSplits, D, c.act));
     }
     GCB_TRY(launch_reduce_partials(p.partial, have ? kEmbedSplits : 0, (int64_t)bv * D, grad + pl.emb_bond, accumulate, s));
   }
   // ---- conv parameters ----
-  finalize_conv_grads_kernel<<<(unsigned)ceil_div(2 * D * D, 256), 256, 0, s>>>(
+  GCB_KERNEL("finalize_conv_grads_kernel", s, finalize_conv_grads_kernel<<<(unsigned)ceil_div(2 * D * D, 256), 256, 0, s>>>(
       p.accWpq, p.accBpq, p.accWat, p.accBat, grad + pl.w_msg, grad + pl.b_msg, grad + pl.w_edge, grad + pl.b_edge,
-      grad + pl.w_bond, grad + pl.b_bond, D, accumulate, L == 0);
-  GCB_LAUNCH_CHECK();
+      grad + pl.w_bond, grad + pl.b_bond, D, accumulate, L == 0));
   return GCB_OK;
 }
 
@@ -484,17 +493,16 @@ extern "C" int gcb_prepare_weights(const gcb_model_cfg* cfg, const float* params
   const int D = cfg->D;
   const unsigned blocks = (unsigned)ceil_div(2 * D * D, 256);
   if (cfg->dtype == GCB_BF16) {
-    prepare_weights_kernel<bf16><<<blocks, 256, 0, s>>>(
+    GCB_KERNEL("prepare_weights_kernel", s, prepare_weights_kernel<bf16><<<blocks, 256, 0, s>>>(
         params + pl.w_msg, params + pl.b_msg, params + pl.w_edge, params + pl.b_edge, params + pl.w_bond,
         params + pl.b_bond, (bf16*)(d.base + d.wpq), (bf16*)(d.base + d.wat), (bf16*)(d.base + d.watT),
-        (bf16*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D);
+        (bf16*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D));
   } else {
-    prepare_weights_kernel<float><<<blocks, 256, 0, s>>>(
+    GCB_KERNEL("prepare_weights_kernel", s, prepare_weights_kernel<float><<<blocks, 256, 0, s>>>(
         params + pl.w_msg, params + pl.b_msg, params + pl.w_edge, params + pl.b_edge, params + pl.w_bond,
         params + pl.b_bond, (float*)(d.base + d.wpq), (float*)(d.base + d.wat), (float*)(d.base + d.watT),
-        (float*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D);
+        (float*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D));
   }
-  GCB_LAUNCH_CHECK();
   return GCB_OK;
 }
 
@@ -554,8 +562,7 @@ extern "C" int gcb_backward(const gcb_model_cfg* cfg, const int32_t* packed, con
 extern "C" int gcb_mse_loss(const float* pred, const float* y, int64_t n, float* loss, float* d_pred,
                             float grad_scale, void* stream) {
   if (!pred || !y || n <= 0) return GCB_ERR_INVALID_ARG;
-  mse_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, y, n, loss, d_pred, grad_scale);
-  GCB_LAUNCH_CHECK();
+  GCB_KERNEL("mse_kernel", (cudaStream_t)stream, mse_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, y, n, loss, d_pred, grad_scale));
   return GCB_OK;
 }
 
@@ -565,11 +572,49 @@ extern "C" int gcb_adam_step(float* params, const float* grad, float* exp_avg, f
   if (!params || !grad || !exp_avg || !exp_avg_sq || !hyper || !step_count || n < 0) return GCB_ERR_INVALID_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (n > 0) {
-    adam_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(params, grad, exp_avg, exp_avg_sq, n, hyper, step_count,
-                                                           beta1, beta2, eps);
-    GCB_LAUNCH_CHECK();
+    GCB_KERNEL("adam_kernel", s, adam_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(params, grad, exp_avg, exp_avg_sq, n, hyper, step_count,
+                                                           beta1, beta2, eps));
   }
-  increment_kernel<<<1, 1, 0, s>>>(step_count);
-  GCB_LAUNCH_CHECK();
+  GCB_KERNEL("increment_kernel", s, increment_kernel<<<1, 1, 0, s>>>(step_count));
   return GCB_OK;
+}
+
+// ---- timing / launch-count facility --------------------------------------------------------------
+extern "C" int64_t gcb_launch_count(void) { return g_launches; }
+extern "C" int gcb_timing_enable(int32_t enable) {
+  g_timing = enable != 0;
+  return GCB_OK;
+}
+extern "C" int64_t gcb_timing_report(char* buf, int64_t buflen) {
+  // Synchronises the recorded events, aggregates by kernel name and clears the table.
+  std::map<std::string, std::pair<int64_t, double>> agg;
+  if (g_slots) {
+    for (auto& t : *g_slots) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+        auto& a = agg[t.name];
+        a.first += 1;
+        a.second += ms;
+      }
+      cudaEventDestroy(t.e0);
+      cudaEventDestroy(t.e1);
+    }
+    g_slots->clear();
+  }
+  std::string out = "[";
+  bool first = true;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s{\"name\":\"%s\",\"launches\":%lld,\"ms\":%.6f}", first ? "" : ",", kv.first.c_str(),
+             (long long)kv.second.first, kv.second.second);
+    out += line;
+    first = false;
+  }
+  out += "]";
+  if (buf && buflen > 0) {
+    const int64_t n = (int64_t)out.size() < buflen - 1 ? (int64_t)out.size() : buflen - 1;
+    std::memcpy(buf, out.data(), (size_t)n);
+    buf[n] = 0;
+  }
+  return (int64_t)out.size();
 }

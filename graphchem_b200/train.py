@@ -1,0 +1,129 @@
+"""Fused training step: the whole notebook loop body (reference examples/predict_cn.ipynb:247-251:
+zero_grad / model(batch) / F.mse_loss / loss.backward() / optimizer.step()) as one sequence of
+C-ABI calls on one CUDA stream, captured into a CUDA graph per resident batch buffer, with the
+data-parallel gradient all-reduce (new) between backward and Adam.
+
+No autograd, no per-step host synchronisation (the reference's `loss.item()` every step,
+predict_cn.ipynb:252, is replaced by a device-side loss scalar the caller reads when it wants).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .data.packed import PackedBatch
+
+
+class TrainStep:
+    def __init__(self, model, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 use_cuda_graph: bool = True, process_group=None):
+        self.model = model
+        self.betas, self.eps = betas, eps
+        dev = model._ensure_device()
+        self.device = dev
+        flat = model.flat_parameters()
+        self.grad = torch.zeros_like(flat)
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.world = 1
+        self.pg = process_group
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self.hyper = torch.tensor([lr, 1.0 / self.world], dtype=torch.float32, device=dev)
+        self._lr = lr
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.use_cuda_graph = use_cuda_graph
+        self._ws: Optional[torch.Tensor] = None
+        self._pred: Optional[torch.Tensor] = None
+        self._dpred: Optional[torch.Tensor] = None
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.launches_per_step = 0
+        model.refresh_weights()
+
+    # lr stays mutable between steps (predict_cn.ipynb:241-242) without re-capturing the graph
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self._lr = float(value)
+        self.hyper[0:1].fill_(self._lr)
+
+    def _buffers(self, pb: PackedBatch, flags: int):
+        cfg = self.model._cfg()
+        need = int(_lib.check(int(_lib.lib().gcb_workspace_bytes(C.byref(cfg), pb.N, pb.E, pb.G, flags)),
+                              "gcb_workspace_bytes"))
+        if self._ws is None or self._ws.numel() < need:
+            if self._graphs:
+                self._graphs.clear()
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out_cols = self.model._dims[2] if self.model._dims[4] > 0 else self.model._dims[3]
+        if self._pred is None or self._pred.shape != (pb.G, out_cols):
+            self._pred = torch.empty(pb.G, out_cols, dtype=torch.float32, device=self.device)
+            self._dpred = torch.empty_like(self._pred)
+
+    def _enqueue(self, pb: PackedBatch) -> None:
+        """Enqueue one full training step on the current stream."""
+        lib, model = _lib.lib(), self.model
+        cfg = model._cfg()
+        flat = model.flat_parameters()
+        flags = _lib.TRAINING | _lib.SAVE_FOR_BWD
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        seed = 0
+        if model._p_dropout > 0:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        hdr = pb.header.ctypes.data
+        _lib.check(lib.gcb_forward(C.byref(cfg), pb.ints.data_ptr(), hdr, flat.data_ptr(), model._derived.data_ptr(),
+                                   self._ws.data_ptr(), self._ws.numel(), flags, seed, self._pred.data_ptr(), None,
+                                   None, s), "gcb_forward")
+        _lib.check(lib.gcb_mse_loss(self._pred.data_ptr(), pb.y.data_ptr(), self._pred.numel(), self.loss.data_ptr(),
+                                    self._dpred.data_ptr(), 1.0, s), "gcb_mse_loss")
+        _lib.check(lib.gcb_backward(C.byref(cfg), pb.ints.data_ptr(), hdr, flat.data_ptr(), model._derived.data_ptr(),
+                                    self._ws.data_ptr(), self._ws.numel(), flags, seed, self._dpred.data_ptr(), None,
+                                    None, self.grad.data_ptr(), 0, s), "gcb_backward")
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        b1, b2 = self.betas
+        _lib.check(lib.gcb_adam_step(flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                     self.exp_avg_sq.data_ptr(), flat.numel(), self.hyper.data_ptr(),
+                                     self.step_count.data_ptr(), b1, b2, self.eps, s), "gcb_adam_step")
+        _lib.check(lib.gcb_prepare_weights(C.byref(cfg), flat.data_ptr(), model._derived.data_ptr(), s),
+                   "gcb_prepare_weights")
+
+    def __call__(self, pb: PackedBatch) -> torch.Tensor:
+        """Run one step on a device-resident PackedBatch; returns the device loss scalar (no sync)."""
+        if pb.device != self.device:
+            raise RuntimeError("TrainStep needs a device-resident PackedBatch (use .to(device) / a prefetcher)")
+        if pb.y is None:
+            raise ValueError("PackedBatch has no targets")
+        self._buffers(pb, _lib.TRAINING | _lib.SAVE_FOR_BWD)
+        graphable = self.use_cuda_graph and self.model._p_dropout == 0
+        if not graphable:
+            self._enqueue(pb)
+            return self.loss
+        key = (pb.ints.data_ptr(), pb.y.data_ptr(), pb.header.tobytes())
+        g = self._graphs.get(key)
+        if g is None:
+            # warm-up on a side stream (required before capture), then capture
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            state = [t.clone() for t in (self.model.flat_parameters(), self.exp_avg, self.exp_avg_sq, self.step_count)]
+            with torch.cuda.stream(side):
+                self._enqueue(pb)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            # undo the warm-up step so that capture does not change the training trajectory
+            for t, s0 in zip((self.model.flat_parameters(), self.exp_avg, self.exp_avg_sq, self.step_count), state):
+                t.copy_(s0)
+            self.model.refresh_weights()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(pb)
+            self._graphs[key] = g
+            self._keepalive = getattr(self, "_keepalive", []) + [pb]
+        g.replay()
+        return self.loss

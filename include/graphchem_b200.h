@@ -152,6 +152,15 @@ int gcb_adam_step(float* params, const float* grad, float* exp_avg, float* exp_a
                   const float* hyper, int32_t* step_count, float beta1, float beta2, float eps,
                   void* stream);
 
+/* ---- bench / debug facility (thread-local) ------------------------------------------------- */
+/* Number of kernels this thread has launched through the library since load. */
+int64_t gcb_launch_count(void);
+/* enable != 0: bracket every kernel launch with CUDA events on its stream (not capturable). */
+int gcb_timing_enable(int32_t enable);
+/* Synchronise the recorded events, write a JSON array [{"name","launches","ms"}] aggregated by
+ * kernel name into buf (NUL-terminated, truncated to buflen), clear the table; returns the length. */
+int64_t gcb_timing_report(char* buf, int64_t buflen);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 int gcb_abi_version(void);
 const char* gcb_last_cuda_error(void);
