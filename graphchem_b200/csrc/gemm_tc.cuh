@@ -1,0 +1,242 @@
+// tcgen05 / TMEM / TMA GEMM for the per-layer linear transforms (bf16 in, fp32 accumulate in TMEM).
+//
+//   C[rows, N] = epilogue( A[rows, K] * W[N, K]^T )          rows ~ 1e5..1e6, K, N in {64,128,256}
+//
+// The problem is "skinny": the weight matrix (<= 64 KB) stays resident in shared memory for the
+// whole kernel, A streams through a TMA-fed ring of 128-row tiles, one elected thread issues
+// tcgen05.mma (M=128, N<=256, K=16 per instruction) into a double-buffered TMEM accumulator, and
+// eight epilogue warps drain TMEM (tcgen05.ld), apply bias / degree-scaled bias / residual /
+// activation, stage the bf16 tile in swizzled shared memory and hand it to a TMA store.  Persistent:
+// one CTA per SM, static round-robin over row tiles.  The kernel is HBM-bound by design
+// (arithmetic intensity 50-100 flop/B); the tensor pipe only has to stay out of the way.
+#pragma once
+#include "tc_common.cuh"
+
+namespace gcb {
+namespace tc {
+
+struct TcEpilogue {
+  const float* bias = nullptr;      // [N] or null
+  const int32_t* rowptr = nullptr;  // when set: bias scaled by deg (add) or [deg > 0] (mean)
+  int aggr = GCB_AGGR_ADD;
+  const bf16* res = nullptr;        // residual [rows, ld_res] or null
+  int ld_res = 0;
+  int act = -1;                     // enum gcb_act or -1
+};
+
+template <int K, int N>
+struct NtShape {
+  static constexpr int BM = 128;
+  static constexpr int KS = K / 64;  // 64-element (128-byte) K slabs
+  static constexpr int NS = N / 64;
+  static constexpr int STAGES = (K <= 128) ? 3 : 2;
+  static constexpr int W_BYTES = N * K * 2;
+  static constexpr int A_STAGE_BYTES = BM * K * 2;
+  static constexpr int OUT_BYTES = BM * N * 2;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 + W_BYTES + STAGES * A_STAGE_BYTES + OUT_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;  // two accumulators; power of two for N in {64,128,256}
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 64 + EPI_WARPS * 32;
+  static_assert(K % 64 == 0 && N % 64 == 0 && N <= 256, "unsupported GEMM shape");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+template <int K, int N>
+__global__ void __launch_bounds__(NtShape<K, N>::THREADS, 1)
+gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmC, int rows, TcEpilogue ep) {
+  using S = NtShape<K, N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;
+  uint8_t* sA = sW + S::W_BYTES;
+  uint8_t* sOut = sA + S::STAGES * S::A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + S::OUT_BYTES);
+  uint64_t* full = bars;                  // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + S::STAGES;     // [STAGES]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * S::STAGES; // [2]       MMA -> epilogue
+  uint64_t* tempty = tfull + 2;           // [2]       epilogue -> MMA
+  uint64_t* wfull = tempty + 2;           // [1]       weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (rows + S::BM - 1) / S::BM;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmW); prefetch_tmap(&tmC);
+    for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], S::EPI_WARPS); }
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull, S::W_BYTES);
+      for (int ks = 0; ks < S::KS; ++ks) tma_load_2d(sW + ks * (N * 128), &tmW, wfull, ks * 64, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], S::A_STAGE_BYTES);
+        uint8_t* dst = sA + stage * S::A_STAGE_BYTES;
+        for (int ks = 0; ks < S::KS; ++ks) tma_load_2d(dst + ks * (S::BM * 128), &tmA, &full[stage], ks * 64, tile * S::BM);
+        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_bf16(S::BM, N, 0, 0);
+      mbar_wait(wfull, 0);
+      const uint32_t w_base = smem_u32(sW);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + stage * S::A_STAGE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < K / 16; ++kk) {
+          const uint32_t ks = kk >> 2, ko = (kk & 3) * 32;
+          const uint64_t da = smem_desc_sw128(a_base + ks * (S::BM * 128) + ko, 16, 1024);
+          const uint64_t dw = smem_desc_sw128(w_base + ks * (N * 128) + ko, 16, 1024);
+          umma_bf16(tmem_base + acc * N, da, dw, idesc, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
+        umma_commit(&tfull[acc]);    // accumulator complete
+        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps) =====================
+    const int ew = warp - 2;              // 0..7
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = ew >> 2;             // column half handled by this warp
+    const int row_in_tile = q * 32 + lane;
+    const int ep_tid = threadIdx.x - 64;
+    constexpr int COLS_PER_WARP = N / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int r = tile * S::BM + row_in_tile;
+      const bool valid = r < rows;
+      float wrow = 1.f;
+      if (ep.rowptr && valid) {
+        const int deg = __ldg(ep.rowptr + r + 1) - __ldg(ep.rowptr + r);
+        wrow = ep.aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      // the previous tile's TMA store must have finished reading the staging buffer
+      if (ep_tid == 0) tma_store_wait_read();
+      named_bar_sync(1, S::EPI_WARPS * 32);
+#pragma unroll 1
+      for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
+        const int c0 = half * COLS_PER_WARP + cc;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + c0, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaf(wrow, __ldg(ep.bias + c0 + j), f[j]);
+        }
+        if (ep.res && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r * ep.ld_res + c0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 t = __ldg(rp + j4);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 x = __bfloat1622float2(h[i]);
+              f[j4 * 8 + 2 * i] += x.x;
+              f[j4 * 8 + 2 * i + 1] += x.y;
+            }
+          }
+        }
+        if (ep.act >= 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
+        }
+        // stage as bf16 in the 128B-swizzled layout the TMA store expects
+        uint8_t* slab = sOut + (c0 >> 6) * (S::BM * 128) + row_in_tile * 128;
+        const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint4 t;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[j4 * 8 + 2 * i], f[j4 * 8 + 2 * i + 1]);
+          *reinterpret_cast<uint4*>(slab + (((chunk0 + j4) ^ (row_in_tile & 7)) << 4)) = t;
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      // publish the staged tile to the async proxy, then one thread issues the store
+      fence_proxy_async_smem();
+      named_bar_sync(1, S::EPI_WARPS * 32);
+      if (ep_tid == 0) {
+        for (int ns = 0; ns < S::NS; ++ns) tma_store_2d(&tmC, sOut + ns * (S::BM * 128), ns * 64, tile * S::BM);
+        tma_store_commit();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (ep_tid == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+template <int K, int N>
+inline int launch_gemm_nt_tc_impl(const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int rows,
+                                  const TcEpilogue& ep, cudaStream_t s) {
+  using S = NtShape<K, N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmW, tmC;
+  if (make_tmap_bf16(&tmA, A, rows, K, lda, S::BM) || make_tmap_bf16(&tmW, W, N, K, K, N) ||
+      make_tmap_bf16(&tmC, C, rows, N, ldc, S::BM))
+    return GCB_ERR_CUDA;
+  const int num_tiles = (rows + S::BM - 1) / S::BM;
+  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  GCB_KERNEL("gemm_nt_tc_kernel", s, gemm_nt_tc_kernel<K, N><<<grid, S::THREADS, S::SMEM_BYTES, s>>>(tmA, tmW, tmC, rows, ep));
+  return GCB_OK;
+}
+
+// Returns GCB_ERR_UNSUPPORTED when the shape has no tcgen05 instantiation (caller falls back to
+// the CUDA-core GEMM).
+inline int launch_gemm_nt_tc(const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int rows, int N, int K,
+                             const TcEpilogue& ep, cudaStream_t s) {
+  if (rows <= 0) return GCB_OK;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15) return GCB_ERR_UNSUPPORTED;
+  if (lda % 8 || ldc % 8) return GCB_ERR_UNSUPPORTED;
+  if (K == 128 && N == 256) return launch_gemm_nt_tc_impl<128, 256>(A, lda, W, C, ldc, rows, ep, s);
+  if (K == 256 && N == 128) return launch_gemm_nt_tc_impl<256, 128>(A, lda, W, C, ldc, rows, ep, s);
+  if (K == 64 && N == 128) return launch_gemm_nt_tc_impl<64, 128>(A, lda, W, C, ldc, rows, ep, s);
+  if (K == 128 && N == 64) return launch_gemm_nt_tc_impl<128, 64>(A, lda, W, C, ldc, rows, ep, s);
+  return GCB_ERR_UNSUPPORTED;
+}
+
+}  // namespace tc
+}  // namespace gcb

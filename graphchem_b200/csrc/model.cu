@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "kernels.cuh"
 
 namespace gcb {
@@ -40,6 +41,23 @@ KernelTimer::KernelTimer(const char* name, cudaStream_t s) : name_(name), s_(s),
 }
 void KernelTimer::stop() {
   if (slot_ >= 0) cudaEventRecord((*g_slots)[slot_].e1, s_);
+}
+
+// ---- GEMM dispatch: tcgen05 kernel for bf16 hot shapes, CUDA-core kernel otherwise ---------------
+namespace tc { bool tc_enabled(); }
+template <typename T>
+static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
+                        const Epilogue& ep, cudaStream_t s) {
+  if constexpr (sizeof(T) == 2) {
+    if (!w_kn && ldw == K && !ep.actgrad_y && tc::tc_enabled()) {
+      tc::TcEpilogue te;
+      te.bias = ep.bias; te.rowptr = ep.rowptr; te.aggr = ep.aggr;
+      te.res = (const bf16*)ep.res; te.ld_res = ep.ld_res; te.act = ep.act;
+      const int rc = tc::launch_gemm_nt_tc(A, lda, W, C, ldc, M, N, K, te, s);
+      if (rc != GCB_ERR_UNSUPPORTED) return rc;
+    }
+  }
+  return launch_gemm_nt<T>(A, lda, W, ldw, w_kn, C, ldc, M, N, K, ep, s);
 }
 
 // ---- parameter layout ---------------------------------------------------------------------------
@@ -301,7 +319,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
     if (M > 0) {
       Epilogue ep;
       ep.bias = bpq;
-      GCB_TRY(launch_gemm_nt<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
+      GCB_TRY(gemm_nt_auto<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
       GCB_KERNEL("bond_update_kernel", s, bond_update_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>((const T*)p.PQ[l], g.in_ptr, g.in_src, (T*)p.B[l],
                                                                        M, D, c.act, db));
     }
@@ -312,7 +330,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       Epilogue ep;
       ep.bias = bat; ep.rowptr = g.in_ptr; ep.aggr = c.aggr;
       ep.res = p.A[l - 1]; ep.ld_res = D; ep.act = c.act;
-      GCB_TRY(launch_gemm_nt<T>((const T*)p.S[l], 2 * D, wat, 2 * D, false, (T*)p.A[l], D, N, D, 2 * D, ep, s));
+      GCB_TRY(gemm_nt_auto<T>((const T*)p.S[l], 2 * D, wat, 2 * D, false, (T*)p.A[l], D, N, D, 2 * D, ep, s));
       if (da.p > 0.f) {
         GCB_KERNEL("dropout_inplace_kernel", s, dropout_inplace_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((T*)p.A[l], N, D, da));
       }
@@ -409,7 +427,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     const int acc_w = l != L;
     if (N > 0) {
       Epilogue ep;
-      GCB_TRY(launch_gemm_nt<T>((const T*)p.dZA[cur], D, watT, D, false, (T*)p.dS, 2 * D, N, 2 * D, D, ep, s));
+      GCB_TRY(gemm_nt_auto<T>((const T*)p.dZA[cur], D, watT, D, false, (T*)p.dS, 2 * D, N, 2 * D, D, ep, s));
     }
     GCB_TRY(launch_gemm_tn<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
                               p.accBat, g.in_ptr, c.aggr, acc_w, s));
@@ -429,7 +447,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
                               p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s));
     if (M > 0) {
       Epilogue ep;
-      GCB_TRY(launch_gemm_nt<T>((const T*)p.dPQ, 2 * D, wpqT, 2 * D, false, (T*)p.dBn[bcur], D, M, D, 2 * D, ep, s));
+      GCB_TRY(gemm_nt_auto<T>((const T*)p.dPQ, 2 * D, wpqT, 2 * D, false, (T*)p.dBn[bcur], D, M, D, 2 * D, ep, s));
       dBnext = (const T*)p.dBn[bcur];
       bcur ^= 1;
     }
@@ -577,6 +595,15 @@ extern "C" int gcb_adam_step(float* params, const float* grad, float* exp_avg, f
   }
   GCB_KERNEL("increment_kernel", s, increment_kernel<<<1, 1, 0, s>>>(step_count));
   return GCB_OK;
+}
+
+// ---- debug entry: one bf16 GEMM through the dispatcher (tests/test_gemm_gpu.py) -------------------
+extern "C" int gcb_debug_gemm_nt_bf16(const void* A, const void* W, void* C, int32_t rows, int32_t N, int32_t K,
+                                      const float* bias, const int32_t* rowptr, int32_t aggr, const void* res,
+                                      int32_t act, void* stream) {
+  Epilogue ep;
+  ep.bias = bias; ep.rowptr = rowptr; ep.aggr = aggr; ep.res = res; ep.ld_res = N; ep.act = act;
+  return gemm_nt_auto<bf16>((const bf16*)A, K, (const bf16*)W, K, false, (bf16*)C, N, rows, N, K, ep, (cudaStream_t)stream);
 }
 
 // ---- timing / launch-count facility --------------------------------------------------------------

@@ -1,0 +1,54 @@
+// Host-side helpers of the tcgen05 path: TMA tensor-map encoding through the driver entry point
+// (resolved at run time: the library links only the static CUDA runtime, never libcuda directly).
+#include <cstdlib>
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace gcb {
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_cuda_error(cudaErrorNotSupported, __FILE__, __LINE__);
+    return 1;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t estride[2] = {1u, 1u};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_cuda_error(cudaErrorInvalidValue, __FILE__, __LINE__);
+    return 1;
+  }
+  return 0;
+}
+
+bool tc_enabled() {
+  const char* e = std::getenv("GCB_DISABLE_TC");
+  return !(e && e[0] == '1');
+}
+
+}  // namespace tc
+}  // namespace gcb

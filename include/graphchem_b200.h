@@ -161,6 +161,12 @@ int gcb_timing_enable(int32_t enable);
  * kernel name into buf (NUL-terminated, truncated to buflen), clear the table; returns the length. */
 int64_t gcb_timing_report(char* buf, int64_t buflen);
 
+/* Debug: C[rows,N] = epilogue(A[rows,K] W[N,K]^T) in bf16 through the same dispatcher the model
+ * uses (tcgen05 kernel when the shape is supported and GCB_DISABLE_TC != 1). */
+int gcb_debug_gemm_nt_bf16(const void* A, const void* W, void* C, int32_t rows, int32_t N, int32_t K,
+                           const float* bias, const int32_t* rowptr, int32_t aggr, const void* res, int32_t act,
+                           void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 int gcb_abi_version(void);
 const char* gcb_last_cuda_error(void);

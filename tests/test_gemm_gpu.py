@@ -1,0 +1,80 @@
+"""-m gpu: the tcgen05/TMEM/TMA GEMM (gemm_tc.cuh) against a torch fp32 reference of the same op
+(inputs rounded to bf16, fp32 accumulation, output rounded to bf16): tolerance 2^-7 relative to
+the row scale, i.e. one bf16 ulp of the result plus accumulation-order noise."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from graphchem_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+ACT = {None: -1, "softplus": 0, "relu": 2, "tanh": 3}
+
+
+def _run(rows, N, K, bias=False, deg=False, res=False, act=None, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = (torch.randn(rows, K, generator=g) * 0.5).bfloat16().cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    Cm = torch.full((rows, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    b = torch.randn(N, generator=g).cuda() if bias else None
+    rp = None
+    if deg:
+        d = torch.randint(0, 4, (rows,), generator=g)
+        rp = torch.cat([torch.zeros(1, dtype=torch.long), d.cumsum(0)]).int().cuda()
+    R = torch.randn(rows, N, generator=g).bfloat16().cuda() if res else None
+    rc = _lib.lib().gcb_debug_gemm_nt_bf16(A.data_ptr(), W.data_ptr(), Cm.data_ptr(), rows, N, K,
+                                           None if b is None else b.data_ptr(), None if rp is None else rp.data_ptr(),
+                                           0, None if R is None else R.data_ptr(), ACT[act],
+                                           torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t()
+    if b is not None:
+        w = (rp[1:] - rp[:-1]).float()[:, None] if rp is not None else 1.0
+        ref = ref + w * b
+    if R is not None:
+        ref = ref + R.float()
+    if act == "softplus":
+        ref = F.softplus(ref)
+    elif act == "relu":
+        ref = F.relu(ref)
+    elif act == "tanh":
+        ref = torch.tanh(ref)
+    err = (Cm.float() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)
+    assert torch.isfinite(Cm.float()).all()
+    assert float(err) < 2 ** -7, float(err)
+
+
+@pytest.mark.parametrize("K,N", [(128, 256), (256, 128), (64, 128), (128, 64)])
+@pytest.mark.parametrize("rows", [1, 127, 128, 129, 1000, 40000])
+def test_tc_gemm_plain(rows, K, N):
+    _run(rows, N, K)
+
+
+@pytest.mark.parametrize("K,N", [(128, 256), (256, 128)])
+def test_tc_gemm_epilogues(K, N):
+    _run(5000, N, K, bias=True)
+    _run(5000, N, K, bias=True, deg=True, res=True, act="softplus")
+    _run(333, N, K, bias=True, res=True, act="tanh")
+    _run(70000, N, K, bias=True, deg=True, res=True, act="relu")
+
+
+def test_tc_gemm_is_deterministic_and_matches_cuda_core_path(monkeypatch):
+    import os
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(3000, 128, generator=g).bfloat16().cuda()
+    W = (torch.randn(256, 128, generator=g) / 11).bfloat16().cuda()
+    outs = []
+    for disable in ("0", "0", "1"):
+        os.environ["GCB_DISABLE_TC"] = disable
+        Cm = torch.empty(3000, 256, dtype=torch.bfloat16, device="cuda")
+        assert _lib.lib().gcb_debug_gemm_nt_bf16(A.data_ptr(), W.data_ptr(), Cm.data_ptr(), 3000, 256, 128, None, None,
+                                                 0, None, -1, torch.cuda.current_stream().cuda_stream) == 0
+        torch.cuda.synchronize()
+        outs.append(Cm.float())
+    os.environ["GCB_DISABLE_TC"] = "0"
+    assert torch.equal(outs[0], outs[1])
+    assert float((outs[0] - outs[2]).abs().max() / outs[2].abs().max()) < 2 ** -7
