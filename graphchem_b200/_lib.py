@@ -78,6 +78,7 @@ SIGNATURES = {
     "gcb_mse_loss": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _f32, _vp]),
     "gcb_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _f32, _f32, _f32, _vp]),
     "gcb_debug_gemm_nt_bf16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp]),
+    "gcb_debug_gemm_tn_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gcb_launch_count": (_i64, []),
     "gcb_timing_enable": (C.c_int, [_i32]),
     "gcb_timing_report": (_i64, [_vp, _i64]),

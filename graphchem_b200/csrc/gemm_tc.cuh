@@ -240,3 +240,212 @@ inline int launch_gemm_nt_tc(const bf16* A, int lda, const bf16* W, bf16* C, int
 
 }  // namespace tc
 }  // namespace gcb
+
+// =================================================================================================
+// Weight-gradient ("TN") GEMM on tcgen05:   dW[NN, KK] = sum_r A[r, NN]^T B[r, KK]   (+ column sums)
+//
+// The reduction runs over graph rows, so both operands are MN-major for the tensor core: a TMA tile
+// of 128 rows x 64 columns (128-byte swizzled rows) is read as "K = row, M/N = column".  Each CTA
+// owns a contiguous set of 128-row tiles and keeps its partial dW in TMEM for the whole kernel
+// (NN/128 accumulators of KK fp32 columns); partials are written once per CTA and summed in CTA
+// order by reduce_partials_kernel -> deterministic.  Warps 2-5 compute the weighted column sums
+// db[n] = sum_r w(r) A[r, n] (bias gradients) from the same shared-memory tile while the MMAs run.
+// =================================================================================================
+namespace gcb {
+namespace tc {
+
+template <int NN, int KK>
+struct TnShape {
+  static constexpr int BR = 128;                 // rows (MMA K extent) per tile
+  static constexpr int AS = NN / 64, BS = KK / 64;
+  static constexpr int MB = NN / 128;            // 128-row output blocks
+  static constexpr int STAGES = 2;
+  static constexpr int A_BYTES = BR * NN * 2, B_BYTES = BR * KK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = MB * KK;      // 256 for both D=128 shapes
+  static constexpr int THREADS = 192;
+  static_assert(NN % 128 == 0 && KK % 64 == 0 && KK <= 256 && MB * KK <= 512, "unsupported TN shape");
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns must be a power of two");
+};
+
+template <int NN, int KK>
+__global__ void __launch_bounds__(192, 1)
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int rows,
+                  float* __restrict__ partial, float* __restrict__ bias_partial, const int32_t* __restrict__ rowptr,
+                  int aggr) {
+  using S = TnShape<NN, KK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sT = smem;  // [STAGES][A tile | B tile]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sT + S::STAGES * S::STAGE_BYTES);
+  uint64_t* full = bars;               // [STAGES]
+  uint64_t* empty = bars + S::STAGES;  // [STAGES]  (MMA commit + colsum warps)
+  uint64_t* done = empty + S::STAGES;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  float* w_s = reinterpret_cast<float*>(bars + 16);  // [128] row weights of the current tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (rows + S::BR - 1) / S::BR;
+  // contiguous tile range of this CTA (fixed partition -> fixed summation order)
+  const int per = (num_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per;
+  const int t_end = min(num_tiles, t_begin + per);
+  const bool want_bias = bias_partial != nullptr;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], want_bias ? 5 : 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
+        uint8_t* a = sT + stage * S::STAGE_BYTES;
+        uint8_t* b = a + S::A_BYTES;
+        for (int k = 0; k < S::AS; ++k) tma_load_2d(a + k * (S::BR * 128), &tmA, &full[stage], k * 64, tile * S::BR);
+        for (int k = 0; k < S::BS; ++k) tma_load_2d(b + k * (S::BR * 128), &tmB, &full[stage], k * 64, tile * S::BR);
+        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_bf16(128, KK, 1, 1);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sT + stage * S::STAGE_BYTES);
+        const uint32_t b_base = a_base + S::A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < S::BR / 16; ++kk) {
+          const uint64_t db = smem_desc_sw128(b_base + kk * 2048, S::BR * 128, 1024);
+#pragma unroll
+          for (int mb = 0; mb < S::MB; ++mb) {
+            const uint64_t da = smem_desc_sw128(a_base + mb * 2 * (S::BR * 128) + kk * 2048, S::BR * 128, 1024);
+            umma_bf16(tmem_base + mb * KK, da, db, idesc, (tile > t_begin || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ---- warps 2..5: weighted column sums during the main loop, then the TMEM -> global epilogue ----
+    const int t = threadIdx.x - 64;  // 0..127
+    float bsum[NN / 128];
+#pragma unroll
+    for (int i = 0; i < NN / 128; ++i) bsum[i] = 0.f;
+    if (want_bias) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int r = tile * S::BR + t;
+        float w = 0.f;
+        if (r < rows) {
+          if (rowptr) {
+            const int deg = __ldg(rowptr + r + 1) - __ldg(rowptr + r);
+            w = aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+          } else w = 1.f;
+        }
+        named_bar_sync(1, 128);  // previous tile's readers are done with w_s
+        w_s[t] = w;
+        mbar_wait(&full[stage], phase);
+        named_bar_sync(1, 128);
+        const uint8_t* a = sT + stage * S::STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < NN / 128; ++i) {
+          const int n = i * 128 + t;
+          const uint8_t* slab = a + (n >> 6) * (S::BR * 128);
+          const int chunk = (n & 63) >> 3, sub = (n & 7) * 2;
+          float acc = bsum[i];
+          for (int rr = 0; rr < S::BR; ++rr) {
+            const bf16 v = *reinterpret_cast<const bf16*>(slab + rr * 128 + ((chunk ^ (rr & 7)) << 4) + sub);
+            acc = fmaf(w_s[rr], __bfloat162float(v), acc);
+          }
+          bsum[i] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+      }
+#pragma unroll
+      for (int i = 0; i < NN / 128; ++i) bias_partial[(size_t)blockIdx.x * NN + i * 128 + t] = bsum[i];
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    float* out = partial + (size_t)blockIdx.x * NN * KK;
+#pragma unroll 1
+    for (int mb = 0; mb < S::MB; ++mb) {
+      const int m = mb * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < KK; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + mb * KK + c0, v);
+        tmem_ld_wait();
+        float4* o = reinterpret_cast<float4*>(out + (size_t)m * KK + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                             __uint_as_float(v[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+constexpr int kTnMaxCtas = kNumSMs;
+
+template <int NN, int KK>
+inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb, int rows, float* partial,
+                                  float* bias_partial, const int32_t* rowptr, int aggr, int* grid_out, cudaStream_t s) {
+  using S = TnShape<NN, KK>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCB_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<NN, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (make_tmap_bf16(&tmA, A, rows, NN, lda, S::BR) || make_tmap_bf16(&tmB, B, rows, KK, ldb, S::BR)) return GCB_ERR_CUDA;
+  const int num_tiles = (rows + S::BR - 1) / S::BR;
+  int grid = num_tiles < kTnMaxCtas ? num_tiles : kTnMaxCtas;
+  const int per = (num_tiles + grid - 1) / grid;
+  grid = (num_tiles + per - 1) / per;  // every CTA owns at least one tile
+  *grid_out = grid;
+  GCB_KERNEL("gemm_tn_tc_kernel", s, gemm_tn_tc_kernel<NN, KK><<<grid, S::THREADS, S::SMEM_BYTES, s>>>(
+      tmA, tmB, rows, partial, bias_partial, rowptr, aggr));
+  return GCB_OK;
+}
+
+// Writes per-CTA partials ([grid][NN*KK] then [grid][NN] bias sums) and reports the CTA count.
+inline int launch_gemm_tn_tc(const bf16* A, int lda, const bf16* B, int ldb, int rows, int NN, int KK, float* partial,
+                             bool want_bias, const int32_t* rowptr, int aggr, int* grid_out, float** bias_partial_out,
+                             cudaStream_t s) {
+  if (rows < 128) return GCB_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return GCB_ERR_UNSUPPORTED;
+  if (lda % 8 || ldb % 8) return GCB_ERR_UNSUPPORTED;
+  float* bp = want_bias ? partial + (size_t)kTnMaxCtas * NN * KK : nullptr;
+  *bias_partial_out = bp;
+  if (NN == 128 && KK == 256) return launch_gemm_tn_tc_impl<128, 256>(A, lda, B, ldb, rows, partial, bp, rowptr, aggr, grid_out, s);
+  if (NN == 256 && KK == 128) return launch_gemm_tn_tc_impl<256, 128>(A, lda, B, ldb, rows, partial, bp, rowptr, aggr, grid_out, s);
+  return GCB_ERR_UNSUPPORTED;
+}
+
+}  // namespace tc
+}  // namespace gcb

@@ -60,6 +60,26 @@ static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* 
   return launch_gemm_nt<T>(A, lda, W, ldw, w_kn, C, ldc, M, N, K, ep, s);
 }
 
+template <typename T>
+static int gemm_tn_auto(const T* A, int lda, const T* B, int ldb, int rows, int Nn, int Kk, float* partial, float* dW,
+                        float* db, const int32_t* rowptr, int aggr, int accumulate, cudaStream_t s) {
+  if constexpr (sizeof(T) == 2) {
+    if (tc::tc_enabled()) {
+      int grid = 0;
+      float* bias_partial = nullptr;
+      const int rc = tc::launch_gemm_tn_tc(A, lda, B, ldb, rows, Nn, Kk, partial, db != nullptr, rowptr, aggr, &grid,
+                                           &bias_partial, s);
+      if (rc == GCB_OK) {
+        GCB_TRY(launch_reduce_partials(partial, grid, (int64_t)Nn * Kk, dW, accumulate, s));
+        if (db) GCB_TRY(launch_reduce_partials(bias_partial, grid, Nn, db, accumulate, s));
+        return GCB_OK;
+      }
+      if (rc != GCB_ERR_UNSUPPORTED) return rc;
+    }
+  }
+  return launch_gemm_tn<T>(A, lda, B, ldb, rows, Nn, Kk, partial, dW, db, rowptr, aggr, accumulate, s);
+}
+
 // ---- parameter layout ---------------------------------------------------------------------------
 struct ParamLayout {
   int n_tensors = 0;
@@ -248,7 +268,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
     p.dH[0] = (float*)take(G * wmax * 4); p.dH[1] = (float*)take(G * wmax * 4);
     p.dPool = (float*)take(G * D * 4);
     // partial sums of the TN GEMMs / embedding gradients
-    int64_t pf = 64 * (2 * D * D + 2 * D);
+    int64_t pf = (int64_t)tc::kTnMaxCtas * (2 * D * D + 2 * D);
     for (int k = 0; k < pl.n_lin; ++k) {
       const int64_t need = (int64_t)tn_splits((int)G) * pl.r_out[k] * (pl.r_in[k] + 1);
       if (need > pf) pf = need;
@@ -429,7 +449,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       Epilogue ep;
       GCB_TRY(gemm_nt_auto<T>((const T*)p.dZA[cur], D, watT, D, false, (T*)p.dS, 2 * D, N, 2 * D, D, ep, s));
     }
-    GCB_TRY(launch_gemm_tn<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
+    GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
                               p.accBat, g.in_ptr, c.aggr, acc_w, s));
     if (N > 0) {
       GCB_KERNEL("atom_bwd_gather_kernel", s, atom_bwd_gather_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>(
@@ -443,7 +463,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       GCB_KERNEL("bond_bwd_scatter_kernel", s, bond_bwd_scatter_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(
           (const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, (T*)p.dPQ, M, D));
     }
-    GCB_TRY(launch_gemm_tn<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
+    GCB_TRY(gemm_tn_auto<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
                               p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s));
     if (M > 0) {
       Epilogue ep;
@@ -604,6 +624,13 @@ extern "C" int gcb_debug_gemm_nt_bf16(const void* A, const void* W, void* C, int
   Epilogue ep;
   ep.bias = bias; ep.rowptr = rowptr; ep.aggr = aggr; ep.res = res; ep.ld_res = N; ep.act = act;
   return gemm_nt_auto<bf16>((const bf16*)A, K, (const bf16*)W, K, false, (bf16*)C, N, rows, N, K, ep, (cudaStream_t)stream);
+}
+
+extern "C" int gcb_debug_gemm_tn_bf16(const void* A, const void* B, int32_t rows, int32_t Nn, int32_t Kk,
+                                      float* partial, float* dW, float* db, const int32_t* rowptr, int32_t aggr,
+                                      void* stream) {
+  return gemm_tn_auto<bf16>((const bf16*)A, Nn, (const bf16*)B, Kk, rows, Nn, Kk, partial, dW, db, rowptr, aggr, 0,
+                            (cudaStream_t)stream);
 }
 
 // ---- timing / launch-count facility --------------------------------------------------------------

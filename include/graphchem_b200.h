@@ -167,6 +167,11 @@ int gcb_debug_gemm_nt_bf16(const void* A, const void* W, void* C, int32_t rows, 
                            const float* bias, const int32_t* rowptr, int32_t aggr, const void* res, int32_t act,
                            void* stream);
 
+/* Debug: dW[Nn,Kk] = A[rows,Nn]^T B[rows,Kk], db[Nn] = sum_r w(r) A[r,:] (bf16 in, fp32 out);
+ * partial: >= 148*(Nn*Kk+Nn) floats of scratch. */
+int gcb_debug_gemm_tn_bf16(const void* A, const void* B, int32_t rows, int32_t Nn, int32_t Kk, float* partial,
+                           float* dW, float* db, const int32_t* rowptr, int32_t aggr, void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 int gcb_abi_version(void);
 const char* gcb_last_cuda_error(void);

@@ -78,3 +78,28 @@ def test_tc_gemm_is_deterministic_and_matches_cuda_core_path(monkeypatch):
     os.environ["GCB_DISABLE_TC"] = "0"
     assert torch.equal(outs[0], outs[1])
     assert float((outs[0] - outs[2]).abs().max() / outs[2].abs().max()) < 2 ** -7
+
+
+@pytest.mark.parametrize("Nn,Kk", [(128, 256), (256, 128)])
+@pytest.mark.parametrize("rows", [128, 129, 1000, 50000, 200000])
+def test_tc_gemm_tn_weight_grad(rows, Nn, Kk):
+    g = torch.Generator().manual_seed(rows)
+    A = (torch.randn(rows, Nn, generator=g) * 0.3).bfloat16().cuda()
+    B = torch.randn(rows, Kk, generator=g).bfloat16().cuda()
+    d = torch.randint(0, 4, (rows,), generator=g)
+    rp = torch.cat([torch.zeros(1, dtype=torch.long), d.cumsum(0)]).int().cuda()
+    partial = torch.empty(148 * (Nn * Kk + Nn), device="cuda")
+    outs = []
+    for _ in range(2):
+        dW = torch.full((Nn, Kk), float("nan"), device="cuda")
+        db = torch.full((Nn,), float("nan"), device="cuda")
+        rc = _lib.lib().gcb_debug_gemm_tn_bf16(A.data_ptr(), B.data_ptr(), rows, Nn, Kk, partial.data_ptr(), dW.data_ptr(),
+                                               db.data_ptr(), rp.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        outs.append((dW.clone(), db.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), "must be deterministic"
+    ref = A.double().t() @ B.double()
+    refb = (A.double() * d.double().cuda()[:, None]).sum(0)
+    assert float((dW.double() - ref).abs().max() / ref.abs().max()) < 1e-4
+    assert float((db.double() - refb).abs().max() / refb.abs().max()) < 1e-4
