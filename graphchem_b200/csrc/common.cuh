@@ -117,6 +117,34 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
   }
 }
 
+// Fast variants for the bf16 mode (results are rounded to 8 mantissa bits anyway): MUFU ex2/lg2
+// based, ~1e-6 absolute error, 5-6 instructions instead of ~40.
+__device__ __forceinline__ float act_fwd_fast(float x, int act) {
+  switch (act) {
+    case GCB_ACT_SOFTPLUS: return x > 20.f ? x : __logf(1.f + __expf(x));
+    case GCB_ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-x));
+    case GCB_ACT_RELU: return fmaxf(x, 0.f);
+    case GCB_ACT_TANH: { const float e = __expf(2.f * fminf(x, 15.f)); return __fdividef(e - 1.f, e + 1.f); }
+    default: return x > 0.f ? x : 0.01f * x;
+  }
+}
+__device__ __forceinline__ float act_grad_from_out_fast(float y, int act) {
+  switch (act) {
+    case GCB_ACT_SOFTPLUS: return 1.f - __expf(-y);
+    case GCB_ACT_SIGMOID: return y * (1.f - y);
+    case GCB_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case GCB_ACT_TANH: return 1.f - y * y;
+    default: return y > 0.f ? 1.f : 0.01f;
+  }
+}
+// Storage-type dispatch: fp32 = parity mode (torch-like precise math), bf16 = fast math.
+template <typename T> __device__ __forceinline__ float act_fwd_t(float x, int act) {
+  if constexpr (sizeof(T) == 2) return act_fwd_fast(x, act); else return act_fwd(x, act);
+}
+template <typename T> __device__ __forceinline__ float act_grad_t(float y, int act) {
+  if constexpr (sizeof(T) == 2) return act_grad_from_out_fast(y, act); else return act_grad_from_out(y, act);
+}
+
 // ---- counter-based RNG for dropout (Philox-4x32-10) --------------------------------------------
 // Keyed by (seed, tensor tag) and indexed by the element's linear index, so that the backward pass
 // regenerates the same keep-mask without storing it.

@@ -33,7 +33,7 @@ struct Epilogue {
 template <typename T, int CNT>
 __device__ __forceinline__ void load_seg(const T* __restrict__ row, int k0, int K, bool vec_ok, float (&out)[CNT]) {
   // CNT contiguous elements row[k0 .. k0+CNT), zero-filled past K.
-  if (vec_ok && k0 + CNT <= K) {
+  if (CNT >= 4 && vec_ok && k0 + CNT <= K) {
     if constexpr (sizeof(T) == 4) {
 #pragma unroll
       for (int i = 0; i < CNT; i += 4) {
@@ -61,17 +61,18 @@ __device__ __forceinline__ void load_seg(const T* __restrict__ row, int k0, int 
 
 // C[M,N] = epilogue( A[M,K] * W ), W given as [N,K] row-major (W_KN == false, y = x W^T like
 // nn.Linear) or as [K,N] row-major (W_KN == true).
-template <typename T, bool W_KN>
+// TM = rows per thread: 8 -> 128-row tiles (large problems), 2 -> 32-row tiles (readout MLP, small batches).
+template <typename T, bool W_KN, int TM>
 __global__ void __launch_bounds__(256)
 gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw, T* __restrict__ C, int ldc,
                int M, int N, int K, Epilogue ep) {
-  constexpr int BM = 128, BN = 64, BK = 16;
+  constexpr int BM = 16 * TM, BN = 64, BK = 16;
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Ws[2][BK][BN + 4];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  // A loader: row a_r (0..127), 8 contiguous k starting at a_k
-  const int a_r = tid & 127, a_k = (tid >> 7) * 8;
+  // A loader: row a_r (0..BM-1), TM contiguous k starting at a_k
+  const int a_r = tid % BM, a_k = (tid / BM) * TM;
   const bool a_vec = (lda % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   const bool a_row_ok = (m0 + a_r) < M;
   const T* a_row = A + (size_t)(a_row_ok ? m0 + a_r : 0) * lda;
@@ -80,12 +81,12 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
   if (W_KN) { w_k = tid >> 4; w_n = (tid & 15) * 4; } else { w_n = tid & 63; w_k = (tid >> 6) * 4; }
   const bool w_vec = (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
 
-  float a_reg[8], w_reg[4];
+  float a_reg[TM], w_reg[4];
   auto fetch = [&](int k0) {
-    if (a_row_ok) load_seg<T, 8>(a_row, k0 + a_k, K, a_vec, a_reg);
+    if (a_row_ok) load_seg<T, TM>(a_row, k0 + a_k, K, a_vec, a_reg);
     else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a_reg[i] = 0.f;
+      for (int i = 0; i < TM; ++i) a_reg[i] = 0.f;
     }
     if (W_KN) {
       const int k = k0 + w_k;
@@ -99,7 +100,7 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
   };
   auto stash = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) As[buf][a_k + i][a_r] = a_reg[i];
+    for (int i = 0; i < TM; ++i) As[buf][a_k + i][a_r] = a_reg[i];
     if (W_KN) {
       *reinterpret_cast<float4*>(&Ws[buf][w_k][w_n]) = make_float4(w_reg[0], w_reg[1], w_reg[2], w_reg[3]);
     } else {
@@ -109,9 +110,9 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
   };
 
   const int ty = tid >> 4, tx = tid & 15;
-  float acc[8][4];
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
@@ -124,13 +125,13 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
     if (kt + 1 < nk) fetch((kt + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      float a[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[buf][k][ty * TM + i];
       float4 w = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float b[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
@@ -143,8 +144,8 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
   const T* ygrad = reinterpret_cast<const T*>(ep.actgrad_y);
   const float keep_scale = ep.p_drop > 0.f ? 1.f / (1.f - ep.p_drop) : 1.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = m0 + ty * 8 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int r = m0 + ty * TM + i;
     if (r >= M) continue;
     float wrow = 1.f;
     if (ep.rowptr) {
@@ -164,11 +165,11 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
           f = keep ? keep_scale : 0.f;
           y = y * (1.f - ep.p_drop);  // undo the 1/(1-p) scaling to recover act(x)
         }
-        v = v * f * act_grad_from_out(y, ep.act);
+        v = v * f * act_grad_t<T>(y, ep.act);
       } else {
         if (ep.bias) v = fmaf(wrow, ep.bias[n], v);
         if (res) v += to_float(res[(size_t)r * ep.ld_res + n]);
-        if (ep.act >= 0) v = act_fwd(v, ep.act);
+        if (ep.act >= 0) v = act_fwd_t<T>(v, ep.act);
       }
       C[(size_t)r * ldc + n] = from_float<T>(v);
     }
@@ -179,11 +180,20 @@ template <typename T>
 inline int launch_gemm_nt(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                           const Epilogue& ep, cudaStream_t s) {
   if (M <= 0 || N <= 0) return GCB_OK;
-  dim3 grid((unsigned)ceil_div(M, 128), (unsigned)ceil_div(N, 64));
-  if (w_kn) {
-    GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_kernel<T, true><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+  if (M > 16384) {
+    dim3 grid((unsigned)ceil_div(M, 128), (unsigned)ceil_div(N, 64));
+    if (w_kn) {
+      GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_kernel<T, true, 8><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+    } else {
+      GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_kernel<T, false, 8><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+    }
   } else {
-    GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_kernel<T, false><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+    dim3 grid((unsigned)ceil_div(M, 32), (unsigned)ceil_div(N, 64));
+    if (w_kn) {
+      GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_kernel<T, true, 2><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+    } else {
+      GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_kernel<T, false, 2><<<grid, 256, 0, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+    }
   }
   return GCB_OK;
 }
@@ -285,25 +295,39 @@ gemm_tn_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ld
 }
 
 // out[i] (+)= sum_{z < splits} partial[z*count + i]   (fixed order)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, int64_t count,
-                                       float* __restrict__ out, int accumulate) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+// 256 threads = 64 elements x 4 z-groups; each group adds its contiguous quarter of the splits
+// in order, the four group sums are combined as (g0 + g1) + (g2 + g3): a fixed summation tree.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int splits, int64_t count, float* __restrict__ out,
+                       int accumulate) {
+  __shared__ float red[4][64];
+  const int e = threadIdx.x & 63, zg = threadIdx.x >> 6;
+  const int64_t i = (int64_t)blockIdx.x * 64 + e;
+  const int per = (splits + 3) / 4;
+  const int z0 = zg * per, z1 = min(splits, z0 + per);
   float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += partial[(size_t)z * count + i];
-  out[i] = accumulate ? out[i] + s : s;
+  if (i < count) {
+#pragma unroll 4
+    for (int z = z0; z < z1; ++z) s += __ldg(partial + (size_t)z * count + i);
+  }
+  red[zg][e] = s;
+  __syncthreads();
+  if (zg == 0 && i < count) {
+    const float t = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+    out[i] = accumulate ? out[i] + t : t;
+  }
 }
 
 inline int launch_reduce_partials(const float* partial, int splits, int64_t count, float* out, int accumulate,
                                   cudaStream_t s) {
   if (count <= 0) return GCB_OK;
-  GCB_KERNEL("reduce_partials_kernel", s, reduce_partials_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, s>>>(partial, splits, count, out, accumulate));
+  GCB_KERNEL("reduce_partials_kernel", s, reduce_partials_kernel<<<(unsigned)ceil_div(count, 64), 256, 0, s>>>(partial, splits, count, out, accumulate));
   return GCB_OK;
 }
 
 inline int tn_splits(int rows) {
   if (rows <= 0) return 0;
-  int s = (int)ceil_div(rows, 1024);
+  int s = (int)ceil_div(rows, 128);
   if (s > 64) s = 64;
   return s;
 }

@@ -33,7 +33,7 @@ struct NtShape {
   static constexpr int W_BYTES = N * K * 2;
   static constexpr int A_STAGE_BYTES = BM * K * 2;
   static constexpr int OUT_BYTES = BM * N * 2;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 256 + N * 4;  // mbarriers + TMEM slot, then the bias vector
   static constexpr int SMEM_BYTES = 1024 + W_BYTES + STAGES * A_STAGE_BYTES + OUT_BYTES + BAR_BYTES;
   static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;  // two accumulators; power of two for N in {64,128,256}
   static constexpr int EPI_WARPS = 8;
@@ -59,10 +59,14 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tempty = tfull + 2;           // [2]       epilogue -> MMA
   uint64_t* wfull = tempty + 2;           // [1]       weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (rows + S::BM - 1) / S::BM;
 
+  if (ep.bias) {
+    for (int i = threadIdx.x; i < N; i += S::THREADS) sBias[i] = __ldg(ep.bias + i);
+  }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmW); prefetch_tmap(&tmC);
     for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -152,7 +156,11 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         if (ep.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaf(wrow, __ldg(ep.bias + c0 + j), f[j]);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j);
+            f[j] = fmaf(wrow, b4.x, f[j]); f[j + 1] = fmaf(wrow, b4.y, f[j + 1]);
+            f[j + 2] = fmaf(wrow, b4.z, f[j + 2]); f[j + 3] = fmaf(wrow, b4.w, f[j + 3]);
+          }
         }
         if (ep.res && valid) {
           const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r * ep.ld_res + c0);
@@ -170,7 +178,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (ep.act >= 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
+          for (int j = 0; j < 32; ++j) f[j] = act_fwd_fast(f[j], ep.act);
         }
         // stage as bf16 in the 128B-swizzled layout the TMA store expects
         uint8_t* slab = sOut + (c0 >> 6) * (S::BM * 128) + row_in_tile * 128;

@@ -42,7 +42,7 @@ __global__ void embed_act_kernel(const float* __restrict__ table, const int32_t*
 #pragma unroll
   for (int i = 0; i < V; i += 4) {
     float4 t = __ldg(reinterpret_cast<const float4*>(src + i));
-    v[i] = act_fwd(t.x, act); v[i + 1] = act_fwd(t.y, act); v[i + 2] = act_fwd(t.z, act); v[i + 3] = act_fwd(t.w, act);
+    v[i] = act_fwd_t<T>(t.x, act); v[i + 1] = act_fwd_t<T>(t.y, act); v[i + 2] = act_fwd_t<T>(t.z, act); v[i + 3] = act_fwd_t<T>(t.w, act);
   }
   store_vec(out + (size_t)r * D + c, v);
 }
@@ -84,7 +84,7 @@ __global__ void bond_update_kernel(const T* __restrict__ PQ, const int32_t* __re
   const int e0 = in_ptr[r], e1 = in_ptr[r + 1];
   float o[V];
   if (e0 == e1) {
-    const float z = act_fwd(0.f, act);
+    const float z = act_fwd_t<T>(0.f, act);
 #pragma unroll
     for (int i = 0; i < V; ++i) o[i] = z;
   } else {
@@ -100,7 +100,7 @@ __global__ void bond_update_kernel(const T* __restrict__ PQ, const int32_t* __re
       for (int i = 0; i < V; ++i) mx[i] = fmaxf(mx[i], q[i]);
     }
 #pragma unroll
-    for (int i = 0; i < V; ++i) o[i] = act_fwd(p[i] + mx[i], act);
+    for (int i = 0; i < V; ++i) o[i] = act_fwd_t<T>(p[i] + mx[i], act);
   }
   apply_dropout<T, V>(o, dr, (uint64_t)r * D + c);
   store_vec(Bout + (size_t)r * D + c, o);
@@ -120,7 +120,7 @@ __global__ void atom_gather_kernel(const T* __restrict__ A, const T* __restrict_
   float sa[V], sb[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) sa[i] = sb[i] = 0.f;
-  const float cst = round_to(act_fwd(0.f, act), (const T*)nullptr);
+  const float cst = round_to(act_fwd_t<T>(0.f, act), (const T*)nullptr);
   for (int e = e0; e < e1; ++e) {
     const int s = __ldg(in_src + e), eid = __ldg(in_eid + e);
     float a[V];
@@ -170,7 +170,7 @@ template <typename T>
 __global__ void fill_const_rows_kernel(T* __restrict__ out, int row0, int rows, int D, int act, Drop dr) {
   GCB_ROW_CHUNK_PROLOGUE(rows)
   float v[V];
-  const float z = act_fwd(0.f, act);
+  const float z = act_fwd_t<T>(0.f, act);
 #pragma unroll
   for (int i = 0; i < V; ++i) v[i] = z;
   apply_dropout<T, V>(v, dr, (uint64_t)(row0 + r) * D + c);

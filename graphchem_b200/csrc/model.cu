@@ -13,6 +13,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "rowops.cuh"
 
 namespace gcb {
 
@@ -203,7 +204,6 @@ __global__ void finalize_conv_grads_kernel(const float* __restrict__ accWpq, con
 
 // ---- workspace plan -----------------------------------------------------------------------------
 constexpr int kMaxLayers = 256;
-constexpr int kEmbedSplits = 32;
 
 struct Plan {
   int64_t total = 0;
@@ -288,7 +288,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
 struct Graph {
   int N, E, G, M;
   const int32_t *x_tok, *e_tok, *src, *dst, *in_ptr, *in_eid, *in_src, *out_ptr, *out_eid, *out_dst, *graph_ptr,
-      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row;
+      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph;
 };
 static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32_t* h, Graph& g) {
   if (!packed || !h || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
@@ -303,6 +303,7 @@ static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32
   g.graph_ptr = packed + h[GCB_H_GRAPH_PTR]; g.graph_node = packed + h[GCB_H_GRAPH_NODE];
   g.atok_ptr = packed + h[GCB_H_ATOK_PTR]; g.atok_node = packed + h[GCB_H_ATOK_NODE];
   g.btok_ptr = packed + h[GCB_H_BTOK_PTR]; g.btok_row = packed + h[GCB_H_BTOK_ROW];
+  g.node_graph = packed + h[GCB_H_NODE_GRAPH];
   return GCB_OK;
 }
 
@@ -340,13 +341,11 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       Epilogue ep;
       ep.bias = bpq;
       GCB_TRY(gemm_nt_auto<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
-      GCB_KERNEL("bond_update_kernel", s, bond_update_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>((const T*)p.PQ[l], g.in_ptr, g.in_src, (T*)p.B[l],
-                                                                       M, D, c.act, db));
+      GCB_TRY(launch_bond_update<T>((const T*)p.PQ[l], g.in_ptr, g.in_src, (T*)p.B[l], M, D, c.act, db, s));
     }
     if (N > 0) {
-      GCB_KERNEL("atom_gather_kernel", s, atom_gather_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr,
-                                                                       g.in_src, g.in_eid, (T*)p.S[l], N, M, D, c.act,
-                                                                       c.aggr, db));
+      GCB_TRY(launch_atom_gather<T>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr, g.in_src, g.in_eid, (T*)p.S[l], N, M, D,
+                                    c.act, c.aggr, db, s));
       Epilogue ep;
       ep.bias = bat; ep.rowptr = g.in_ptr; ep.aggr = c.aggr;
       ep.res = p.A[l - 1]; ep.ld_res = D; ep.act = c.act;
@@ -433,9 +432,8 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   int cur = 0;
   if (N > 0) {
     if (G > 0) {
-      GCB_KERNEL("pool_bwd_kernel", s, pool_bwd_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>(
-          dPool, d_out_atom, (const T*)p.A[L], g.graph_ptr, g.graph_node, (T*)p.dZA[cur], G, D, c.act,
-          L >= 1 ? make_drop(c, flags, seed, tag_atom(L)) : Drop()));
+      GCB_TRY(launch_pool_bwd<T>(dPool, d_out_atom, (const T*)p.A[L], g.graph_ptr, g.graph_node, g.node_graph, (T*)p.dZA[cur],
+                                 N, G, D, c.act, L >= 1 ? make_drop(c, flags, seed, tag_atom(L)) : Drop(), s));
     } else {
       GCB_CUDA(cudaMemsetAsync(p.dZA[cur], 0, (size_t)N * D * sizeof(T), s));
     }
@@ -452,16 +450,15 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
                               p.accBat, g.in_ptr, c.aggr, acc_w, s));
     if (N > 0) {
-      GCB_KERNEL("atom_bwd_gather_kernel", s, atom_bwd_gather_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>(
-          (const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.in_ptr, (const T*)p.A[l - 1], (T*)p.dZA[cur ^ 1],
-          N, D, c.act, c.aggr, l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop()));
+      GCB_TRY(launch_atom_bwd_gather<T>((const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.in_ptr, (const T*)p.A[l - 1],
+                                        (T*)p.dZA[cur ^ 1], N, D, c.act, c.aggr,
+                                        l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop(), s));
     }
     if (M > 0) {
-      GCB_KERNEL("bond_bwd_tie_kernel", s, bond_bwd_tie_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(
-          (const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l], g.dst, g.in_ptr,
-          g.in_src, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit, M, D, c.act, c.aggr, make_drop(c, flags, seed, tag_bond(l))));
-      GCB_KERNEL("bond_bwd_scatter_kernel", s, bond_bwd_scatter_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(
-          (const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, (T*)p.dPQ, M, D));
+      GCB_TRY(launch_bond_bwd_tie<T>((const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l],
+                                     g.dst, g.in_ptr, g.in_src, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit, M, D, c.act, c.aggr,
+                                     make_drop(c, flags, seed, tag_bond(l)), s));
+      GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, (T*)p.dPQ, M, D, s));
     }
     GCB_TRY(gemm_tn_auto<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
                               p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s));
@@ -477,15 +474,13 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   {
     const int av = c.atom_vocab, bv = c.bond_vocab, CH = D / V;
     if (N > 0) {
-      GCB_KERNEL("embed_bwd_partial_kernel", s, embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)av * kEmbedSplits * CH, 256), 256, 0, s>>>(
-          (const T*)p.dZA[cur], nullptr, g.atok_ptr, g.atok_node, p.partial, av, kEmbedSplits, D, c.act));
+      GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dZA[cur], nullptr, g.atok_ptr, g.atok_node, p.partial, av, D, c.act, s));
     }
     GCB_TRY(launch_reduce_partials(p.partial, N > 0 ? kEmbedSplits : 0, (int64_t)av * D, grad + pl.emb_atom, accumulate, s));
     const T* dB0 = L >= 1 ? dBnext : d_out_bond;
     const bool have = dB0 != nullptr && M > 0;
     if (have) {
-      GCB_KERNEL("embed_bwd_partial_kernel", s, embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)bv * kEmbedSplits * CH, 256), 256, 0, s>>>(
-          dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, p.partial, bv, kEmbedSplits, D, c.act));
+      GCB_TRY(launch_embed_bwd_partial<T>(dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, p.partial, bv, D, c.act, s));
     }
     GCB_TRY(launch_reduce_partials(p.partial, have ? kEmbedSplits : 0, (int64_t)bv * D, grad + pl.emb_bond, accumulate, s));
   }

@@ -32,6 +32,7 @@ static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, in
   put(GCB_H_GRAPH_PTR, (int64_t)G + 1); put(GCB_H_GRAPH_NODE, N);
   put(GCB_H_ATOK_PTR, (int64_t)av + 1); put(GCB_H_ATOK_NODE, N);
   put(GCB_H_BTOK_PTR, (int64_t)bv + 1); put(GCB_H_BTOK_ROW, E);
+  put(GCB_H_NODE_GRAPH, N);
   if (off > INT32_MAX) return -1;
   if (h) h[GCB_H_TOTAL_INTS] = (int32_t)off;
   return off;
@@ -70,8 +71,10 @@ static int finish_pack(int32_t* packed, const int32_t* h, const int32_t* batch_i
   for (int64_t k = 0; k < E; ++k) out_dst[k] = dst[out_eid[k]];
   int32_t* graph_ptr = packed + h[GCB_H_GRAPH_PTR];
   int32_t* graph_node = packed + h[GCB_H_GRAPH_NODE];
+  int32_t* node_graph = packed + h[GCB_H_NODE_GRAPH];
   if (batch_i32) {
     bucket(batch_i32, N, G, graph_ptr, graph_node);
+    std::memcpy(node_graph, batch_i32, sizeof(int32_t) * (size_t)N);
   } else {
     graph_ptr[0] = 0;
     for (int32_t g = 1; g <= G; ++g) graph_ptr[g] = N;

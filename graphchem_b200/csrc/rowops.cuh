@@ -1,0 +1,94 @@
+// Launch wrappers for the row-wise kernels: pick the group-cooperative kernels of kernels_v2.cuh when
+// the row width is 8, 16 or 32 sixteen-byte chunks (D = 64/128/256 in bf16, 32/64/128 in fp32) and the
+// generic kernels of kernels.cuh otherwise.
+#pragma once
+#include "kernels_v2.cuh"
+
+namespace gcb {
+
+#define GCB_ROW_DISPATCH(NAME, ROWS, DVAL, V2CALL, V1CALL)                                          \
+  do {                                                                                              \
+    if ((ROWS) <= 0) return GCB_OK;                                                                 \
+    switch ((DVAL) / Vec<T>::N) {                                                                   \
+      case 8: { constexpr int CH = 8; GCB_KERNEL(NAME, s, V2CALL); break; }                         \
+      case 16: { constexpr int CH = 16; GCB_KERNEL(NAME, s, V2CALL); break; }                       \
+      case 32: { constexpr int CH = 32; GCB_KERNEL(NAME, s, V2CALL); break; }                       \
+      default: { GCB_KERNEL(NAME, s, V1CALL); break; }                                              \
+    }                                                                                               \
+    return GCB_OK;                                                                                  \
+  } while (0)
+
+#define GCB_V2_GRID(ROWS) v2::blocks_for<CH>(ROWS), v2::kThreads, 0, s
+#define GCB_V1_GRID(ROWS, DVAL) row_chunk_blocks(ROWS, DVAL, Vec<T>::N), 256, 0, s
+
+template <typename T>
+int launch_bond_update(const T* PQ, const int32_t* in_ptr, const int32_t* in_src, T* Bout, int M, int D, int act,
+                       Drop dr, cudaStream_t s) {
+  GCB_ROW_DISPATCH("bond_update_kernel", M, D,
+                   (v2::bond_update_kernel<T, CH><<<GCB_V2_GRID(M)>>>(PQ, in_ptr, in_src, Bout, M, act, dr)),
+                   (bond_update_kernel<T><<<GCB_V1_GRID(M, D)>>>(PQ, in_ptr, in_src, Bout, M, D, act, dr)));
+}
+
+template <typename T>
+int launch_atom_gather(const T* A, const T* Bnew, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
+                       T* S, int N, int M, int D, int act, int aggr, Drop dr_bond, cudaStream_t s) {
+  GCB_ROW_DISPATCH("atom_gather_kernel", N, D,
+                   (v2::atom_gather_kernel<T, CH><<<GCB_V2_GRID(N)>>>(A, Bnew, in_ptr, in_src, in_eid, S, N, M, act, aggr, dr_bond)),
+                   (atom_gather_kernel<T><<<GCB_V1_GRID(N, D)>>>(A, Bnew, in_ptr, in_src, in_eid, S, N, M, D, act, aggr, dr_bond)));
+}
+
+template <typename T>
+int launch_atom_bwd_gather(const T* dZA, const T* dS, const int32_t* out_ptr, const int32_t* out_dst,
+                           const int32_t* in_ptr, const T* A_prev, T* dZA_prev, int N, int D, int act, int aggr,
+                           Drop dr_prev, cudaStream_t s) {
+  GCB_ROW_DISPATCH("atom_bwd_gather_kernel", N, D,
+                   (v2::atom_bwd_gather_kernel<T, CH><<<GCB_V2_GRID(N)>>>(dZA, dS, out_ptr, out_dst, in_ptr, A_prev, dZA_prev, N, act, aggr, dr_prev)),
+                   (atom_bwd_gather_kernel<T><<<GCB_V1_GRID(N, D)>>>(dZA, dS, out_ptr, out_dst, in_ptr, A_prev, dZA_prev, N, D, act, aggr, dr_prev)));
+}
+
+template <typename T>
+int launch_bond_bwd_tie(const T* dS, const T* dBnext, const T* d_out_bond, const T* B_l, const T* PQ, const int32_t* dst,
+                        const int32_t* in_ptr, const int32_t* in_src, T* dPQ, T* mx, T* gsplit, int M, int D, int act,
+                        int aggr, Drop dr, cudaStream_t s) {
+  GCB_ROW_DISPATCH("bond_bwd_tie_kernel", M, D,
+                   (v2::bond_bwd_tie_kernel<T, CH><<<GCB_V2_GRID(M)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, dPQ, mx, gsplit, M, act, aggr, dr)),
+                   (bond_bwd_tie_kernel<T><<<GCB_V1_GRID(M, D)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, dPQ, mx, gsplit, M, D, act, aggr, dr)));
+}
+
+template <typename T>
+int launch_bond_bwd_scatter(const T* PQ, const T* mx, const T* gsplit, const int32_t* out_ptr, const int32_t* out_dst,
+                            T* dPQ, int M, int D, cudaStream_t s) {
+  GCB_ROW_DISPATCH("bond_bwd_scatter_kernel", M, D,
+                   (v2::bond_bwd_scatter_kernel<T, CH><<<GCB_V2_GRID(M)>>>(PQ, mx, gsplit, out_ptr, out_dst, dPQ, M)),
+                   (bond_bwd_scatter_kernel<T><<<GCB_V1_GRID(M, D)>>>(PQ, mx, gsplit, out_ptr, out_dst, dPQ, M, D)));
+}
+
+// Pool backward: node-parallel (v2, via node_graph) or graph-parallel (generic).
+template <typename T>
+int launch_pool_bwd(const float* dPool, const T* d_out_atom, const T* A_last, const int32_t* graph_ptr,
+                    const int32_t* graph_node, const int32_t* node_graph, T* dZA, int N, int G, int D, int act, Drop dr,
+                    cudaStream_t s) {
+  GCB_ROW_DISPATCH("pool_bwd_kernel", N, D,
+                   (v2::pool_bwd_kernel<T, CH><<<GCB_V2_GRID(N)>>>(dPool, d_out_atom, A_last, node_graph, dZA, N, act, dr)),
+                   (pool_bwd_kernel<T><<<GCB_V1_GRID(G, D)>>>(dPool, d_out_atom, A_last, graph_ptr, graph_node, dZA, G, D, act, dr)));
+}
+
+constexpr int kEmbedSplits = 32;
+
+// partial[split][token][D]; the caller reduces over the kEmbedSplits splits in order.
+template <typename T>
+int launch_embed_bwd_partial(const T* dZ, const T* Y, const int32_t* tok_ptr, const int32_t* tok_row, float* partial,
+                             int vocab, int D, int act, cudaStream_t s) {
+  if (vocab <= 0) return GCB_OK;
+  constexpr int V = Vec<T>::N;
+  switch (D / V) {
+    case 8: GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 8><<<vocab * kEmbedSplits, v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, kEmbedSplits, act))); break;
+    case 16: GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 16><<<vocab * kEmbedSplits, v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, kEmbedSplits, act))); break;
+    case 32: GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 32><<<vocab * kEmbedSplits, v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, kEmbedSplits, act))); break;
+    default:
+      GCB_KERNEL("embed_bwd_partial_kernel", s, (embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)vocab * kEmbedSplits * (D / V), 256), 256, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, kEmbedSplits, D, act)));
+  }
+  return GCB_OK;
+}
+
+}  // namespace gcb

@@ -64,7 +64,8 @@ class PackedBatch:
             out_eid=self.section(L.H_OUT_EID, E), out_dst=self.section(L.H_OUT_DST, E),
             graph_ptr=self.section(L.H_GRAPH_PTR, G + 1), graph_node=self.section(L.H_GRAPH_NODE, N),
             atok_ptr=self.section(L.H_ATOK_PTR, av + 1), atok_node=self.section(L.H_ATOK_NODE, N),
-            btok_ptr=self.section(L.H_BTOK_PTR, bv + 1), btok_row=self.section(L.H_BTOK_ROW, M))
+            btok_ptr=self.section(L.H_BTOK_PTR, bv + 1), btok_row=self.section(L.H_BTOK_ROW, M),
+            node_graph=self.section(L.H_NODE_GRAPH, N))
 
 
 def _alloc_ints(n: int, pin: bool) -> Tensor:

@@ -74,6 +74,7 @@ enum gcb_pack_field {
   GCB_H_OUT_PTR, GCB_H_OUT_EID, GCB_H_OUT_DST,
   GCB_H_GRAPH_PTR, GCB_H_GRAPH_NODE,
   GCB_H_ATOK_PTR, GCB_H_ATOK_NODE, GCB_H_BTOK_PTR, GCB_H_BTOK_ROW,
+  GCB_H_NODE_GRAPH, /* [N] graph id of every node (the PyG `batch` vector as int32) */
   GCB_H_FIELDS
 };
 

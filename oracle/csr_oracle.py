@@ -43,4 +43,5 @@ def build_index(x_tok, e_tok, edge_index, batch, n_graphs, atom_vocab, bond_voca
         out_ptr=out_ptr, out_eid=out_eid, out_dst=dst[out_eid] if E else out_eid,
         graph_ptr=graph_ptr, graph_node=graph_node,
         atok_ptr=atok_ptr, atok_node=atok_node, btok_ptr=btok_ptr, btok_row=btok_row,
+        node_graph=np.asarray(batch).astype(np.int32),
     )
