@@ -60,11 +60,24 @@ def kernel_alg_bytes(name, N, E, M, G, D, s):
         "atom_bwd_gather_kernel": 2 * N * D * s + N * D * s + (N + E) * i4 + N * D * s,
         "bond_bwd_tie_kernel": 4 * M * D * s + (2 * M + E) * i4 + 4 * M * D * s,
         "bond_bwd_scatter_kernel": 3 * M * D * s + (M + E) * i4 + M * D * s,
-        # GEMMs: per-layer average of the two NT shapes ([M,D]x[D,2D] and [N,2D]x[2D,D]) fwd / bwd
-        "gemm_nt_kernel": (3 * M * D * s + 4 * N * D * s) / 2,
-        "gemm_tn_kernel": (3 * N * D * s + 3 * M * D * s) / 2,
+        # GEMMs, averaged over the launch shapes of one message step (operands read once, result
+        # written once; weights are smem/L2 resident): fwd PQ 3MDs, fwd atom (S + residual + out) 4NDs,
+        # bwd dS 3NDs, bwd dB 3MDs;  weight gradients read both operands: 3NDs and 3MDs.
+        "gemm_nt_tc_kernel": (3 * M + 4 * N + 3 * N + 3 * M) * D * s / 4,
+        "gemm_tn_tc_kernel": (3 * N + 3 * M) * D * s / 2,
+        "gemm_nt_kernel": None, "gemm_tn_kernel": None,  # CUDA-core GEMMs: readout MLP only in bf16 mode
     }
     return table.get(name)
+
+
+def measured_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+    capture of the same workload (profiles/r1_traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        return t.get(name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -338,7 +351,7 @@ def run_ours(args):
         alg_top = kernel_alg_bytes(top["name"], N, E, M, B, CFG["D"], s_bytes)
         roofline = {
             "bound": "hbm", "kernel": top["name"], "achieved": top["alg_GBps"], "peak": peak_hbm, "unit": "GB/s",
-            "frac": (top["alg_GBps"] / peak_hbm) if top["alg_GBps"] else None, "traffic": None,
+            "frac": (top["alg_GBps"] / peak_hbm) if top["alg_GBps"] else None, "traffic": measured_traffic(top["name"]),
             "alg_bytes_per_launch": alg_top, "ms_per_launch": top["ms_per_launch"], "share_of_step": top["share"],
             "peak_source": peak_src,
             "step": {"alg_bytes": train_step_bytes(N, E, CFG["D"], CFG["L"], s_bytes),

@@ -1,10 +1,15 @@
-// Second-generation row-wise kernels: same arithmetic and the same summation order as kernels.cuh
-// (so results are bit-identical to the generic path), restructured for memory-level parallelism:
+// Second-generation row-wise kernels: same arithmetic and the same per-row summation order as
+// kernels.cuh (the embedding-gradient kernel uses a different, equally fixed, order), restructured
+// for memory-level parallelism:
 //
 //   * a row is owned by a GROUP of CH = D / (16 bytes) lanes (8, 16 or 32 -> 4, 2 or 1 rows per warp);
-//   * the group loads the row's CSR segment cooperatively (one coalesced index load, then
-//     __shfl_sync broadcasts) instead of one dependent scalar load per edge per lane;
-//   * neighbour-row loads are issued four at a time before they are consumed;
+//   * the first four CSR entries of every row come from the packed batch's ELL-4 view (one int4
+//     broadcast load, -1 padded): no pointer -> index -> data chain, no data-dependent loop, no
+//     divergence between rows of different degree; rows with more than four entries finish in a
+//     short CSR loop (rare for molecules: valence <= 4);
+//   * all neighbour-row loads of a row are issued back to back and kept RAW (4 registers per
+//     16-byte chunk) until they are consumed;
+//   * max / tie counting runs on packed bf16x2 (exact), sums accumulate in fp32;
 //   * all index arithmetic is 32-bit with compile-time D (no 64-bit divisions).
 //
 // Used when D / vec is 8, 16 or 32; other widths fall back to kernels.cuh.
@@ -27,10 +32,75 @@ template <int CH> inline unsigned blocks_for(int rows) { return (unsigned)ceil_d
   const int gig = lane / CH;                                                                         \
   const unsigned gmask = CH == 32 ? 0xffffffffu : (((1u << (CH & 31)) - 1u) << (gig * CH));          \
   const int row_raw = ((int)blockIdx.x * (kThreads / 32) + ((int)threadIdx.x >> 5)) * RPW + gig;     \
-  const bool row_ok = row_raw < (ROWS);                                                              \
-  const int r = row_ok ? row_raw : (ROWS) - 1;                                                       \
+  if (row_raw >= (ROWS)) return;                                                                     \
+  const int r = row_raw;                                                                             \
   const int c = lig * V;                                                                             \
   (void)D; (void)gmask; (void)c;
+
+// 16-byte chunks are kept RAW (4 registers) between the load and the point of use, so that four
+// neighbour rows in flight cost 16 registers instead of 32.
+template <typename T> struct Raw;
+template <> struct Raw<float> {
+  static __device__ __forceinline__ uint4 load(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ void to_float(const uint4& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
+  static __device__ __forceinline__ uint4 neg_inf() { return make_uint4(0xFF800000u, 0xFF800000u, 0xFF800000u, 0xFF800000u); }
+  static __device__ __forceinline__ uint4 zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ uint32_t cnt1(uint32_t c, uint32_t q, uint32_t m) {
+    return __float_as_uint(__uint_as_float(c) + (__uint_as_float(q) == __uint_as_float(m) ? 1.f : 0.f));
+  }
+  static __device__ __forceinline__ void count_eq(uint4& c, const uint4& q, const uint4& m) {
+    c.x = cnt1(c.x, q.x, m.x); c.y = cnt1(c.y, q.y, m.y); c.z = cnt1(c.z, q.z, m.z); c.w = cnt1(c.w, q.w, m.w);
+  }
+  static __device__ __forceinline__ uint4 vmax(const uint4& a, const uint4& b) {
+    return make_uint4(__float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x))),
+                      __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y))),
+                      __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z))),
+                      __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w))));
+  }
+};
+template <> struct Raw<bf16> {
+  static __device__ __forceinline__ uint4 load(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ void to_float(const uint4& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+  }
+  static __device__ __forceinline__ uint4 neg_inf() { return make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u); }
+  static __device__ __forceinline__ uint4 zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ uint32_t cnt2(uint32_t c, uint32_t q, uint32_t m) {  // c += (q == m) per bf16 lane
+    __nv_bfloat162 cc = *reinterpret_cast<__nv_bfloat162*>(&c), qq = *reinterpret_cast<__nv_bfloat162*>(&q),
+                   mm = *reinterpret_cast<__nv_bfloat162*>(&m);
+    cc = __hadd2(cc, __heq2(qq, mm));
+    return *reinterpret_cast<uint32_t*>(&cc);
+  }
+  static __device__ __forceinline__ void count_eq(uint4& c, const uint4& q, const uint4& m) {
+    c.x = cnt2(c.x, q.x, m.x); c.y = cnt2(c.y, q.y, m.y); c.z = cnt2(c.z, q.z, m.z); c.w = cnt2(c.w, q.w, m.w);
+  }
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a), y = *reinterpret_cast<__nv_bfloat162*>(&b);
+    __nv_bfloat162 m = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t*>(&m);
+  }
+  static __device__ __forceinline__ uint4 vmax(const uint4& a, const uint4& b) {  // exact in bf16
+    return make_uint4(max2(a.x, b.x), max2(a.y, b.y), max2(a.z, b.z), max2(a.w, b.w));
+  }
+};
+template <typename T, int V>
+__device__ __forceinline__ void raw_add(const uint4& r, float (&acc)[V]) {
+  float v[V];
+  Raw<T>::to_float(r, v);
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] += v[i];
+}
+template <typename T, int V>
+__device__ __forceinline__ void raw_fma(float w, const uint4& r, float (&acc)[V]) {
+  float v[V];
+  Raw<T>::to_float(r, v);
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+}
 
 template <typename T, int V>
 __device__ __forceinline__ void vzero(float (&a)[V]) {
@@ -40,11 +110,24 @@ __device__ __forceinline__ void vzero(float (&a)[V]) {
 
 // Bond update: Bout[r] = dropout(act(P[r] + max_{e->r} Q[src e])), act(0) for rows without in-edges.
 template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
-                   T* __restrict__ Bout, int M, int act, Drop dr) {
+                   const int4* __restrict__ in_src4, T* __restrict__ Bout, int M, int act, Drop dr) {
   GCB_V2_PROLOGUE(M)
+  const int4 s4 = __ldg(in_src4 + r);
   const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
+  const uint4 praw = Raw<T>::load(PQ + (size_t)r * (2 * D) + c);
+  const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
+  uint4 q[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (sidx[u] >= 0) q[u] = Raw<T>::load(PQ + (size_t)sidx[u] * (2 * D) + D + c);
+  uint4 mraw = Raw<T>::neg_inf();
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (sidx[u] >= 0) mraw = Raw<T>::vmax(mraw, q[u]);
+  for (int e = e0 + 4; e < e1; ++e)
+    mraw = Raw<T>::vmax(mraw, Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c));
   float o[V];
   if (e0 == e1) {
     const float z = act_fwd_t<T>(0.f, act);
@@ -52,129 +135,102 @@ bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr,
     for (int i = 0; i < V; ++i) o[i] = z;
   } else {
     float p[V], mx[V];
-    load_vec(PQ + (size_t)r * (2 * D) + c, p);
-#pragma unroll
-    for (int i = 0; i < V; ++i) mx[i] = -CUDART_INF_F;
-    for (int base = e0; base < e1; base += CH) {
-      const int cnt = min(CH, e1 - base);
-      const int my_src = lig < cnt ? __ldg(in_src + base + lig) : 0;
-      for (int j = 0; j < cnt; j += 4) {
-        float q[4][V];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (j + u < cnt) {
-            const int s = __shfl_sync(gmask, my_src, j + u, CH);
-            load_vec(PQ + (size_t)s * (2 * D) + D + c, q[u]);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (j + u < cnt) {
-#pragma unroll
-            for (int i = 0; i < V; ++i) mx[i] = fmaxf(mx[i], q[u][i]);
-          }
-        }
-      }
-    }
+    Raw<T>::to_float(praw, p);
+    Raw<T>::to_float(mraw, mx);
 #pragma unroll
     for (int i = 0; i < V; ++i) o[i] = act_fwd_t<T>(p[i] + mx[i], act);
   }
   apply_dropout<T, V>(o, dr, (uint64_t)r * D + c);
-  if (row_ok) store_vec(Bout + (size_t)r * D + c, o);
+  store_vec(Bout + (size_t)r * D + c, o);
 }
 
 // Atom aggregation: S[i] = [ sum_{e->i} A[src e] | sum_{e->i} Bnew[eid e] ]  (Bnew[e >= M] = act(0)).
 template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 atom_gather_kernel(const T* __restrict__ A, const T* __restrict__ Bnew, const int32_t* __restrict__ in_ptr,
-                   const int32_t* __restrict__ in_src, const int32_t* __restrict__ in_eid, T* __restrict__ S, int N, int M,
+                   const int32_t* __restrict__ in_src, const int32_t* __restrict__ in_eid,
+                   const int4* __restrict__ in_src4, const int4* __restrict__ in_eid4, T* __restrict__ S, int N, int M,
                    int act, int aggr, Drop dr_bond) {
   GCB_V2_PROLOGUE(N)
+  const int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
   const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
+  const int sidx[4] = {s4.x, s4.y, s4.z, s4.w}, eidx[4] = {e4.x, e4.y, e4.z, e4.w};
+  uint4 a[4], b[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (sidx[u] >= 0) {
+      a[u] = Raw<T>::load(A + (size_t)sidx[u] * D + c);
+      if (eidx[u] < M) b[u] = Raw<T>::load(Bnew + (size_t)eidx[u] * D + c);
+    }
+  }
   float sa[V], sb[V];
   vzero<T, V>(sa);
   vzero<T, V>(sb);
   const float cst = round_to(act_fwd_t<T>(0.f, act), (const T*)nullptr);
-  for (int base = e0; base < e1; base += CH) {
-    const int cnt = min(CH, e1 - base);
-    const int my_src = lig < cnt ? __ldg(in_src + base + lig) : 0;
-    const int my_eid = lig < cnt ? __ldg(in_eid + base + lig) : 0;
-    for (int j = 0; j < cnt; j += 4) {
-      float a[4][V], b[4][V];
-      int eid[4];
+  auto add_const = [&](int eid) {
+    float bc[V];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (j + u < cnt) {
-          const int s = __shfl_sync(gmask, my_src, j + u, CH);
-          eid[u] = __shfl_sync(gmask, my_eid, j + u, CH);
-          load_vec(A + (size_t)s * D + c, a[u]);
-          if (eid[u] < M) load_vec(Bnew + (size_t)eid[u] * D + c, b[u]);
-        }
-      }
+    for (int i = 0; i < V; ++i) bc[i] = cst;
+    apply_dropout<T, V>(bc, dr_bond, (uint64_t)eid * D + c);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (j + u < cnt) {
-          if (eid[u] >= M) {
+    for (int i = 0; i < V; ++i) sb[i] += round_to(bc[i], (const T*)nullptr);
+  };
 #pragma unroll
-            for (int i = 0; i < V; ++i) b[u][i] = cst;
-            apply_dropout<T, V>(b[u], dr_bond, (uint64_t)eid[u] * D + c);
-#pragma unroll
-            for (int i = 0; i < V; ++i) b[u][i] = round_to(b[u][i], (const T*)nullptr);
-          }
-#pragma unroll
-          for (int i = 0; i < V; ++i) { sa[i] += a[u][i]; sb[i] += b[u][i]; }
-        }
-      }
+  for (int u = 0; u < 4; ++u) {
+    if (sidx[u] >= 0) {
+      raw_add<T, V>(a[u], sa);
+      if (eidx[u] < M) raw_add<T, V>(b[u], sb);
+      else add_const(eidx[u]);
     }
+  }
+  for (int e = e0 + 4; e < e1; ++e) {
+    const int s = __ldg(in_src + e), eid = __ldg(in_eid + e);
+    raw_add<T, V>(Raw<T>::load(A + (size_t)s * D + c), sa);
+    if (eid < M) raw_add<T, V>(Raw<T>::load(Bnew + (size_t)eid * D + c), sb);
+    else add_const(eid);
   }
   if (aggr == GCB_AGGR_MEAN && e1 > e0) {
     const float inv = 1.f / (float)(e1 - e0);
 #pragma unroll
     for (int i = 0; i < V; ++i) { sa[i] *= inv; sb[i] *= inv; }
   }
-  if (row_ok) {
-    store_vec(S + (size_t)r * (2 * D) + c, sa);
-    store_vec(S + (size_t)r * (2 * D) + D + c, sb);
-  }
+  store_vec(S + (size_t)r * (2 * D) + c, sa);
+  store_vec(S + (size_t)r * (2 * D) + D + c, sb);
 }
 
 // dZA_prev[j] = ( dZA[j] + sum_{e: src e = j} w(dst e) dS[dst e, 0:D] ) * dropfactor * act'(A_prev[j])
 template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 atom_bwd_gather_kernel(const T* __restrict__ dZA, const T* __restrict__ dS, const int32_t* __restrict__ out_ptr,
-                       const int32_t* __restrict__ out_dst, const int32_t* __restrict__ in_ptr,
-                       const T* __restrict__ A_prev, T* __restrict__ dZA_prev, int N, int act, int aggr, Drop dr_prev) {
+                       const int32_t* __restrict__ out_dst, const int4* __restrict__ out_dst4,
+                       const int32_t* __restrict__ in_ptr, const T* __restrict__ A_prev, T* __restrict__ dZA_prev, int N,
+                       int act, int aggr, Drop dr_prev) {
   GCB_V2_PROLOGUE(N)
+  const int4 t4 = __ldg(out_dst4 + r);
   const int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
+  const uint4 draw = Raw<T>::load(dZA + (size_t)r * D + c);
+  const uint4 yraw = Raw<T>::load(A_prev + (size_t)r * D + c);
+  const int tidx[4] = {t4.x, t4.y, t4.z, t4.w};
+  uint4 g[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (tidx[u] >= 0) g[u] = Raw<T>::load(dS + (size_t)tidx[u] * (2 * D) + c);
   float d[V], y[V];
-  load_vec(dZA + (size_t)r * D + c, d);
-  load_vec(A_prev + (size_t)r * D + c, y);
-  for (int base = e0; base < e1; base += CH) {
-    const int cnt = min(CH, e1 - base);
-    int my_t = 0;
-    float my_w = 1.f;
-    if (lig < cnt) {
-      my_t = __ldg(out_dst + base + lig);
-      if (aggr == GCB_AGGR_MEAN) my_w = 1.f / (float)max(__ldg(in_ptr + my_t + 1) - __ldg(in_ptr + my_t), 1);
+  Raw<T>::to_float(draw, d);
+  Raw<T>::to_float(yraw, y);
+  auto weight = [&](int t) -> float {
+    return aggr == GCB_AGGR_MEAN ? 1.f / (float)max(__ldg(in_ptr + t + 1) - __ldg(in_ptr + t), 1) : 1.f;
+  };
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (tidx[u] >= 0) {
+      if (aggr == GCB_AGGR_MEAN) raw_fma<T, V>(weight(tidx[u]), g[u], d);
+      else raw_add<T, V>(g[u], d);
     }
-    for (int j = 0; j < cnt; j += 4) {
-      float g[4][V], w[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (j + u < cnt) {
-          const int t = __shfl_sync(gmask, my_t, j + u, CH);
-          w[u] = __shfl_sync(gmask, my_w, j + u, CH);
-          load_vec(dS + (size_t)t * (2 * D) + c, g[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (j + u < cnt) {
-#pragma unroll
-          for (int i = 0; i < V; ++i) d[i] = fmaf(w[u], g[u][i], d[i]);
-        }
-      }
-    }
+  }
+  for (int e = e0 + 4; e < e1; ++e) {
+    const int t = __ldg(out_dst + e);
+    raw_fma<T, V>(weight(t), Raw<T>::load(dS + (size_t)t * (2 * D) + c), d);
   }
   if (dr_prev.p > 0.f) {
     mul_act_grad<V>(d, y, act, dr_prev, (uint64_t)r * D + c);
@@ -182,120 +238,108 @@ atom_bwd_gather_kernel(const T* __restrict__ dZA, const T* __restrict__ dS, cons
 #pragma unroll
     for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
   }
-  if (row_ok) store_vec(dZA_prev + (size_t)r * D + c, d);
+  store_vec(dZA_prev + (size_t)r * D + c, d);
 }
 
 // Destination side of the bond backward (see kernels.cuh::bond_bwd_tie_kernel for the math).
 template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, const T* __restrict__ d_out_bond,
                     const T* __restrict__ B_l, const T* __restrict__ PQ, const int32_t* __restrict__ dst,
-                    const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src, T* __restrict__ dPQ,
-                    T* __restrict__ mx_out, T* __restrict__ gsplit, int M, int act, int aggr, Drop dr) {
+                    const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
+                    const int4* __restrict__ in_src4, T* __restrict__ dPQ, T* __restrict__ mx_out, T* __restrict__ gsplit,
+                    int M, int act, int aggr, Drop dr) {
   GCB_V2_PROLOGUE(M)
+  const int4 s4 = __ldg(in_src4 + r);
   const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
-  float d[V], mx[V], cnt_t[V];
+  const int t = __ldg(dst + r);
+  const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
+  uint4 q[4];
 #pragma unroll
-  for (int i = 0; i < V; ++i) { d[i] = 0.f; mx[i] = 0.f; cnt_t[i] = 1.f; }
+  for (int u = 0; u < 4; ++u)
+    if (sidx[u] >= 0) q[u] = Raw<T>::load(PQ + (size_t)sidx[u] * (2 * D) + D + c);
+  float d[V], mx[V], cnt[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { d[i] = 0.f; mx[i] = 0.f; cnt[i] = 1.f; }
   if (e1 > e0) {
-    const int t = __ldg(dst + r);
-    float y[V];
-    load_vec(dS + (size_t)t * (2 * D) + D + c, d);
-    load_vec(B_l + (size_t)r * D + c, y);
+    const uint4 yraw = Raw<T>::load(B_l + (size_t)r * D + c);
+    Raw<T>::to_float(Raw<T>::load(dS + (size_t)t * (2 * D) + D + c), d);
     if (aggr == GCB_AGGR_MEAN) {
       const float w = 1.f / (float)max(__ldg(in_ptr + t + 1) - __ldg(in_ptr + t), 1);
 #pragma unroll
       for (int i = 0; i < V; ++i) d[i] *= w;
     }
-    if (dBnext) {
-      float u[V];
-      load_vec(dBnext + (size_t)r * D + c, u);
-#pragma unroll
-      for (int i = 0; i < V; ++i) d[i] += u[i];
-    }
-    if (d_out_bond) {
-      float u[V];
-      load_vec(d_out_bond + (size_t)r * D + c, u);
-#pragma unroll
-      for (int i = 0; i < V; ++i) d[i] += u[i];
-    }
+    if (dBnext) raw_add<T, V>(Raw<T>::load(dBnext + (size_t)r * D + c), d);
+    if (d_out_bond) raw_add<T, V>(Raw<T>::load(d_out_bond + (size_t)r * D + c), d);
+    float y[V];
+    Raw<T>::to_float(yraw, y);
     if (dr.p > 0.f) {
       mul_act_grad<V>(d, y, act, dr, (uint64_t)r * D + c);
     } else {
 #pragma unroll
       for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
     }
+    // max over the in-edges, then count the ties (packed, exact)
+    uint4 mraw = Raw<T>::neg_inf();
 #pragma unroll
-    for (int i = 0; i < V; ++i) { mx[i] = -CUDART_INF_F; cnt_t[i] = 0.f; }
-    for (int base = e0; base < e1; base += CH) {
-      const int cnt = min(CH, e1 - base);
-      const int my_src = lig < cnt ? __ldg(in_src + base + lig) : 0;
-      for (int j = 0; j < cnt; j += 4) {
-        float q[4][V];
+    for (int u = 0; u < 4; ++u)
+      if (sidx[u] >= 0) mraw = Raw<T>::vmax(mraw, q[u]);
+    for (int e = e0 + 4; e < e1; ++e)
+      mraw = Raw<T>::vmax(mraw, Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c));
+    uint4 craw = Raw<T>::zero();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (j + u < cnt) {
-            const int s = __shfl_sync(gmask, my_src, j + u, CH);
-            load_vec(PQ + (size_t)s * (2 * D) + D + c, q[u]);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (j + u < cnt) {
-#pragma unroll
-            for (int i = 0; i < V; ++i) {
-              if (q[u][i] > mx[i]) { mx[i] = q[u][i]; cnt_t[i] = 1.f; }
-              else if (q[u][i] == mx[i]) cnt_t[i] += 1.f;
-            }
-          }
-        }
-      }
-    }
+    for (int u = 0; u < 4; ++u)
+      if (sidx[u] >= 0) Raw<T>::count_eq(craw, q[u], mraw);
+    for (int e = e0 + 4; e < e1; ++e)
+      Raw<T>::count_eq(craw, Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c), mraw);
+    Raw<T>::to_float(mraw, mx);
+    Raw<T>::to_float(craw, cnt);
   }
   float g[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) g[i] = cnt_t[i] == 1.f ? d[i] : d[i] / cnt_t[i];
-  if (row_ok) {
-    store_vec(dPQ + (size_t)r * (2 * D) + c, d);
-    store_vec(mx_out + (size_t)r * D + c, mx);
-    store_vec(gsplit + (size_t)r * D + c, g);
-  }
+  for (int i = 0; i < V; ++i) g[i] = cnt[i] == 1.f ? d[i] : __fdividef(d[i], cnt[i]);
+  store_vec(dPQ + (size_t)r * (2 * D) + c, d);
+  store_vec(mx_out + (size_t)r * D + c, mx);
+  store_vec(gsplit + (size_t)r * D + c, g);
 }
 
 // Source side: dPQ[j, D:2D] = sum_{e: src e = j} [Q[j] == mx[dst e]] * gsplit[dst e]
 template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 bond_bwd_scatter_kernel(const T* __restrict__ PQ, const T* __restrict__ mx, const T* __restrict__ gsplit,
-                        const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_dst, T* __restrict__ dPQ,
-                        int M) {
+                        const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_dst,
+                        const int4* __restrict__ out_dst4, T* __restrict__ dPQ, int M) {
   GCB_V2_PROLOGUE(M)
+  const int4 t4 = __ldg(out_dst4 + r);
   const int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
-  float q[V], acc[V];
-  load_vec(PQ + (size_t)r * (2 * D) + D + c, q);
-  vzero<T, V>(acc);
-  for (int base = e0; base < e1; base += CH) {
-    const int cnt = min(CH, e1 - base);
-    const int my_t = lig < cnt ? __ldg(out_dst + base + lig) : 0;
-    for (int j = 0; j < cnt; j += 4) {
-      float m[4][V], g[4][V];
+  const uint4 qraw = Raw<T>::load(PQ + (size_t)r * (2 * D) + D + c);
+  const int tidx[4] = {t4.x, t4.y, t4.z, t4.w};
+  uint4 m[4], g[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (j + u < cnt) {
-          const int t = __shfl_sync(gmask, my_t, j + u, CH);
-          load_vec(mx + (size_t)t * D + c, m[u]);
-          load_vec(gsplit + (size_t)t * D + c, g[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (j + u < cnt) {
-#pragma unroll
-          for (int i = 0; i < V; ++i) acc[i] += (q[i] == m[u][i]) ? g[u][i] : 0.f;
-        }
-      }
+  for (int u = 0; u < 4; ++u) {
+    if (tidx[u] >= 0) {
+      m[u] = Raw<T>::load(mx + (size_t)tidx[u] * D + c);
+      g[u] = Raw<T>::load(gsplit + (size_t)tidx[u] * D + c);
     }
   }
-  if (row_ok) store_vec(dPQ + (size_t)r * (2 * D) + D + c, acc);
+  float q[V], acc[V];
+  Raw<T>::to_float(qraw, q);
+  vzero<T, V>(acc);
+  auto consume = [&](const uint4& mr, const uint4& gr) {
+    float mf[V], gf[V];
+    Raw<T>::to_float(mr, mf);
+    Raw<T>::to_float(gr, gf);
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] += (q[i] == mf[i]) ? gf[i] : 0.f;
+  };
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (tidx[u] >= 0) consume(m[u], g[u]);
+  for (int e = e0 + 4; e < e1; ++e) {
+    const int t = __ldg(out_dst + e);
+    consume(Raw<T>::load(mx + (size_t)t * D + c), Raw<T>::load(gsplit + (size_t)t * D + c));
+  }
+  store_vec(dPQ + (size_t)r * (2 * D) + D + c, acc);
 }
 
 // dZA_L[n] = (dPool[graph(n)] + d_out_atom[n]) * dropfactor * act'(A_L[n]); one group per NODE
@@ -328,7 +372,7 @@ pool_bwd_kernel(const float* __restrict__ dPool, const T* __restrict__ d_out_ato
 #pragma unroll
     for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
   }
-  if (row_ok) store_vec(dZA + (size_t)r * D + c, d);
+  store_vec(dZA + (size_t)r * D + c, d);
 }
 
 // Embedding gradient: one CTA per (token, split); 256 threads = (256/CH) row lanes x CH chunks.  Row

@@ -288,7 +288,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
 struct Graph {
   int N, E, G, M;
   const int32_t *x_tok, *e_tok, *src, *dst, *in_ptr, *in_eid, *in_src, *out_ptr, *out_eid, *out_dst, *graph_ptr,
-      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph;
+      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph, *in_src4, *in_eid4, *out_dst4;
 };
 static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32_t* h, Graph& g) {
   if (!packed || !h || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
@@ -304,6 +304,7 @@ static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32
   g.atok_ptr = packed + h[GCB_H_ATOK_PTR]; g.atok_node = packed + h[GCB_H_ATOK_NODE];
   g.btok_ptr = packed + h[GCB_H_BTOK_PTR]; g.btok_row = packed + h[GCB_H_BTOK_ROW];
   g.node_graph = packed + h[GCB_H_NODE_GRAPH];
+  g.in_src4 = packed + h[GCB_H_IN_SRC4]; g.in_eid4 = packed + h[GCB_H_IN_EID4]; g.out_dst4 = packed + h[GCB_H_OUT_DST4];
   return GCB_OK;
 }
 
@@ -341,10 +342,10 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       Epilogue ep;
       ep.bias = bpq;
       GCB_TRY(gemm_nt_auto<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
-      GCB_TRY(launch_bond_update<T>((const T*)p.PQ[l], g.in_ptr, g.in_src, (T*)p.B[l], M, D, c.act, db, s));
+      GCB_TRY(launch_bond_update<T>((const T*)p.PQ[l], g.in_ptr, g.in_src, g.in_src4, (T*)p.B[l], M, D, c.act, db, s));
     }
     if (N > 0) {
-      GCB_TRY(launch_atom_gather<T>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr, g.in_src, g.in_eid, (T*)p.S[l], N, M, D,
+      GCB_TRY(launch_atom_gather<T>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.S[l], N, M, D,
                                     c.act, c.aggr, db, s));
       Epilogue ep;
       ep.bias = bat; ep.rowptr = g.in_ptr; ep.aggr = c.aggr;
@@ -450,15 +451,15 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
                               p.accBat, g.in_ptr, c.aggr, acc_w, s));
     if (N > 0) {
-      GCB_TRY(launch_atom_bwd_gather<T>((const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.in_ptr, (const T*)p.A[l - 1],
+      GCB_TRY(launch_atom_bwd_gather<T>((const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.out_dst4, g.in_ptr, (const T*)p.A[l - 1],
                                         (T*)p.dZA[cur ^ 1], N, D, c.act, c.aggr,
                                         l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop(), s));
     }
     if (M > 0) {
       GCB_TRY(launch_bond_bwd_tie<T>((const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l],
-                                     g.dst, g.in_ptr, g.in_src, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit, M, D, c.act, c.aggr,
+                                     g.dst, g.in_ptr, g.in_src, g.in_src4, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit, M, D, c.act, c.aggr,
                                      make_drop(c, flags, seed, tag_bond(l)), s));
-      GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, (T*)p.dPQ, M, D, s));
+      GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, g.out_dst4, (T*)p.dPQ, M, D, s));
     }
     GCB_TRY(gemm_tn_auto<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
                               p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s));

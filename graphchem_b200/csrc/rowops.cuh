@@ -22,44 +22,45 @@ namespace gcb {
 #define GCB_V1_GRID(ROWS, DVAL) row_chunk_blocks(ROWS, DVAL, Vec<T>::N), 256, 0, s
 
 template <typename T>
-int launch_bond_update(const T* PQ, const int32_t* in_ptr, const int32_t* in_src, T* Bout, int M, int D, int act,
+int launch_bond_update(const T* PQ, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_src4, T* Bout, int M, int D, int act,
                        Drop dr, cudaStream_t s) {
   GCB_ROW_DISPATCH("bond_update_kernel", M, D,
-                   (v2::bond_update_kernel<T, CH><<<GCB_V2_GRID(M)>>>(PQ, in_ptr, in_src, Bout, M, act, dr)),
+                   (v2::bond_update_kernel<T, CH><<<GCB_V2_GRID(M)>>>(PQ, in_ptr, in_src, (const int4*)in_src4, Bout, M, act, dr)),
                    (bond_update_kernel<T><<<GCB_V1_GRID(M, D)>>>(PQ, in_ptr, in_src, Bout, M, D, act, dr)));
 }
 
 template <typename T>
 int launch_atom_gather(const T* A, const T* Bnew, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
-                       T* S, int N, int M, int D, int act, int aggr, Drop dr_bond, cudaStream_t s) {
+                       const int32_t* in_src4, const int32_t* in_eid4, T* S, int N, int M, int D, int act, int aggr, Drop dr_bond, cudaStream_t s) {
   GCB_ROW_DISPATCH("atom_gather_kernel", N, D,
-                   (v2::atom_gather_kernel<T, CH><<<GCB_V2_GRID(N)>>>(A, Bnew, in_ptr, in_src, in_eid, S, N, M, act, aggr, dr_bond)),
+                   (v2::atom_gather_kernel<T, CH><<<GCB_V2_GRID(N)>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond)),
                    (atom_gather_kernel<T><<<GCB_V1_GRID(N, D)>>>(A, Bnew, in_ptr, in_src, in_eid, S, N, M, D, act, aggr, dr_bond)));
 }
 
 template <typename T>
 int launch_atom_bwd_gather(const T* dZA, const T* dS, const int32_t* out_ptr, const int32_t* out_dst,
-                           const int32_t* in_ptr, const T* A_prev, T* dZA_prev, int N, int D, int act, int aggr,
+                           const int32_t* out_dst4, const int32_t* in_ptr, const T* A_prev, T* dZA_prev, int N, int D, int act, int aggr,
                            Drop dr_prev, cudaStream_t s) {
   GCB_ROW_DISPATCH("atom_bwd_gather_kernel", N, D,
-                   (v2::atom_bwd_gather_kernel<T, CH><<<GCB_V2_GRID(N)>>>(dZA, dS, out_ptr, out_dst, in_ptr, A_prev, dZA_prev, N, act, aggr, dr_prev)),
+                   (v2::atom_bwd_gather_kernel<T, CH><<<GCB_V2_GRID(N)>>>(dZA, dS, out_ptr, out_dst, (const int4*)out_dst4, in_ptr, A_prev, dZA_prev, N, act, aggr, dr_prev)),
                    (atom_bwd_gather_kernel<T><<<GCB_V1_GRID(N, D)>>>(dZA, dS, out_ptr, out_dst, in_ptr, A_prev, dZA_prev, N, D, act, aggr, dr_prev)));
 }
 
 template <typename T>
 int launch_bond_bwd_tie(const T* dS, const T* dBnext, const T* d_out_bond, const T* B_l, const T* PQ, const int32_t* dst,
-                        const int32_t* in_ptr, const int32_t* in_src, T* dPQ, T* mx, T* gsplit, int M, int D, int act,
+                        const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_src4, T* dPQ, T* mx, T* gsplit,
+                        int M, int D, int act,
                         int aggr, Drop dr, cudaStream_t s) {
   GCB_ROW_DISPATCH("bond_bwd_tie_kernel", M, D,
-                   (v2::bond_bwd_tie_kernel<T, CH><<<GCB_V2_GRID(M)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, dPQ, mx, gsplit, M, act, aggr, dr)),
+                   (v2::bond_bwd_tie_kernel<T, CH><<<GCB_V2_GRID(M)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, (const int4*)in_src4, dPQ, mx, gsplit, M, act, aggr, dr)),
                    (bond_bwd_tie_kernel<T><<<GCB_V1_GRID(M, D)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, dPQ, mx, gsplit, M, D, act, aggr, dr)));
 }
 
 template <typename T>
 int launch_bond_bwd_scatter(const T* PQ, const T* mx, const T* gsplit, const int32_t* out_ptr, const int32_t* out_dst,
-                            T* dPQ, int M, int D, cudaStream_t s) {
+                            const int32_t* out_dst4, T* dPQ, int M, int D, cudaStream_t s) {
   GCB_ROW_DISPATCH("bond_bwd_scatter_kernel", M, D,
-                   (v2::bond_bwd_scatter_kernel<T, CH><<<GCB_V2_GRID(M)>>>(PQ, mx, gsplit, out_ptr, out_dst, dPQ, M)),
+                   (v2::bond_bwd_scatter_kernel<T, CH><<<GCB_V2_GRID(M)>>>(PQ, mx, gsplit, out_ptr, out_dst, (const int4*)out_dst4, dPQ, M)),
                    (bond_bwd_scatter_kernel<T><<<GCB_V1_GRID(M, D)>>>(PQ, mx, gsplit, out_ptr, out_dst, dPQ, M, D)));
 }
 

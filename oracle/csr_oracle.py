@@ -37,7 +37,17 @@ def build_index(x_tok, e_tok, edge_index, batch, n_graphs, atom_vocab, bond_voca
     graph_ptr, graph_node = stable_buckets(np.asarray(batch), n_graphs)
     atok_ptr, atok_node = stable_buckets(x_tok, atom_vocab)
     btok_ptr, btok_row = stable_buckets(e_tok[:live_rows], bond_vocab)
+    def ell4(ptr, vals):
+        out = np.full((N, 4), -1, dtype=np.int32)
+        for u in range(4):
+            k = ptr[:-1].astype(np.int64) + u
+            ok = k < ptr[1:]
+            out[ok, u] = vals[k[ok]]
+        return out.reshape(-1)
+    in_src_sorted = src[in_eid] if E else in_eid
+    out_dst_sorted = dst[out_eid] if E else out_eid
     return dict(
+        in_src4=ell4(in_ptr, in_src_sorted), in_eid4=ell4(in_ptr, in_eid), out_dst4=ell4(out_ptr, out_dst_sorted),
         x_tok=x_tok, e_tok=e_tok, src=src, dst=dst,
         in_ptr=in_ptr, in_eid=in_eid, in_src=src[in_eid] if E else in_eid,
         out_ptr=out_ptr, out_eid=out_eid, out_dst=dst[out_eid] if E else out_eid,

@@ -1,0 +1,33 @@
+"""ncu --set full report(s) -> profiles/r1_traffic.json: per kernel class the average DRAM traffic
+(dram__bytes_read.sum + dram__bytes_write.sum) and duration per launch.
+usage: python profiles/extract_traffic.py out.json rep1.ncu-rep [rep2.ncu-rep ...]"""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+TIME = {"ns": 1e-3, "us": 1.0, "ms": 1e3}
+out = {}
+for rep in sys.argv[2:]:
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    h, units = rows[0], rows[1]
+    ki, ri, wi, ti = (h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"),
+                      h.index("gpu__time_duration.sum"))
+    for r in rows[2:]:
+        name = r[ki].split("<")[0].split("(")[0].replace("void ", "").split("::")[-1].strip()
+        b = float(r[ri]) * UNIT[units[ri]] + float(r[wi]) * UNIT[units[wi]]
+        e = out.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "us": 0.0, "source": []})
+        e["launches"] += 1
+        e["dram_bytes"] += b
+        e["us"] += float(r[ti]) * TIME[units[ti]]
+        if rep not in e["source"]:
+            e["source"].append(rep)
+for e in out.values():
+    e["dram_bytes_per_launch"] = e["dram_bytes"] / e["launches"]
+    e["us_per_launch"] = e["us"] / e["launches"]
+json.dump(out, open(sys.argv[1], "w"), indent=1)
+for k, e in sorted(out.items()):
+    print(f"{k:32s} n={e['launches']:2d} {e['dram_bytes_per_launch'] / 1e6:8.1f} MB/launch {e['us_per_launch']:8.1f} us")

@@ -1,0 +1,75 @@
+"""-m "not gpu": the N>1 host logic on CPU with world_size-2 gloo -- molecule sharding, per-rank
+collate, flat-gradient all-reduce and the 1/world scaling.  Each rank runs the CPU
+oracle on ITS OWN per-rank batch (the bond-matrix quirk couples molecules inside a rank-local batch,
+so the single-process comparison uses the same two per-rank batches, gradients averaged)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _flat_oracle_grad(idx, seed=0):
+    from graphchem_b200.synthetic import make_molecules
+    from oracle.gcn_oracle import OracleMoleculeGCN
+    from oracle.pyg_restated import Data as OData, collate
+    store = make_molecules(64, seed=5, atom_vocab=16, bond_vocab=8)
+    graphs = []
+    for i in idx:
+        a0, a1 = store.atom_off[i], store.atom_off[i + 1]
+        e0, e1 = store.edge_off[i], store.edge_off[i + 1]
+        graphs.append(OData(x=store.atoms[a0:a1], edge_attr=store.bonds[e0:e1],
+                            edge_index=store.conn[2 * e0:2 * e1].view(2, -1), y=store.targets[i:i + 1]))
+    data = collate(graphs)
+    torch.manual_seed(seed)
+    model = OracleMoleculeGCN(16, 8, 1, embedding_dim=32, n_messages=2)
+    pred, _, _ = model(data)
+    F.mse_loss(pred, data.y).backward()
+    return torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from graphchem_b200.distributed import allreduce_mean_, init_from_env, shard_indices
+    r, w, _ = init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    idx = shard_indices(64, r, w, per_rank_batch=8, step=3, seed=11)
+    g = _flat_oracle_grad(idx)
+    allreduce_mean_(g, w)
+    if rank == 0:
+        torch.save({"grad": g, "idx": idx}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_equals_mean_of_per_rank_gradients(tmp_path):
+    from graphchem_b200.distributed import shard_indices
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    i0 = shard_indices(64, 0, 2, 8, step=3, seed=11)
+    i1 = shard_indices(64, 1, 2, 8, step=3, seed=11)
+    assert np.array_equal(got["idx"], i0) and len(set(i0) & set(i1)) == 0
+    ref = 0.5 * (_flat_oracle_grad(i0) + _flat_oracle_grad(i1))
+    assert torch.allclose(got["grad"], ref, rtol=1e-6, atol=1e-8)
+
+
+def test_shards_partition_each_epoch():
+    from graphchem_b200.distributed import shard_indices
+    seen = []
+    for step in range(4):  # 64 items / (2 ranks * 8) = 4 steps per epoch
+        for rank in range(2):
+            seen.append(shard_indices(64, rank, 2, 8, step, seed=3))
+    allidx = np.concatenate(seen)
+    assert sorted(allidx.tolist()) == list(range(64))
+    nxt = shard_indices(64, 0, 2, 8, 4, seed=3)  # next epoch reshuffles
+    assert not np.array_equal(nxt, seen[0])
