@@ -205,6 +205,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("GCB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
 
@@ -234,7 +235,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def note(msg):
+        print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     # ---- (1) device-resident throughput -------------------------------------------------------
+    note("warm-up / graph capture")
     for i in range(max(W, N_RESIDENT)):  # captures one CUDA graph per resident batch, then warms up
         step(dev_batches[i % N_RESIDENT])
     barrier()
@@ -261,6 +266,7 @@ def run_ours(args):
     loss_resident = float(step.loss.item())
     value = B * world * K / (ms * 1e-3)
 
+    note(f"resident: {value:.0f} mol/s")
     # ---- (2) end to end through the public API with HOST buffers ---------------------------------
     # per step: pinned packed batch -> HBM (copy stream, double buffered), step, loss -> pinned host
     copy_stream = torch.cuda.Stream(dev)
@@ -309,26 +315,38 @@ def run_ours(args):
         ms_e2e = float(t.item())
     e2e_value = B * world * K / (ms_e2e * 1e-3)
     h2d = host_batches[0].ints.numel() * 4 + B * 4
-    launches_per_step = None
 
+    note(f"e2e: {e2e_value:.0f} mol/s")
     # ---- (3) per-kernel timing with CUDA events (un-graphed pass, rank 0, N == 1 only) -------------
     roofline, kernels, cpu_baseline = None, None, None
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        plain = TrainStep(model, lr=1e-3, use_cuda_graph=False)
-        plain.exp_avg, plain.exp_avg_sq, plain.step_count = step.exp_avg, step.exp_avg_sq, step.step_count
-        for i in range(3):
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    step_bytes = train_step_bytes(N, E, CFG["D"], CFG["L"], s_bytes)
+    step_roofline = {"alg_bytes": step_bytes, "achieved": step_bytes * world / (ms / K * 1e-3) / 1e9,
+                     "peak": peak_hbm * world, "frac": step_bytes / (ms / K * 1e-3) / 1e9 / peak_hbm}
+    # every rank: one un-graphed step to count kernel launches (collective-safe: all ranks take part)
+    plain = TrainStep(model, lr=1e-3, use_cuda_graph=False)
+    plain.exp_avg, plain.exp_avg_sq, plain.step_count = step.exp_avg, step.exp_avg_sq, step.step_count
+    plain(dev_batches[0])
+    torch.cuda.synchronize()
+    l0 = lib.gcb_launch_count()
+    plain(dev_batches[1])
+    launches_per_step = int(lib.gcb_launch_count() - l0)
+    barrier()
+    note(f"launches/step {launches_per_step}")
+    if world > 1:
+        roofline = {"bound": "hbm", "kernel": "whole train step (per-kernel breakdown is reported at N=1)",
+                    "achieved": step_roofline["achieved"], "peak": step_roofline["peak"], "unit": "GB/s",
+                    "frac": step_roofline["frac"], "traffic": None, "peak_source": peak_src, "step": step_roofline}
+    if rank == 0 and world == 1:
+        for i in range(2):
             plain(dev_batches[i % N_RESIDENT])
         torch.cuda.synchronize()
-        l0 = lib.gcb_launch_count()
-        plain(dev_batches[0])
-        launches_per_step = int(lib.gcb_launch_count() - l0)
         lib.gcb_timing_enable(1)
         n_prof = 8
         for i in range(n_prof):
@@ -354,12 +372,10 @@ def run_ours(args):
             "frac": (top["alg_GBps"] / peak_hbm) if top["alg_GBps"] else None, "traffic": measured_traffic(top["name"]),
             "alg_bytes_per_launch": alg_top, "ms_per_launch": top["ms_per_launch"], "share_of_step": top["share"],
             "peak_source": peak_src,
-            "step": {"alg_bytes": train_step_bytes(N, E, CFG["D"], CFG["L"], s_bytes),
-                     "achieved": train_step_bytes(N, E, CFG["D"], CFG["L"], s_bytes) / (ms / K * 1e-3) / 1e9,
-                     "frac": train_step_bytes(N, E, CFG["D"], CFG["L"], s_bytes) / (ms / K * 1e-3) / 1e9 / peak_hbm},
+            "step": step_roofline,
         }
         # ---- (4) reference CPU path on this box's host cores, bounded sample -----------------------
-        if world == 1 and not args.no_cpu_baseline:
+        if not args.no_cpu_baseline:
             cb, cb_spb, cores = oracle_train_throughput(2048, 3, 1)
             cpu_baseline = {"value": cb, "unit": "molecules/s", "cores": cores, "kind": "port",
                             "sample": "3 train steps of a 2048-molecule batch of the same synthetic shape, fp32 torch "
@@ -378,10 +394,17 @@ def run_ours(args):
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kernels,
             "loss": loss_resident, "host_pack_ms_per_batch": pack_ms,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # tear down in order: CUDA graphs that captured NCCL work first, then the communicator; a
+        # watchdog guarantees the process exits even if NCCL teardown stalls
+        sys.stdout.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        step._graphs.clear()
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
