@@ -298,8 +298,8 @@ gemm_tn_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ld
 // 256 threads = 64 elements x 4 z-groups; each group adds its contiguous quarter of the splits
 // in order, the four group sums are combined as (g0 + g1) + (g2 + g3): a fixed summation tree.
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const float* __restrict__ partial, int splits, int64_t count, float* __restrict__ out,
-                       int accumulate) {
+reduce_partials_kernel(const float* __restrict__ partial, int splits, int64_t stride, int64_t count,
+                       float* __restrict__ out, int accumulate) {
   __shared__ float red[4][64];
   const int e = threadIdx.x & 63, zg = threadIdx.x >> 6;
   const int64_t i = (int64_t)blockIdx.x * 64 + e;
@@ -308,7 +308,7 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, int64_t co
   float s = 0.f;
   if (i < count) {
 #pragma unroll 4
-    for (int z = z0; z < z1; ++z) s += __ldg(partial + (size_t)z * count + i);
+    for (int z = z0; z < z1; ++z) s += __ldg(partial + (size_t)z * stride + i);
   }
   red[zg][e] = s;
   __syncthreads();
@@ -319,9 +319,10 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, int64_t co
 }
 
 inline int launch_reduce_partials(const float* partial, int splits, int64_t count, float* out, int accumulate,
-                                  cudaStream_t s) {
+                                  cudaStream_t s, int64_t stride = -1) {
   if (count <= 0) return GCB_OK;
-  GCB_KERNEL("reduce_partials_kernel", s, reduce_partials_kernel<<<(unsigned)ceil_div(count, 64), 256, 0, s>>>(partial, splits, count, out, accumulate));
+  if (stride < 0) stride = count;
+  GCB_KERNEL("reduce_partials_kernel", s, reduce_partials_kernel<<<(unsigned)ceil_div(count, 64), 256, 0, s>>>(partial, splits, stride, count, out, accumulate));
   return GCB_OK;
 }
 

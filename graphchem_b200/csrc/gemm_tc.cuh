@@ -36,7 +36,10 @@ struct NtShape {
   static constexpr int BAR_BYTES = 256 + N * 4;  // mbarriers + TMEM slot, then the bias vector
   static constexpr int SMEM_BYTES = 1024 + W_BYTES + STAGES * A_STAGE_BYTES + OUT_BYTES + BAR_BYTES;
   static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;  // two accumulators; power of two for N in {64,128,256}
-  static constexpr int EPI_WARPS = 8;
+  // four warps per TMEM lane quarter when the tile is wide enough: the epilogue (tcgen05.ld -> bias /
+  // residual / activation -> swizzled staging) is a dependent chain per warp, so it needs warps, not ILP
+  static constexpr int EPI_WARPS = N == 128 ? 16 : 8;
+  static constexpr int COL_PARTS = EPI_WARPS / 4;
   static constexpr int THREADS = 64 + EPI_WARPS * 32;
   static_assert(K % 64 == 0 && N % 64 == 0 && N <= 256, "unsupported GEMM shape");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
@@ -123,31 +126,54 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (8 warps) =====================
-    const int ew = warp - 2;              // 0..7
+    // ===================== epilogue (EPI_WARPS warps) =====================
+    const int ew = warp - 2;              // 0..EPI_WARPS-1
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int half = ew >> 2;             // column half handled by this warp
+    const int half = ew >> 2;             // column part handled by this warp
     const int row_in_tile = q * 32 + lane;
     const int ep_tid = threadIdx.x - 64;
-    constexpr int COLS_PER_WARP = N / 2;
+    constexpr int COLS_PER_WARP = N / S::COL_PARTS;
+    constexpr int NCHUNK = COLS_PER_WARP / 32;
+    // Software pipeline across tiles: the residual row chunk and the row degree of the NEXT tile are
+    // loaded into registers while the current tile is being finished, so that no global-memory latency
+    // sits between "accumulator ready" and "tile staged".
+    uint4 res_raw[NCHUNK][4];
+    int deg_pref = 0;
+    const int res_col0 = half * COLS_PER_WARP;
+    if ((int)blockIdx.x < num_tiles) {
+      const int r0 = blockIdx.x * S::BM + row_in_tile;
+      if (r0 < rows) {
+        if (ep.rowptr) deg_pref = __ldg(ep.rowptr + r0 + 1) - __ldg(ep.rowptr + r0);
+        if (ep.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r0 * ep.ld_res + res_col0);
+#pragma unroll
+          for (int ci = 0; ci < NCHUNK; ++ci)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) res_raw[ci][j4] = __ldg(rp + ci * 4 + j4);
+        }
+      }
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int r = tile * S::BM + row_in_tile;
       const bool valid = r < rows;
+      const int r_next = r + (int)gridDim.x * S::BM;
+      const bool next_valid = (tile + (int)gridDim.x < num_tiles) && r_next < rows;
       float wrow = 1.f;
-      if (ep.rowptr && valid) {
-        const int deg = __ldg(ep.rowptr + r + 1) - __ldg(ep.rowptr + r);
-        wrow = ep.aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+      if (ep.rowptr) {
+        wrow = ep.aggr == GCB_AGGR_MEAN ? (deg_pref > 0 ? 1.f : 0.f) : (float)deg_pref;
+        if (next_valid) deg_pref = __ldg(ep.rowptr + r_next + 1) - __ldg(ep.rowptr + r_next);
       }
+      const uint4* rp_next = reinterpret_cast<const uint4*>(ep.res + (size_t)(next_valid ? r_next : 0) * ep.ld_res + res_col0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       // the previous tile's TMA store must have finished reading the staging buffer
       if (ep_tid == 0) tma_store_wait_read();
       named_bar_sync(1, S::EPI_WARPS * 32);
-#pragma unroll 1
-      for (int cc = 0; cc < COLS_PER_WARP; cc += 32) {
-        const int c0 = half * COLS_PER_WARP + cc;
+#pragma unroll
+      for (int ci = 0; ci < NCHUNK; ++ci) {
+        const int c0 = res_col0 + ci * 32;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + c0, v);
         tmem_ld_wait();
@@ -162,18 +188,21 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             f[j + 2] = fmaf(wrow, b4.z, f[j + 2]); f[j + 3] = fmaf(wrow, b4.w, f[j + 3]);
           }
         }
-        if (ep.res && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r * ep.ld_res + c0);
+        if (ep.res) {
+          if (valid) {
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const uint4 t = __ldg(rp + j4);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint32_t w[4] = {res_raw[ci][j4].x, res_raw[ci][j4].y, res_raw[ci][j4].z, res_raw[ci][j4].w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 x = __bfloat1622float2(h[i]);
-              f[j4 * 8 + 2 * i] += x.x;
-              f[j4 * 8 + 2 * i + 1] += x.y;
+              for (int i = 0; i < 4; ++i) {
+                f[j4 * 8 + 2 * i] += __uint_as_float(w[i] << 16);
+                f[j4 * 8 + 2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+              }
             }
+          }
+          if (next_valid) {  // refill this chunk's registers for the next tile
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) res_raw[ci][j4] = __ldg(rp_next + ci * 4 + j4);
           }
         }
         if (ep.act >= 0) {
@@ -280,7 +309,7 @@ struct TnShape {
 template <int NN, int KK>
 __global__ void __launch_bounds__(192, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int rows,
-                  float* __restrict__ partial, float* __restrict__ bias_partial, const int32_t* __restrict__ rowptr,
+                  float* __restrict__ partial, int want_bias_i, const int32_t* __restrict__ rowptr,
                   int aggr) {
   using S = TnShape<NN, KK>;
   extern __shared__ uint8_t smem_raw[];
@@ -299,7 +328,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int per = (num_tiles + gridDim.x - 1) / gridDim.x;
   const int t_begin = blockIdx.x * per;
   const int t_end = min(num_tiles, t_begin + per);
-  const bool want_bias = bias_partial != nullptr;
+  const bool want_bias = want_bias_i != 0;
+  // per-CTA partial block: [NN*KK weight-gradient partial | NN bias sums]
+  float* const cta_partial = partial + (size_t)blockIdx.x * (NN * KK + (want_bias ? NN : 0));
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -391,12 +422,12 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
       }
 #pragma unroll
-      for (int i = 0; i < NN / 128; ++i) bias_partial[(size_t)blockIdx.x * NN + i * 128 + t] = bsum[i];
+      for (int i = 0; i < NN / 128; ++i) cta_partial[NN * KK + i * 128 + t] = bsum[i];
     }
     mbar_wait(done, 0);
     tc_fence_after();
     const int q = warp & 3;
-    float* out = partial + (size_t)blockIdx.x * NN * KK;
+    float* out = cta_partial;
 #pragma unroll 1
     for (int mb = 0; mb < S::MB; ++mb) {
       const int m = mb * 128 + q * 32 + lane;
@@ -422,7 +453,7 @@ constexpr int kTnMaxCtas = kNumSMs;
 
 template <int NN, int KK>
 inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb, int rows, float* partial,
-                                  float* bias_partial, const int32_t* rowptr, int aggr, int* grid_out, cudaStream_t s) {
+                                  bool want_bias, const int32_t* rowptr, int aggr, int* grid_out, cudaStream_t s) {
   using S = TnShape<NN, KK>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -437,21 +468,19 @@ inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb
   grid = (num_tiles + per - 1) / per;  // every CTA owns at least one tile
   *grid_out = grid;
   GCB_KERNEL("gemm_tn_tc_kernel", s, gemm_tn_tc_kernel<NN, KK><<<grid, S::THREADS, S::SMEM_BYTES, s>>>(
-      tmA, tmB, rows, partial, bias_partial, rowptr, aggr));
+      tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr));
   return GCB_OK;
 }
 
-// Writes per-CTA partials ([grid][NN*KK] then [grid][NN] bias sums) and reports the CTA count.
+// Writes per-CTA partial blocks [grid][NN*KK (+ NN bias sums)] and reports the CTA count.
 inline int launch_gemm_tn_tc(const bf16* A, int lda, const bf16* B, int ldb, int rows, int NN, int KK, float* partial,
-                             bool want_bias, const int32_t* rowptr, int aggr, int* grid_out, float** bias_partial_out,
+                             bool want_bias, const int32_t* rowptr, int aggr, int* grid_out,
                              cudaStream_t s) {
   if (rows < 128) return GCB_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return GCB_ERR_UNSUPPORTED;
   if (lda % 8 || ldb % 8) return GCB_ERR_UNSUPPORTED;
-  float* bp = want_bias ? partial + (size_t)kTnMaxCtas * NN * KK : nullptr;
-  *bias_partial_out = bp;
-  if (NN == 128 && KK == 256) return launch_gemm_tn_tc_impl<128, 256>(A, lda, B, ldb, rows, partial, bp, rowptr, aggr, grid_out, s);
-  if (NN == 256 && KK == 128) return launch_gemm_tn_tc_impl<256, 128>(A, lda, B, ldb, rows, partial, bp, rowptr, aggr, grid_out, s);
+  if (NN == 128 && KK == 256) return launch_gemm_tn_tc_impl<128, 256>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, grid_out, s);
+  if (NN == 256 && KK == 128) return launch_gemm_tn_tc_impl<256, 128>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, grid_out, s);
   return GCB_ERR_UNSUPPORTED;
 }
 

@@ -22,6 +22,12 @@ namespace v2 {
 constexpr int kThreads = 256;
 template <int CH> constexpr int rows_per_block() { return (kThreads / 32) * (32 / CH); }
 template <int CH> inline unsigned blocks_for(int rows) { return (unsigned)ceil_div(rows, rows_per_block<CH>()); }
+// Gather kernels walk rows with a grid stride and prefetch the NEXT row's ELL/CSR indices while the
+// current row's data is in flight; the grid is capped so that every thread sees several rows.
+template <int CH> inline unsigned blocks_strided(int rows) {
+  const unsigned need = blocks_for<CH>(rows), cap = (unsigned)kNumSMs * 8u;
+  return need < cap ? need : cap;
+}
 
 #define GCB_V2_PROLOGUE(ROWS)                                                                        \
   constexpr int V = Vec<T>::N;                                                                       \
@@ -33,9 +39,10 @@ template <int CH> inline unsigned blocks_for(int rows) { return (unsigned)ceil_d
   const unsigned gmask = CH == 32 ? 0xffffffffu : (((1u << (CH & 31)) - 1u) << (gig * CH));          \
   const int row_raw = ((int)blockIdx.x * (kThreads / 32) + ((int)threadIdx.x >> 5)) * RPW + gig;     \
   if (row_raw >= (ROWS)) return;                                                                     \
-  const int r = row_raw;                                                                             \
+  const int row_stride = (int)gridDim.x * (kThreads / 32) * RPW;                                     \
+  int r = row_raw;                                                                                   \
   const int c = lig * V;                                                                             \
-  (void)D; (void)gmask; (void)c;
+  (void)D; (void)gmask; (void)c; (void)row_stride;
 
 // 16-byte chunks are kept RAW (4 registers) between the load and the point of use, so that four
 // neighbour rows in flight cost 16 registers instead of 32.
@@ -52,6 +59,11 @@ template <> struct Raw<float> {
   }
   static __device__ __forceinline__ void count_eq(uint4& c, const uint4& q, const uint4& m) {
     c.x = cnt1(c.x, q.x, m.x); c.y = cnt1(c.y, q.y, m.y); c.z = cnt1(c.z, q.z, m.z); c.w = cnt1(c.w, q.w, m.w);
+  }
+  // bit i set <=> channel i of q equals channel i of m (channels in to_float order)
+  static __device__ __forceinline__ uint32_t eq_bits(const uint4& q, const uint4& m) {
+    return (__uint_as_float(q.x) == __uint_as_float(m.x) ? 1u : 0u) | (__uint_as_float(q.y) == __uint_as_float(m.y) ? 2u : 0u) |
+           (__uint_as_float(q.z) == __uint_as_float(m.z) ? 4u : 0u) | (__uint_as_float(q.w) == __uint_as_float(m.w) ? 8u : 0u);
   }
   static __device__ __forceinline__ uint4 vmax(const uint4& a, const uint4& b) {
     return make_uint4(__float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x))),
@@ -77,6 +89,13 @@ template <> struct Raw<bf16> {
   }
   static __device__ __forceinline__ void count_eq(uint4& c, const uint4& q, const uint4& m) {
     c.x = cnt2(c.x, q.x, m.x); c.y = cnt2(c.y, q.y, m.y); c.z = cnt2(c.z, q.z, m.z); c.w = cnt2(c.w, q.w, m.w);
+  }
+  static __device__ __forceinline__ uint32_t eq2(uint32_t q, uint32_t m) {  // 2 bits: (lo == lo) | (hi == hi) << 1
+    const unsigned k = __heq2_mask(*reinterpret_cast<__nv_bfloat162*>(&q), *reinterpret_cast<__nv_bfloat162*>(&m));
+    return (k & 1u) | ((k >> 15) & 2u);
+  }
+  static __device__ __forceinline__ uint32_t eq_bits(const uint4& q, const uint4& m) {
+    return eq2(q.x, m.x) | (eq2(q.y, m.y) << 2) | (eq2(q.z, m.z) << 4) | (eq2(q.w, m.w) << 6);
   }
   static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
     __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a), y = *reinterpret_cast<__nv_bfloat162*>(&b);
@@ -114,8 +133,14 @@ __global__ void __launch_bounds__(kThreads, 4)
 bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
                    const int4* __restrict__ in_src4, T* __restrict__ Bout, int M, int act, Drop dr) {
   GCB_V2_PROLOGUE(M)
-  const int4 s4 = __ldg(in_src4 + r);
-  const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
+  int4 s4 = __ldg(in_src4 + r);
+  int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
+  for (;;) {
+  const int rn = r + row_stride;
+  const bool has_next = rn < M;
+  int4 s4n = s4;
+  int e0n = 0, e1n = 0;
+  if (has_next) { s4n = __ldg(in_src4 + rn); e0n = __ldg(in_ptr + rn); e1n = __ldg(in_ptr + rn + 1); }
   const uint4 praw = Raw<T>::load(PQ + (size_t)r * (2 * D) + c);
   const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
   uint4 q[4];
@@ -142,6 +167,9 @@ bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr,
   }
   apply_dropout<T, V>(o, dr, (uint64_t)r * D + c);
   store_vec(Bout + (size_t)r * D + c, o);
+  if (!has_next) break;
+  r = rn; s4 = s4n; e0 = e0n; e1 = e1n;
+  }
 }
 
 // Atom aggregation: S[i] = [ sum_{e->i} A[src e] | sum_{e->i} Bnew[eid e] ]  (Bnew[e >= M] = act(0)).
@@ -152,8 +180,17 @@ atom_gather_kernel(const T* __restrict__ A, const T* __restrict__ Bnew, const in
                    const int4* __restrict__ in_src4, const int4* __restrict__ in_eid4, T* __restrict__ S, int N, int M,
                    int act, int aggr, Drop dr_bond) {
   GCB_V2_PROLOGUE(N)
-  const int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
-  const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
+  int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
+  int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
+  for (;;) {
+  const int rn = r + row_stride;
+  const bool has_next = rn < N;
+  int4 s4n = s4, e4n = e4;
+  int e0n = 0, e1n = 0;
+  if (has_next) {
+    s4n = __ldg(in_src4 + rn); e4n = __ldg(in_eid4 + rn);
+    e0n = __ldg(in_ptr + rn); e1n = __ldg(in_ptr + rn + 1);
+  }
   const int sidx[4] = {s4.x, s4.y, s4.z, s4.w}, eidx[4] = {e4.x, e4.y, e4.z, e4.w};
   uint4 a[4], b[4];
 #pragma unroll
@@ -196,6 +233,9 @@ atom_gather_kernel(const T* __restrict__ A, const T* __restrict__ Bnew, const in
   }
   store_vec(S + (size_t)r * (2 * D) + c, sa);
   store_vec(S + (size_t)r * (2 * D) + D + c, sb);
+  if (!has_next) break;
+  r = rn; s4 = s4n; e4 = e4n; e0 = e0n; e1 = e1n;
+  }
 }
 
 // dZA_prev[j] = ( dZA[j] + sum_{e: src e = j} w(dst e) dS[dst e, 0:D] ) * dropfactor * act'(A_prev[j])
@@ -206,8 +246,14 @@ atom_bwd_gather_kernel(const T* __restrict__ dZA, const T* __restrict__ dS, cons
                        const int32_t* __restrict__ in_ptr, const T* __restrict__ A_prev, T* __restrict__ dZA_prev, int N,
                        int act, int aggr, Drop dr_prev) {
   GCB_V2_PROLOGUE(N)
-  const int4 t4 = __ldg(out_dst4 + r);
-  const int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
+  int4 t4 = __ldg(out_dst4 + r);
+  int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
+  for (;;) {
+  const int rn = r + row_stride;
+  const bool has_next = rn < N;
+  int4 t4n = t4;
+  int e0n = 0, e1n = 0;
+  if (has_next) { t4n = __ldg(out_dst4 + rn); e0n = __ldg(out_ptr + rn); e1n = __ldg(out_ptr + rn + 1); }
   const uint4 draw = Raw<T>::load(dZA + (size_t)r * D + c);
   const uint4 yraw = Raw<T>::load(A_prev + (size_t)r * D + c);
   const int tidx[4] = {t4.x, t4.y, t4.z, t4.w};
@@ -239,28 +285,44 @@ atom_bwd_gather_kernel(const T* __restrict__ dZA, const T* __restrict__ dS, cons
     for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
   }
   store_vec(dZA_prev + (size_t)r * D + c, d);
+  if (!has_next) break;
+  r = rn; t4 = t4n; e0 = e0n; e1 = e1n;
+  }
 }
 
-// Destination side of the bond backward (see kernels.cuh::bond_bwd_tie_kernel for the math).
+// Destination side of the bond backward (math: kernels.cuh::bond_bwd_tie_kernel).  Instead of the
+// per-row maximum, this version publishes, for every in-edge, one BYTE per lane whose bits say for
+// which of the lane's channels that edge attains the maximum (tiemask[eid][lane]); the source-side
+// kernel then needs neither Q nor the maxima: 16 bytes per edge instead of two 256-byte rows.
 template <typename T, int CH>
 __global__ void __launch_bounds__(kThreads, 4)
 bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, const T* __restrict__ d_out_bond,
                     const T* __restrict__ B_l, const T* __restrict__ PQ, const int32_t* __restrict__ dst,
                     const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
-                    const int4* __restrict__ in_src4, T* __restrict__ dPQ, T* __restrict__ mx_out, T* __restrict__ gsplit,
-                    int M, int act, int aggr, Drop dr) {
+                    const int32_t* __restrict__ in_eid, const int4* __restrict__ in_src4,
+                    const int4* __restrict__ in_eid4, T* __restrict__ dPQ, T* __restrict__ gsplit,
+                    uint8_t* __restrict__ tiemask, int M, int act, int aggr, Drop dr) {
   GCB_V2_PROLOGUE(M)
-  const int4 s4 = __ldg(in_src4 + r);
-  const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
-  const int t = __ldg(dst + r);
-  const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
+  int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
+  int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
+  int t = __ldg(dst + r);
+  for (;;) {
+  const int rn = r + row_stride;
+  const bool has_next = rn < M;
+  int4 s4n = s4, e4n = e4;
+  int e0n = 0, e1n = 0, tn = 0;
+  if (has_next) {
+    s4n = __ldg(in_src4 + rn); e4n = __ldg(in_eid4 + rn);
+    e0n = __ldg(in_ptr + rn); e1n = __ldg(in_ptr + rn + 1); tn = __ldg(dst + rn);
+  }
+  const int sidx[4] = {s4.x, s4.y, s4.z, s4.w}, eidx[4] = {e4.x, e4.y, e4.z, e4.w};
   uint4 q[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u)
     if (sidx[u] >= 0) q[u] = Raw<T>::load(PQ + (size_t)sidx[u] * (2 * D) + D + c);
-  float d[V], mx[V], cnt[V];
+  float d[V], cnt[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) { d[i] = 0.f; mx[i] = 0.f; cnt[i] = 1.f; }
+  for (int i = 0; i < V; ++i) { d[i] = 0.f; cnt[i] = 1.f; }
   if (e1 > e0) {
     const uint4 yraw = Raw<T>::load(B_l + (size_t)r * D + c);
     Raw<T>::to_float(Raw<T>::load(dS + (size_t)t * (2 * D) + D + c), d);
@@ -279,7 +341,6 @@ bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, cons
 #pragma unroll
       for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
     }
-    // max over the in-edges, then count the ties (packed, exact)
     uint4 mraw = Raw<T>::neg_inf();
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -288,58 +349,77 @@ bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, cons
       mraw = Raw<T>::vmax(mraw, Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c));
     uint4 craw = Raw<T>::zero();
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (sidx[u] >= 0) Raw<T>::count_eq(craw, q[u], mraw);
-    for (int e = e0 + 4; e < e1; ++e)
-      Raw<T>::count_eq(craw, Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c), mraw);
-    Raw<T>::to_float(mraw, mx);
+    for (int u = 0; u < 4; ++u) {
+      if (sidx[u] >= 0) {
+        Raw<T>::count_eq(craw, q[u], mraw);
+        tiemask[(size_t)eidx[u] * CH + lig] = (uint8_t)Raw<T>::eq_bits(q[u], mraw);
+      }
+    }
+    for (int e = e0 + 4; e < e1; ++e) {
+      const uint4 qe = Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c);
+      Raw<T>::count_eq(craw, qe, mraw);
+      tiemask[(size_t)__ldg(in_eid + e) * CH + lig] = (uint8_t)Raw<T>::eq_bits(qe, mraw);
+    }
     Raw<T>::to_float(craw, cnt);
   }
   float g[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) g[i] = cnt[i] == 1.f ? d[i] : __fdividef(d[i], cnt[i]);
   store_vec(dPQ + (size_t)r * (2 * D) + c, d);
-  store_vec(mx_out + (size_t)r * D + c, mx);
   store_vec(gsplit + (size_t)r * D + c, g);
+  if (!has_next) break;
+  r = rn; s4 = s4n; e4 = e4n; e0 = e0n; e1 = e1n; t = tn;
+  }
 }
 
-// Source side: dPQ[j, D:2D] = sum_{e: src e = j} [Q[j] == mx[dst e]] * gsplit[dst e]
+// Source side: dPQ[j, D:2D] = sum_{e: src e = j} tie(e) * gsplit[dst e]   (tie bits from tiemask[e]).
 template <typename T, int CH>
 __global__ void __launch_bounds__(kThreads, 4)
-bond_bwd_scatter_kernel(const T* __restrict__ PQ, const T* __restrict__ mx, const T* __restrict__ gsplit,
+bond_bwd_scatter_kernel(const T* __restrict__ gsplit, const uint8_t* __restrict__ tiemask,
                         const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_dst,
-                        const int4* __restrict__ out_dst4, T* __restrict__ dPQ, int M) {
+                        const int32_t* __restrict__ out_eid, const int4* __restrict__ out_dst4,
+                        const int4* __restrict__ out_eid4, T* __restrict__ dPQ, int M) {
   GCB_V2_PROLOGUE(M)
-  const int4 t4 = __ldg(out_dst4 + r);
-  const int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
-  const uint4 qraw = Raw<T>::load(PQ + (size_t)r * (2 * D) + D + c);
-  const int tidx[4] = {t4.x, t4.y, t4.z, t4.w};
-  uint4 m[4], g[4];
+  int4 t4 = __ldg(out_dst4 + r), o4 = __ldg(out_eid4 + r);
+  int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
+  for (;;) {
+  const int rn = r + row_stride;
+  const bool has_next = rn < M;
+  int4 t4n = t4, o4n = o4;
+  int e0n = 0, e1n = 0;
+  if (has_next) {
+    t4n = __ldg(out_dst4 + rn); o4n = __ldg(out_eid4 + rn);
+    e0n = __ldg(out_ptr + rn); e1n = __ldg(out_ptr + rn + 1);
+  }
+  const int tidx[4] = {t4.x, t4.y, t4.z, t4.w}, oidx[4] = {o4.x, o4.y, o4.z, o4.w};
+  uint4 g[4];
+  uint32_t bits[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     if (tidx[u] >= 0) {
-      m[u] = Raw<T>::load(mx + (size_t)tidx[u] * D + c);
       g[u] = Raw<T>::load(gsplit + (size_t)tidx[u] * D + c);
+      bits[u] = __ldg(tiemask + (size_t)oidx[u] * CH + lig);
     }
   }
-  float q[V], acc[V];
-  Raw<T>::to_float(qraw, q);
+  float acc[V];
   vzero<T, V>(acc);
-  auto consume = [&](const uint4& mr, const uint4& gr) {
-    float mf[V], gf[V];
-    Raw<T>::to_float(mr, mf);
+  auto consume = [&](const uint4& gr, uint32_t b) {
+    float gf[V];
     Raw<T>::to_float(gr, gf);
 #pragma unroll
-    for (int i = 0; i < V; ++i) acc[i] += (q[i] == mf[i]) ? gf[i] : 0.f;
+    for (int i = 0; i < V; ++i) acc[i] += ((b >> i) & 1u) ? gf[i] : 0.f;
   };
 #pragma unroll
   for (int u = 0; u < 4; ++u)
-    if (tidx[u] >= 0) consume(m[u], g[u]);
+    if (tidx[u] >= 0) consume(g[u], bits[u]);
   for (int e = e0 + 4; e < e1; ++e) {
     const int t = __ldg(out_dst + e);
-    consume(Raw<T>::load(mx + (size_t)t * D + c), Raw<T>::load(gsplit + (size_t)t * D + c));
+    consume(Raw<T>::load(gsplit + (size_t)t * D + c), __ldg(tiemask + (size_t)__ldg(out_eid + e) * CH + lig));
   }
   store_vec(dPQ + (size_t)r * (2 * D) + D + c, acc);
+  if (!has_next) break;
+  r = rn; t4 = t4n; o4 = o4n; e0 = e0n; e1 = e1n;
+  }
 }
 
 // dZA_L[n] = (dPool[graph(n)] + d_out_atom[n]) * dropfactor * act'(A_L[n]); one group per NODE

@@ -67,12 +67,15 @@ static int gemm_tn_auto(const T* A, int lda, const T* B, int ldb, int rows, int 
   if constexpr (sizeof(T) == 2) {
     if (tc::tc_enabled()) {
       int grid = 0;
-      float* bias_partial = nullptr;
-      const int rc = tc::launch_gemm_tn_tc(A, lda, B, ldb, rows, Nn, Kk, partial, db != nullptr, rowptr, aggr, &grid,
-                                           &bias_partial, s);
+      const int rc = tc::launch_gemm_tn_tc(A, lda, B, ldb, rows, Nn, Kk, partial, db != nullptr, rowptr, aggr, &grid, s);
       if (rc == GCB_OK) {
-        GCB_TRY(launch_reduce_partials(partial, grid, (int64_t)Nn * Kk, dW, accumulate, s));
-        if (db) GCB_TRY(launch_reduce_partials(bias_partial, grid, Nn, db, accumulate, s));
+        const int64_t wcount = (int64_t)Nn * Kk, stride = wcount + (db ? Nn : 0);
+        if (db && db == dW + wcount) {  // weight and bias accumulators are contiguous: one ordered reduction
+          GCB_TRY(launch_reduce_partials(partial, grid, stride, dW, accumulate, s, stride));
+        } else {
+          GCB_TRY(launch_reduce_partials(partial, grid, wcount, dW, accumulate, s, stride));
+          if (db) GCB_TRY(launch_reduce_partials(partial + wcount, grid, Nn, db, accumulate, s, stride));
+        }
         return GCB_OK;
       }
       if (rc != GCB_ERR_UNSUPPORTED) return rc;
@@ -222,6 +225,7 @@ struct Plan {
   void* dPQ = nullptr;
   void* mx = nullptr;
   void* gsplit = nullptr;
+  uint8_t* tiemask = nullptr;  // [E][32] per-edge, per-channel "this edge attains the max" bits
   float* dH[2];
   float* dPool = nullptr;
   float* partial = nullptr;
@@ -264,6 +268,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
     p.dPQ = take(M * 2 * D * es);
     p.mx = take(M * D * es);
     p.gsplit = take(M * D * es);
+    p.tiemask = (uint8_t*)take(E * 32);
     const int64_t wmax = D > R ? D : R;
     p.dH[0] = (float*)take(G * wmax * 4); p.dH[1] = (float*)take(G * wmax * 4);
     p.dPool = (float*)take(G * D * 4);
@@ -276,10 +281,11 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
     const int64_t vmax = c.atom_vocab > c.bond_vocab ? c.atom_vocab : c.bond_vocab;
     if (kEmbedSplits * vmax * D > pf) pf = kEmbedSplits * vmax * D;
     p.partial = (float*)take(pf * 4);
-    p.accWpq = (float*)take(2 * D * D * 4);
-    p.accBpq = (float*)take(2 * D * 4);
-    p.accWat = (float*)take(2 * D * D * 4);
-    p.accBat = (float*)take(D * 4);
+    // weight accumulator immediately followed by its bias accumulator (one reduction covers both)
+    p.accWpq = (float*)take((2 * D * D + 2 * D) * 4);
+    p.accBpq = p.accWpq + 2 * D * D;
+    p.accWat = (float*)take((2 * D * D + D) * 4);
+    p.accBat = p.accWat + 2 * D * D;
   }
   p.total = o;
   return GCB_OK;
@@ -288,7 +294,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
 struct Graph {
   int N, E, G, M;
   const int32_t *x_tok, *e_tok, *src, *dst, *in_ptr, *in_eid, *in_src, *out_ptr, *out_eid, *out_dst, *graph_ptr,
-      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph, *in_src4, *in_eid4, *out_dst4;
+      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph, *in_src4, *in_eid4, *out_dst4, *out_eid4;
 };
 static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32_t* h, Graph& g) {
   if (!packed || !h || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
@@ -304,7 +310,7 @@ static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32
   g.atok_ptr = packed + h[GCB_H_ATOK_PTR]; g.atok_node = packed + h[GCB_H_ATOK_NODE];
   g.btok_ptr = packed + h[GCB_H_BTOK_PTR]; g.btok_row = packed + h[GCB_H_BTOK_ROW];
   g.node_graph = packed + h[GCB_H_NODE_GRAPH];
-  g.in_src4 = packed + h[GCB_H_IN_SRC4]; g.in_eid4 = packed + h[GCB_H_IN_EID4]; g.out_dst4 = packed + h[GCB_H_OUT_DST4];
+  g.in_src4 = packed + h[GCB_H_IN_SRC4]; g.in_eid4 = packed + h[GCB_H_IN_EID4]; g.out_dst4 = packed + h[GCB_H_OUT_DST4]; g.out_eid4 = packed + h[GCB_H_OUT_EID4];
   return GCB_OK;
 }
 
@@ -457,9 +463,11 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     }
     if (M > 0) {
       GCB_TRY(launch_bond_bwd_tie<T>((const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l],
-                                     g.dst, g.in_ptr, g.in_src, g.in_src4, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit, M, D, c.act, c.aggr,
+                                     g.dst, g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit,
+                                     p.tiemask, M, D, c.act, c.aggr,
                                      make_drop(c, flags, seed, tag_bond(l)), s));
-      GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, g.out_dst4, (T*)p.dPQ, M, D, s));
+      GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, g.out_eid, g.out_dst4, g.out_eid4,
+                                         p.tiemask, (T*)p.dPQ, M, D, s));
     }
     GCB_TRY(gemm_tn_auto<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
                               p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s));

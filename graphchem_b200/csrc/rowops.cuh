@@ -18,7 +18,8 @@ namespace gcb {
     return GCB_OK;                                                                                  \
   } while (0)
 
-#define GCB_V2_GRID(ROWS) v2::blocks_for<CH>(ROWS), v2::kThreads, 0, s
+#define GCB_V2_GRID(ROWS) v2::blocks_strided<CH>(ROWS), v2::kThreads, 0, s
+#define GCB_V2_GRID_FLAT(ROWS) v2::blocks_for<CH>(ROWS), v2::kThreads, 0, s
 #define GCB_V1_GRID(ROWS, DVAL) row_chunk_blocks(ROWS, DVAL, Vec<T>::N), 256, 0, s
 
 template <typename T>
@@ -48,19 +49,20 @@ int launch_atom_bwd_gather(const T* dZA, const T* dS, const int32_t* out_ptr, co
 
 template <typename T>
 int launch_bond_bwd_tie(const T* dS, const T* dBnext, const T* d_out_bond, const T* B_l, const T* PQ, const int32_t* dst,
-                        const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_src4, T* dPQ, T* mx, T* gsplit,
-                        int M, int D, int act,
+                        const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid, const int32_t* in_src4,
+                        const int32_t* in_eid4, T* dPQ, T* mx, T* gsplit, uint8_t* tiemask, int M, int D, int act,
                         int aggr, Drop dr, cudaStream_t s) {
   GCB_ROW_DISPATCH("bond_bwd_tie_kernel", M, D,
-                   (v2::bond_bwd_tie_kernel<T, CH><<<GCB_V2_GRID(M)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, (const int4*)in_src4, dPQ, mx, gsplit, M, act, aggr, dr)),
+                   (v2::bond_bwd_tie_kernel<T, CH><<<GCB_V2_GRID(M)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, dPQ, gsplit, tiemask, M, act, aggr, dr)),
                    (bond_bwd_tie_kernel<T><<<GCB_V1_GRID(M, D)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, dPQ, mx, gsplit, M, D, act, aggr, dr)));
 }
 
 template <typename T>
 int launch_bond_bwd_scatter(const T* PQ, const T* mx, const T* gsplit, const int32_t* out_ptr, const int32_t* out_dst,
-                            const int32_t* out_dst4, T* dPQ, int M, int D, cudaStream_t s) {
+                            const int32_t* out_eid, const int32_t* out_dst4, const int32_t* out_eid4,
+                            const uint8_t* tiemask, T* dPQ, int M, int D, cudaStream_t s) {
   GCB_ROW_DISPATCH("bond_bwd_scatter_kernel", M, D,
-                   (v2::bond_bwd_scatter_kernel<T, CH><<<GCB_V2_GRID(M)>>>(PQ, mx, gsplit, out_ptr, out_dst, (const int4*)out_dst4, dPQ, M)),
+                   (v2::bond_bwd_scatter_kernel<T, CH><<<GCB_V2_GRID(M)>>>(gsplit, tiemask, out_ptr, out_dst, out_eid, (const int4*)out_dst4, (const int4*)out_eid4, dPQ, M)),
                    (bond_bwd_scatter_kernel<T><<<GCB_V1_GRID(M, D)>>>(PQ, mx, gsplit, out_ptr, out_dst, dPQ, M, D)));
 }
 
@@ -70,7 +72,7 @@ int launch_pool_bwd(const float* dPool, const T* d_out_atom, const T* A_last, co
                     const int32_t* graph_node, const int32_t* node_graph, T* dZA, int N, int G, int D, int act, Drop dr,
                     cudaStream_t s) {
   GCB_ROW_DISPATCH("pool_bwd_kernel", N, D,
-                   (v2::pool_bwd_kernel<T, CH><<<GCB_V2_GRID(N)>>>(dPool, d_out_atom, A_last, node_graph, dZA, N, act, dr)),
+                   (v2::pool_bwd_kernel<T, CH><<<GCB_V2_GRID_FLAT(N)>>>(dPool, d_out_atom, A_last, node_graph, dZA, N, act, dr)),
                    (pool_bwd_kernel<T><<<GCB_V1_GRID(G, D)>>>(dPool, d_out_atom, A_last, graph_ptr, graph_node, dZA, G, D, act, dr)));
 }
 

@@ -66,7 +66,8 @@ class PackedBatch:
             atok_ptr=self.section(L.H_ATOK_PTR, av + 1), atok_node=self.section(L.H_ATOK_NODE, N),
             btok_ptr=self.section(L.H_BTOK_PTR, bv + 1), btok_row=self.section(L.H_BTOK_ROW, M),
             node_graph=self.section(L.H_NODE_GRAPH, N), in_src4=self.section(L.H_IN_SRC4, 4 * N),
-            in_eid4=self.section(L.H_IN_EID4, 4 * N), out_dst4=self.section(L.H_OUT_DST4, 4 * N))
+            in_eid4=self.section(L.H_IN_EID4, 4 * N), out_dst4=self.section(L.H_OUT_DST4, 4 * N),
+            out_eid4=self.section(L.H_OUT_EID4, 4 * N))
 
 
 def _alloc_ints(n: int, pin: bool) -> Tensor:
