@@ -299,7 +299,7 @@ struct TnShape {
   static constexpr int STAGES = 2;
   static constexpr int A_BYTES = BR * NN * 2, B_BYTES = BR * KK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 1024;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 128 + 512 + 4096;  // + barriers, row weights, bias reduction
   static constexpr int TMEM_COLS = MB * KK;      // 256 for both D=128 shapes
   static constexpr int THREADS = 192;
   static_assert(NN % 128 == 0 && KK % 64 == 0 && KK <= 256 && MB * KK <= 512, "unsupported TN shape");
@@ -384,10 +384,14 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ---- warps 2..5: weighted column sums during the main loop, then the TMEM -> global epilogue ----
+    // Only the first 128 columns of A carry a bias gradient (all of dZA; the dP half of [dP|dQ]).
+    // Thread (cl, rl): 16-byte chunk cl (8 columns) of rows rl, rl+8, ... ; the 8 row lanes are
+    // combined once, in lane order, after the last tile.
     const int t = threadIdx.x - 64;  // 0..127
-    float bsum[NN / 128];
+    const int cl = t & 15, rl = t >> 4;
+    float bsum[8];
 #pragma unroll
-    for (int i = 0; i < NN / 128; ++i) bsum[i] = 0.f;
+    for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
     if (want_bias) {
       int stage = 0;
       uint32_t phase = 0;
@@ -404,25 +408,34 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         w_s[t] = w;
         mbar_wait(&full[stage], phase);
         named_bar_sync(1, 128);
-        const uint8_t* a = sT + stage * S::STAGE_BYTES;
+        const uint8_t* slab = sT + stage * S::STAGE_BYTES + (cl >> 3) * (S::BR * 128);
+        const int chunk = cl & 7;
+#pragma unroll 4
+        for (int rr = rl; rr < S::BR; rr += 8) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(slab + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+          const float wr = w_s[rr];
+          const uint32_t wd[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-        for (int i = 0; i < NN / 128; ++i) {
-          const int n = i * 128 + t;
-          const uint8_t* slab = a + (n >> 6) * (S::BR * 128);
-          const int chunk = (n & 63) >> 3, sub = (n & 7) * 2;
-          float acc = bsum[i];
-          for (int rr = 0; rr < S::BR; ++rr) {
-            const bf16 v = *reinterpret_cast<const bf16*>(slab + rr * 128 + ((chunk ^ (rr & 7)) << 4) + sub);
-            acc = fmaf(w_s[rr], __bfloat162float(v), acc);
+          for (int i = 0; i < 4; ++i) {
+            bsum[2 * i] = fmaf(wr, __uint_as_float(wd[i] << 16), bsum[2 * i]);
+            bsum[2 * i + 1] = fmaf(wr, __uint_as_float(wd[i] & 0xFFFF0000u), bsum[2 * i + 1]);
           }
-          bsum[i] = acc;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
       }
+      // combine the 8 row lanes in order (red_s: [8][128] floats, after w_s)
+      float* red_s = w_s + 128;
 #pragma unroll
-      for (int i = 0; i < NN / 128; ++i) cta_partial[NN * KK + i * 128 + t] = bsum[i];
+      for (int i = 0; i < 8; ++i) red_s[rl * 128 + cl * 8 + i] = bsum[i];
+      named_bar_sync(1, 128);
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += red_s[k * 128 + t];
+      cta_partial[NN * KK + t] = tot;
+#pragma unroll
+      for (int i = 1; i < NN / 128; ++i) cta_partial[NN * KK + i * 128 + t] = 0.f;
     }
     mbar_wait(done, 0);
     tc_fence_after();
