@@ -28,6 +28,7 @@ struct Epilogue {
   float p_drop = 0.f;
   uint64_t seed = 0;
   uint32_t drop_tag = 0;
+  int rev = 0;  // tcgen05 path only: walk the row tiles last-to-first
 };
 
 template <typename T, int CNT>

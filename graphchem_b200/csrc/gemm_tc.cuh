@@ -22,6 +22,7 @@ struct TcEpilogue {
   const bf16* res = nullptr;        // residual [rows, ld_res] or null
   int ld_res = 0;
   int act = -1;                     // enum gcb_act or -1
+  int rev = 0;                      // walk the row tiles last-to-first (L2 reuse of a just-written operand)
 };
 
 template <int K, int N>
@@ -94,7 +95,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], S::A_STAGE_BYTES);
         uint8_t* dst = sA + stage * S::A_STAGE_BYTES;
-        for (int ks = 0; ks < S::KS; ++ks) tma_load_2d(dst + ks * (S::BM * 128), &tmA, &full[stage], ks * 64, tile * S::BM);
+        const int ptile = ep.rev ? num_tiles - 1 - tile : tile;
+        for (int ks = 0; ks < S::KS; ++ks) tma_load_2d(dst + ks * (S::BM * 128), &tmA, &full[stage], ks * 64, ptile * S::BM);
         if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -141,7 +143,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int deg_pref = 0;
     const int res_col0 = half * COLS_PER_WARP;
     if ((int)blockIdx.x < num_tiles) {
-      const int r0 = blockIdx.x * S::BM + row_in_tile;
+      const int r0 = (ep.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * S::BM + row_in_tile;
       if (r0 < rows) {
         if (ep.rowptr) deg_pref = __ldg(ep.rowptr + r0 + 1) - __ldg(ep.rowptr + r0);
         if (ep.res) {
@@ -156,9 +158,10 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int r = tile * S::BM + row_in_tile;
+      const int ptile = ep.rev ? num_tiles - 1 - tile : tile;
+      const int r = ptile * S::BM + row_in_tile;
       const bool valid = r < rows;
-      const int r_next = r + (int)gridDim.x * S::BM;
+      const int r_next = r + (ep.rev ? -1 : 1) * (int)gridDim.x * S::BM;
       const bool next_valid = (tile + (int)gridDim.x < num_tiles) && r_next < rows;
       float wrow = 1.f;
       if (ep.rowptr) {
@@ -229,7 +232,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       fence_proxy_async_smem();
       named_bar_sync(1, S::EPI_WARPS * 32);
       if (ep_tid == 0) {
-        for (int ns = 0; ns < S::NS; ++ns) tma_store_2d(&tmC, sOut + ns * (S::BM * 128), ns * 64, tile * S::BM);
+        for (int ns = 0; ns < S::NS; ++ns) tma_store_2d(&tmC, sOut + ns * (S::BM * 128), ns * 64, ptile * S::BM);
         tma_store_commit();
       }
       acc ^= 1;
@@ -310,7 +313,7 @@ template <int NN, int KK>
 __global__ void __launch_bounds__(192, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int rows,
                   float* __restrict__ partial, int want_bias_i, const int32_t* __restrict__ rowptr,
-                  int aggr) {
+                  int aggr, int rev) {
   using S = TnShape<NN, KK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -353,8 +356,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
         uint8_t* a = sT + stage * S::STAGE_BYTES;
         uint8_t* b = a + S::A_BYTES;
-        for (int k = 0; k < S::AS; ++k) tma_load_2d(a + k * (S::BR * 128), &tmA, &full[stage], k * 64, tile * S::BR);
-        for (int k = 0; k < S::BS; ++k) tma_load_2d(b + k * (S::BR * 128), &tmB, &full[stage], k * 64, tile * S::BR);
+        const int ptile = rev ? num_tiles - 1 - tile : tile;
+        for (int k = 0; k < S::AS; ++k) tma_load_2d(a + k * (S::BR * 128), &tmA, &full[stage], k * 64, ptile * S::BR);
+        for (int k = 0; k < S::BS; ++k) tma_load_2d(b + k * (S::BR * 128), &tmB, &full[stage], k * 64, ptile * S::BR);
         if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -396,7 +400,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = t_begin; tile < t_end; ++tile) {
-        const int r = tile * S::BR + t;
+        const int r = (rev ? num_tiles - 1 - tile : tile) * S::BR + t;
         float w = 0.f;
         if (r < rows) {
           if (rowptr) {
@@ -466,7 +470,7 @@ constexpr int kTnMaxCtas = kNumSMs;
 
 template <int NN, int KK>
 inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb, int rows, float* partial,
-                                  bool want_bias, const int32_t* rowptr, int aggr, int* grid_out, cudaStream_t s) {
+                                  bool want_bias, const int32_t* rowptr, int aggr, int rev, int* grid_out, cudaStream_t s) {
   using S = TnShape<NN, KK>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -481,19 +485,19 @@ inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb
   grid = (num_tiles + per - 1) / per;  // every CTA owns at least one tile
   *grid_out = grid;
   GCB_KERNEL("gemm_tn_tc_kernel", s, gemm_tn_tc_kernel<NN, KK><<<grid, S::THREADS, S::SMEM_BYTES, s>>>(
-      tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr));
+      tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr, rev));
   return GCB_OK;
 }
 
 // Writes per-CTA partial blocks [grid][NN*KK (+ NN bias sums)] and reports the CTA count.
 inline int launch_gemm_tn_tc(const bf16* A, int lda, const bf16* B, int ldb, int rows, int NN, int KK, float* partial,
-                             bool want_bias, const int32_t* rowptr, int aggr, int* grid_out,
+                             bool want_bias, const int32_t* rowptr, int aggr, int rev, int* grid_out,
                              cudaStream_t s) {
   if (rows < 128) return GCB_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return GCB_ERR_UNSUPPORTED;
   if (lda % 8 || ldb % 8) return GCB_ERR_UNSUPPORTED;
-  if (NN == 128 && KK == 256) return launch_gemm_tn_tc_impl<128, 256>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, grid_out, s);
-  if (NN == 256 && KK == 128) return launch_gemm_tn_tc_impl<256, 128>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, grid_out, s);
+  if (NN == 128 && KK == 256) return launch_gemm_tn_tc_impl<128, 256>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, rev, grid_out, s);
+  if (NN == 256 && KK == 128) return launch_gemm_tn_tc_impl<256, 128>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, rev, grid_out, s);
   return GCB_ERR_UNSUPPORTED;
 }
 

@@ -39,10 +39,9 @@ template <int CH> inline unsigned blocks_strided(int rows) {
   const unsigned gmask = CH == 32 ? 0xffffffffu : (((1u << (CH & 31)) - 1u) << (gig * CH));          \
   const int row_raw = ((int)blockIdx.x * (kThreads / 32) + ((int)threadIdx.x >> 5)) * RPW + gig;     \
   if (row_raw >= (ROWS)) return;                                                                     \
-  const int row_stride = (int)gridDim.x * (kThreads / 32) * RPW;                                     \
-  int r = row_raw;                                                                                   \
+  const int r = rev ? (ROWS) - 1 - row_raw : row_raw;                                                \
   const int c = lig * V;                                                                             \
-  (void)D; (void)gmask; (void)c; (void)row_stride;
+  (void)D; (void)gmask; (void)c;
 
 // 16-byte chunks are kept RAW (4 registers) between the load and the point of use, so that four
 // neighbour rows in flight cost 16 registers instead of 32.
@@ -128,19 +127,13 @@ __device__ __forceinline__ void vzero(float (&a)[V]) {
 }
 
 // Bond update: Bout[r] = dropout(act(P[r] + max_{e->r} Q[src e])), act(0) for rows without in-edges.
-template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads, 4)
+template <typename T, int CH, bool DROP>
+__global__ void __launch_bounds__(kThreads, 6)
 bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
-                   const int4* __restrict__ in_src4, T* __restrict__ Bout, int M, int act, Drop dr) {
+                   const int4* __restrict__ in_src4, T* __restrict__ Bout, int M, int act, Drop dr, int rev) {
   GCB_V2_PROLOGUE(M)
-  int4 s4 = __ldg(in_src4 + r);
-  int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
-  for (;;) {
-  const int rn = r + row_stride;
-  const bool has_next = rn < M;
-  int4 s4n = s4;
-  int e0n = 0, e1n = 0;
-  if (has_next) { s4n = __ldg(in_src4 + rn); e0n = __ldg(in_ptr + rn); e1n = __ldg(in_ptr + rn + 1); }
+  const int4 s4 = __ldg(in_src4 + r);
+  const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
   const uint4 praw = Raw<T>::load(PQ + (size_t)r * (2 * D) + c);
   const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
   uint4 q[4];
@@ -165,32 +158,20 @@ bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr,
 #pragma unroll
     for (int i = 0; i < V; ++i) o[i] = act_fwd_t<T>(p[i] + mx[i], act);
   }
-  apply_dropout<T, V>(o, dr, (uint64_t)r * D + c);
+  if (DROP) apply_dropout<T, V>(o, dr, (uint64_t)r * D + c);
   store_vec(Bout + (size_t)r * D + c, o);
-  if (!has_next) break;
-  r = rn; s4 = s4n; e0 = e0n; e1 = e1n;
-  }
 }
 
 // Atom aggregation: S[i] = [ sum_{e->i} A[src e] | sum_{e->i} Bnew[eid e] ]  (Bnew[e >= M] = act(0)).
-template <typename T, int CH>
+template <typename T, int CH, bool DROP>
 __global__ void __launch_bounds__(kThreads, 4)
 atom_gather_kernel(const T* __restrict__ A, const T* __restrict__ Bnew, const int32_t* __restrict__ in_ptr,
                    const int32_t* __restrict__ in_src, const int32_t* __restrict__ in_eid,
                    const int4* __restrict__ in_src4, const int4* __restrict__ in_eid4, T* __restrict__ S, int N, int M,
-                   int act, int aggr, Drop dr_bond) {
+                   int act, int aggr, Drop dr_bond, int rev) {
   GCB_V2_PROLOGUE(N)
-  int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
-  int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
-  for (;;) {
-  const int rn = r + row_stride;
-  const bool has_next = rn < N;
-  int4 s4n = s4, e4n = e4;
-  int e0n = 0, e1n = 0;
-  if (has_next) {
-    s4n = __ldg(in_src4 + rn); e4n = __ldg(in_eid4 + rn);
-    e0n = __ldg(in_ptr + rn); e1n = __ldg(in_ptr + rn + 1);
-  }
+  const int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
+  const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
   const int sidx[4] = {s4.x, s4.y, s4.z, s4.w}, eidx[4] = {e4.x, e4.y, e4.z, e4.w};
   uint4 a[4], b[4];
 #pragma unroll
@@ -208,7 +189,7 @@ atom_gather_kernel(const T* __restrict__ A, const T* __restrict__ Bnew, const in
     float bc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) bc[i] = cst;
-    apply_dropout<T, V>(bc, dr_bond, (uint64_t)eid * D + c);
+    if (DROP) apply_dropout<T, V>(bc, dr_bond, (uint64_t)eid * D + c);
 #pragma unroll
     for (int i = 0; i < V; ++i) sb[i] += round_to(bc[i], (const T*)nullptr);
   };
@@ -233,27 +214,18 @@ atom_gather_kernel(const T* __restrict__ A, const T* __restrict__ Bnew, const in
   }
   store_vec(S + (size_t)r * (2 * D) + c, sa);
   store_vec(S + (size_t)r * (2 * D) + D + c, sb);
-  if (!has_next) break;
-  r = rn; s4 = s4n; e4 = e4n; e0 = e0n; e1 = e1n;
-  }
 }
 
 // dZA_prev[j] = ( dZA[j] + sum_{e: src e = j} w(dst e) dS[dst e, 0:D] ) * dropfactor * act'(A_prev[j])
-template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads, 4)
+template <typename T, int CH, bool DROP>
+__global__ void __launch_bounds__(kThreads, 5)
 atom_bwd_gather_kernel(const T* __restrict__ dZA, const T* __restrict__ dS, const int32_t* __restrict__ out_ptr,
                        const int32_t* __restrict__ out_dst, const int4* __restrict__ out_dst4,
                        const int32_t* __restrict__ in_ptr, const T* __restrict__ A_prev, T* __restrict__ dZA_prev, int N,
-                       int act, int aggr, Drop dr_prev) {
+                       int act, int aggr, Drop dr_prev, int rev) {
   GCB_V2_PROLOGUE(N)
-  int4 t4 = __ldg(out_dst4 + r);
-  int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
-  for (;;) {
-  const int rn = r + row_stride;
-  const bool has_next = rn < N;
-  int4 t4n = t4;
-  int e0n = 0, e1n = 0;
-  if (has_next) { t4n = __ldg(out_dst4 + rn); e0n = __ldg(out_ptr + rn); e1n = __ldg(out_ptr + rn + 1); }
+  const int4 t4 = __ldg(out_dst4 + r);
+  const int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
   const uint4 draw = Raw<T>::load(dZA + (size_t)r * D + c);
   const uint4 yraw = Raw<T>::load(A_prev + (size_t)r * D + c);
   const int tidx[4] = {t4.x, t4.y, t4.z, t4.w};
@@ -278,43 +250,31 @@ atom_bwd_gather_kernel(const T* __restrict__ dZA, const T* __restrict__ dS, cons
     const int t = __ldg(out_dst + e);
     raw_fma<T, V>(weight(t), Raw<T>::load(dS + (size_t)t * (2 * D) + c), d);
   }
-  if (dr_prev.p > 0.f) {
+  if (DROP) {
     mul_act_grad<V>(d, y, act, dr_prev, (uint64_t)r * D + c);
   } else {
 #pragma unroll
     for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
   }
   store_vec(dZA_prev + (size_t)r * D + c, d);
-  if (!has_next) break;
-  r = rn; t4 = t4n; e0 = e0n; e1 = e1n;
-  }
 }
 
 // Destination side of the bond backward (math: kernels.cuh::bond_bwd_tie_kernel).  Instead of the
 // per-row maximum, this version publishes, for every in-edge, one BYTE per lane whose bits say for
 // which of the lane's channels that edge attains the maximum (tiemask[eid][lane]); the source-side
 // kernel then needs neither Q nor the maxima: 16 bytes per edge instead of two 256-byte rows.
-template <typename T, int CH>
+template <typename T, int CH, bool DROP>
 __global__ void __launch_bounds__(kThreads, 4)
 bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, const T* __restrict__ d_out_bond,
                     const T* __restrict__ B_l, const T* __restrict__ PQ, const int32_t* __restrict__ dst,
                     const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
                     const int32_t* __restrict__ in_eid, const int4* __restrict__ in_src4,
                     const int4* __restrict__ in_eid4, T* __restrict__ dPQ, T* __restrict__ gsplit,
-                    uint8_t* __restrict__ tiemask, int M, int act, int aggr, Drop dr) {
+                    uint8_t* __restrict__ tiemask, int M, int act, int aggr, Drop dr, int rev) {
   GCB_V2_PROLOGUE(M)
-  int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
-  int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
-  int t = __ldg(dst + r);
-  for (;;) {
-  const int rn = r + row_stride;
-  const bool has_next = rn < M;
-  int4 s4n = s4, e4n = e4;
-  int e0n = 0, e1n = 0, tn = 0;
-  if (has_next) {
-    s4n = __ldg(in_src4 + rn); e4n = __ldg(in_eid4 + rn);
-    e0n = __ldg(in_ptr + rn); e1n = __ldg(in_ptr + rn + 1); tn = __ldg(dst + rn);
-  }
+  const int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
+  const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
+  const int t = __ldg(dst + r);
   const int sidx[4] = {s4.x, s4.y, s4.z, s4.w}, eidx[4] = {e4.x, e4.y, e4.z, e4.w};
   uint4 q[4];
 #pragma unroll
@@ -335,7 +295,7 @@ bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, cons
     if (d_out_bond) raw_add<T, V>(Raw<T>::load(d_out_bond + (size_t)r * D + c), d);
     float y[V];
     Raw<T>::to_float(yraw, y);
-    if (dr.p > 0.f) {
+    if (DROP) {
       mul_act_grad<V>(d, y, act, dr, (uint64_t)r * D + c);
     } else {
 #pragma unroll
@@ -367,30 +327,18 @@ bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, cons
   for (int i = 0; i < V; ++i) g[i] = cnt[i] == 1.f ? d[i] : __fdividef(d[i], cnt[i]);
   store_vec(dPQ + (size_t)r * (2 * D) + c, d);
   store_vec(gsplit + (size_t)r * D + c, g);
-  if (!has_next) break;
-  r = rn; s4 = s4n; e4 = e4n; e0 = e0n; e1 = e1n; t = tn;
-  }
 }
 
 // Source side: dPQ[j, D:2D] = sum_{e: src e = j} tie(e) * gsplit[dst e]   (tie bits from tiemask[e]).
-template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads, 4)
+template <typename T, int CH, bool DROP>
+__global__ void __launch_bounds__(kThreads, 6)
 bond_bwd_scatter_kernel(const T* __restrict__ gsplit, const uint8_t* __restrict__ tiemask,
                         const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_dst,
                         const int32_t* __restrict__ out_eid, const int4* __restrict__ out_dst4,
-                        const int4* __restrict__ out_eid4, T* __restrict__ dPQ, int M) {
+                        const int4* __restrict__ out_eid4, T* __restrict__ dPQ, int M, int rev) {
   GCB_V2_PROLOGUE(M)
-  int4 t4 = __ldg(out_dst4 + r), o4 = __ldg(out_eid4 + r);
-  int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
-  for (;;) {
-  const int rn = r + row_stride;
-  const bool has_next = rn < M;
-  int4 t4n = t4, o4n = o4;
-  int e0n = 0, e1n = 0;
-  if (has_next) {
-    t4n = __ldg(out_dst4 + rn); o4n = __ldg(out_eid4 + rn);
-    e0n = __ldg(out_ptr + rn); e1n = __ldg(out_ptr + rn + 1);
-  }
+  const int4 t4 = __ldg(out_dst4 + r), o4 = __ldg(out_eid4 + r);
+  const int e0 = __ldg(out_ptr + r), e1 = __ldg(out_ptr + r + 1);
   const int tidx[4] = {t4.x, t4.y, t4.z, t4.w}, oidx[4] = {o4.x, o4.y, o4.z, o4.w};
   uint4 g[4];
   uint32_t bits[4];
@@ -417,17 +365,14 @@ bond_bwd_scatter_kernel(const T* __restrict__ gsplit, const uint8_t* __restrict_
     consume(Raw<T>::load(gsplit + (size_t)t * D + c), __ldg(tiemask + (size_t)__ldg(out_eid + e) * CH + lig));
   }
   store_vec(dPQ + (size_t)r * (2 * D) + D + c, acc);
-  if (!has_next) break;
-  r = rn; t4 = t4n; o4 = o4n; e0 = e0n; e1 = e1n;
-  }
 }
 
 // dZA_L[n] = (dPool[graph(n)] + d_out_atom[n]) * dropfactor * act'(A_L[n]); one group per NODE
 // (node -> graph map from the packed batch).
-template <typename T, int CH>
+template <typename T, int CH, bool DROP>
 __global__ void __launch_bounds__(kThreads)
 pool_bwd_kernel(const float* __restrict__ dPool, const T* __restrict__ d_out_atom, const T* __restrict__ A_last,
-                const int32_t* __restrict__ node_graph, T* __restrict__ dZA, int N, int act, Drop dr) {
+                const int32_t* __restrict__ node_graph, T* __restrict__ dZA, int N, int act, Drop dr, int rev) {
   GCB_V2_PROLOGUE(N)
   float d[V], y[V];
   vzero<T, V>(d);
@@ -446,7 +391,7 @@ pool_bwd_kernel(const float* __restrict__ dPool, const T* __restrict__ d_out_ato
     for (int i = 0; i < V; ++i) d[i] += u[i];
   }
   load_vec(A_last + (size_t)r * D + c, y);
-  if (dr.p > 0.f) {
+  if (DROP) {
     mul_act_grad<V>(d, y, act, dr, (uint64_t)r * D + c);
   } else {
 #pragma unroll

@@ -45,7 +45,7 @@ void KernelTimer::stop() {
 }
 
 // ---- GEMM dispatch: tcgen05 kernel for bf16 hot shapes, CUDA-core kernel otherwise ---------------
-namespace tc { bool tc_enabled(); }
+namespace tc { bool tc_enabled(); bool pingpong_enabled(); }
 template <typename T>
 static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                         const Epilogue& ep, cudaStream_t s) {
@@ -53,7 +53,7 @@ static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* 
     if (!w_kn && ldw == K && !ep.actgrad_y && tc::tc_enabled()) {
       tc::TcEpilogue te;
       te.bias = ep.bias; te.rowptr = ep.rowptr; te.aggr = ep.aggr;
-      te.res = (const bf16*)ep.res; te.ld_res = ep.ld_res; te.act = ep.act;
+      te.res = (const bf16*)ep.res; te.ld_res = ep.ld_res; te.act = ep.act; te.rev = ep.rev;
       const int rc = tc::launch_gemm_nt_tc(A, lda, W, C, ldc, M, N, K, te, s);
       if (rc != GCB_ERR_UNSUPPORTED) return rc;
     }
@@ -63,11 +63,11 @@ static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* 
 
 template <typename T>
 static int gemm_tn_auto(const T* A, int lda, const T* B, int ldb, int rows, int Nn, int Kk, float* partial, float* dW,
-                        float* db, const int32_t* rowptr, int aggr, int accumulate, cudaStream_t s) {
+                        float* db, const int32_t* rowptr, int aggr, int accumulate, cudaStream_t s, int rev = 0) {
   if constexpr (sizeof(T) == 2) {
     if (tc::tc_enabled()) {
       int grid = 0;
-      const int rc = tc::launch_gemm_tn_tc(A, lda, B, ldb, rows, Nn, Kk, partial, db != nullptr, rowptr, aggr, &grid, s);
+      const int rc = tc::launch_gemm_tn_tc(A, lda, B, ldb, rows, Nn, Kk, partial, db != nullptr, rowptr, aggr, rev, &grid, s);
       if (rc == GCB_OK) {
         const int64_t wcount = (int64_t)Nn * Kk, stride = wcount + (db ? Nn : 0);
         if (db && db == dW + wcount) {  // weight and bias accumulators are contiguous: one ordered reduction
@@ -341,21 +341,26 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
   if (M > 0) {
     GCB_KERNEL("embed_act_kernel", s, embed_act_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(params + pl.emb_bond, g.e_tok, (T*)p.B[0], M, D, c.act));
   }
+  // Boustrophedon traversal: every large kernel walks its rows in the direction opposite to the
+  // previous one, so it starts on the rows its producer wrote LAST (still L2 resident).
+  int rev = 0;
+  const bool pingpong = tc::pingpong_enabled();
+  auto flip = [&]() { if (pingpong) rev ^= 1; return rev; };
   for (int l = 1; l <= L; ++l) {
     const Drop db = make_drop(c, flags, seed, tag_bond(l));
     const Drop da = make_drop(c, flags, seed, tag_atom(l));
     if (M > 0) {
       Epilogue ep;
-      ep.bias = bpq;
+      ep.bias = bpq; ep.rev = flip();
       GCB_TRY(gemm_nt_auto<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
-      GCB_TRY(launch_bond_update<T>((const T*)p.PQ[l], g.in_ptr, g.in_src, g.in_src4, (T*)p.B[l], M, D, c.act, db, s));
+      GCB_TRY(launch_bond_update<T>((const T*)p.PQ[l], g.in_ptr, g.in_src, g.in_src4, (T*)p.B[l], M, D, c.act, db, flip(), s));
     }
     if (N > 0) {
       GCB_TRY(launch_atom_gather<T>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.S[l], N, M, D,
-                                    c.act, c.aggr, db, s));
+                                    c.act, c.aggr, db, flip(), s));
       Epilogue ep;
       ep.bias = bat; ep.rowptr = g.in_ptr; ep.aggr = c.aggr;
-      ep.res = p.A[l - 1]; ep.ld_res = D; ep.act = c.act;
+      ep.res = p.A[l - 1]; ep.ld_res = D; ep.act = c.act; ep.rev = flip();
       GCB_TRY(gemm_nt_auto<T>((const T*)p.S[l], 2 * D, wat, 2 * D, false, (T*)p.A[l], D, N, D, 2 * D, ep, s));
       if (da.p > 0.f) {
         GCB_KERNEL("dropout_inplace_kernel", s, dropout_inplace_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((T*)p.A[l], N, D, da));
@@ -448,31 +453,36 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   // ---- message-passing layers, last to first ----
   const T* dBnext = nullptr;
   int bcur = 0;
+  int rev = 0;
+  const bool pingpong = tc::pingpong_enabled();
+  auto flip = [&]() { if (pingpong) rev ^= 1; return rev; };
   for (int l = L; l >= 1; --l) {
     const int acc_w = l != L;
     if (N > 0) {
       Epilogue ep;
+      ep.rev = flip();
       GCB_TRY(gemm_nt_auto<T>((const T*)p.dZA[cur], D, watT, D, false, (T*)p.dS, 2 * D, N, 2 * D, D, ep, s));
     }
     GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
-                              p.accBat, g.in_ptr, c.aggr, acc_w, s));
+                              p.accBat, g.in_ptr, c.aggr, acc_w, s, rev));
     if (N > 0) {
       GCB_TRY(launch_atom_bwd_gather<T>((const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.out_dst4, g.in_ptr, (const T*)p.A[l - 1],
                                         (T*)p.dZA[cur ^ 1], N, D, c.act, c.aggr,
-                                        l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop(), s));
+                                        l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop(), flip(), s));
     }
     if (M > 0) {
       GCB_TRY(launch_bond_bwd_tie<T>((const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l],
                                      g.dst, g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit,
                                      p.tiemask, M, D, c.act, c.aggr,
-                                     make_drop(c, flags, seed, tag_bond(l)), s));
+                                     make_drop(c, flags, seed, tag_bond(l)), flip(), s));
       GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, g.out_eid, g.out_dst4, g.out_eid4,
-                                         p.tiemask, (T*)p.dPQ, M, D, s));
+                                         p.tiemask, (T*)p.dPQ, M, D, flip(), s));
     }
     GCB_TRY(gemm_tn_auto<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
-                              p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s));
+                              p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s, flip()));
     if (M > 0) {
       Epilogue ep;
+      ep.rev = flip();
       GCB_TRY(gemm_nt_auto<T>((const T*)p.dPQ, 2 * D, wpqT, 2 * D, false, (T*)p.dBn[bcur], D, M, D, 2 * D, ep, s));
       dBnext = (const T*)p.dBn[bcur];
       bcur ^= 1;

@@ -2,48 +2,82 @@
 // the row width is 8, 16 or 32 sixteen-byte chunks (D = 64/128/256 in bf16, 32/64/128 in fp32) and the
 // generic kernels of kernels.cuh otherwise.
 #pragma once
-#include "kernels_v2.cuh"
+#include "kernels_v3.cuh"
 
 namespace gcb {
 
-#define GCB_ROW_DISPATCH(NAME, ROWS, DVAL, V2CALL, V1CALL)                                          \
+#define GCB_ROW_CASE(NAME, CHVAL, DROPFLAG, V2CALL)                                                 \
+  case CHVAL: {                                                                                     \
+    constexpr int CH = CHVAL;                                                                       \
+    if (DROPFLAG) { constexpr bool DROP = true; GCB_KERNEL(NAME, s, V2CALL); }                      \
+    else { constexpr bool DROP = false; GCB_KERNEL(NAME, s, V2CALL); }                              \
+    break;                                                                                          \
+  }
+#define GCB_ROW_DISPATCH(NAME, ROWS, DVAL, DROPFLAG, V2CALL, V1CALL)                                \
   do {                                                                                              \
     if ((ROWS) <= 0) return GCB_OK;                                                                 \
     switch ((DVAL) / Vec<T>::N) {                                                                   \
-      case 8: { constexpr int CH = 8; GCB_KERNEL(NAME, s, V2CALL); break; }                         \
-      case 16: { constexpr int CH = 16; GCB_KERNEL(NAME, s, V2CALL); break; }                       \
-      case 32: { constexpr int CH = 32; GCB_KERNEL(NAME, s, V2CALL); break; }                       \
+      GCB_ROW_CASE(NAME, 8, DROPFLAG, V2CALL)                                                       \
+      GCB_ROW_CASE(NAME, 16, DROPFLAG, V2CALL)                                                      \
+      GCB_ROW_CASE(NAME, 32, DROPFLAG, V2CALL)                                                      \
       default: { GCB_KERNEL(NAME, s, V1CALL); break; }                                              \
     }                                                                                               \
     return GCB_OK;                                                                                  \
   } while (0)
 
-#define GCB_V2_GRID(ROWS) v2::blocks_strided<CH>(ROWS), v2::kThreads, 0, s
+#define GCB_V2_GRID(ROWS) v2::blocks_for<CH>(ROWS), v2::kThreads, 0, s
 #define GCB_V2_GRID_FLAT(ROWS) v2::blocks_for<CH>(ROWS), v2::kThreads, 0, s
 #define GCB_V1_GRID(ROWS, DVAL) row_chunk_blocks(ROWS, DVAL, Vec<T>::N), 256, 0, s
 
+namespace tc { bool v3_enabled(); }
+inline unsigned v3_grid(int rows, int rows_per_block, int blocks_per_sm) {
+  const unsigned need = (unsigned)ceil_div(rows, rows_per_block), cap = (unsigned)(kNumSMs * blocks_per_sm);
+  return need < cap ? need : cap;
+}
+template <typename T, int CH>
+int launch_bond_update_v3(const T* PQ, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_src4, T* Bout, int M,
+                          int act, Drop dr, cudaStream_t s) {
+  constexpr int SM = v3::smem_bytes<5>();
+  static bool attr = false;
+  if (!attr) {
+    GCB_CUDA(cudaFuncSetAttribute(v3::bond_update_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+    attr = true;
+  }
+  GCB_KERNEL("bond_update_kernel", s, (v3::bond_update_kernel<T, CH><<<v3_grid(M, v2::rows_per_block<CH>(), 3), v2::kThreads, SM, s>>>(
+      PQ, in_ptr, in_src, (const int4*)in_src4, Bout, M, act, dr)));
+  return GCB_OK;
+}
+
 template <typename T>
 int launch_bond_update(const T* PQ, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_src4, T* Bout, int M, int D, int act,
-                       Drop dr, cudaStream_t s) {
-  GCB_ROW_DISPATCH("bond_update_kernel", M, D,
-                   (v2::bond_update_kernel<T, CH><<<GCB_V2_GRID(M)>>>(PQ, in_ptr, in_src, (const int4*)in_src4, Bout, M, act, dr)),
+                       Drop dr, int rev, cudaStream_t s) {
+  if (false && M > 0 && tc::v3_enabled()) {
+    switch (D / Vec<T>::N) {
+      case 8: return launch_bond_update_v3<T, 8>(PQ, in_ptr, in_src, in_src4, Bout, M, act, dr, s);
+      case 16: return launch_bond_update_v3<T, 16>(PQ, in_ptr, in_src, in_src4, Bout, M, act, dr, s);
+      case 32: return launch_bond_update_v3<T, 32>(PQ, in_ptr, in_src, in_src4, Bout, M, act, dr, s);
+      default: break;
+    }
+  }
+  GCB_ROW_DISPATCH("bond_update_kernel", M, D, dr.p > 0.f,
+                   (v2::bond_update_kernel<T, CH, DROP><<<GCB_V2_GRID(M)>>>(PQ, in_ptr, in_src, (const int4*)in_src4, Bout, M, act, dr, rev)),
                    (bond_update_kernel<T><<<GCB_V1_GRID(M, D)>>>(PQ, in_ptr, in_src, Bout, M, D, act, dr)));
 }
 
 template <typename T>
 int launch_atom_gather(const T* A, const T* Bnew, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
-                       const int32_t* in_src4, const int32_t* in_eid4, T* S, int N, int M, int D, int act, int aggr, Drop dr_bond, cudaStream_t s) {
-  GCB_ROW_DISPATCH("atom_gather_kernel", N, D,
-                   (v2::atom_gather_kernel<T, CH><<<GCB_V2_GRID(N)>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond)),
+                       const int32_t* in_src4, const int32_t* in_eid4, T* S, int N, int M, int D, int act, int aggr, Drop dr_bond, int rev, cudaStream_t s) {
+  GCB_ROW_DISPATCH("atom_gather_kernel", N, D, dr_bond.p > 0.f,
+                   (v2::atom_gather_kernel<T, CH, DROP><<<GCB_V2_GRID(N)>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, rev)),
                    (atom_gather_kernel<T><<<GCB_V1_GRID(N, D)>>>(A, Bnew, in_ptr, in_src, in_eid, S, N, M, D, act, aggr, dr_bond)));
 }
 
 template <typename T>
 int launch_atom_bwd_gather(const T* dZA, const T* dS, const int32_t* out_ptr, const int32_t* out_dst,
                            const int32_t* out_dst4, const int32_t* in_ptr, const T* A_prev, T* dZA_prev, int N, int D, int act, int aggr,
-                           Drop dr_prev, cudaStream_t s) {
-  GCB_ROW_DISPATCH("atom_bwd_gather_kernel", N, D,
-                   (v2::atom_bwd_gather_kernel<T, CH><<<GCB_V2_GRID(N)>>>(dZA, dS, out_ptr, out_dst, (const int4*)out_dst4, in_ptr, A_prev, dZA_prev, N, act, aggr, dr_prev)),
+                           Drop dr_prev, int rev, cudaStream_t s) {
+  GCB_ROW_DISPATCH("atom_bwd_gather_kernel", N, D, dr_prev.p > 0.f,
+                   (v2::atom_bwd_gather_kernel<T, CH, DROP><<<GCB_V2_GRID(N)>>>(dZA, dS, out_ptr, out_dst, (const int4*)out_dst4, in_ptr, A_prev, dZA_prev, N, act, aggr, dr_prev, rev)),
                    (atom_bwd_gather_kernel<T><<<GCB_V1_GRID(N, D)>>>(dZA, dS, out_ptr, out_dst, in_ptr, A_prev, dZA_prev, N, D, act, aggr, dr_prev)));
 }
 
@@ -51,18 +85,18 @@ template <typename T>
 int launch_bond_bwd_tie(const T* dS, const T* dBnext, const T* d_out_bond, const T* B_l, const T* PQ, const int32_t* dst,
                         const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid, const int32_t* in_src4,
                         const int32_t* in_eid4, T* dPQ, T* mx, T* gsplit, uint8_t* tiemask, int M, int D, int act,
-                        int aggr, Drop dr, cudaStream_t s) {
-  GCB_ROW_DISPATCH("bond_bwd_tie_kernel", M, D,
-                   (v2::bond_bwd_tie_kernel<T, CH><<<GCB_V2_GRID(M)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, dPQ, gsplit, tiemask, M, act, aggr, dr)),
+                        int aggr, Drop dr, int rev, cudaStream_t s) {
+  GCB_ROW_DISPATCH("bond_bwd_tie_kernel", M, D, dr.p > 0.f,
+                   (v2::bond_bwd_tie_kernel<T, CH, DROP><<<GCB_V2_GRID(M)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, dPQ, gsplit, tiemask, M, act, aggr, dr, rev)),
                    (bond_bwd_tie_kernel<T><<<GCB_V1_GRID(M, D)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, dPQ, mx, gsplit, M, D, act, aggr, dr)));
 }
 
 template <typename T>
 int launch_bond_bwd_scatter(const T* PQ, const T* mx, const T* gsplit, const int32_t* out_ptr, const int32_t* out_dst,
                             const int32_t* out_eid, const int32_t* out_dst4, const int32_t* out_eid4,
-                            const uint8_t* tiemask, T* dPQ, int M, int D, cudaStream_t s) {
-  GCB_ROW_DISPATCH("bond_bwd_scatter_kernel", M, D,
-                   (v2::bond_bwd_scatter_kernel<T, CH><<<GCB_V2_GRID(M)>>>(gsplit, tiemask, out_ptr, out_dst, out_eid, (const int4*)out_dst4, (const int4*)out_eid4, dPQ, M)),
+                            const uint8_t* tiemask, T* dPQ, int M, int D, int rev, cudaStream_t s) {
+  GCB_ROW_DISPATCH("bond_bwd_scatter_kernel", M, D, false,
+                   (v2::bond_bwd_scatter_kernel<T, CH, DROP><<<GCB_V2_GRID(M)>>>(gsplit, tiemask, out_ptr, out_dst, out_eid, (const int4*)out_dst4, (const int4*)out_eid4, dPQ, M, rev)),
                    (bond_bwd_scatter_kernel<T><<<GCB_V1_GRID(M, D)>>>(PQ, mx, gsplit, out_ptr, out_dst, dPQ, M, D)));
 }
 
@@ -71,8 +105,8 @@ template <typename T>
 int launch_pool_bwd(const float* dPool, const T* d_out_atom, const T* A_last, const int32_t* graph_ptr,
                     const int32_t* graph_node, const int32_t* node_graph, T* dZA, int N, int G, int D, int act, Drop dr,
                     cudaStream_t s) {
-  GCB_ROW_DISPATCH("pool_bwd_kernel", N, D,
-                   (v2::pool_bwd_kernel<T, CH><<<GCB_V2_GRID_FLAT(N)>>>(dPool, d_out_atom, A_last, node_graph, dZA, N, act, dr)),
+  GCB_ROW_DISPATCH("pool_bwd_kernel", N, D, dr.p > 0.f,
+                   (v2::pool_bwd_kernel<T, CH, DROP><<<GCB_V2_GRID_FLAT(N)>>>(dPool, d_out_atom, A_last, node_graph, dZA, N, act, dr, 0)),
                    (pool_bwd_kernel<T><<<GCB_V1_GRID(G, D)>>>(dPool, d_out_atom, A_last, graph_ptr, graph_node, dZA, G, D, act, dr)));
 }
 

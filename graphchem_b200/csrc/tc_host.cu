@@ -50,5 +50,15 @@ bool tc_enabled() {
   return !(e && e[0] == '1');
 }
 
+bool v3_enabled() {
+  const char* e = std::getenv("GCB_NO_V3");
+  return !(e && e[0] == '1');
+}
+
+bool pingpong_enabled() {
+  const char* e = std::getenv("GCB_NO_PINGPONG");
+  return !(e && e[0] == '1');
+}
+
 }  // namespace tc
 }  // namespace gcb

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import warnings
 from typing import Callable, List, Optional, Tuple
 
@@ -30,6 +31,7 @@ _ACT_IDS = {
     F.tanh: _lib.ACT_TANH, torch.tanh: _lib.ACT_TANH,
     F.leaky_relu: _lib.ACT_LEAKY_RELU,
 }
+_POISON = os.environ.get("GCB_DEBUG_POISON", "0") == "1"
 _AGGR_IDS = {"add": _lib.AGGR_ADD, "sum": _lib.AGGR_ADD, "mean": _lib.AGGR_MEAN}
 
 
@@ -238,6 +240,8 @@ class MoleculeGCN(nn.Module):
             ws_bytes = int(_lib.check(int(_lib.lib().gcb_workspace_bytes(C.byref(cfg), N, E, G, flags)),
                                       "gcb_workspace_bytes"))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            if _POISON:  # debug: make any read of unwritten workspace show up as NaN
+                ws.fill_(0xFF)
             out_cols = int(out_dim) if n_readout > 0 else D
             out = torch.empty(G, out_cols, dtype=torch.float32, device=dev)
             out_atom = torch.empty(N, D, dtype=self._compute_dtype, device=dev)
