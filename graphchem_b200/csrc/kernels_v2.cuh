@@ -39,7 +39,8 @@ template <int CH> inline unsigned blocks_strided(int rows) {
   const unsigned gmask = CH == 32 ? 0xffffffffu : (((1u << (CH & 31)) - 1u) << (gig * CH));          \
   const int row_raw = ((int)blockIdx.x * (kThreads / 32) + ((int)threadIdx.x >> 5)) * RPW + gig;     \
   if (row_raw >= (ROWS)) return;                                                                     \
-  const int r = rev ? (ROWS) - 1 - row_raw : row_raw;                                                \
+  const int r = row_raw; /* `rev` (reverse traversal) made no measurable difference and is ignored */ \
+  (void)rev;                                                                                         \
   const int c = lig * V;                                                                             \
   (void)D; (void)gmask; (void)c;
 
@@ -127,10 +128,12 @@ __device__ __forceinline__ void vzero(float (&a)[V]) {
 }
 
 // Bond update: Bout[r] = dropout(act(P[r] + max_{e->r} Q[src e])), act(0) for rows without in-edges.
-template <typename T, int CH, bool DROP>
-__global__ void __launch_bounds__(kThreads, 6)
+template <typename T, int CH, bool DROP, bool TIES>
+__global__ void __launch_bounds__(kThreads, TIES ? 4 : 6)
 bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
-                   const int4* __restrict__ in_src4, T* __restrict__ Bout, int M, int act, Drop dr, int rev) {
+                   const int32_t* __restrict__ in_eid, const int4* __restrict__ in_src4,
+                   const int4* __restrict__ in_eid4, T* __restrict__ Bout, uint8_t* __restrict__ tiemask,
+                   uint8_t* __restrict__ tiecnt, int M, int act, Drop dr, int rev) {
   GCB_V2_PROLOGUE(M)
   const int4 s4 = __ldg(in_src4 + r);
   const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
@@ -146,6 +149,37 @@ bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr,
     if (sidx[u] >= 0) mraw = Raw<T>::vmax(mraw, q[u]);
   for (int e = e0 + 4; e < e1; ++e)
     mraw = Raw<T>::vmax(mraw, Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c));
+  if (TIES && e1 > e0) {
+    // Training: record, per in-edge, which channels attain the maximum (one byte per lane) and, per
+    // channel, how many edges tie -- everything the amax backward needs, so that it never has to
+    // gather Q again (torch splits the gradient evenly among tied maxima).
+    // tiemask is indexed by dst-CSR position (rows write consecutive bytes: coalesced)
+    uint4 craw = Raw<T>::zero();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (sidx[u] >= 0) {
+        Raw<T>::count_eq(craw, q[u], mraw);
+        tiemask[(size_t)(e0 + u) * CH + lig] = (uint8_t)Raw<T>::eq_bits(q[u], mraw);
+      }
+    }
+    for (int e = e0 + 4; e < e1; ++e) {
+      const uint4 qe = Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c);
+      Raw<T>::count_eq(craw, qe, mraw);
+      tiemask[(size_t)e * CH + lig] = (uint8_t)Raw<T>::eq_bits(qe, mraw);
+    }
+    float cf[V];
+    Raw<T>::to_float(craw, cf);
+    uint8_t* cp = tiecnt + (size_t)r * D + c;
+    if constexpr (V == 8) {
+      uint2 pk;
+      pk.x = (uint32_t)cf[0] | ((uint32_t)cf[1] << 8) | ((uint32_t)cf[2] << 16) | ((uint32_t)cf[3] << 24);
+      pk.y = (uint32_t)cf[4] | ((uint32_t)cf[5] << 8) | ((uint32_t)cf[6] << 16) | ((uint32_t)cf[7] << 24);
+      *reinterpret_cast<uint2*>(cp) = pk;
+    } else {
+      *reinterpret_cast<uint32_t*>(cp) =
+          (uint32_t)cf[0] | ((uint32_t)cf[1] << 8) | ((uint32_t)cf[2] << 16) | ((uint32_t)cf[3] << 24);
+    }
+  }
   float o[V];
   if (e0 == e1) {
     const float z = act_fwd_t<T>(0.f, act);
@@ -163,57 +197,69 @@ bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr,
 }
 
 // Atom aggregation: S[i] = [ sum_{e->i} A[src e] | sum_{e->i} Bnew[eid e] ]  (Bnew[e >= M] = act(0)).
-template <typename T, int CH, bool DROP>
-__global__ void __launch_bounds__(kThreads, 4)
+// HALF = 0: only the A half, 1: only the B half, 2: both in one pass.  Two single-stream passes keep
+// each kernel at <= 40 registers (full occupancy), which is faster than one two-stream pass.
+// DROP doubles as the "generic" switch: dropout and mean aggregation are only compiled in when set.
+template <typename T, int CH, bool DROP, int HALF>
+__global__ void __launch_bounds__(kThreads, HALF == 2 ? 4 : 6)
 atom_gather_kernel(const T* __restrict__ A, const T* __restrict__ Bnew, const int32_t* __restrict__ in_ptr,
                    const int32_t* __restrict__ in_src, const int32_t* __restrict__ in_eid,
                    const int4* __restrict__ in_src4, const int4* __restrict__ in_eid4, T* __restrict__ S, int N, int M,
                    int act, int aggr, Drop dr_bond, int rev) {
   GCB_V2_PROLOGUE(N)
-  const int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
+  constexpr bool DO_A = HALF != 1, DO_B = HALF != 0;
   const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
-  const int sidx[4] = {s4.x, s4.y, s4.z, s4.w}, eidx[4] = {e4.x, e4.y, e4.z, e4.w};
-  uint4 a[4], b[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (sidx[u] >= 0) {
-      a[u] = Raw<T>::load(A + (size_t)sidx[u] * D + c);
-      if (eidx[u] < M) b[u] = Raw<T>::load(Bnew + (size_t)eidx[u] * D + c);
-    }
-  }
   float sa[V], sb[V];
   vzero<T, V>(sa);
   vzero<T, V>(sb);
-  const float cst = round_to(act_fwd_t<T>(0.f, act), (const T*)nullptr);
-  auto add_const = [&](int eid) {
-    float bc[V];
+  if (DO_A) {
+    const int4 s4 = __ldg(in_src4 + r);
+    const int sidx[4] = {s4.x, s4.y, s4.z, s4.w};
+    uint4 a[4];
 #pragma unroll
-    for (int i = 0; i < V; ++i) bc[i] = cst;
-    if (DROP) apply_dropout<T, V>(bc, dr_bond, (uint64_t)eid * D + c);
+    for (int u = 0; u < 4; ++u)
+      if (sidx[u] >= 0) a[u] = Raw<T>::load(A + (size_t)sidx[u] * D + c);
 #pragma unroll
-    for (int i = 0; i < V; ++i) sb[i] += round_to(bc[i], (const T*)nullptr);
-  };
+    for (int u = 0; u < 4; ++u)
+      if (sidx[u] >= 0) raw_add<T, V>(a[u], sa);
+    for (int e = e0 + 4; e < e1; ++e) raw_add<T, V>(Raw<T>::load(A + (size_t)__ldg(in_src + e) * D + c), sa);
+  }
+  if (DO_B) {
+    const int4 e4 = __ldg(in_eid4 + r);
+    const int eidx[4] = {e4.x, e4.y, e4.z, e4.w};
+    const float cst = round_to(act_fwd_t<T>(0.f, act), (const T*)nullptr);
+    auto add_const = [&](int eid) {
+      float bc[V];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (sidx[u] >= 0) {
-      raw_add<T, V>(a[u], sa);
-      if (eidx[u] < M) raw_add<T, V>(b[u], sb);
-      else add_const(eidx[u]);
+      for (int i = 0; i < V; ++i) bc[i] = cst;
+      if (DROP) apply_dropout<T, V>(bc, dr_bond, (uint64_t)eid * D + c);
+#pragma unroll
+      for (int i = 0; i < V; ++i) sb[i] += round_to(bc[i], (const T*)nullptr);
+    };
+    uint4 b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (eidx[u] >= 0 && eidx[u] < M) b[u] = Raw<T>::load(Bnew + (size_t)eidx[u] * D + c);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (eidx[u] >= 0) {
+        if (eidx[u] < M) raw_add<T, V>(b[u], sb);
+        else add_const(eidx[u]);
+      }
+    }
+    for (int e = e0 + 4; e < e1; ++e) {
+      const int eid = __ldg(in_eid + e);
+      if (eid < M) raw_add<T, V>(Raw<T>::load(Bnew + (size_t)eid * D + c), sb);
+      else add_const(eid);
     }
   }
-  for (int e = e0 + 4; e < e1; ++e) {
-    const int s = __ldg(in_src + e), eid = __ldg(in_eid + e);
-    raw_add<T, V>(Raw<T>::load(A + (size_t)s * D + c), sa);
-    if (eid < M) raw_add<T, V>(Raw<T>::load(Bnew + (size_t)eid * D + c), sb);
-    else add_const(eid);
-  }
-  if (aggr == GCB_AGGR_MEAN && e1 > e0) {
+  if ((DROP && aggr == GCB_AGGR_MEAN) && e1 > e0) {
     const float inv = 1.f / (float)(e1 - e0);
 #pragma unroll
     for (int i = 0; i < V; ++i) { sa[i] *= inv; sb[i] *= inv; }
   }
-  store_vec(S + (size_t)r * (2 * D) + c, sa);
-  store_vec(S + (size_t)r * (2 * D) + D + c, sb);
+  if (DO_A) store_vec(S + (size_t)r * (2 * D) + c, sa);
+  if (DO_B) store_vec(S + (size_t)r * (2 * D) + D + c, sb);
 }
 
 // dZA_prev[j] = ( dZA[j] + sum_{e: src e = j} w(dst e) dS[dst e, 0:D] ) * dropfactor * act'(A_prev[j])
@@ -237,12 +283,12 @@ atom_bwd_gather_kernel(const T* __restrict__ dZA, const T* __restrict__ dS, cons
   Raw<T>::to_float(draw, d);
   Raw<T>::to_float(yraw, y);
   auto weight = [&](int t) -> float {
-    return aggr == GCB_AGGR_MEAN ? 1.f / (float)max(__ldg(in_ptr + t + 1) - __ldg(in_ptr + t), 1) : 1.f;
+    return (DROP && aggr == GCB_AGGR_MEAN) ? 1.f / (float)max(__ldg(in_ptr + t + 1) - __ldg(in_ptr + t), 1) : 1.f;
   };
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     if (tidx[u] >= 0) {
-      if (aggr == GCB_AGGR_MEAN) raw_fma<T, V>(weight(tidx[u]), g[u], d);
+      if ((DROP && aggr == GCB_AGGR_MEAN)) raw_fma<T, V>(weight(tidx[u]), g[u], d);
       else raw_add<T, V>(g[u], d);
     }
   }
@@ -259,34 +305,34 @@ atom_bwd_gather_kernel(const T* __restrict__ dZA, const T* __restrict__ dS, cons
   store_vec(dZA_prev + (size_t)r * D + c, d);
 }
 
-// Destination side of the bond backward (math: kernels.cuh::bond_bwd_tie_kernel).  Instead of the
-// per-row maximum, this version publishes, for every in-edge, one BYTE per lane whose bits say for
-// which of the lane's channels that edge attains the maximum (tiemask[eid][lane]); the source-side
-// kernel then needs neither Q nor the maxima: 16 bytes per edge instead of two 256-byte rows.
+// Destination side of the bond backward.  The tie bits and tie counts were recorded by the forward
+// bond update, so this is a pure row-wise kernel:
+//   dzb[r]    = ( w(dst r) dS[dst r, D:2D] + dBnext[r] + d_out_bond[r] ) * dropfactor * act'(B_l[r])   (0 if deg_in(r) = 0)
+//   dPQ[r,:D] = dzb[r]  (= dP),   gsplit[r] = dzb[r] / count[r]
 template <typename T, int CH, bool DROP>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 6)
 bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, const T* __restrict__ d_out_bond,
-                    const T* __restrict__ B_l, const T* __restrict__ PQ, const int32_t* __restrict__ dst,
-                    const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
-                    const int32_t* __restrict__ in_eid, const int4* __restrict__ in_src4,
-                    const int4* __restrict__ in_eid4, T* __restrict__ dPQ, T* __restrict__ gsplit,
-                    uint8_t* __restrict__ tiemask, int M, int act, int aggr, Drop dr, int rev) {
+                    const T* __restrict__ B_l, const int32_t* __restrict__ dst, const int32_t* __restrict__ in_ptr,
+                    const uint8_t* __restrict__ tiecnt, T* __restrict__ dPQ, T* __restrict__ gsplit, int M, int act,
+                    int aggr, Drop dr, int rev) {
   GCB_V2_PROLOGUE(M)
-  const int4 s4 = __ldg(in_src4 + r), e4 = __ldg(in_eid4 + r);
   const int e0 = __ldg(in_ptr + r), e1 = __ldg(in_ptr + r + 1);
-  const int t = __ldg(dst + r);
-  const int sidx[4] = {s4.x, s4.y, s4.z, s4.w}, eidx[4] = {e4.x, e4.y, e4.z, e4.w};
-  uint4 q[4];
+  float d[V], g[V];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
-    if (sidx[u] >= 0) q[u] = Raw<T>::load(PQ + (size_t)sidx[u] * (2 * D) + D + c);
-  float d[V], cnt[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) { d[i] = 0.f; cnt[i] = 1.f; }
+  for (int i = 0; i < V; ++i) d[i] = g[i] = 0.f;
   if (e1 > e0) {
+    const int t = __ldg(dst + r);
+    const uint4 sraw = Raw<T>::load(dS + (size_t)t * (2 * D) + D + c);
     const uint4 yraw = Raw<T>::load(B_l + (size_t)r * D + c);
-    Raw<T>::to_float(Raw<T>::load(dS + (size_t)t * (2 * D) + D + c), d);
-    if (aggr == GCB_AGGR_MEAN) {
+    uint32_t cw[2] = {0u, 0u};
+    if constexpr (V == 8) {
+      const uint2 pk = __ldg(reinterpret_cast<const uint2*>(tiecnt + (size_t)r * D + c));
+      cw[0] = pk.x; cw[1] = pk.y;
+    } else {
+      cw[0] = __ldg(reinterpret_cast<const uint32_t*>(tiecnt + (size_t)r * D + c));
+    }
+    Raw<T>::to_float(sraw, d);
+    if ((DROP && aggr == GCB_AGGR_MEAN)) {
       const float w = 1.f / (float)max(__ldg(in_ptr + t + 1) - __ldg(in_ptr + t), 1);
 #pragma unroll
       for (int i = 0; i < V; ++i) d[i] *= w;
@@ -301,35 +347,17 @@ bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, cons
 #pragma unroll
       for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
     }
-    uint4 mraw = Raw<T>::neg_inf();
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (sidx[u] >= 0) mraw = Raw<T>::vmax(mraw, q[u]);
-    for (int e = e0 + 4; e < e1; ++e)
-      mraw = Raw<T>::vmax(mraw, Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c));
-    uint4 craw = Raw<T>::zero();
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (sidx[u] >= 0) {
-        Raw<T>::count_eq(craw, q[u], mraw);
-        tiemask[(size_t)eidx[u] * CH + lig] = (uint8_t)Raw<T>::eq_bits(q[u], mraw);
-      }
+    for (int i = 0; i < V; ++i) {
+      const uint32_t cnt = (cw[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+      g[i] = cnt <= 1u ? d[i] : __fdividef(d[i], (float)cnt);
     }
-    for (int e = e0 + 4; e < e1; ++e) {
-      const uint4 qe = Raw<T>::load(PQ + (size_t)__ldg(in_src + e) * (2 * D) + D + c);
-      Raw<T>::count_eq(craw, qe, mraw);
-      tiemask[(size_t)__ldg(in_eid + e) * CH + lig] = (uint8_t)Raw<T>::eq_bits(qe, mraw);
-    }
-    Raw<T>::to_float(craw, cnt);
   }
-  float g[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) g[i] = cnt[i] == 1.f ? d[i] : __fdividef(d[i], cnt[i]);
   store_vec(dPQ + (size_t)r * (2 * D) + c, d);
   store_vec(gsplit + (size_t)r * D + c, g);
 }
 
-// Source side: dPQ[j, D:2D] = sum_{e: src e = j} tie(e) * gsplit[dst e]   (tie bits from tiemask[e]).
+// Source side: dPQ[j, D:2D] = sum_{e: src e = j} tie(e) * gsplit[dst e]   (tie bits from tiemask[dst-CSR position of e]).
 template <typename T, int CH, bool DROP>
 __global__ void __launch_bounds__(kThreads, 6)
 bond_bwd_scatter_kernel(const T* __restrict__ gsplit, const uint8_t* __restrict__ tiemask,

@@ -225,7 +225,9 @@ struct Plan {
   void* dPQ = nullptr;
   void* mx = nullptr;
   void* gsplit = nullptr;
-  uint8_t* tiemask = nullptr;  // [E][32] per-edge, per-channel "this edge attains the max" bits
+  // per layer (training): [E][32] per-edge, per-lane "this edge attains the max" bits; [M][D] tie counts
+  uint8_t* tiemask[kMaxLayers];
+  uint8_t* tiecnt[kMaxLayers];
   float* dH[2];
   float* dPool = nullptr;
   float* partial = nullptr;
@@ -268,7 +270,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
     p.dPQ = take(M * 2 * D * es);
     p.mx = take(M * D * es);
     p.gsplit = take(M * D * es);
-    p.tiemask = (uint8_t*)take(E * 32);
+    for (int l = 1; l <= L; ++l) { p.tiemask[l] = (uint8_t*)take(E * 32); p.tiecnt[l] = (uint8_t*)take(M * D); }
     const int64_t wmax = D > R ? D : R;
     p.dH[0] = (float*)take(G * wmax * 4); p.dH[1] = (float*)take(G * wmax * 4);
     p.dPool = (float*)take(G * D * 4);
@@ -294,7 +296,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
 struct Graph {
   int N, E, G, M;
   const int32_t *x_tok, *e_tok, *src, *dst, *in_ptr, *in_eid, *in_src, *out_ptr, *out_eid, *out_dst, *graph_ptr,
-      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph, *in_src4, *in_eid4, *out_dst4, *out_eid4;
+      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph, *in_src4, *in_eid4, *out_dst4, *out_inpos4, *out_inpos;
 };
 static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32_t* h, Graph& g) {
   if (!packed || !h || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
@@ -310,7 +312,7 @@ static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32
   g.atok_ptr = packed + h[GCB_H_ATOK_PTR]; g.atok_node = packed + h[GCB_H_ATOK_NODE];
   g.btok_ptr = packed + h[GCB_H_BTOK_PTR]; g.btok_row = packed + h[GCB_H_BTOK_ROW];
   g.node_graph = packed + h[GCB_H_NODE_GRAPH];
-  g.in_src4 = packed + h[GCB_H_IN_SRC4]; g.in_eid4 = packed + h[GCB_H_IN_EID4]; g.out_dst4 = packed + h[GCB_H_OUT_DST4]; g.out_eid4 = packed + h[GCB_H_OUT_EID4];
+  g.in_src4 = packed + h[GCB_H_IN_SRC4]; g.in_eid4 = packed + h[GCB_H_IN_EID4]; g.out_dst4 = packed + h[GCB_H_OUT_DST4]; g.out_inpos4 = packed + h[GCB_H_OUT_INPOS4]; g.out_inpos = packed + h[GCB_H_OUT_INPOS];
   return GCB_OK;
 }
 
@@ -353,7 +355,9 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       Epilogue ep;
       ep.bias = bpq; ep.rev = flip();
       GCB_TRY(gemm_nt_auto<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
-      GCB_TRY(launch_bond_update<T>((const T*)p.PQ[l], g.in_ptr, g.in_src, g.in_src4, (T*)p.B[l], M, D, c.act, db, flip(), s));
+      GCB_TRY(launch_bond_update<T>((const T*)p.PQ[l], g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.B[l],
+                                    (flags & GCB_SAVE_FOR_BWD) ? p.tiemask[l] : nullptr,
+                                    (flags & GCB_SAVE_FOR_BWD) ? p.tiecnt[l] : nullptr, M, D, c.act, db, flip(), s));
     }
     if (N > 0) {
       GCB_TRY(launch_atom_gather<T>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.S[l], N, M, D,
@@ -473,10 +477,10 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     if (M > 0) {
       GCB_TRY(launch_bond_bwd_tie<T>((const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l],
                                      g.dst, g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit,
-                                     p.tiemask, M, D, c.act, c.aggr,
+                                     p.tiemask[l], p.tiecnt[l], M, D, c.act, c.aggr,
                                      make_drop(c, flags, seed, tag_bond(l)), flip(), s));
-      GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, g.out_eid, g.out_dst4, g.out_eid4,
-                                         p.tiemask, (T*)p.dPQ, M, D, flip(), s));
+      GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, g.out_inpos, g.out_dst4, g.out_inpos4,
+                                         p.tiemask[l], (T*)p.dPQ, M, D, flip(), s));
     }
     GCB_TRY(gemm_tn_auto<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
                               p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s, flip()));

@@ -34,7 +34,8 @@ static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, in
   put(GCB_H_BTOK_PTR, (int64_t)bv + 1); put(GCB_H_BTOK_ROW, E);
   put(GCB_H_NODE_GRAPH, N);
   put(GCB_H_IN_SRC4, 4 * (int64_t)N); put(GCB_H_IN_EID4, 4 * (int64_t)N); put(GCB_H_OUT_DST4, 4 * (int64_t)N);
-  put(GCB_H_OUT_EID4, 4 * (int64_t)N);
+  put(GCB_H_OUT_INPOS4, 4 * (int64_t)N);
+  put(GCB_H_OUT_INPOS, E);
   if (off > INT32_MAX) return -1;
   if (h) h[GCB_H_TOTAL_INTS] = (int32_t)off;
   return off;
@@ -75,14 +76,20 @@ static int finish_pack(int32_t* packed, const int32_t* h, const int32_t* batch_i
     int32_t* s4 = packed + h[GCB_H_IN_SRC4];
     int32_t* e4 = packed + h[GCB_H_IN_EID4];
     int32_t* d4 = packed + h[GCB_H_OUT_DST4];
-    int32_t* o4 = packed + h[GCB_H_OUT_EID4];
+    int32_t* o4 = packed + h[GCB_H_OUT_INPOS4];
+    int32_t* out_inpos = packed + h[GCB_H_OUT_INPOS];
+    {
+      std::vector<int32_t> pos_of_eid((size_t)E);
+      for (int64_t k = 0; k < E; ++k) pos_of_eid[(size_t)in_eid[k]] = (int32_t)k;
+      for (int64_t k = 0; k < E; ++k) out_inpos[k] = pos_of_eid[(size_t)out_eid[k]];
+    }
     for (int64_t i = 0; i < N; ++i) {
       for (int u = 0; u < 4; ++u) {
         const int64_t ki = (int64_t)in_ptr[i] + u, ko = (int64_t)out_ptr[i] + u;
         s4[4 * i + u] = ki < in_ptr[i + 1] ? in_src[ki] : -1;
         e4[4 * i + u] = ki < in_ptr[i + 1] ? in_eid[ki] : -1;
         d4[4 * i + u] = ko < out_ptr[i + 1] ? out_dst[ko] : -1;
-        o4[4 * i + u] = ko < out_ptr[i + 1] ? out_eid[ko] : -1;
+        o4[4 * i + u] = ko < out_ptr[i + 1] ? out_inpos[ko] : -1;
       }
     }
   }

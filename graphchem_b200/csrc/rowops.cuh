@@ -49,8 +49,9 @@ int launch_bond_update_v3(const T* PQ, const int32_t* in_ptr, const int32_t* in_
 }
 
 template <typename T>
-int launch_bond_update(const T* PQ, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_src4, T* Bout, int M, int D, int act,
-                       Drop dr, int rev, cudaStream_t s) {
+int launch_bond_update(const T* PQ, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
+                       const int32_t* in_src4, const int32_t* in_eid4, T* Bout, uint8_t* tiemask, uint8_t* tiecnt, int M,
+                       int D, int act, Drop dr, int rev, cudaStream_t s) {
   if (false && M > 0 && tc::v3_enabled()) {
     switch (D / Vec<T>::N) {
       case 8: return launch_bond_update_v3<T, 8>(PQ, in_ptr, in_src, in_src4, Bout, M, act, dr, s);
@@ -59,16 +60,39 @@ int launch_bond_update(const T* PQ, const int32_t* in_ptr, const int32_t* in_src
       default: break;
     }
   }
+  if (tiemask != nullptr) {
+    GCB_ROW_DISPATCH("bond_update_kernel", M, D, dr.p > 0.f,
+                     (v2::bond_update_kernel<T, CH, DROP, true><<<GCB_V2_GRID(M)>>>(PQ, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, Bout, tiemask, tiecnt, M, act, dr, rev)),
+                     (bond_update_kernel<T><<<GCB_V1_GRID(M, D)>>>(PQ, in_ptr, in_src, Bout, M, D, act, dr)));
+  }
   GCB_ROW_DISPATCH("bond_update_kernel", M, D, dr.p > 0.f,
-                   (v2::bond_update_kernel<T, CH, DROP><<<GCB_V2_GRID(M)>>>(PQ, in_ptr, in_src, (const int4*)in_src4, Bout, M, act, dr, rev)),
+                   (v2::bond_update_kernel<T, CH, DROP, false><<<GCB_V2_GRID(M)>>>(PQ, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, Bout, tiemask, tiecnt, M, act, dr, rev)),
                    (bond_update_kernel<T><<<GCB_V1_GRID(M, D)>>>(PQ, in_ptr, in_src, Bout, M, D, act, dr)));
 }
 
 template <typename T>
 int launch_atom_gather(const T* A, const T* Bnew, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
                        const int32_t* in_src4, const int32_t* in_eid4, T* S, int N, int M, int D, int act, int aggr, Drop dr_bond, int rev, cudaStream_t s) {
-  GCB_ROW_DISPATCH("atom_gather_kernel", N, D, dr_bond.p > 0.f,
-                   (v2::atom_gather_kernel<T, CH, DROP><<<GCB_V2_GRID(N)>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, rev)),
+  const bool generic = dr_bond.p > 0.f || aggr == GCB_AGGR_MEAN;
+  const int ch = D / Vec<T>::N;
+  if (!generic && N > 0 && (ch == 8 || ch == 16 || ch == 32)) {  // lean path: one single-stream pass per half
+    switch (ch) {
+      case 8:
+        GCB_KERNEL("atom_gather_kernel", s, (v2::atom_gather_kernel<T, 8, false, 0><<<v2::blocks_for<8>(N), v2::kThreads, 0, s>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, 0)));
+        GCB_KERNEL("atom_gather_kernel", s, (v2::atom_gather_kernel<T, 8, false, 1><<<v2::blocks_for<8>(N), v2::kThreads, 0, s>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, 0)));
+        break;
+      case 16:
+        GCB_KERNEL("atom_gather_kernel", s, (v2::atom_gather_kernel<T, 16, false, 0><<<v2::blocks_for<16>(N), v2::kThreads, 0, s>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, 0)));
+        GCB_KERNEL("atom_gather_kernel", s, (v2::atom_gather_kernel<T, 16, false, 1><<<v2::blocks_for<16>(N), v2::kThreads, 0, s>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, 0)));
+        break;
+      default:
+        GCB_KERNEL("atom_gather_kernel", s, (v2::atom_gather_kernel<T, 32, false, 0><<<v2::blocks_for<32>(N), v2::kThreads, 0, s>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, 0)));
+        GCB_KERNEL("atom_gather_kernel", s, (v2::atom_gather_kernel<T, 32, false, 1><<<v2::blocks_for<32>(N), v2::kThreads, 0, s>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, 0)));
+    }
+    return GCB_OK;
+  }
+  GCB_ROW_DISPATCH("atom_gather_kernel", N, D, generic,
+                   (v2::atom_gather_kernel<T, CH, DROP, 2><<<GCB_V2_GRID(N)>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, rev)),
                    (atom_gather_kernel<T><<<GCB_V1_GRID(N, D)>>>(A, Bnew, in_ptr, in_src, in_eid, S, N, M, D, act, aggr, dr_bond)));
 }
 
@@ -76,7 +100,7 @@ template <typename T>
 int launch_atom_bwd_gather(const T* dZA, const T* dS, const int32_t* out_ptr, const int32_t* out_dst,
                            const int32_t* out_dst4, const int32_t* in_ptr, const T* A_prev, T* dZA_prev, int N, int D, int act, int aggr,
                            Drop dr_prev, int rev, cudaStream_t s) {
-  GCB_ROW_DISPATCH("atom_bwd_gather_kernel", N, D, dr_prev.p > 0.f,
+  GCB_ROW_DISPATCH("atom_bwd_gather_kernel", N, D, dr_prev.p > 0.f || aggr == GCB_AGGR_MEAN,
                    (v2::atom_bwd_gather_kernel<T, CH, DROP><<<GCB_V2_GRID(N)>>>(dZA, dS, out_ptr, out_dst, (const int4*)out_dst4, in_ptr, A_prev, dZA_prev, N, act, aggr, dr_prev, rev)),
                    (atom_bwd_gather_kernel<T><<<GCB_V1_GRID(N, D)>>>(dZA, dS, out_ptr, out_dst, in_ptr, A_prev, dZA_prev, N, D, act, aggr, dr_prev)));
 }
@@ -84,10 +108,10 @@ int launch_atom_bwd_gather(const T* dZA, const T* dS, const int32_t* out_ptr, co
 template <typename T>
 int launch_bond_bwd_tie(const T* dS, const T* dBnext, const T* d_out_bond, const T* B_l, const T* PQ, const int32_t* dst,
                         const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid, const int32_t* in_src4,
-                        const int32_t* in_eid4, T* dPQ, T* mx, T* gsplit, uint8_t* tiemask, int M, int D, int act,
+                        const int32_t* in_eid4, T* dPQ, T* mx, T* gsplit, uint8_t* tiemask, const uint8_t* tiecnt, int M, int D, int act,
                         int aggr, Drop dr, int rev, cudaStream_t s) {
-  GCB_ROW_DISPATCH("bond_bwd_tie_kernel", M, D, dr.p > 0.f,
-                   (v2::bond_bwd_tie_kernel<T, CH, DROP><<<GCB_V2_GRID(M)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, dPQ, gsplit, tiemask, M, act, aggr, dr, rev)),
+  GCB_ROW_DISPATCH("bond_bwd_tie_kernel", M, D, dr.p > 0.f || aggr == GCB_AGGR_MEAN,
+                   (v2::bond_bwd_tie_kernel<T, CH, DROP><<<GCB_V2_GRID(M)>>>(dS, dBnext, d_out_bond, B_l, dst, in_ptr, tiecnt, dPQ, gsplit, M, act, aggr, dr, rev)),
                    (bond_bwd_tie_kernel<T><<<GCB_V1_GRID(M, D)>>>(dS, dBnext, d_out_bond, B_l, PQ, dst, in_ptr, in_src, dPQ, mx, gsplit, M, D, act, aggr, dr)));
 }
 

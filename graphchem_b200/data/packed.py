@@ -67,7 +67,7 @@ class PackedBatch:
             btok_ptr=self.section(L.H_BTOK_PTR, bv + 1), btok_row=self.section(L.H_BTOK_ROW, M),
             node_graph=self.section(L.H_NODE_GRAPH, N), in_src4=self.section(L.H_IN_SRC4, 4 * N),
             in_eid4=self.section(L.H_IN_EID4, 4 * N), out_dst4=self.section(L.H_OUT_DST4, 4 * N),
-            out_eid4=self.section(L.H_OUT_EID4, 4 * N))
+            out_inpos4=self.section(L.H_OUT_INPOS4, 4 * N), out_inpos=self.section(L.H_OUT_INPOS, E))
 
 
 def _alloc_ints(n: int, pin: bool) -> Tensor:

@@ -76,7 +76,8 @@ enum gcb_pack_field {
   GCB_H_ATOK_PTR, GCB_H_ATOK_NODE, GCB_H_BTOK_PTR, GCB_H_BTOK_ROW,
   GCB_H_NODE_GRAPH, /* [N] graph id of every node (the PyG `batch` vector as int32) */
   /* ELL-4 views of the CSRs: first four entries of every row, -1 padded, one int4 per row */
-  GCB_H_IN_SRC4, GCB_H_IN_EID4, GCB_H_OUT_DST4, GCB_H_OUT_EID4,
+  GCB_H_IN_SRC4, GCB_H_IN_EID4, GCB_H_OUT_DST4, GCB_H_OUT_INPOS4,
+  GCB_H_OUT_INPOS, /* [E] for every src-CSR entry: position of the same edge in the dst-CSR */
   GCB_H_FIELDS
 };
 

@@ -44,10 +44,13 @@ def build_index(x_tok, e_tok, edge_index, batch, n_graphs, atom_vocab, bond_voca
             ok = k < ptr[1:]
             out[ok, u] = vals[k[ok]]
         return out.reshape(-1)
+    pos_of_eid = np.empty(E, dtype=np.int32)
+    pos_of_eid[in_eid] = np.arange(E, dtype=np.int32)
+    out_inpos = pos_of_eid[out_eid] if E else out_eid
     in_src_sorted = src[in_eid] if E else in_eid
     out_dst_sorted = dst[out_eid] if E else out_eid
     return dict(
-        in_src4=ell4(in_ptr, in_src_sorted), in_eid4=ell4(in_ptr, in_eid), out_dst4=ell4(out_ptr, out_dst_sorted), out_eid4=ell4(out_ptr, out_eid),
+        in_src4=ell4(in_ptr, in_src_sorted), in_eid4=ell4(in_ptr, in_eid), out_dst4=ell4(out_ptr, out_dst_sorted), out_inpos4=ell4(out_ptr, out_inpos), out_inpos=out_inpos,
         x_tok=x_tok, e_tok=e_tok, src=src, dst=dst,
         in_ptr=in_ptr, in_eid=in_eid, in_src=src[in_eid] if E else in_eid,
         out_ptr=out_ptr, out_eid=out_eid, out_dst=dst[out_eid] if E else out_eid,
