@@ -4,6 +4,7 @@
 // Reference path being replaced: graphchem/nn/gcn.py:120-202 (forward), autograd through it
 // (examples/predict_cn.ipynb:250), F.mse_loss (:249) and torch.optim.Adam.step (:251).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -45,7 +46,7 @@ void KernelTimer::stop() {
 }
 
 // ---- GEMM dispatch: tcgen05 kernel for bf16 hot shapes, CUDA-core kernel otherwise ---------------
-namespace tc { bool tc_enabled(); bool pingpong_enabled(); }
+namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); }
 template <typename T>
 static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                         const Epilogue& ep, cudaStream_t s) {
@@ -82,6 +83,31 @@ static int gemm_tn_auto(const T* A, int lda, const T* B, int ldb, int rows, int 
     }
   }
   return launch_gemm_tn<T>(A, lda, B, ldb, rows, Nn, Kk, partial, dW, db, rowptr, aggr, accumulate, s);
+}
+
+// ---- side stream for off-critical-path work (weight-gradient GEMMs of the backward pass) ----------
+// Internal, per host thread, created lazily; joins the caller's stream through events only, so it is
+// captured together with it when the caller is recording a CUDA graph.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> events;
+  bool ok = false;
+  cudaEvent_t event(size_t i) {
+    while (events.size() <= i) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      events.push_back(e);
+    }
+    return events[i];
+  }
+};
+static SideStream* side_stream() {
+  static thread_local SideStream ss;
+  if (!ss.ok) {
+    if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    ss.ok = true;
+  }
+  return &ss;
 }
 
 // ---- parameter layout ---------------------------------------------------------------------------
@@ -223,6 +249,7 @@ struct Plan {
   void* dS = nullptr;
   void* dBn[2];
   void* dPQ = nullptr;
+  void* dPQ2[2];  // [dP|dQ] of alternate layers (lets the weight-gradient GEMM of layer l overlap layer l-1)
   void* mx = nullptr;
   void* gsplit = nullptr;
   // per layer (training): [E][32] per-edge, per-lane "this edge attains the max" bits; [M][D] tie counts
@@ -267,7 +294,8 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
     p.dZA[0] = take(N * D * es); p.dZA[1] = take(N * D * es);
     p.dS = take(N * 2 * D * es);
     p.dBn[0] = take(M * D * es); p.dBn[1] = take(M * D * es);
-    p.dPQ = take(M * 2 * D * es);
+    p.dPQ2[0] = take(M * 2 * D * es); p.dPQ2[1] = take(M * 2 * D * es);
+    p.dPQ = p.dPQ2[0];
     p.mx = take(M * D * es);
     p.gsplit = take(M * D * es);
     for (int l = 1; l <= L; ++l) { p.tiemask[l] = (uint8_t*)take(E * 32); p.tiecnt[l] = (uint8_t*)take(M * D); }
@@ -460,38 +488,88 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   int rev = 0;
   const bool pingpong = tc::pingpong_enabled();
   auto flip = [&]() { if (pingpong) rev ^= 1; return rev; };
+  // Weight-gradient GEMMs (and their partial reductions) feed nothing until the optimiser step, so
+  // they run on a side stream next to the latency-bound row kernels of the same / the next layer:
+  //   W_at(l) = dZA_l^T S_l        may start when layer l starts; dZA_l is overwritten by atom_bwd(l-1)
+  //   W_pq(l) = [dP|dQ]_l^T B_l-1  may start after scatter(l);   dPQ[l&1] is overwritten by tie(l-2)
+  SideStream* ss = tc::overlap_enabled() ? side_stream() : nullptr;
+  const bool overlap = ss != nullptr;
+  cudaStream_t sw = overlap ? ss->stream : s;
+  size_t evi = 0;
+  cudaEvent_t done_at[kMaxLayers + 2], done_pq[kMaxLayers + 2];
+  for (int i = 0; i < kMaxLayers + 2; ++i) done_at[i] = done_pq[i] = nullptr;
+  auto fork = [&]() -> int {  // side stream continues from the caller stream's current point
+    if (!overlap) return GCB_OK;
+    cudaEvent_t e = ss->event(evi++);
+    if (!e) return GCB_ERR_CUDA;
+    GCB_CUDA(cudaEventRecord(e, s));
+    GCB_CUDA(cudaStreamWaitEvent(sw, e, 0));
+    return GCB_OK;
+  };
+  auto mark = [&](cudaEvent_t& slot) -> int {  // remember "side stream reached this point"
+    if (!overlap) return GCB_OK;
+    slot = ss->event(evi++);
+    if (!slot) return GCB_ERR_CUDA;
+    GCB_CUDA(cudaEventRecord(slot, sw));
+    return GCB_OK;
+  };
+  auto join = [&](cudaEvent_t e) -> int {
+    if (overlap && e) GCB_CUDA(cudaStreamWaitEvent(s, e, 0));
+    return GCB_OK;
+  };
   for (int l = L; l >= 1; --l) {
     const int acc_w = l != L;
+    T* dPQ_l = (T*)p.dPQ2[l & 1];
+    static const bool fork_early = std::getenv("GCB_FORK_EARLY") != nullptr;
+    if (fork_early) {
+      GCB_TRY(fork());
+      GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
+                                p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0));
+      GCB_TRY(mark(done_at[l]));
+    }
     if (N > 0) {
       Epilogue ep;
       ep.rev = flip();
       GCB_TRY(gemm_nt_auto<T>((const T*)p.dZA[cur], D, watT, D, false, (T*)p.dS, 2 * D, N, 2 * D, D, ep, s));
     }
-    GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
-                              p.accBat, g.in_ptr, c.aggr, acc_w, s, rev));
+    if (!fork_early) {
+      GCB_TRY(fork());
+      GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
+                                p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0));
+      GCB_TRY(mark(done_at[l]));
+    }
+    GCB_TRY(join(done_at[l + 1]));  // W_at(l+1) read the buffer atom_bwd(l) is about to overwrite
     if (N > 0) {
       GCB_TRY(launch_atom_bwd_gather<T>((const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.out_dst4, g.in_ptr, (const T*)p.A[l - 1],
                                         (T*)p.dZA[cur ^ 1], N, D, c.act, c.aggr,
                                         l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop(), flip(), s));
     }
+    GCB_TRY(join(done_pq[l + 2]));  // W_pq(l+2) read dPQ[l&1]
     if (M > 0) {
       GCB_TRY(launch_bond_bwd_tie<T>((const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l],
-                                     g.dst, g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.dPQ, (T*)p.mx, (T*)p.gsplit,
+                                     g.dst, g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, dPQ_l, (T*)p.mx, (T*)p.gsplit,
                                      p.tiemask[l], p.tiecnt[l], M, D, c.act, c.aggr,
                                      make_drop(c, flags, seed, tag_bond(l)), flip(), s));
       GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, g.out_inpos, g.out_dst4, g.out_inpos4,
-                                         p.tiemask[l], (T*)p.dPQ, M, D, flip(), s));
+                                         p.tiemask[l], dPQ_l, M, D, flip(), s));
     }
-    GCB_TRY(gemm_tn_auto<T>((const T*)p.dPQ, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
-                              p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, s, flip()));
+    GCB_TRY(fork());
+    GCB_TRY(gemm_tn_auto<T>((const T*)dPQ_l, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
+                              p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, sw, flip()));
+    GCB_TRY(mark(done_pq[l]));
     if (M > 0) {
       Epilogue ep;
       ep.rev = flip();
-      GCB_TRY(gemm_nt_auto<T>((const T*)p.dPQ, 2 * D, wpqT, 2 * D, false, (T*)p.dBn[bcur], D, M, D, 2 * D, ep, s));
+      GCB_TRY(gemm_nt_auto<T>((const T*)dPQ_l, 2 * D, wpqT, 2 * D, false, (T*)p.dBn[bcur], D, M, D, 2 * D, ep, s));
       dBnext = (const T*)p.dBn[bcur];
       bcur ^= 1;
     }
     cur ^= 1;
+  }
+  if (overlap && L >= 1) {  // everything on the side stream must be done before its results are used
+    cudaEvent_t last = nullptr;
+    GCB_TRY(mark(last));
+    GCB_TRY(join(last));
   }
   // ---- embeddings ----
   {

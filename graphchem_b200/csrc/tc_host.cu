@@ -55,6 +55,11 @@ bool v3_enabled() {
   return !(e && e[0] == '1');
 }
 
+bool overlap_enabled() {
+  const char* e = std::getenv("GCB_NO_OVERLAP");
+  return !(e && e[0] == '1');
+}
+
 bool pingpong_enabled() {
   const char* e = std::getenv("GCB_NO_PINGPONG");
   return !(e && e[0] == '1');
