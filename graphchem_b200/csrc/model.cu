@@ -14,6 +14,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "readout.cuh"
 #include "rowops.cuh"
 
 namespace gcb {
@@ -308,6 +309,10 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
       const int64_t need = (int64_t)tn_splits((int)G) * pl.r_out[k] * (pl.r_in[k] + 1);
       if (need > pf) pf = need;
     }
+    if (pl.n_lin > 0) {
+      const int64_t need = ceil_div(G, kReadoutGB) * (pl.total - pl.r_w[0]);
+      if (need > pf) pf = need;
+    }
     const int64_t vmax = c.atom_vocab > c.bond_vocab ? c.atom_vocab : c.bond_vocab;
     if (kEmbedSplits * vmax * D > pf) pf = kEmbedSplits * vmax * D;
     p.partial = (float*)take(pf * 4);
@@ -319,6 +324,29 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
   }
   p.total = o;
   return GCB_OK;
+}
+
+// The fused readout kernels win in the latency regime (a few CTAs instead of ~13 launches); for large
+// batches the tiled GEMM path is faster, so the fused path is used up to 1024 graphs.
+static bool make_readout_desc(const ParamLayout& pl, ReadoutDesc& rd, int G) {
+  if (pl.n_lin <= 0 || pl.n_lin > kReadoutMaxLin || G > 1024) return false;
+  rd.n_lin = pl.n_lin;
+  rd.max_dim = 0;
+  for (int k = 0; k < pl.n_lin; ++k) {
+    rd.in_dim[k] = pl.r_in[k]; rd.out_dim[k] = pl.r_out[k];
+    rd.w_off[k] = pl.r_w[k]; rd.b_off[k] = pl.r_b[k];
+    rd.p_off[k] = pl.r_w[k] - pl.r_w[0];
+    rd.max_dim = rd.max_dim > pl.r_in[k] ? rd.max_dim : pl.r_in[k];
+    rd.max_dim = rd.max_dim > pl.r_out[k] ? rd.max_dim : pl.r_out[k];
+  }
+  rd.partial_stride = pl.total - pl.r_w[0];
+  rd.max_w = 0;
+  for (int k = 0; k < pl.n_lin; ++k) {
+    const int w = (pl.r_in[k] + 1) * (pl.r_out[k] + 1);
+    rd.max_w = rd.max_w > w ? rd.max_w : w;
+  }
+  // shared memory: 3 activation panels of 32 x (max_dim + 1) floats + one weight matrix
+  return (3 * kReadoutGB * (rd.max_dim + 1) + rd.max_w) * 4 <= 200 * 1024;
 }
 
 struct Graph {
@@ -404,6 +432,14 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
     GCB_KERNEL("pool_kernel", s, pool_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>((const T*)p.A[L], g.graph_ptr, g.graph_node, p.pooled, G, D));
     if (pl.n_lin == 0) {
       if (out) GCB_CUDA(cudaMemcpyAsync(out, p.pooled, (size_t)G * D * 4, cudaMemcpyDeviceToDevice, s));
+    } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
+      ReadoutPtrs hp;
+      for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
+      const int smem = (2 * kReadoutGB * (rd.max_dim + 1) + rd.max_w) * (int)sizeof(float);
+      static bool attr = false;
+      if (!attr) { GCB_CUDA(cudaFuncSetAttribute(readout_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+      Drop drb = make_drop(c, flags, seed, tag_readout(0));
+      GCB_KERNEL("readout_fwd_kernel", s, readout_fwd_kernel<<<(unsigned)ceil_div(G, kReadoutGB), 256, smem, s>>>(rd, params, hp, out, G, c.act, drb));
     } else {
       for (int k = 0; k < pl.n_lin; ++k) {
         const bool last = k == pl.n_lin - 1;
@@ -448,6 +484,17 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   if (d_out && G > 0) {
     if (pl.n_lin == 0) {
       dPool = d_out;
+    } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
+      ReadoutPtrs hp;
+      for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
+      const int smem = (3 * kReadoutGB * (rd.max_dim + 1) + rd.max_w) * (int)sizeof(float);
+      static bool attr = false;
+      if (!attr) { GCB_CUDA(cudaFuncSetAttribute(readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+      const int blocks = (int)ceil_div(G, kReadoutGB);
+      Drop drb = make_drop(c, flags, seed, tag_readout(0));
+      GCB_KERNEL("readout_bwd_kernel", s, readout_bwd_kernel<<<blocks, 256, smem, s>>>(rd, params, hp, d_out, p.partial, p.dPool, G, c.act, drb));
+      GCB_TRY(launch_reduce_partials(p.partial, blocks, rd.partial_stride, grad + pl.r_w[0], accumulate, s));
+      dPool = p.dPool;
     } else {
       const float* dcur = d_out;
       for (int k = pl.n_lin - 1; k >= 0; --k) {
