@@ -53,13 +53,15 @@ def kernel_alg_bytes(name, N, E, M, G, D, s):
     i4 = 4
     table = {
         "embed_act_kernel": N * i4 + N * D * s,
-        "bond_update_kernel": M * 2 * D * s + (M + E) * i4 + M * D * s,
-        "atom_gather_kernel": (N + M) * D * s + (N + 2 * E) * i4 + N * 2 * D * s,
+        # forward row kernels (per launch)
+        "bond_update_kernel": M * 2 * D * s + 4 * M * i4 + M * D * s + M * D + E * 16,   # PQ in, B' out, tie counts + masks
+        "atom_gather_kernel": N * D * s + 4 * N * i4 + N * D * s,                          # one half per launch: rows in, half of S out
         "pool_kernel": N * D * s + (G + N) * i4 + G * D * 4,
-        "pool_bwd_kernel": G * D * 4 + N * D * s + (G + N) * i4 + N * D * s,
-        "atom_bwd_gather_kernel": 2 * N * D * s + N * D * s + (N + E) * i4 + N * D * s,
-        "bond_bwd_tie_kernel": 4 * M * D * s + (2 * M + E) * i4 + 4 * M * D * s,
-        "bond_bwd_scatter_kernel": 3 * M * D * s + (M + E) * i4 + M * D * s,
+        # backward row kernels
+        "pool_bwd_kernel": G * D * 4 + N * D * s + N * i4 + N * D * s,
+        "atom_bwd_gather_kernel": 3 * N * D * s + 4 * N * i4 + N * D * s,                  # dZA, dS half, A_prev in; dZA_prev out
+        "bond_bwd_tie_kernel": 3 * M * D * s + M * D + 2 * M * i4 + 2 * M * D * s,          # dS half, dBnext, B_l, counts in; dP, g out
+        "bond_bwd_scatter_kernel": M * D * s + E * 16 + 8 * M * i4 + M * D * s,             # g (each row once), masks in; dQ out
         # GEMMs, averaged over the launch shapes of one message step (operands read once, result
         # written once; weights are smem/L2 resident): fwd PQ 3MDs, fwd atom (S + residual + out) 4NDs,
         # bwd dS 3NDs, bwd dB 3MDs;  weight gradients read both operands: 3NDs and 3MDs.
