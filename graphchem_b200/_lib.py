@@ -30,7 +30,9 @@ TRAINING, SAVE_FOR_BWD = 1, 2
 PACK_HEADER_INTS = 32
 (H_MAGIC, H_N, H_E, H_G, H_M, H_AV, H_BV, H_TOTAL_INTS, H_X_TOK, H_E_TOK, H_SRC, H_DST, H_IN_PTR, H_IN_EID,
  H_IN_SRC, H_OUT_PTR, H_OUT_EID, H_OUT_DST, H_GRAPH_PTR, H_GRAPH_NODE, H_ATOK_PTR, H_ATOK_NODE, H_BTOK_PTR,
- H_BTOK_ROW, H_NODE_GRAPH, H_IN_SRC4, H_IN_EID4, H_OUT_DST4, H_OUT_INPOS4, H_OUT_INPOS) = range(30)
+ H_BTOK_ROW, H_NODE_GRAPH, H_IN_SRC4, H_IN_EID4, H_OUT_DST4, H_OUT_INPOS4, H_OUT_INPOS, H_TILE_PTR,
+ H_NTILES) = range(32)
+TILE_ROWS = 128
 PACK_MAGIC = 0x47434231
 MAX_PARAM_TENSORS = 64
 

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "fused_tc.cuh"
 #include "kernels.cuh"
 #include "readout.cuh"
 #include "rowops.cuh"
@@ -47,7 +48,7 @@ void KernelTimer::stop() {
 }
 
 // ---- GEMM dispatch: tcgen05 kernel for bf16 hot shapes, CUDA-core kernel otherwise ---------------
-namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); }
+namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(); }
 template <typename T>
 static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                         const Epilogue& ep, cudaStream_t s) {
@@ -352,7 +353,9 @@ static bool make_readout_desc(const ParamLayout& pl, ReadoutDesc& rd, int G) {
 struct Graph {
   int N, E, G, M;
   const int32_t *x_tok, *e_tok, *src, *dst, *in_ptr, *in_eid, *in_src, *out_ptr, *out_eid, *out_dst, *graph_ptr,
-      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph, *in_src4, *in_eid4, *out_dst4, *out_inpos4, *out_inpos;
+      *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph, *in_src4, *in_eid4, *out_dst4, *out_inpos4, *out_inpos,
+      *tile_ptr;
+  int n_tiles;  // closed row tiles (0: none, use the unfused kernels)
 };
 static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32_t* h, Graph& g) {
   if (!packed || !h || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
@@ -368,6 +371,8 @@ static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32
   g.atok_ptr = packed + h[GCB_H_ATOK_PTR]; g.atok_node = packed + h[GCB_H_ATOK_NODE];
   g.btok_ptr = packed + h[GCB_H_BTOK_PTR]; g.btok_row = packed + h[GCB_H_BTOK_ROW];
   g.node_graph = packed + h[GCB_H_NODE_GRAPH];
+  g.tile_ptr = packed + h[GCB_H_TILE_PTR];
+  g.n_tiles = h[GCB_H_TILE_PTR] > 0 ? h[GCB_H_NTILES] : 0;
   g.in_src4 = packed + h[GCB_H_IN_SRC4]; g.in_eid4 = packed + h[GCB_H_IN_EID4]; g.out_dst4 = packed + h[GCB_H_OUT_DST4]; g.out_inpos4 = packed + h[GCB_H_OUT_INPOS4]; g.out_inpos = packed + h[GCB_H_OUT_INPOS];
   return GCB_OK;
 }
@@ -380,6 +385,15 @@ static inline Drop make_drop(const gcb_model_cfg& c, int flags, uint64_t seed, u
 static inline uint32_t tag_bond(int l) { return 4u * (uint32_t)l; }
 static inline uint32_t tag_atom(int l) { return 4u * (uint32_t)l + 1u; }
 static inline uint32_t tag_readout(int k) { return 100000u + (uint32_t)k; }
+
+// The fused GEMM + message kernels (fused_tc.cuh) take bf16, D = 128, closed row tiles, every atom
+// row a live bond row, and no active dropout; anything else runs on the unfused kernels.
+template <typename T>
+static bool fused_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
+  if constexpr (sizeof(T) != 2) return false;
+  return tc::tc_enabled() && tc::fused_enabled() && c.D == 128 && g.n_tiles > 0 && g.N > 0 && g.M == g.N &&
+         !((flags & GCB_TRAINING) && c.p_dropout > 0.f);
+}
 
 // ---- forward ------------------------------------------------------------------------------------
 template <typename T>
@@ -407,7 +421,22 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
   for (int l = 1; l <= L; ++l) {
     const Drop db = make_drop(c, flags, seed, tag_bond(l));
     const Drop da = make_drop(c, flags, seed, tag_atom(l));
-    if (M > 0) {
+    bool bond_done = false;
+    if constexpr (sizeof(T) == 2) {
+      if (M > 0 && fused_ok<T>(c, g, flags)) {
+        const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
+        tc::FusedArgs fa;
+        fa.tile_ptr = g.tile_ptr; fa.n_tiles = g.n_tiles; fa.rows = M; fa.act = c.act;
+        fa.ptr = g.in_ptr; fa.nbr = g.in_src; fa.nbr4 = (const int4*)g.in_src4;
+        fa.bias = bpq; fa.Bout = (bf16*)p.B[l];
+        fa.tiemask = save ? p.tiemask[l] : nullptr; fa.tiecnt = save ? p.tiecnt[l] : nullptr;
+        const int rc = save ? tc::launch_fused_rows_tc<tc::FUSED_BOND_FWD, true>("fused_bond_fwd_kernel", (const bf16*)p.B[l - 1], (const bf16*)wpq, fa, s)
+                            : tc::launch_fused_rows_tc<tc::FUSED_BOND_FWD, false>("fused_bond_fwd_kernel", (const bf16*)p.B[l - 1], (const bf16*)wpq, fa, s);
+        if (rc == GCB_OK) bond_done = true;
+        else if (rc != GCB_ERR_UNSUPPORTED) return rc;
+      }
+    }
+    if (M > 0 && !bond_done) {
       Epilogue ep;
       ep.bias = bpq; ep.rev = flip();
       GCB_TRY(gemm_nt_auto<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
@@ -567,29 +596,41 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   for (int l = L; l >= 1; --l) {
     const int acc_w = l != L;
     T* dPQ_l = (T*)p.dPQ2[l & 1];
-    static const bool fork_early = std::getenv("GCB_FORK_EARLY") != nullptr;
-    if (fork_early) {
+    bool atom_done = false;
+    if constexpr (sizeof(T) == 2) {
+      if (N > 0 && c.aggr == GCB_AGGR_ADD && fused_ok<T>(c, g, flags)) {
+        GCB_TRY(join(done_at[l + 1]));  // W_at(l+1) read the buffer this layer's dZA_{l-1} goes to
+        tc::FusedArgs fa;
+        fa.tile_ptr = g.tile_ptr; fa.n_tiles = g.n_tiles; fa.rows = N; fa.act = c.act;
+        fa.ptr = g.out_ptr; fa.nbr = g.out_dst; fa.nbr4 = (const int4*)g.out_dst4;
+        fa.dZA = (const bf16*)p.dZA[cur]; fa.A_prev = (const bf16*)p.A[l - 1]; fa.dZA_prev = (bf16*)p.dZA[cur ^ 1];
+        fa.dS = (bf16*)p.dS;
+        const int rc = tc::launch_fused_rows_tc<tc::FUSED_ATOM_BWD, false>("fused_atom_bwd_kernel", (const bf16*)p.dZA[cur], (const bf16*)watT, fa, s);
+        if (rc == GCB_OK) atom_done = true;
+        else if (rc != GCB_ERR_UNSUPPORTED) return rc;
+      }
+    }
+    if (atom_done) {
       GCB_TRY(fork());
       GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
                                 p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0));
       GCB_TRY(mark(done_at[l]));
-    }
-    if (N > 0) {
-      Epilogue ep;
-      ep.rev = flip();
-      GCB_TRY(gemm_nt_auto<T>((const T*)p.dZA[cur], D, watT, D, false, (T*)p.dS, 2 * D, N, 2 * D, D, ep, s));
-    }
-    if (!fork_early) {
+    } else {
+      if (N > 0) {
+        Epilogue ep;
+        ep.rev = flip();
+        GCB_TRY(gemm_nt_auto<T>((const T*)p.dZA[cur], D, watT, D, false, (T*)p.dS, 2 * D, N, 2 * D, D, ep, s));
+      }
       GCB_TRY(fork());
       GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
                                 p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0));
       GCB_TRY(mark(done_at[l]));
-    }
-    GCB_TRY(join(done_at[l + 1]));  // W_at(l+1) read the buffer atom_bwd(l) is about to overwrite
-    if (N > 0) {
-      GCB_TRY(launch_atom_bwd_gather<T>((const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.out_dst4, g.in_ptr, (const T*)p.A[l - 1],
-                                        (T*)p.dZA[cur ^ 1], N, D, c.act, c.aggr,
-                                        l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop(), flip(), s));
+      GCB_TRY(join(done_at[l + 1]));  // W_at(l+1) read the buffer atom_bwd(l) is about to overwrite
+      if (N > 0) {
+        GCB_TRY(launch_atom_bwd_gather<T>((const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.out_dst4, g.in_ptr, (const T*)p.A[l - 1],
+                                          (T*)p.dZA[cur ^ 1], N, D, c.act, c.aggr,
+                                          l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop(), flip(), s));
+      }
     }
     GCB_TRY(join(done_pq[l + 2]));  // W_pq(l+2) read dPQ[l&1]
     if (M > 0) {

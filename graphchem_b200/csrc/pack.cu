@@ -36,6 +36,7 @@ static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, in
   put(GCB_H_IN_SRC4, 4 * (int64_t)N); put(GCB_H_IN_EID4, 4 * (int64_t)N); put(GCB_H_OUT_DST4, 4 * (int64_t)N);
   put(GCB_H_OUT_INPOS4, 4 * (int64_t)N);
   put(GCB_H_OUT_INPOS, E);
+  put(GCB_H_TILE_PTR, (int64_t)N + 1);
   if (off > INT32_MAX) return -1;
   if (h) h[GCB_H_TOTAL_INTS] = (int32_t)off;
   return off;
@@ -106,6 +107,31 @@ static int finish_pack(int32_t* packed, const int32_t* h, const int32_t* batch_i
   }
   bucket(x_tok, N, av, packed + h[GCB_H_ATOK_PTR], packed + h[GCB_H_ATOK_NODE]);
   bucket(e_tok, M, bv, packed + h[GCB_H_BTOK_PTR], packed + h[GCB_H_BTOK_ROW]);
+  {  // closed row tiles: cut positions are the rows no edge spans; greedy fill up to GCB_TILE_ROWS
+    int32_t* tile_ptr = packed + h[GCB_H_TILE_PTR];
+    std::vector<int32_t> span((size_t)N + 2, 0);  // span[p] > 0 after the prefix sum: some edge has lo < p <= hi
+    for (int64_t e = 0; e < E; ++e) {
+      const int32_t lo = src[e] < dst[e] ? src[e] : dst[e], hi = src[e] < dst[e] ? dst[e] : src[e];
+      if (lo < hi) { span[(size_t)lo + 1]++; span[(size_t)hi + 1]--; }
+    }
+    int32_t nt = 0, start = 0, last_cut = 0, cover = 0;
+    bool ok = true;
+    tile_ptr[0] = 0;
+    for (int32_t p = 1; p <= N && ok; ++p) {
+      cover += span[(size_t)p];
+      const bool cut = p == N || cover == 0;
+      if (!cut) continue;
+      if (p - start > GCB_TILE_ROWS) {  // close the tile at the previous cut
+        if (last_cut == start) { ok = false; break; }
+        tile_ptr[++nt] = last_cut;
+        start = last_cut;
+        if (p - start > GCB_TILE_ROWS) { ok = false; break; }
+      }
+      last_cut = p;
+    }
+    if (ok && N > 0) tile_ptr[++nt] = N;
+    packed[GCB_H_NTILES] = ok ? nt : 0;
+  }
   return GCB_OK;
 }
 

@@ -50,6 +50,11 @@ bool tc_enabled() {
   return !(e && e[0] == '1');
 }
 
+bool fused_enabled() {
+  const char* e = std::getenv("GCB_NO_FUSED");
+  return !(e && e[0] == '1');
+}
+
 bool v3_enabled() {
   const char* e = std::getenv("GCB_NO_V3");
   return !(e && e[0] == '1');

@@ -37,6 +37,12 @@ class PackedBatch:
                                           int(header[_lib.H_M]))
 
     @property
+    def n_tiles(self) -> int:
+        """Closed row tiles of at most 128 rows (no edge leaves a tile); 0 = the batch has a component
+        wider than a tile and runs on the unfused kernels."""
+        return int(self.header[_lib.H_NTILES])
+
+    @property
     def device(self) -> torch.device:
         return self.ints.device
 
@@ -67,7 +73,8 @@ class PackedBatch:
             btok_ptr=self.section(L.H_BTOK_PTR, bv + 1), btok_row=self.section(L.H_BTOK_ROW, M),
             node_graph=self.section(L.H_NODE_GRAPH, N), in_src4=self.section(L.H_IN_SRC4, 4 * N),
             in_eid4=self.section(L.H_IN_EID4, 4 * N), out_dst4=self.section(L.H_OUT_DST4, 4 * N),
-            out_inpos4=self.section(L.H_OUT_INPOS4, 4 * N), out_inpos=self.section(L.H_OUT_INPOS, E))
+            out_inpos4=self.section(L.H_OUT_INPOS4, 4 * N), out_inpos=self.section(L.H_OUT_INPOS, E),
+            tile_ptr=self.section(L.H_TILE_PTR, self.n_tiles + 1))
 
 
 def _alloc_ints(n: int, pin: bool) -> Tensor:
@@ -126,6 +133,7 @@ def pack_batch(data, n_messages: int, atom_vocab: int, bond_vocab: int, pin: boo
                                   b_h.data_ptr() if b_h is not None else None, 8, N, E, G, M, atom_vocab, bond_vocab,
                                   1 if n_messages >= 1 else 0, ints.data_ptr(), total)
     _lib.check(rc, "gcb_pack_host")
+    header[:] = ints[:_lib.PACK_HEADER_INTS].numpy()  # the packer fills the data-dependent fields (tile count)
     y = getattr(data, "y", None)
     y = None if y is None else y.detach().to("cpu", torch.float32).contiguous()
     return PackedBatch(ints, header, y)
@@ -184,4 +192,5 @@ class MoleculeStore:
                                               conn_p.ctypes.data, ne.ctypes.data, y_p, nt, G, n_messages, atom_vocab,
                                               bond_vocab, ints.data_ptr(), total, yo_p)
         _lib.check(rc, "gcb_collate_pack_host")
+        header[:] = ints[:_lib.PACK_HEADER_INTS].numpy()
         return PackedBatch(ints, header, y)

@@ -67,6 +67,7 @@ typedef struct gcb_model_cfg {
  */
 #define GCB_PACK_MAGIC 0x47434231 /* "GCB1" */
 #define GCB_PACK_HEADER_INTS 32
+#define GCB_TILE_ROWS 128
 enum gcb_pack_field {
   GCB_H_MAGIC = 0, GCB_H_N, GCB_H_E, GCB_H_G, GCB_H_M, GCB_H_AV, GCB_H_BV, GCB_H_TOTAL_INTS,
   GCB_H_X_TOK, GCB_H_E_TOK, GCB_H_SRC, GCB_H_DST,
@@ -78,6 +79,11 @@ enum gcb_pack_field {
   /* ELL-4 views of the CSRs: first four entries of every row, -1 padded, one int4 per row */
   GCB_H_IN_SRC4, GCB_H_IN_EID4, GCB_H_OUT_DST4, GCB_H_OUT_INPOS4,
   GCB_H_OUT_INPOS, /* [E] for every src-CSR entry: position of the same edge in the dst-CSR */
+  /* Closed row tiles for the fused GEMM + message kernels: tile t covers rows [tile_ptr[t],
+   * tile_ptr[t+1]), at most GCB_TILE_ROWS of them, and no edge leaves a tile (molecules are never
+   * split).  GCB_H_NTILES = 0 when some connected component spans more than GCB_TILE_ROWS rows
+   * (the unfused kernels are used then).  Written by the packer, data dependent. */
+  GCB_H_TILE_PTR, GCB_H_NTILES,
   GCB_H_FIELDS
 };
 

@@ -23,6 +23,31 @@ def stable_buckets(keys: np.ndarray, n_buckets: int):
     return ptr, perm
 
 
+def closed_tiles(src, dst, n_rows, tile_rows=128):
+    """Greedy partition of rows [0, n_rows) into tiles of at most `tile_rows` rows that no edge leaves
+    (a cut at p is legal iff no edge has min(src,dst) < p <= max(src,dst)).  Returns tile_ptr, or [0]
+    when some connected run of rows is wider than a tile."""
+    lo, hi = np.minimum(src, dst).astype(np.int64), np.maximum(src, dst).astype(np.int64)
+    span = np.zeros(n_rows + 2, dtype=np.int64)
+    np.add.at(span, lo[lo < hi] + 1, 1)
+    np.add.at(span, hi[lo < hi] + 1, -1)
+    cover = np.cumsum(span)
+    cuts = [p for p in range(1, n_rows + 1) if p == n_rows or cover[p] == 0]
+    ptr, start, last = [0], 0, 0
+    for p in cuts:
+        if p - start > tile_rows:
+            if last == start:
+                return np.zeros(1, dtype=np.int32)
+            ptr.append(last)
+            start = last
+            if p - start > tile_rows:
+                return np.zeros(1, dtype=np.int32)
+        last = p
+    if n_rows > 0:
+        ptr.append(n_rows)
+    return np.asarray(ptr, dtype=np.int32)
+
+
 def build_index(x_tok, e_tok, edge_index, batch, n_graphs, atom_vocab, bond_vocab, live_rows):
     """All index arrays of a packed batch, as a dict of int32 numpy arrays."""
     x_tok = np.asarray(x_tok).astype(np.int32)
@@ -57,4 +82,5 @@ def build_index(x_tok, e_tok, edge_index, batch, n_graphs, atom_vocab, bond_voca
         graph_ptr=graph_ptr, graph_node=graph_node,
         atok_ptr=atok_ptr, atok_node=atok_node, btok_ptr=btok_ptr, btok_row=btok_row,
         node_graph=np.asarray(batch).astype(np.int32),
+        tile_ptr=closed_tiles(src, dst, N),
     )

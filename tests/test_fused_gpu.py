@@ -1,0 +1,105 @@
+"""-m gpu: the fused tcgen05 GEMM + message kernels (csrc/fused_tc.cuh) against the unfused pipeline.
+
+Both paths round at the same points and sum in the same order, so they must agree BIT FOR BIT:
+predictions, per-atom / per-bond activations and every parameter gradient.  The oracle parity of
+either path is covered by tests/test_parity_gpu.py (which runs the fused path whenever the batch
+has closed row tiles)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import make_pair, nerr, random_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(data):
+    from graphchem_b200.data import Data
+    return Data(x=data.x.cuda(), edge_index=data.edge_index.cuda(), edge_attr=data.edge_attr.cuda(), y=data.y.cuda(),
+                batch=data.batch.cuda(), num_graphs=int(data.batch.max()) + 1)
+
+
+def _run(model, dev, train, fused):
+    os.environ["GCB_NO_FUSED"] = "0" if fused else "1"
+    try:
+        model.train(train)
+        if not train:
+            with torch.no_grad():
+                return [t.clone() for t in model(dev)], None
+        out = model(dev)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        loss = (F.mse_loss(out[0], dev.y) + (out[1].float() * torch.randn(out[1].shape, device="cuda", generator=g)).mean()
+                + (out[2].float() * torch.randn(out[2].shape, device="cuda", generator=g)).mean())
+        model.zero_grad()
+        loss.backward()
+        torch.cuda.synchronize()
+        return [t.detach().clone() for t in out], [p.grad.clone() for p in model.parameters()]
+    finally:
+        os.environ.pop("GCB_NO_FUSED", None)
+
+
+@pytest.mark.parametrize("n_graphs,max_atoms,L", [(1, 12, 1), (7, 12, 2), (64, 30, 3), (700, 40, 4)])
+@pytest.mark.parametrize("act", [F.softplus, F.relu])
+def test_fused_equals_unfused_bitwise(n_graphs, max_atoms, L, act):
+    data, _ = random_batch(seed=n_graphs, n_graphs=n_graphs, max_atoms=max_atoms)
+    _, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=L, act_fn=act)
+    dev = _dev(data)
+    from graphchem_b200.data import pack_batch
+    assert pack_batch(data, L, 12, 7, pin=False).n_tiles > 0
+    for train in (False, True):
+        out_f, grad_f = _run(model, dev, train, fused=True)
+        out_u, grad_u = _run(model, dev, train, fused=False)
+        for k, (a, b) in enumerate(zip(out_f, out_u)):
+            assert torch.equal(a, b), f"output {k} differs (train={train}): max diff {float((a.float() - b.float()).abs().max())}"
+        if train:
+            for (name, _), a, b in zip(model.named_parameters(), grad_f, grad_u):
+                assert torch.equal(a, b), f"grad {name} differs: {nerr(a, b)}"
+
+
+def test_fused_kernels_are_launched_and_relu_ties_match():
+    """The fused kernels must actually run (timing facility lists them), including the tie
+    bookkeeping of the max aggregation (relu makes exact ties common)."""
+    import ctypes as C
+    from graphchem_b200 import _lib
+    data, _ = random_batch(seed=11, n_graphs=200, max_atoms=25)
+    _, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=2, act_fn=F.relu)
+    dev = _dev(data)
+    from graphchem_b200.train import TrainStep
+    pb = model.pack(data).to("cuda")
+    step = TrainStep(model, use_cuda_graph=False)  # forward and backward on this thread (the timing table is thread-local)
+    lib = _lib.lib()
+    lib.gcb_timing_enable(1)
+    try:
+        step(pb)
+        torch.cuda.synchronize()
+    finally:
+        lib.gcb_timing_enable(0)
+    buf = C.create_string_buffer(1 << 16)
+    lib.gcb_timing_report(buf, len(buf))
+    names = buf.value.decode()
+    assert "fused_bond_fwd_kernel" in names and "fused_atom_bwd_kernel" in names, names
+    assert "bond_update_kernel" not in names and "atom_bwd_gather_kernel" not in names, names
+
+
+def test_wide_component_falls_back_to_unfused():
+    """A connected component wider than a tile has no closed tiling: n_tiles == 0 and the unfused
+    kernels run (results still match the oracle within the bf16 bound)."""
+    from graphchem_b200.data import pack_batch
+    from oracle.pyg_restated import Data as OData
+    n = 300  # a 300-atom chain
+    src = torch.arange(n - 1)
+    ei = torch.stack([torch.cat([src, src + 1]), torch.cat([src + 1, src])])
+    g = torch.Generator().manual_seed(0)
+    d = OData(x=torch.randint(2, 12, (n,), generator=g).int(), edge_index=ei,
+              edge_attr=torch.randint(2, 7, (ei.size(1),), generator=g).int(), y=torch.zeros(1, 1))
+    d.batch = torch.zeros(n, dtype=torch.long)
+    assert pack_batch(d, 2, 12, 7, pin=False).n_tiles == 0
+    oracle, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=2)
+    oracle.eval(); model.eval()
+    with torch.no_grad():
+        ro = oracle(d)
+        rm = model(_dev(d))
+    assert nerr(rm[0].float(), ro[0]) <= 2e-2 and nerr(rm[1].float(), ro[1]) <= 2e-2
