@@ -145,6 +145,53 @@ template <typename T> __device__ __forceinline__ float act_grad_t(float y, int a
   if constexpr (sizeof(T) == 2) return act_grad_from_out_fast(y, act); else return act_grad_from_out(y, act);
 }
 
+// Vector forms.  A switch on `act` per ELEMENT compiles to one indirect branch per element and
+// serialises the MUFU latencies; one uniform switch per VECTOR leaves N independent evaluations of
+// straight-line code inside each case.  Same arithmetic per element as the scalar forms.
+template <bool FAST, int N>
+__device__ __forceinline__ void act_fwd_vec_impl(float (&v)[N], int act) {
+#define GCB_ACT_CASE(A)                                                                   \
+  case A: {                                                                               \
+    _Pragma("unroll") for (int i = 0; i < N; ++i) v[i] = FAST ? act_fwd_fast(v[i], A) : act_fwd(v[i], A); \
+    break;                                                                                \
+  }
+  switch (act) {
+    GCB_ACT_CASE(GCB_ACT_SOFTPLUS)
+    GCB_ACT_CASE(GCB_ACT_SIGMOID)
+    GCB_ACT_CASE(GCB_ACT_RELU)
+    GCB_ACT_CASE(GCB_ACT_TANH)
+    default: {
+      _Pragma("unroll") for (int i = 0; i < N; ++i) v[i] = FAST ? act_fwd_fast(v[i], GCB_ACT_LEAKY_RELU) : act_fwd(v[i], GCB_ACT_LEAKY_RELU);
+    }
+  }
+#undef GCB_ACT_CASE
+}
+// d[i] *= act'(y[i]) with y the stored activation output
+template <bool FAST, int N>
+__device__ __forceinline__ void act_grad_mul_vec_impl(float (&d)[N], const float (&y)[N], int act) {
+#define GCB_ACT_CASE(A)                                                                   \
+  case A: {                                                                               \
+    _Pragma("unroll") for (int i = 0; i < N; ++i) d[i] *= FAST ? act_grad_from_out_fast(y[i], A) : act_grad_from_out(y[i], A); \
+    break;                                                                                \
+  }
+  switch (act) {
+    GCB_ACT_CASE(GCB_ACT_SOFTPLUS)
+    GCB_ACT_CASE(GCB_ACT_SIGMOID)
+    GCB_ACT_CASE(GCB_ACT_RELU)
+    GCB_ACT_CASE(GCB_ACT_TANH)
+    default: {
+      _Pragma("unroll") for (int i = 0; i < N; ++i) d[i] *= FAST ? act_grad_from_out_fast(y[i], GCB_ACT_LEAKY_RELU) : act_grad_from_out(y[i], GCB_ACT_LEAKY_RELU);
+    }
+  }
+#undef GCB_ACT_CASE
+}
+template <typename T, int N> __device__ __forceinline__ void act_fwd_vec(float (&v)[N], int act) {
+  act_fwd_vec_impl<sizeof(T) == 2, N>(v, act);
+}
+template <typename T, int N> __device__ __forceinline__ void act_grad_mul_vec(float (&d)[N], const float (&y)[N], int act) {
+  act_grad_mul_vec_impl<sizeof(T) == 2, N>(d, y, act);
+}
+
 // ---- counter-based RNG for dropout (Philox-4x32-10) --------------------------------------------
 // Keyed by (seed, tensor tag) and indexed by the element's linear index, so that the backward pass
 // regenerates the same keep-mask without storing it.

@@ -23,6 +23,7 @@
 #pragma once
 #include "gemm_tc.cuh"
 #include "kernels_v2.cuh"
+#include "tile_rows.cuh"
 
 namespace gcb {
 namespace tc {
@@ -111,6 +112,7 @@ fused_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sTa = smem_u32(sT);  // staged tile, 32-bit shared address (explicit ld/st.shared)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -212,7 +214,7 @@ fused_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
 #pragma unroll
           for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[j4 * 8 + 2 * i], f[j4 * 8 + 2 * i + 1]);
-          *reinterpret_cast<uint4*>(sT + fused_chunk_off(drain_row, (c0 >> 3) + j4)) = t;
+          sts128(sTa + fused_chunk_off(drain_row, (c0 >> 3) + j4), t);
         }
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -229,37 +231,28 @@ fused_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int r = r0 + rr;
           if (r >= r1) continue;
           const int sidx[4] = {n4[ps].x, n4[ps].y, n4[ps].z, n4[ps].w};
-          const uint4 praw = *reinterpret_cast<const uint4*>(sT + fused_chunk_off(rr, lig));
+          const uint4 praw = lds128(sTa + fused_chunk_off(rr, lig));
           uint4 qv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (sidx[u] >= 0) qv[u] = *reinterpret_cast<const uint4*>(sT + fused_chunk_off((sidx[u] - r0) & 127, 16 + lig));
+            if (sidx[u] >= 0) qv[u] = lds128(sTa + fused_chunk_off((sidx[u] - r0) & 127, 16 + lig));
           uint4 mraw = R::neg_inf();
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (sidx[u] >= 0) mraw = R::vmax(mraw, qv[u]);
           for (int e = e0[ps] + 4; e < e1[ps]; ++e)
-            mraw = R::vmax(mraw, *reinterpret_cast<const uint4*>(sT + fused_chunk_off((__ldg(fa.nbr + e) - r0) & 127, 16 + lig)));
+            mraw = R::vmax(mraw, lds128(sTa + fused_chunk_off((__ldg(fa.nbr + e) - r0) & 127, 16 + lig)));
           if (TIES && e1[ps] > e0[ps]) {
-            uint4 craw = R::zero();
+            uint32_t cnt_lo = 0u, cnt_hi = 0u;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              if (sidx[u] >= 0) {
-                R::count_eq(craw, qv[u], mraw);
-                fa.tiemask[(size_t)(e0[ps] + u) * 16 + lig] = (uint8_t)R::eq_bits(qv[u], mraw);
-              }
+              if (sidx[u] >= 0) fa.tiemask[(size_t)(e0[ps] + u) * 16 + lig] = (uint8_t)tile::tie_bits(qv[u], mraw, cnt_lo, cnt_hi);
             }
             for (int e = e0[ps] + 4; e < e1[ps]; ++e) {
-              const uint4 qe = *reinterpret_cast<const uint4*>(sT + fused_chunk_off((__ldg(fa.nbr + e) - r0) & 127, 16 + lig));
-              R::count_eq(craw, qe, mraw);
-              fa.tiemask[(size_t)e * 16 + lig] = (uint8_t)R::eq_bits(qe, mraw);
+              const uint4 qe = lds128(sTa + fused_chunk_off((__ldg(fa.nbr + e) - r0) & 127, 16 + lig));
+              fa.tiemask[(size_t)e * 16 + lig] = (uint8_t)tile::tie_bits(qe, mraw, cnt_lo, cnt_hi);
             }
-            float cf[8];
-            R::to_float(craw, cf);
-            uint2 pk;
-            pk.x = (uint32_t)cf[0] | ((uint32_t)cf[1] << 8) | ((uint32_t)cf[2] << 16) | ((uint32_t)cf[3] << 24);
-            pk.y = (uint32_t)cf[4] | ((uint32_t)cf[5] << 8) | ((uint32_t)cf[6] << 16) | ((uint32_t)cf[7] << 24);
-            *reinterpret_cast<uint2*>(fa.tiecnt + (size_t)r * S::D + c) = pk;
+            *reinterpret_cast<uint2*>(fa.tiecnt + (size_t)r * S::D + c) = make_uint2(cnt_lo, cnt_hi);
           }
           float o[8];
           if (e0[ps] == e1[ps]) {
@@ -271,7 +264,8 @@ fused_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             R::to_float(praw, p);
             R::to_float(mraw, mx);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = act_fwd_t<bf16>(p[i] + mx[i], fa.act);
+            for (int i = 0; i < 8; ++i) o[i] = p[i] + mx[i];
+            act_fwd_vec<bf16, 8>(o, fa.act);
           }
           store_vec(fa.Bout + (size_t)r * S::D + c, o);
         }
@@ -295,10 +289,10 @@ fused_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           uint4 g[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (tidx[u] >= 0) g[u] = *reinterpret_cast<const uint4*>(sT + fused_chunk_off((tidx[u] - r0) & 127, lig));
+            if (tidx[u] >= 0) g[u] = lds128(sTa + fused_chunk_off((tidx[u] - r0) & 127, lig));
           // second half of this row of dS goes to HBM for the bond backward
           *reinterpret_cast<uint4*>(fa.dS + (size_t)r * (2 * S::D) + S::D + c) =
-              *reinterpret_cast<const uint4*>(sT + fused_chunk_off(rr, 16 + lig));
+              lds128(sTa + fused_chunk_off(rr, 16 + lig));
           float d[8], y[8];
           R::to_float(draw[ps], d);
           R::to_float(yraw[ps], y);
@@ -306,9 +300,8 @@ fused_rows_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int u = 0; u < 4; ++u)
             if (tidx[u] >= 0) v2::raw_add<bf16, 8>(g[u], d);
           for (int e = e0[ps] + 4; e < e1[ps]; ++e)
-            v2::raw_fma<bf16, 8>(1.f, *reinterpret_cast<const uint4*>(sT + fused_chunk_off((__ldg(fa.nbr + e) - r0) & 127, lig)), d);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] *= act_grad_t<bf16>(y[i], fa.act);
+            v2::raw_fma<bf16, 8>(1.f, lds128(sTa + fused_chunk_off((__ldg(fa.nbr + e) - r0) & 127, lig)), d);
+          act_grad_mul_vec<bf16, 8>(d, y, fa.act);
           store_vec(fa.dZA_prev + (size_t)r * S::D + c, d);
         }
       }

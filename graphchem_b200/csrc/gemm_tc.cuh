@@ -208,10 +208,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j4 = 0; j4 < 4; ++j4) res_raw[ci][j4] = __ldg(rp_next + ci * 4 + j4);
           }
         }
-        if (ep.act >= 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = act_fwd_fast(f[j], ep.act);
-        }
+        if (ep.act >= 0) act_fwd_vec_impl<true, 32>(f, ep.act);
         // stage as bf16 in the 128B-swizzled layout the TMA store expects
         uint8_t* slab = sOut + (c0 >> 6) * (S::BM * 128) + row_in_tile * 128;
         const int chunk0 = (c0 & 63) >> 3;

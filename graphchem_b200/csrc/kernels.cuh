@@ -42,8 +42,9 @@ __global__ void embed_act_kernel(const float* __restrict__ table, const int32_t*
 #pragma unroll
   for (int i = 0; i < V; i += 4) {
     float4 t = __ldg(reinterpret_cast<const float4*>(src + i));
-    v[i] = act_fwd_t<T>(t.x, act); v[i + 1] = act_fwd_t<T>(t.y, act); v[i + 2] = act_fwd_t<T>(t.z, act); v[i + 3] = act_fwd_t<T>(t.w, act);
+    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
   }
+  act_fwd_vec<T, V>(v, act);
   store_vec(out + (size_t)r * D + c, v);
 }
 
@@ -68,8 +69,7 @@ __device__ __forceinline__ void mul_act_grad(float (&d)[V], const float (&y)[V],
       d[i] = keep ? d[i] * sc * act_grad_from_out(y[i] * un, act) : 0.f;
     }
   } else {
-#pragma unroll
-    for (int i = 0; i < V; ++i) d[i] *= act_grad_from_out(y[i], act);
+    act_grad_mul_vec_impl<false, V>(d, y, act);
   }
 }
 

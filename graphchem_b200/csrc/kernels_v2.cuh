@@ -190,7 +190,8 @@ bond_update_kernel(const T* __restrict__ PQ, const int32_t* __restrict__ in_ptr,
     Raw<T>::to_float(praw, p);
     Raw<T>::to_float(mraw, mx);
 #pragma unroll
-    for (int i = 0; i < V; ++i) o[i] = act_fwd_t<T>(p[i] + mx[i], act);
+    for (int i = 0; i < V; ++i) o[i] = p[i] + mx[i];
+    act_fwd_vec<T, V>(o, act);
   }
   if (DROP) apply_dropout<T, V>(o, dr, (uint64_t)r * D + c);
   store_vec(Bout + (size_t)r * D + c, o);
@@ -299,8 +300,7 @@ atom_bwd_gather_kernel(const T* __restrict__ dZA, const T* __restrict__ dS, cons
   if (DROP) {
     mul_act_grad<V>(d, y, act, dr_prev, (uint64_t)r * D + c);
   } else {
-#pragma unroll
-    for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
+    act_grad_mul_vec<T, V>(d, y, act);
   }
   store_vec(dZA_prev + (size_t)r * D + c, d);
 }
@@ -344,8 +344,7 @@ bond_bwd_tie_kernel(const T* __restrict__ dS, const T* __restrict__ dBnext, cons
     if (DROP) {
       mul_act_grad<V>(d, y, act, dr, (uint64_t)r * D + c);
     } else {
-#pragma unroll
-      for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
+      act_grad_mul_vec<T, V>(d, y, act);
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -422,8 +421,7 @@ pool_bwd_kernel(const float* __restrict__ dPool, const T* __restrict__ d_out_ato
   if (DROP) {
     mul_act_grad<V>(d, y, act, dr, (uint64_t)r * D + c);
   } else {
-#pragma unroll
-    for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
+    act_grad_mul_vec<T, V>(d, y, act);
   }
   store_vec(dZA + (size_t)r * D + c, d);
 }
@@ -453,8 +451,7 @@ embed_bwd_partial_kernel(const T* __restrict__ dZ, const T* __restrict__ Y, cons
     if (Y) {
       float y[V];
       load_vec(Y + (size_t)row * D + c, y);
-#pragma unroll
-      for (int i = 0; i < V; ++i) d[i] *= act_grad_t<T>(y[i], act);
+      act_grad_mul_vec<T, V>(d, y, act);
     }
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] += d[i];

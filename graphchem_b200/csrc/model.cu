@@ -14,6 +14,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "fused_tc.cuh"
+#include "tile_rows.cuh"
 #include "kernels.cuh"
 #include "readout.cuh"
 #include "rowops.cuh"
@@ -48,7 +49,7 @@ void KernelTimer::stop() {
 }
 
 // ---- GEMM dispatch: tcgen05 kernel for bf16 hot shapes, CUDA-core kernel otherwise ---------------
-namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(); }
+namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(); bool tile_enabled(); }
 template <typename T>
 static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                         const Epilogue& ep, cudaStream_t s) {
@@ -395,6 +396,14 @@ static bool fused_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
          !((flags & GCB_TRAINING) && c.p_dropout > 0.f);
 }
 
+// Tile-staged row kernels (tile_rows.cuh): same preconditions, without the tensor-core coupling.
+template <typename T>
+static bool tiles_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
+  if constexpr (sizeof(T) != 2) return false;
+  return tc::tile_enabled() && c.D == 128 && g.n_tiles > 0 && g.N > 0 && g.M == g.N &&
+         !((flags & GCB_TRAINING) && c.p_dropout > 0.f);
+}
+
 // ---- forward ------------------------------------------------------------------------------------
 template <typename T>
 static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Graph& g, const float* params,
@@ -440,11 +449,31 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       Epilogue ep;
       ep.bias = bpq; ep.rev = flip();
       GCB_TRY(gemm_nt_auto<T>((const T*)p.B[l - 1], D, wpq, D, false, (T*)p.PQ[l], 2 * D, M, 2 * D, D, ep, s));
+      bool tiled = false;
+      if constexpr (sizeof(T) == 2) {
+        if (tiles_ok<T>(c, g, flags)) {
+          const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
+          const tile::TileCommon cm{g.tile_ptr, M, g.in_ptr, g.in_src, (const int4*)g.in_src4, nullptr, nullptr};
+          GCB_TRY(tile::launch_bond_update((const bf16*)p.PQ[l], cm, g.n_tiles, (bf16*)p.B[l], save ? p.tiemask[l] : nullptr,
+                                           save ? p.tiecnt[l] : nullptr, c.act, s));
+          tiled = true;
+        }
+      }
+      if (!tiled)
       GCB_TRY(launch_bond_update<T>((const T*)p.PQ[l], g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.B[l],
                                     (flags & GCB_SAVE_FOR_BWD) ? p.tiemask[l] : nullptr,
                                     (flags & GCB_SAVE_FOR_BWD) ? p.tiecnt[l] : nullptr, M, D, c.act, db, flip(), s));
     }
     if (N > 0) {
+      bool a_tiled = false;
+      if constexpr (sizeof(T) == 2) {
+        if (c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags)) {
+          const tile::TileCommon cm{g.tile_ptr, N, g.in_ptr, g.in_src, (const int4*)g.in_src4, (const int4*)g.in_eid4, g.in_eid};
+          GCB_TRY(tile::launch_atom_gather((const bf16*)p.A[l - 1], (const bf16*)p.B[l], M, cm, g.n_tiles, (bf16*)p.S[l], c.act, s));
+          a_tiled = true;
+        }
+      }
+      if (!a_tiled)
       GCB_TRY(launch_atom_gather<T>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, (T*)p.S[l], N, M, D,
                                     c.act, c.aggr, db, flip(), s));
       Epilogue ep;
@@ -626,7 +655,16 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
                                 p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0));
       GCB_TRY(mark(done_at[l]));
       GCB_TRY(join(done_at[l + 1]));  // W_at(l+1) read the buffer atom_bwd(l) is about to overwrite
-      if (N > 0) {
+      bool tiled = false;
+      if constexpr (sizeof(T) == 2) {
+        if (N > 0 && c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags)) {
+          const tile::TileCommon cm{g.tile_ptr, N, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, nullptr, nullptr};
+          GCB_TRY(tile::launch_atom_bwd((const bf16*)p.dS, (const bf16*)p.dZA[cur], (const bf16*)p.A[l - 1], cm, g.n_tiles,
+                                        (bf16*)p.dZA[cur ^ 1], c.act, s));
+          tiled = true;
+        }
+      }
+      if (N > 0 && !tiled) {
         GCB_TRY(launch_atom_bwd_gather<T>((const T*)p.dZA[cur], (const T*)p.dS, g.out_ptr, g.out_dst, g.out_dst4, g.in_ptr, (const T*)p.A[l - 1],
                                           (T*)p.dZA[cur ^ 1], N, D, c.act, c.aggr,
                                           l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop(), flip(), s));
@@ -638,12 +676,21 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
                                      g.dst, g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, dPQ_l, (T*)p.mx, (T*)p.gsplit,
                                      p.tiemask[l], p.tiecnt[l], M, D, c.act, c.aggr,
                                      make_drop(c, flags, seed, tag_bond(l)), flip(), s));
+      bool tiled = false;
+      if constexpr (sizeof(T) == 2) {
+        if (tiles_ok<T>(c, g, flags)) {
+          const tile::TileCommon cm{g.tile_ptr, M, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, (const int4*)g.out_inpos4, g.out_inpos};
+          GCB_TRY(tile::launch_bond_scatter((const bf16*)p.gsplit, cm, g.n_tiles, p.tiemask[l], (bf16*)dPQ_l, s));
+          tiled = true;
+        }
+      }
+      if (!tiled)
       GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, g.out_inpos, g.out_dst4, g.out_inpos4,
                                          p.tiemask[l], dPQ_l, M, D, flip(), s));
     }
     GCB_TRY(fork());
     GCB_TRY(gemm_tn_auto<T>((const T*)dPQ_l, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
-                              p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, sw, flip()));
+                              p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, sw, 0));
     GCB_TRY(mark(done_pq[l]));
     if (M > 0) {
       Epilogue ep;

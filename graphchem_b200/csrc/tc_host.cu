@@ -45,13 +45,42 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
   return 0;
 }
 
+int make_tmap_bf16_plain(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                         int box_cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_cuda_error(cudaErrorNotSupported, __FILE__, __LINE__);
+    return 1;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estride[2] = {1u, 1u};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_cuda_error(cudaErrorInvalidValue, __FILE__, __LINE__);
+    return 1;
+  }
+  return 0;
+}
+
 bool tc_enabled() {
   const char* e = std::getenv("GCB_DISABLE_TC");
   return !(e && e[0] == '1');
 }
 
+// Fused tcgen05 GEMM + message kernels: correct (bit-identical) but, with one CTA per SM, slower than
+// GEMM + tile-staged row kernels on B200; opt-in.
 bool fused_enabled() {
-  const char* e = std::getenv("GCB_NO_FUSED");
+  const char* e = std::getenv("GCB_FUSED_TC");
+  return e && e[0] == '1';
+}
+
+// Tile-staged row kernels (tile_rows.cuh); on unless GCB_NO_TILE=1.
+bool tile_enabled() {
+  const char* e = std::getenv("GCB_NO_TILE");
   return !(e && e[0] == '1');
 }
 

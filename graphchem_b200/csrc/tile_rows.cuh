@@ -1,0 +1,339 @@
+// Tile-staged row kernels (bf16, D = 128): the message-passing gathers out of shared memory.
+//
+// The unfused row kernels (kernels_v2.cuh) chase  index -> neighbour row  through global memory and
+// are bound by that dependent latency at the occupancy their registers allow (25-35 % of HBM
+// bandwidth in the round-1 profiles).  Every neighbour of a row lives in the same molecule, and the
+// packed batch carries CLOSED row tiles (<= 128 rows, no edge leaves a tile; GCB_H_TILE_PTR).  Here
+// one CTA owns one tile: a single thread asks TMA for the tile's operand rows (one or more
+// 128-row boxes, no swizzle: a staged row is 256 contiguous bytes), the threads stage the tile's CSR
+// indices (ELL-4 views + row pointers) in shared memory meanwhile, and after ONE barrier wait all
+// tile-local gathers are shared-memory reads.  16 lanes own a row (16-byte chunks), a warp owns two
+// adjacent rows, so global stores stay coalesced.  CTAs are small (256 threads, <= 64 registers) so
+// that 3-4 of them per SM overlap each other's load and compute phases.
+//
+// Arithmetic, rounding points and summation order are those of the v2 kernels: results are
+// bit-identical (tests/test_fused_gpu.py).
+#pragma once
+#include "kernels_v2.cuh"
+#include "tc_common.cuh"
+
+namespace gcb {
+namespace tc {
+// Row-major bf16 matrix [rows, cols] (leading dimension ld), box = [box_rows x box_cols], no swizzle.
+int make_tmap_bf16_plain(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                         int box_cols);
+}  // namespace tc
+
+namespace tile {
+
+constexpr int kD = 128;
+constexpr int kRows = GCB_TILE_ROWS;              // 128
+constexpr int kThreads = 256;                     // 16 row slots x 16 lanes
+constexpr int kSlots = kThreads / 16;             // rows per pass
+constexpr int kPasses = kRows / kSlots;           // 8
+constexpr int kRowBytes = kD * 2;                 // 256
+constexpr int kBoxBytes = kRows * kRowBytes;      // 32 KB: one staged [128 x 128] bf16 box
+constexpr int kIdxBytes = 2 * kRows * 16 + 544;   // two ELL-4 arrays + 129 row pointers (padded)
+
+using R = v2::Raw<bf16>;
+
+struct TileCommon {
+  const int32_t* tile_ptr;  // [n_tiles + 1]
+  int rows;                 // live rows
+  const int32_t* ptr;       // CSR row pointer of the row phase
+  const int32_t* nbr;       // CSR neighbour rows
+  const int4* nbr4;         // ELL-4 view of nbr
+  const int4* aux4;         // second ELL-4 view walked with the same CSR (edge ids / dst-CSR positions) or null
+  const int32_t* aux;       // CSR form of aux4 (rows with more than four entries) or null
+};
+
+__device__ __forceinline__ uint4 lds16(uint32_t saddr) { return gcb::tc::lds128(saddr); }
+__device__ __forceinline__ int lds32(uint32_t saddr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+
+// Tile prologue: [r0, r1) of this CTA's tile; one thread issues the TMA boxes (ISSUE, BOX_BYTES in
+// total, 0 = none) while all threads stage the indices; ends with everything visible.
+#define GCB_TILE_PROLOGUE(BOX_BYTES, ISSUE)                                                         \
+  extern __shared__ uint8_t smem_raw[];                                                             \
+  const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u; /* 32-bit shared address */   \
+  const uint32_t s_n4 = smem + (BOX_BYTES), s_a4 = s_n4 + kRows * 16, s_ptr = s_a4 + kRows * 16;    \
+  __shared__ uint64_t bar;                                                                          \
+  const int r0 = __ldg(cm.tile_ptr + blockIdx.x);                                                   \
+  const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);                                 \
+  if ((BOX_BYTES) > 0 && threadIdx.x == 0) {                                                        \
+    gcb::tc::mbar_init(&bar, 1);                                                                    \
+    gcb::tc::fence_barrier_init();                                                                  \
+    gcb::tc::mbar_arrive_expect_tx(&bar, (BOX_BYTES));                                              \
+    ISSUE;                                                                                          \
+  }                                                                                                 \
+  for (int i = threadIdx.x; i <= kRows; i += kThreads) {                                            \
+    const int r = r0 + i;                                                                           \
+    if (i < kRows) {                                                                                \
+      int4 v = make_int4(-1, -1, -1, -1), w = v;                                                    \
+      if (r < r1) {                                                                                 \
+        v = __ldg(cm.nbr4 + r);                                                                     \
+        if (cm.aux4) w = __ldg(cm.aux4 + r);                                                        \
+      }                                                                                             \
+      gcb::tc::sts128(s_n4 + i * 16, make_uint4(v.x, v.y, v.z, v.w));                               \
+      gcb::tc::sts128(s_a4 + i * 16, make_uint4(w.x, w.y, w.z, w.w));                               \
+    }                                                                                               \
+    sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);                                          \
+  }                                                                                                 \
+  const int grp = threadIdx.x >> 4, lig = threadIdx.x & 15, c = lig * 8;                            \
+  (void)c; (void)s_a4;                                                                              \
+  __syncthreads(); /* indices staged, barrier initialised */                                        \
+  if ((BOX_BYTES) > 0) gcb::tc::mbar_wait(&bar, 0);
+
+#define GCB_TILE_ROW(PS)                                                                            \
+  const int rr = (PS) * kSlots + grp;                                                               \
+  const int r = r0 + rr;                                                                            \
+  if (r >= r1) continue;                                                                            \
+  const uint4 n4_ = lds16(s_n4 + rr * 16);                                                          \
+  const int nidx[4] = {(int)n4_.x, (int)n4_.y, (int)n4_.z, (int)n4_.w};                             \
+  const int e0 = lds32(s_ptr + rr * 4), e1 = lds32(s_ptr + rr * 4 + 4);
+
+// Tie bookkeeping of the max aggregation on packed words.  q, m: 8 bf16 channels (channel 2i = low
+// half of word i).  Returns bit i = (q_i == m_i) and adds 1 to byte counter i of cnt_lo (channels
+// 0-3) / cnt_hi (channels 4-7); exact up to 255 in-edges per row, like the bf16 counters of the v2
+// kernels.
+__device__ __forceinline__ uint32_t tie_bits(const uint4& q, const uint4& m, uint32_t& cnt_lo, uint32_t& cnt_hi) {
+  auto eqm = [](uint32_t a, uint32_t b) -> uint32_t {  // 0xFFFF per equal half
+    return __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  };
+  // bytes 0/2 of each mask word = lo/hi half flags -> one flag byte per channel
+  const uint32_t f_lo = __byte_perm(eqm(q.x, m.x), eqm(q.y, m.y), 0x6420);  // channels 0,1,2,3
+  const uint32_t f_hi = __byte_perm(eqm(q.z, m.z), eqm(q.w, m.w), 0x6420);  // channels 4,5,6,7
+  cnt_lo += f_lo & 0x01010101u;
+  cnt_hi += f_hi & 0x01010101u;
+  const uint32_t t = (f_lo & 0x08040201u) | (f_hi & 0x80402010u);
+  return (t * 0x01010101u) >> 24;
+}
+
+// ---- bond update: Bout[r] = act(P[r] + max_{e->r} Q[src e]);  staged: [P|Q] rows of the tile (512 B each) ----
+template <bool TIES>
+__global__ void __launch_bounds__(kThreads, 3)
+bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, bf16* __restrict__ Bout,
+                   uint8_t* __restrict__ tiemask, uint8_t* __restrict__ tiecnt, int act) {
+  GCB_TILE_PROLOGUE(2 * kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmPQ, &bar, 0, r0))
+#pragma unroll 2
+  for (int ps = 0; ps < kPasses; ++ps) {
+    GCB_TILE_ROW(ps)
+    const uint4 praw = lds16(smem + rr * (2 * kRowBytes) + lig * 16);
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) q[u] = lds16(smem + ((nidx[u] - r0) & 127) * (2 * kRowBytes) + kRowBytes + lig * 16);
+    uint4 mraw = R::neg_inf();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) mraw = R::vmax(mraw, q[u]);
+    for (int e = e0 + 4; e < e1; ++e)
+      mraw = R::vmax(mraw, lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * (2 * kRowBytes) + kRowBytes + lig * 16));
+    if (TIES && e1 > e0) {
+      // per in-edge: which of the 8 channels attain the max (one byte); per channel: how many edges tie
+      uint32_t cnt_lo = 0u, cnt_hi = 0u;  // four byte counters each: channels 0-3 / 4-7
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (nidx[u] >= 0) tiemask[(size_t)(e0 + u) * 16 + lig] = (uint8_t)tie_bits(q[u], mraw, cnt_lo, cnt_hi);
+      }
+      for (int e = e0 + 4; e < e1; ++e) {
+        const uint4 qe = lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * (2 * kRowBytes) + kRowBytes + lig * 16);
+        tiemask[(size_t)e * 16 + lig] = (uint8_t)tie_bits(qe, mraw, cnt_lo, cnt_hi);
+      }
+      *reinterpret_cast<uint2*>(tiecnt + (size_t)r * kD + c) = make_uint2(cnt_lo, cnt_hi);
+    }
+    float o[8];
+    if (e0 == e1) {
+      const float z = act_fwd_t<bf16>(0.f, act);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = z;
+    } else {
+      float p[8], mx[8];
+      R::to_float(praw, p);
+      R::to_float(mraw, mx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = p[i] + mx[i];
+      act_fwd_vec<bf16, 8>(o, act);
+    }
+    store_vec(Bout + (size_t)r * kD + c, o);
+  }
+}
+
+// ---- atom aggregation: S[i] = [ sum_{e->i} A[src e] | sum_{e->i} Bnew[eid e] ]  (Bnew[e >= M] = act(0)) ----
+// staged: A rows of the tile (neighbours are tile-local); the bond rows are addressed by EDGE id and
+// live in other tiles, so they are gathered from global memory, issued before the shared-memory half.
+__global__ void __launch_bounds__(kThreads, 4)
+atom_gather_kernel(const __grid_constant__ CUtensorMap tmA, TileCommon cm, const bf16* __restrict__ Bnew, int M,
+                   bf16* __restrict__ S, int act) {
+  GCB_TILE_PROLOGUE(kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmA, &bar, 0, r0))
+  const float cst = round_to(act_fwd_t<bf16>(0.f, act), (const bf16*)nullptr);
+#pragma unroll 2
+  for (int ps = 0; ps < kPasses; ++ps) {
+    GCB_TILE_ROW(ps)
+    const uint4 e4_ = lds16(s_a4 + rr * 16);
+    const int eidx[4] = {(int)e4_.x, (int)e4_.y, (int)e4_.z, (int)e4_.w};
+    uint4 b[4], a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (eidx[u] >= 0 && eidx[u] < M) b[u] = R::load(Bnew + (size_t)eidx[u] * kD + c);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) a[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
+    float sa[8], sb[8];
+    v2::vzero<bf16, 8>(sa);
+    v2::vzero<bf16, 8>(sb);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) v2::raw_add<bf16, 8>(a[u], sa);
+    for (int e = e0 + 4; e < e1; ++e)
+      v2::raw_add<bf16, 8>(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16), sa);
+    store_vec(S + (size_t)r * (2 * kD) + c, sa);
+    auto add_const = [&]() {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sb[i] += cst;
+    };
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (eidx[u] >= 0) {
+        if (eidx[u] < M) v2::raw_add<bf16, 8>(b[u], sb);
+        else add_const();
+      }
+    }
+    for (int e = e0 + 4; e < e1; ++e) {
+      const int eid = __ldg(cm.aux + e);
+      if (eid < M) v2::raw_add<bf16, 8>(R::load(Bnew + (size_t)eid * kD + c), sb);
+      else add_const();
+    }
+    store_vec(S + (size_t)r * (2 * kD) + kD + c, sb);
+  }
+}
+
+// ---- atom backward: dZA_prev[j] = (dZA[j] + sum_{e: src e = j} dS[dst e, :D]) * act'(A_prev[j]) ----
+// staged: dS[:, :D] rows of the tile (neighbours); the row's own dZA / A_prev chunks stream from global.
+__global__ void __launch_bounds__(kThreads, 4)
+atom_bwd_kernel(const __grid_constant__ CUtensorMap tmdS, TileCommon cm, const bf16* __restrict__ dZA,
+                const bf16* __restrict__ A_prev, bf16* __restrict__ dZA_prev, int act) {
+  GCB_TILE_PROLOGUE(kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmdS, &bar, 0, r0))
+#pragma unroll 2
+  for (int ps = 0; ps < kPasses; ++ps) {
+    GCB_TILE_ROW(ps)
+    const uint4 draw = R::load(dZA + (size_t)r * kD + c);
+    const uint4 yraw = R::load(A_prev + (size_t)r * kD + c);
+    uint4 g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) g[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
+    float d[8], y[8];
+    R::to_float(draw, d);
+    R::to_float(yraw, y);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) v2::raw_add<bf16, 8>(g[u], d);
+    for (int e = e0 + 4; e < e1; ++e)
+      v2::raw_fma<bf16, 8>(1.f, lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16), d);
+    act_grad_mul_vec<bf16, 8>(d, y, act);
+    store_vec(dZA_prev + (size_t)r * kD + c, d);
+  }
+}
+
+// ---- bond backward, source side: dQ[j] = sum_{e: src e = j} tie(e) * gsplit[dst e];  staged: gsplit rows ----
+// tie bits come from tiemask[dst-CSR position of e] (global; 16 contiguous bytes per edge).
+__global__ void __launch_bounds__(kThreads, 4)
+bond_scatter_kernel(const __grid_constant__ CUtensorMap tmG, TileCommon cm, const uint8_t* __restrict__ tiemask,
+                    bf16* __restrict__ dPQ) {
+  GCB_TILE_PROLOGUE(kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmG, &bar, 0, r0))
+#pragma unroll 2
+  for (int ps = 0; ps < kPasses; ++ps) {
+    GCB_TILE_ROW(ps)
+    const uint4 o4_ = lds16(s_a4 + rr * 16);
+    const int oidx[4] = {(int)o4_.x, (int)o4_.y, (int)o4_.z, (int)o4_.w};
+    uint4 g[4];
+    uint32_t bits[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (nidx[u] >= 0) {
+        bits[u] = __ldg(tiemask + (size_t)oidx[u] * 16 + lig);
+        g[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
+      }
+    }
+    float acc[8];
+    v2::vzero<bf16, 8>(acc);
+    auto consume = [&](const uint4& gr, uint32_t b) {
+      float gf[8];
+      R::to_float(gr, gf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += ((b >> i) & 1u) ? gf[i] : 0.f;
+    };
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) consume(g[u], bits[u]);
+    for (int e = e0 + 4; e < e1; ++e)
+      consume(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16),
+              __ldg(tiemask + (size_t)__ldg(cm.aux + e) * 16 + lig));
+    store_vec(dPQ + (size_t)r * (2 * kD) + kD + c, acc);
+  }
+}
+
+// ---- launchers ----------------------------------------------------------------------------------
+inline int smem_for(int boxes) { return boxes * kBoxBytes + kIdxBytes + 128; }
+
+template <typename K>
+inline int set_smem(K kernel, int bytes) {
+  GCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return GCB_OK;
+}
+
+inline int launch_bond_update(const bf16* PQ, const TileCommon& cm, int n_tiles, bf16* Bout, uint8_t* tiemask,
+                              uint8_t* tiecnt, int act, cudaStream_t s) {
+  CUtensorMap tm;
+  if (gcb::tc::make_tmap_bf16_plain(&tm, PQ, cm.rows, 2 * kD, 2 * kD, kRows, 2 * kD)) return GCB_ERR_CUDA;
+  const int smem = smem_for(2);
+  static bool attr = false;
+  if (!attr) { GCB_TRY(set_smem(bond_update_kernel<true>, smem)); GCB_TRY(set_smem(bond_update_kernel<false>, smem)); attr = true; }
+  if (tiemask) {
+    GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<true><<<n_tiles, kThreads, smem, s>>>(tm, cm, Bout, tiemask, tiecnt, act)));
+  } else {
+    GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<false><<<n_tiles, kThreads, smem, s>>>(tm, cm, Bout, tiemask, tiecnt, act)));
+  }
+  return GCB_OK;
+}
+
+inline int launch_atom_gather(const bf16* A, const bf16* Bnew, int M, const TileCommon& cm, int n_tiles, bf16* S, int act,
+                              cudaStream_t s) {
+  CUtensorMap tm;
+  if (gcb::tc::make_tmap_bf16_plain(&tm, A, cm.rows, kD, kD, kRows, kD)) return GCB_ERR_CUDA;
+  const int smem = smem_for(1);
+  static bool attr = false;
+  if (!attr) { GCB_TRY(set_smem(atom_gather_kernel, smem)); attr = true; }
+  GCB_KERNEL("tile_atom_gather_kernel", s, (atom_gather_kernel<<<n_tiles, kThreads, smem, s>>>(tm, cm, Bnew, M, S, act)));
+  return GCB_OK;
+}
+
+inline int launch_atom_bwd(const bf16* dS, const bf16* dZA, const bf16* A_prev, const TileCommon& cm, int n_tiles,
+                           bf16* dZA_prev, int act, cudaStream_t s) {
+  CUtensorMap tmS;
+  if (gcb::tc::make_tmap_bf16_plain(&tmS, dS, cm.rows, kD, 2 * kD, kRows, kD)) return GCB_ERR_CUDA;
+  const int smem = smem_for(1);
+  static bool attr = false;
+  if (!attr) { GCB_TRY(set_smem(atom_bwd_kernel, smem)); attr = true; }
+  GCB_KERNEL("tile_atom_bwd_kernel", s, (atom_bwd_kernel<<<n_tiles, kThreads, smem, s>>>(tmS, cm, dZA, A_prev, dZA_prev, act)));
+  return GCB_OK;
+}
+
+inline int launch_bond_scatter(const bf16* gsplit, const TileCommon& cm, int n_tiles, const uint8_t* tiemask, bf16* dPQ,
+                               cudaStream_t s) {
+  CUtensorMap tm;
+  if (gcb::tc::make_tmap_bf16_plain(&tm, gsplit, cm.rows, kD, kD, kRows, kD)) return GCB_ERR_CUDA;
+  const int smem = smem_for(1);
+  static bool attr = false;
+  if (!attr) { GCB_TRY(set_smem(bond_scatter_kernel, smem)); attr = true; }
+  GCB_KERNEL("tile_bond_scatter_kernel", s, (bond_scatter_kernel<<<n_tiles, kThreads, smem, s>>>(tm, cm, tiemask, dPQ)));
+  return GCB_OK;
+}
+
+}  // namespace tile
+}  // namespace gcb

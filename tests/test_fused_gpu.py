@@ -1,6 +1,8 @@
-"""-m gpu: the fused tcgen05 GEMM + message kernels (csrc/fused_tc.cuh) against the unfused pipeline.
+"""-m gpu: the tile-staged row kernels (csrc/tile_rows.cuh, default when the batch has closed row
+tiles) and the opt-in fused tcgen05 GEMM + message kernels (csrc/fused_tc.cuh, GCB_FUSED_TC=1)
+against the plain row kernels (kernels_v2.cuh, GCB_NO_TILE=1).
 
-Both paths round at the same points and sum in the same order, so they must agree BIT FOR BIT:
+All paths round at the same points and sum in the same order, so they must agree BIT FOR BIT:
 predictions, per-atom / per-bond activations and every parameter gradient.  The oracle parity of
 either path is covered by tests/test_parity_gpu.py (which runs the fused path whenever the batch
 has closed row tiles)."""
@@ -22,8 +24,11 @@ def _dev(data):
                 batch=data.batch.cuda(), num_graphs=int(data.batch.max()) + 1)
 
 
-def _run(model, dev, train, fused):
-    os.environ["GCB_NO_FUSED"] = "0" if fused else "1"
+ENV = {"tile": {}, "fused": {"GCB_FUSED_TC": "1"}, "v2": {"GCB_NO_TILE": "1"}}
+
+
+def _run(model, dev, train, mode):
+    os.environ.update(ENV[mode])
     try:
         model.train(train)
         if not train:
@@ -38,20 +43,22 @@ def _run(model, dev, train, fused):
         torch.cuda.synchronize()
         return [t.detach().clone() for t in out], [p.grad.clone() for p in model.parameters()]
     finally:
-        os.environ.pop("GCB_NO_FUSED", None)
+        for k in ENV[mode]:
+            os.environ.pop(k, None)
 
 
 @pytest.mark.parametrize("n_graphs,max_atoms,L", [(1, 12, 1), (7, 12, 2), (64, 30, 3), (700, 40, 4)])
 @pytest.mark.parametrize("act", [F.softplus, F.relu])
-def test_fused_equals_unfused_bitwise(n_graphs, max_atoms, L, act):
+@pytest.mark.parametrize("mode", ["tile", "fused"])
+def test_fused_equals_unfused_bitwise(n_graphs, max_atoms, L, act, mode):
     data, _ = random_batch(seed=n_graphs, n_graphs=n_graphs, max_atoms=max_atoms)
     _, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=L, act_fn=act)
     dev = _dev(data)
     from graphchem_b200.data import pack_batch
     assert pack_batch(data, L, 12, 7, pin=False).n_tiles > 0
     for train in (False, True):
-        out_f, grad_f = _run(model, dev, train, fused=True)
-        out_u, grad_u = _run(model, dev, train, fused=False)
+        out_f, grad_f = _run(model, dev, train, mode)
+        out_u, grad_u = _run(model, dev, train, "v2")
         for k, (a, b) in enumerate(zip(out_f, out_u)):
             assert torch.equal(a, b), f"output {k} differs (train={train}): max diff {float((a.float() - b.float()).abs().max())}"
         if train:
@@ -71,17 +78,29 @@ def test_fused_kernels_are_launched_and_relu_ties_match():
     pb = model.pack(data).to("cuda")
     step = TrainStep(model, use_cuda_graph=False)  # forward and backward on this thread (the timing table is thread-local)
     lib = _lib.lib()
-    lib.gcb_timing_enable(1)
-    try:
-        step(pb)
-        torch.cuda.synchronize()
-    finally:
-        lib.gcb_timing_enable(0)
-    buf = C.create_string_buffer(1 << 16)
-    lib.gcb_timing_report(buf, len(buf))
-    names = buf.value.decode()
+
+    def kernels_of_a_step(env):
+        os.environ.update(env)
+        lib.gcb_timing_enable(1)
+        try:
+            step(pb)
+            torch.cuda.synchronize()
+        finally:
+            lib.gcb_timing_enable(0)
+            for k in env:
+                os.environ.pop(k, None)
+        buf = C.create_string_buffer(1 << 16)
+        lib.gcb_timing_report(buf, len(buf))
+        return buf.value.decode()
+
+    names = kernels_of_a_step({})
+    for k in ("tile_bond_update_kernel", "tile_atom_gather_kernel", "tile_atom_bwd_kernel", "tile_bond_scatter_kernel"):
+        assert k in names, (k, names)
+    for k in ('"bond_update_kernel"', '"atom_gather_kernel"', "atom_bwd_gather_kernel", "bond_bwd_scatter_kernel"):
+        assert k not in names, (k, names)
+    names = kernels_of_a_step({"GCB_FUSED_TC": "1"})
     assert "fused_bond_fwd_kernel" in names and "fused_atom_bwd_kernel" in names, names
-    assert "bond_update_kernel" not in names and "atom_bwd_gather_kernel" not in names, names
+    assert "tile_bond_update_kernel" not in names and "tile_atom_bwd_kernel" not in names, names
 
 
 def test_wide_component_falls_back_to_unfused():
