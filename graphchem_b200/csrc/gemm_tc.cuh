@@ -310,7 +310,7 @@ template <int NN, int KK>
 __global__ void __launch_bounds__(192, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int rows,
                   float* __restrict__ partial, int want_bias_i, const int32_t* __restrict__ rowptr,
-                  int aggr, int rev) {
+                  int aggr, int rev, int acc_partial) {
   using S = TnShape<NN, KK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -434,7 +434,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float tot = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) tot += red_s[k * 128 + t];
-      cta_partial[NN * KK + t] = tot;
+      cta_partial[NN * KK + t] = acc_partial ? cta_partial[NN * KK + t] + tot : tot;
 #pragma unroll
       for (int i = 1; i < NN / 128; ++i) cta_partial[NN * KK + i * 128 + t] = 0.f;
     }
@@ -451,10 +451,19 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + mb * KK + c0, v);
         tmem_ld_wait();
         float4* o = reinterpret_cast<float4*>(out + (size_t)m * KK + c0);
+        if (acc_partial) {  // keep summing this CTA's partial across launches (layers); one reduction at the end
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                             __uint_as_float(v[4 * j + 3]));
+          for (int j = 0; j < 8; ++j) {
+            const float4 old = o[j];
+            o[j] = make_float4(old.x + __uint_as_float(v[4 * j]), old.y + __uint_as_float(v[4 * j + 1]),
+                               old.z + __uint_as_float(v[4 * j + 2]), old.w + __uint_as_float(v[4 * j + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+        }
       }
     }
   }
@@ -467,7 +476,8 @@ constexpr int kTnMaxCtas = kNumSMs;
 
 template <int NN, int KK>
 inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb, int rows, float* partial,
-                                  bool want_bias, const int32_t* rowptr, int aggr, int rev, int* grid_out, cudaStream_t s) {
+                                  bool want_bias, const int32_t* rowptr, int aggr, int rev, int* grid_out, cudaStream_t s,
+                                  int acc_partial) {
   using S = TnShape<NN, KK>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -482,19 +492,19 @@ inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb
   grid = (num_tiles + per - 1) / per;  // every CTA owns at least one tile
   *grid_out = grid;
   GCB_KERNEL("gemm_tn_tc_kernel", s, gemm_tn_tc_kernel<NN, KK><<<grid, S::THREADS, S::SMEM_BYTES, s>>>(
-      tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr, rev));
+      tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr, rev, acc_partial));
   return GCB_OK;
 }
 
 // Writes per-CTA partial blocks [grid][NN*KK (+ NN bias sums)] and reports the CTA count.
 inline int launch_gemm_tn_tc(const bf16* A, int lda, const bf16* B, int ldb, int rows, int NN, int KK, float* partial,
                              bool want_bias, const int32_t* rowptr, int aggr, int rev, int* grid_out,
-                             cudaStream_t s) {
+                             cudaStream_t s, int acc_partial = 0) {
   if (rows < 128) return GCB_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) return GCB_ERR_UNSUPPORTED;
   if (lda % 8 || ldb % 8) return GCB_ERR_UNSUPPORTED;
-  if (NN == 128 && KK == 256) return launch_gemm_tn_tc_impl<128, 256>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, rev, grid_out, s);
-  if (NN == 256 && KK == 128) return launch_gemm_tn_tc_impl<256, 128>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, rev, grid_out, s);
+  if (NN == 128 && KK == 256) return launch_gemm_tn_tc_impl<128, 256>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, rev, grid_out, s, acc_partial);
+  if (NN == 256 && KK == 128) return launch_gemm_tn_tc_impl<256, 128>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, rev, grid_out, s, acc_partial);
   return GCB_ERR_UNSUPPORTED;
 }
 

@@ -49,7 +49,7 @@ void KernelTimer::stop() {
 }
 
 // ---- GEMM dispatch: tcgen05 kernel for bf16 hot shapes, CUDA-core kernel otherwise ---------------
-namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(); bool tile_enabled(); }
+namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(); bool tile_enabled(); bool bond_bwd_merged_enabled(); }
 template <typename T>
 static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                         const Epilogue& ep, cudaStream_t s) {
@@ -65,14 +65,25 @@ static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* 
   return launch_gemm_nt<T>(A, lda, W, ldw, w_kn, C, ldc, M, N, K, ep, s);
 }
 
+// `defer_partial` (tcgen05 path only): keep this GEMM's per-CTA partials in that buffer, summed across
+// calls (`defer_first` starts a new sum), and report the CTA count in *defer_grid; the caller runs ONE
+// ordered reduction after the last call instead of one per call.  *defer_grid stays 0 when the
+// CUDA-core path (which reduces immediately into dW/db with `accumulate`) had to take the call.
 template <typename T>
 static int gemm_tn_auto(const T* A, int lda, const T* B, int ldb, int rows, int Nn, int Kk, float* partial, float* dW,
-                        float* db, const int32_t* rowptr, int aggr, int accumulate, cudaStream_t s, int rev = 0) {
+                        float* db, const int32_t* rowptr, int aggr, int accumulate, cudaStream_t s, int rev = 0,
+                        float* defer_partial = nullptr, int* defer_grid = nullptr, int defer_first = 1) {
   if constexpr (sizeof(T) == 2) {
     if (tc::tc_enabled()) {
       int grid = 0;
-      const int rc = tc::launch_gemm_tn_tc(A, lda, B, ldb, rows, Nn, Kk, partial, db != nullptr, rowptr, aggr, rev, &grid, s);
+      // measured on B200 (batch 8192): the read-modify-write of the partials costs more than the reductions it
+      // saves (1.867 vs 1.852 ms/step), so this stays opt-in
+      static const bool defer_on = std::getenv("GCB_TN_DEFER") && std::getenv("GCB_TN_DEFER")[0] == '1';
+      const bool defer = defer_on && defer_partial != nullptr && defer_grid != nullptr && db != nullptr && db == dW + (int64_t)Nn * Kk;
+      const int rc = tc::launch_gemm_tn_tc(A, lda, B, ldb, rows, Nn, Kk, defer ? defer_partial : partial, db != nullptr, rowptr,
+                                           aggr, rev, &grid, s, defer && !defer_first ? 1 : 0);
       if (rc == GCB_OK) {
+        if (defer) { *defer_grid = grid; return GCB_OK; }
         const int64_t wcount = (int64_t)Nn * Kk, stride = wcount + (db ? Nn : 0);
         if (db && db == dW + wcount) {  // weight and bias accumulators are contiguous: one ordered reduction
           GCB_TRY(launch_reduce_partials(partial, grid, stride, dW, accumulate, s, stride));
@@ -261,6 +272,7 @@ struct Plan {
   float* dH[2];
   float* dPool = nullptr;
   float* partial = nullptr;
+  float *partialAt = nullptr, *partialPq = nullptr;  // per-CTA partials of the two conv weight gradients, summed over layers
   float *accWpq = nullptr, *accBpq = nullptr, *accWat = nullptr, *accBat = nullptr;
 };
 
@@ -318,6 +330,8 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
     const int64_t vmax = c.atom_vocab > c.bond_vocab ? c.atom_vocab : c.bond_vocab;
     if (kEmbedSplits * vmax * D > pf) pf = kEmbedSplits * vmax * D;
     p.partial = (float*)take(pf * 4);
+    p.partialAt = (float*)take((int64_t)tc::kTnMaxCtas * (2 * D * D + 2 * D) * 4);
+    p.partialPq = (float*)take((int64_t)tc::kTnMaxCtas * (2 * D * D + 2 * D) * 4);
     // weight accumulator immediately followed by its bias accumulator (one reduction covers both)
     p.accWpq = (float*)take((2 * D * D + 2 * D) * 4);
     p.accBpq = p.accWpq + 2 * D * D;
@@ -331,7 +345,8 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
 // The fused readout kernels win in the latency regime (a few CTAs instead of ~13 launches); for large
 // batches the tiled GEMM path is faster, so the fused path is used up to 1024 graphs.
 static bool make_readout_desc(const ParamLayout& pl, ReadoutDesc& rd, int G) {
-  if (pl.n_lin <= 0 || pl.n_lin > kReadoutMaxLin || G > 1024) return false;
+  static const int fused_max = std::getenv("GCB_READOUT_FUSED_MAX") ? std::atoi(std::getenv("GCB_READOUT_FUSED_MAX")) : 1024;
+  if (pl.n_lin <= 0 || pl.n_lin > kReadoutMaxLin || G > fused_max) return false;
   rd.n_lin = pl.n_lin;
   rd.max_dim = 0;
   for (int k = 0; k < pl.n_lin; ++k) {
@@ -622,6 +637,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     if (overlap && e) GCB_CUDA(cudaStreamWaitEvent(s, e, 0));
     return GCB_OK;
   };
+  int grid_at = 0, grid_pq = 0;  // > 0: partials deferred in p.partialAt / p.partialPq
   for (int l = L; l >= 1; --l) {
     const int acc_w = l != L;
     T* dPQ_l = (T*)p.dPQ2[l & 1];
@@ -642,7 +658,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     if (atom_done) {
       GCB_TRY(fork());
       GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
-                                p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0));
+                                p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0, p.partialAt, &grid_at, l == L));
       GCB_TRY(mark(done_at[l]));
     } else {
       if (N > 0) {
@@ -652,7 +668,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       }
       GCB_TRY(fork());
       GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
-                                p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0));
+                                p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0, p.partialAt, &grid_at, l == L));
       GCB_TRY(mark(done_at[l]));
       GCB_TRY(join(done_at[l + 1]));  // W_at(l+1) read the buffer atom_bwd(l) is about to overwrite
       bool tiled = false;
@@ -671,7 +687,17 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       }
     }
     GCB_TRY(join(done_pq[l + 2]));  // W_pq(l+2) read dPQ[l&1]
-    if (M > 0) {
+    bool bond_tiled = false;
+    if constexpr (sizeof(T) == 2) {
+      if (M > 0 && c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags) && tc::bond_bwd_merged_enabled()) {
+        const tile::TileCommon cm{g.tile_ptr, M, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, (const int4*)g.out_inpos4, g.out_inpos};
+        GCB_TRY(tile::launch_bond_bwd(cm, g.n_tiles, g.in_ptr, g.dst, (const bf16*)p.dS, (const bf16*)dBnext,
+                                      l == L ? (const bf16*)d_out_bond : nullptr, (const bf16*)p.B[l], p.tiecnt[l], p.tiemask[l],
+                                      (bf16*)dPQ_l, c.act, s));
+        bond_tiled = true;
+      }
+    }
+    if (M > 0 && !bond_tiled) {
       GCB_TRY(launch_bond_bwd_tie<T>((const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l],
                                      g.dst, g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, dPQ_l, (T*)p.mx, (T*)p.gsplit,
                                      p.tiemask[l], p.tiecnt[l], M, D, c.act, c.aggr,
@@ -690,7 +716,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     }
     GCB_TRY(fork());
     GCB_TRY(gemm_tn_auto<T>((const T*)dPQ_l, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
-                              p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, sw, 0));
+                              p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, sw, 0, p.partialPq, &grid_pq, l == L));
     GCB_TRY(mark(done_pq[l]));
     if (M > 0) {
       Epilogue ep;
@@ -701,6 +727,8 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     }
     cur ^= 1;
   }
+  if (grid_at > 0) GCB_TRY(launch_reduce_partials(p.partialAt, grid_at, (int64_t)2 * D * D + D, p.accWat, 0, sw, (int64_t)2 * D * D + D));
+  if (grid_pq > 0) GCB_TRY(launch_reduce_partials(p.partialPq, grid_pq, (int64_t)2 * D * D + 2 * D, p.accWpq, 0, sw, (int64_t)2 * D * D + 2 * D));
   if (overlap && L >= 1) {  // everything on the side stream must be done before its results are used
     cudaEvent_t last = nullptr;
     GCB_TRY(mark(last));

@@ -84,6 +84,12 @@ bool tile_enabled() {
   return !(e && e[0] == '1');
 }
 
+// One tile kernel for both sides of the bond backward (GCB_NO_BOND_MERGE=1: tie kernel + tile scatter).
+bool bond_bwd_merged_enabled() {
+  const char* e = std::getenv("GCB_NO_BOND_MERGE");
+  return !(e && e[0] == '1');
+}
+
 bool v3_enabled() {
   const char* e = std::getenv("GCB_NO_V3");
   return !(e && e[0] == '1');

@@ -278,6 +278,114 @@ bond_scatter_kernel(const __grid_constant__ CUtensorMap tmG, TileCommon cm, cons
   }
 }
 
+// ---- bond backward, both sides in one pass over the tile -------------------------------------------
+//   phase 1 (destination side, = v2::bond_bwd_tie_kernel):
+//       dzb[r] = (dS[dst r, D:2D] + dBnext[r] + d_out_bond[r]) * act'(B_l[r])      (0 when r has no in-edge)
+//       dPQ[r, :D] = dzb[r]  (= dP);   g[r] = dzb[r] / tie count   -> shared memory (bf16, as gsplit would be)
+//   phase 2 (source side, = bond_scatter_kernel):
+//       dPQ[j, D:] = sum_{e: src e = j} tie(e) * g[dst e]          (dst e is tile-local)
+// The split gradient never goes to HBM.  `dst` is the edge list's destination array: bond row r is
+// EDGE r, and it collects the gradient of the atom it points to (gcn.py:163 quirk).
+__global__ void __launch_bounds__(kThreads, 4)
+bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ dst,
+                const bf16* __restrict__ dS, const bf16* __restrict__ dBnext, const bf16* __restrict__ d_out_bond,
+                const bf16* __restrict__ B_l, const uint8_t* __restrict__ tiecnt, const uint8_t* __restrict__ tiemask,
+                bf16* __restrict__ dPQ, int act) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u;  // g tile [128][256 B]
+  const uint32_t s_n4 = smem + kBoxBytes, s_a4 = s_n4 + kRows * 16, s_ptr = s_a4 + kRows * 16;
+  const uint32_t s_dst = s_ptr + 544;  // [128] destination atom of bond row r, or -1 when r has no in-edge
+  const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
+  const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
+  for (int i = threadIdx.x; i <= kRows; i += kThreads) {
+    const int r = r0 + i;
+    if (i < kRows) {
+      int4 v = make_int4(-1, -1, -1, -1), w = v;
+      int t = -1;
+      if (r < r1) {
+        v = __ldg(cm.nbr4 + r);
+        w = __ldg(cm.aux4 + r);
+        if (__ldg(in_ptr + r + 1) > __ldg(in_ptr + r)) t = __ldg(dst + r);
+      }
+      gcb::tc::sts128(s_n4 + i * 16, make_uint4(v.x, v.y, v.z, v.w));
+      gcb::tc::sts128(s_a4 + i * 16, make_uint4(w.x, w.y, w.z, w.w));
+      sts32(s_dst + i * 4, t);
+    }
+    sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);
+  }
+  const int grp = threadIdx.x >> 4, lig = threadIdx.x & 15, c = lig * 8;
+  __syncthreads();
+  // ---- phase 1 ----
+#pragma unroll 2
+  for (int ps = 0; ps < kPasses; ++ps) {
+    const int rr = ps * kSlots + grp;
+    const int r = r0 + rr;
+    if (r >= r1) continue;
+    const int t = lds32(s_dst + rr * 4);
+    float d[8], g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = g[i] = 0.f;
+    if (t >= 0) {
+      const uint4 sraw = R::load(dS + (size_t)t * (2 * kD) + kD + c);
+      const uint4 yraw = R::load(B_l + (size_t)r * kD + c);
+      const uint2 cw = __ldg(reinterpret_cast<const uint2*>(tiecnt + (size_t)r * kD + c));
+      uint4 nraw = R::zero(), oraw = R::zero();
+      if (dBnext) nraw = R::load(dBnext + (size_t)r * kD + c);
+      if (d_out_bond) oraw = R::load(d_out_bond + (size_t)r * kD + c);
+      R::to_float(sraw, d);
+      if (dBnext) v2::raw_add<bf16, 8>(nraw, d);
+      if (d_out_bond) v2::raw_add<bf16, 8>(oraw, d);
+      float y[8];
+      R::to_float(yraw, y);
+      act_grad_mul_vec<bf16, 8>(d, y, act);
+      const uint32_t cwv[2] = {cw.x, cw.y};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t cnt = (cwv[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+        g[i] = cnt <= 1u ? d[i] : __fdividef(d[i], (float)cnt);
+      }
+    }
+    store_vec(dPQ + (size_t)r * (2 * kD) + c, d);
+    uint4 gp;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&gp);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(g[2 * i], g[2 * i + 1]);
+    gcb::tc::sts128(smem + rr * kRowBytes + lig * 16, gp);
+  }
+  __syncthreads();
+  // ---- phase 2 ----
+#pragma unroll 2
+  for (int ps = 0; ps < kPasses; ++ps) {
+    GCB_TILE_ROW(ps)
+    const uint4 o4_ = lds16(s_a4 + rr * 16);
+    const int oidx[4] = {(int)o4_.x, (int)o4_.y, (int)o4_.z, (int)o4_.w};
+    uint4 gq[4];
+    uint32_t bits[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (nidx[u] >= 0) {
+        bits[u] = __ldg(tiemask + (size_t)oidx[u] * 16 + lig);
+        gq[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
+      }
+    }
+    float acc[8];
+    v2::vzero<bf16, 8>(acc);
+    auto consume = [&](const uint4& gr, uint32_t b) {
+      float gf[8];
+      R::to_float(gr, gf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += ((b >> i) & 1u) ? gf[i] : 0.f;
+    };
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) consume(gq[u], bits[u]);
+    for (int e = e0 + 4; e < e1; ++e)
+      consume(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16),
+              __ldg(tiemask + (size_t)__ldg(cm.aux + e) * 16 + lig));
+    store_vec(dPQ + (size_t)r * (2 * kD) + kD + c, acc);
+  }
+}
+
 // ---- launchers ----------------------------------------------------------------------------------
 inline int smem_for(int boxes) { return boxes * kBoxBytes + kIdxBytes + 128; }
 
@@ -332,6 +440,17 @@ inline int launch_bond_scatter(const bf16* gsplit, const TileCommon& cm, int n_t
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(bond_scatter_kernel, smem)); attr = true; }
   GCB_KERNEL("tile_bond_scatter_kernel", s, (bond_scatter_kernel<<<n_tiles, kThreads, smem, s>>>(tm, cm, tiemask, dPQ)));
+  return GCB_OK;
+}
+
+inline int launch_bond_bwd(const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
+                           const bf16* dBnext, const bf16* d_out_bond, const bf16* B_l, const uint8_t* tiecnt,
+                           const uint8_t* tiemask, bf16* dPQ, int act, cudaStream_t s) {
+  const int smem = smem_for(1) + kRows * 4;
+  static bool attr = false;
+  if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel, smem)); attr = true; }
+  GCB_KERNEL("tile_bond_bwd_kernel", s, (bond_bwd_kernel<<<n_tiles, kThreads, smem, s>>>(cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
+                                                                                         tiecnt, tiemask, dPQ, act)));
   return GCB_OK;
 }
 

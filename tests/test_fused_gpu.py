@@ -24,7 +24,7 @@ def _dev(data):
                 batch=data.batch.cuda(), num_graphs=int(data.batch.max()) + 1)
 
 
-ENV = {"tile": {}, "fused": {"GCB_FUSED_TC": "1"}, "v2": {"GCB_NO_TILE": "1"}}
+ENV = {"tile": {}, "tile_split": {"GCB_NO_BOND_MERGE": "1"}, "fused": {"GCB_FUSED_TC": "1"}, "v2": {"GCB_NO_TILE": "1"}}
 
 
 def _run(model, dev, train, mode):
@@ -49,7 +49,7 @@ def _run(model, dev, train, mode):
 
 @pytest.mark.parametrize("n_graphs,max_atoms,L", [(1, 12, 1), (7, 12, 2), (64, 30, 3), (700, 40, 4)])
 @pytest.mark.parametrize("act", [F.softplus, F.relu])
-@pytest.mark.parametrize("mode", ["tile", "fused"])
+@pytest.mark.parametrize("mode", ["tile", "tile_split", "fused"])
 def test_fused_equals_unfused_bitwise(n_graphs, max_atoms, L, act, mode):
     data, _ = random_batch(seed=n_graphs, n_graphs=n_graphs, max_atoms=max_atoms)
     _, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=L, act_fn=act)
@@ -94,10 +94,12 @@ def test_fused_kernels_are_launched_and_relu_ties_match():
         return buf.value.decode()
 
     names = kernels_of_a_step({})
-    for k in ("tile_bond_update_kernel", "tile_atom_gather_kernel", "tile_atom_bwd_kernel", "tile_bond_scatter_kernel"):
+    for k in ("tile_bond_update_kernel", "tile_atom_gather_kernel", "tile_atom_bwd_kernel", "tile_bond_bwd_kernel"):
         assert k in names, (k, names)
-    for k in ('"bond_update_kernel"', '"atom_gather_kernel"', "atom_bwd_gather_kernel", "bond_bwd_scatter_kernel"):
+    for k in ('"bond_update_kernel"', '"atom_gather_kernel"', "atom_bwd_gather_kernel", "bond_bwd_scatter_kernel", "bond_bwd_tie_kernel"):
         assert k not in names, (k, names)
+    names = kernels_of_a_step({"GCB_NO_BOND_MERGE": "1"})
+    assert "tile_bond_scatter_kernel" in names and "bond_bwd_tie_kernel" in names, names
     names = kernels_of_a_step({"GCB_FUSED_TC": "1"})
     assert "fused_bond_fwd_kernel" in names and "fused_atom_bwd_kernel" in names, names
     assert "tile_bond_update_kernel" not in names and "tile_atom_bwd_kernel" not in names, names
