@@ -56,6 +56,14 @@ def kernel_alg_bytes(name, N, E, M, G, D, s):
         # forward row kernels (per launch)
         "bond_update_kernel": M * 2 * D * s + 4 * M * i4 + M * D * s + M * D + E * 16,   # PQ in, B' out, tie counts + masks
         "atom_gather_kernel": N * D * s + 4 * N * i4 + N * D * s,                          # one half per launch: rows in, half of S out
+        # tile-staged row kernels (closed row tiles; indices = ELL-4 views + row pointers)
+        "tile_bond_update_kernel": M * 2 * D * s + M * D * s + M * D + E * 16 + 5 * M * i4,   # PQ in; B', tie counts, tie masks out
+        "tile_atom_gather_kernel": N * D * s + M * D * s + N * 2 * D * s + 9 * N * i4,           # A tile + B' rows (by edge id) in; S out
+        "tile_atom_bwd_kernel": 3 * N * D * s + N * D * s + 5 * N * i4,                           # dS half, dZA, A_prev in; dZA_prev out
+        "tile_bond_bwd_kernel": 3 * M * D * s + M * D + E * 16 + M * 2 * D * s + 12 * M * i4,   # dS half, dBnext, B_l, counts, masks in; [dP|dQ] out
+        "tile_bond_scatter_kernel": M * D * s + E * 16 + 9 * M * i4 + M * D * s,
+        "fused_bond_fwd_kernel": M * D * s + M * D * s + M * D + E * 16 + 5 * M * i4,           # B_{l-1} in; B', tie data out
+        "fused_atom_bwd_kernel": 2 * N * D * s + 2 * N * D * s + 5 * N * i4,                      # dZA, A_prev in; dZA_prev, dS half out
         "pool_kernel": N * D * s + (G + N) * i4 + G * D * 4,
         # backward row kernels
         "pool_bwd_kernel": G * D * 4 + N * D * s + N * i4 + N * D * s,
@@ -207,7 +215,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("GCB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL_DEBUG=WARN/VERSION prints a banner on stdout
+        if "GCB_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["GCB_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
 
