@@ -25,7 +25,7 @@ struct TcEpilogue {
   int rev = 0;                      // walk the row tiles last-to-first (L2 reuse of a just-written operand)
 };
 
-template <int K, int N>
+template <int K, int N, bool RES = true>
 struct NtShape {
   static constexpr int BM = 128;
   static constexpr int KS = K / 64;  // 64-element (128-byte) K slabs
@@ -39,18 +39,19 @@ struct NtShape {
   static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;  // two accumulators; power of two for N in {64,128,256}
   // four warps per TMEM lane quarter when the tile is wide enough: the epilogue (tcgen05.ld -> bias /
   // residual / activation -> swizzled staging) is a dependent chain per warp, so it needs warps, not ILP
-  static constexpr int EPI_WARPS = N == 128 ? 16 : 8;
+  // (the residual prefetch registers of a 256-wide tile do not fit next to 16 warps' worth of threads)
+  static constexpr int EPI_WARPS = (N == 128 || (N == 256 && !RES)) ? 16 : 8;
   static constexpr int COL_PARTS = EPI_WARPS / 4;
   static constexpr int THREADS = 64 + EPI_WARPS * 32;
   static_assert(K % 64 == 0 && N % 64 == 0 && N <= 256, "unsupported GEMM shape");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-template <int K, int N>
-__global__ void __launch_bounds__(NtShape<K, N>::THREADS, 1)
+template <int K, int N, bool RES>
+__global__ void __launch_bounds__(NtShape<K, N, RES>::THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmC, int rows, TcEpilogue ep) {
-  using S = NtShape<K, N>;
+  using S = NtShape<K, N, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
@@ -139,14 +140,14 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // Software pipeline across tiles: the residual row chunk and the row degree of the NEXT tile are
     // loaded into registers while the current tile is being finished, so that no global-memory latency
     // sits between "accumulator ready" and "tile staged".
-    uint4 res_raw[NCHUNK][4];
+    uint4 res_raw[RES ? NCHUNK : 1][4];
     int deg_pref = 0;
     const int res_col0 = half * COLS_PER_WARP;
     if ((int)blockIdx.x < num_tiles) {
       const int r0 = (ep.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * S::BM + row_in_tile;
       if (r0 < rows) {
         if (ep.rowptr) deg_pref = __ldg(ep.rowptr + r0 + 1) - __ldg(ep.rowptr + r0);
-        if (ep.res) {
+        if constexpr (RES) {
           const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r0 * ep.ld_res + res_col0);
 #pragma unroll
           for (int ci = 0; ci < NCHUNK; ++ci)
@@ -168,7 +169,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         wrow = ep.aggr == GCB_AGGR_MEAN ? (deg_pref > 0 ? 1.f : 0.f) : (float)deg_pref;
         if (next_valid) deg_pref = __ldg(ep.rowptr + r_next + 1) - __ldg(ep.rowptr + r_next);
       }
-      const uint4* rp_next = reinterpret_cast<const uint4*>(ep.res + (size_t)(next_valid ? r_next : 0) * ep.ld_res + res_col0);
+      const uint4* rp_next = RES ? reinterpret_cast<const uint4*>(ep.res + (size_t)(next_valid ? r_next : 0) * ep.ld_res + res_col0) : nullptr;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       // the previous tile's TMA store must have finished reading the staging buffer
@@ -191,7 +192,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             f[j + 2] = fmaf(wrow, b4.z, f[j + 2]); f[j + 3] = fmaf(wrow, b4.w, f[j + 3]);
           }
         }
-        if (ep.res) {
+        if constexpr (RES) {
           if (valid) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -242,13 +243,13 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
-template <int K, int N>
-inline int launch_gemm_nt_tc_impl(const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int rows,
-                                  const TcEpilogue& ep, cudaStream_t s) {
-  using S = NtShape<K, N>;
+template <int K, int N, bool RES>
+inline int launch_gemm_nt_tc_res(const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int rows,
+                                 const TcEpilogue& ep, cudaStream_t s) {
+  using S = NtShape<K, N, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    GCB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    GCB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<K, N, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap tmA, tmW, tmC;
@@ -257,8 +258,16 @@ inline int launch_gemm_nt_tc_impl(const bf16* A, int lda, const bf16* W, bf16* C
     return GCB_ERR_CUDA;
   const int num_tiles = (rows + S::BM - 1) / S::BM;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  GCB_KERNEL("gemm_nt_tc_kernel", s, gemm_nt_tc_kernel<K, N><<<grid, S::THREADS, S::SMEM_BYTES, s>>>(tmA, tmW, tmC, rows, ep));
+  GCB_KERNEL("gemm_nt_tc_kernel", s, (gemm_nt_tc_kernel<K, N, RES><<<grid, S::THREADS, S::SMEM_BYTES, s>>>(tmA, tmW, tmC, rows, ep)));
   return GCB_OK;
+}
+
+// The residual is a compile-time variant: without it the epilogue keeps no prefetch registers.
+template <int K, int N>
+inline int launch_gemm_nt_tc_impl(const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int rows,
+                                  const TcEpilogue& ep, cudaStream_t s) {
+  return ep.res ? launch_gemm_nt_tc_res<K, N, true>(A, lda, W, C, ldc, rows, ep, s)
+                : launch_gemm_nt_tc_res<K, N, false>(A, lda, W, C, ldc, rows, ep, s);
 }
 
 // Returns GCB_ERR_UNSUPPORTED when the shape has no tcgen05 instantiation (caller falls back to

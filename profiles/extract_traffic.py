@@ -1,6 +1,6 @@
-"""ncu --set full report(s) -> profiles/r1_traffic.json: per kernel class the average DRAM traffic
+"""ncu --set full report(s) -> profiles/r1_traffic.json (names as bench.py / gcb_timing_report use them): per kernel class the average DRAM traffic
 (dram__bytes_read.sum + dram__bytes_write.sum) and duration per launch.
-usage: python profiles/extract_traffic.py out.json rep1.ncu-rep [rep2.ncu-rep ...]"""
+usage: python profiles/extract_traffic.py out.json rep1.ncu-rep|raw1.csv [...]"""
 import csv
 import io
 import json
@@ -11,13 +11,20 @@ UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 TIME = {"ns": 1e-3, "us": 1.0, "ms": 1e3}
 out = {}
 for rep in sys.argv[2:]:
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .csv argument is the `ncu -i rep --page raw --csv` dump made on the GPU box (reports of a whole step
+    # exceed what gpurun copies back)
+    txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     h, units = rows[0], rows[1]
     ki, ri, wi, ti = (h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"),
                       h.index("gpu__time_duration.sum"))
     for r in rows[2:]:
-        name = r[ki].split("<")[0].split("(")[0].replace("void ", "").split("::")[-1].strip()
+        full = r[ki]
+        name = full.split("<")[0].split("(")[0].replace("void ", "").split("::")[-1].strip()
+        if "TileCommon" in full:  # gcb::tile kernels are timed under a tile_ prefix (bench.py / gcb_timing_report)
+            name = "tile_" + name
+        elif name == "fused_rows_tc_kernel":
+            name = "fused_bond_fwd_kernel" if "<0" in full else "fused_atom_bwd_kernel"
         b = float(r[ri]) * UNIT[units[ri]] + float(r[wi]) * UNIT[units[wi]]
         e = out.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "us": 0.0, "source": []})
         e["launches"] += 1
