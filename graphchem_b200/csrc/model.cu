@@ -366,6 +366,27 @@ static bool make_readout_desc(const ParamLayout& pl, ReadoutDesc& rd, int G) {
   return (3 * kReadoutGB * (rd.max_dim + 1) + rd.max_w) * 4 <= 200 * 1024;
 }
 
+// Register-tiled readout (readout.cuh, second half): large batches, every layer input a multiple of 4 wide.
+static bool readout2_ok(const ParamLayout& pl, ReadoutDesc& rd, int G) {
+  const char* e = std::getenv("GCB_NO_READOUT2");
+  const bool off = e && e[0] == '1';
+  if (off || pl.n_lin <= 0 || pl.n_lin > kReadoutMaxLin || G <= 1024) return false;
+  rd.n_lin = pl.n_lin;
+  rd.max_dim = 0;
+  for (int k = 0; k < pl.n_lin; ++k) {
+    if (pl.r_in[k] % 4) return false;
+    rd.in_dim[k] = pl.r_in[k]; rd.out_dim[k] = pl.r_out[k];
+    rd.w_off[k] = pl.r_w[k]; rd.b_off[k] = pl.r_b[k];
+    rd.p_off[k] = pl.r_w[k] - pl.r_w[0];
+    rd.max_dim = rd.max_dim > pl.r_in[k] ? rd.max_dim : pl.r_in[k];
+    rd.max_dim = rd.max_dim > pl.r_out[k] ? rd.max_dim : pl.r_out[k];
+  }
+  rd.max_dim = (rd.max_dim + 3) & ~3;
+  rd.partial_stride = (pl.total - pl.r_w[0] + 3) & ~int64_t(3);  // 16-byte aligned per-CTA partial blocks
+  rd.max_w = 0;
+  return readout2_bwd_smem(rd) <= 200 * 1024;
+}
+
 struct Graph {
   int N, E, G, M;
   const int32_t *x_tok, *e_tok, *src, *dst, *in_ptr, *in_eid, *in_src, *out_ptr, *out_eid, *out_dst, *graph_ptr,
@@ -505,6 +526,13 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
     GCB_KERNEL("pool_kernel", s, pool_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>((const T*)p.A[L], g.graph_ptr, g.graph_node, p.pooled, G, D));
     if (pl.n_lin == 0) {
       if (out) GCB_CUDA(cudaMemcpyAsync(out, p.pooled, (size_t)G * D * 4, cudaMemcpyDeviceToDevice, s));
+    } else if (ReadoutDesc rd2; readout2_ok(pl, rd2, G)) {
+      ReadoutPtrs hp;
+      for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
+      static bool attr2 = false;
+      if (!attr2) { GCB_CUDA(cudaFuncSetAttribute(readout2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr2 = true; }
+      Drop drb = make_drop(c, flags, seed, tag_readout(0));
+      GCB_KERNEL("readout_fwd_kernel", s, readout2_fwd_kernel<<<(unsigned)ceil_div(G, kReadoutGB2), 256, readout2_fwd_smem(rd2), s>>>(rd2, params, hp, out, G, c.act, drb));
     } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
       ReadoutPtrs hp;
       for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
@@ -557,6 +585,16 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   if (d_out && G > 0) {
     if (pl.n_lin == 0) {
       dPool = d_out;
+    } else if (ReadoutDesc rd2; readout2_ok(pl, rd2, G)) {
+      ReadoutPtrs hp;
+      for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
+      static bool attr2 = false;
+      if (!attr2) { GCB_CUDA(cudaFuncSetAttribute(readout2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr2 = true; }
+      const int blocks = (int)ceil_div(G, kReadoutGB2);
+      Drop drb = make_drop(c, flags, seed, tag_readout(0));
+      GCB_KERNEL("readout_bwd_kernel", s, readout2_bwd_kernel<<<blocks, 256, readout2_bwd_smem(rd2), s>>>(rd2, params, hp, d_out, p.partial, p.dPool, G, c.act, drb));
+      GCB_TRY(launch_reduce_partials(p.partial, blocks, pl.total - pl.r_w[0], grad + pl.r_w[0], accumulate, s, rd2.partial_stride));
+      dPool = p.dPool;
     } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
       ReadoutPtrs hp;
       for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;

@@ -149,4 +149,226 @@ readout_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Register-tiled variants for large batches (thousands of graphs): 64 graphs per CTA, every thread
+// owns a 4 x 4 (forward) or 4 x 8 (backward) output tile and walks the reduction with 16-byte
+// shared-memory loads, so the inner loops are FFMA-bound instead of LDS-bound (the kernels above
+// issue two shared loads per FFMA).  Weights are kept [out][in + 4] in shared memory: with in % 32 == 0
+// the row stride is 4 banks and the 16 output lanes of a warp hit disjoint banks.  Needs every
+// layer's input width to be a multiple of 4.
+constexpr int kReadoutGB2 = 64;
+
+__host__ __device__ inline int readout2_ld(const ReadoutDesc& rd) { return rd.max_dim + 4; }
+inline size_t readout2_fwd_smem(const ReadoutDesc& rd) {
+  return (size_t)(2 * kReadoutGB2 * readout2_ld(rd) + rd.max_dim * readout2_ld(rd)) * sizeof(float);
+}
+inline size_t readout2_bwd_smem(const ReadoutDesc& rd) {
+  return (size_t)(3 * kReadoutGB2 * readout2_ld(rd) + rd.max_dim * readout2_ld(rd)) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(256)
+readout2_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs hp, float* __restrict__ out, int G,
+                    int act, Drop dr_base) {
+  extern __shared__ __align__(16) float rs2[];
+  const int ld = readout2_ld(rd);
+  float* cur = rs2;
+  float* nxt = rs2 + kReadoutGB2 * ld;
+  float* Ws = rs2 + 2 * kReadoutGB2 * ld;  // [on][ld]
+  const int g0 = blockIdx.x * kReadoutGB2;
+  const int ng = min(kReadoutGB2, G - g0);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  {
+    const int in4 = rd.in_dim[0] >> 2;
+    for (int i = threadIdx.x; i < kReadoutGB2 * in4; i += 256) {
+      const int g = i / in4, j4 = i % in4;
+      const float4 v = g < ng ? __ldg(reinterpret_cast<const float4*>(hp.h[0] + (size_t)(g0 + g) * rd.in_dim[0]) + j4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(cur + g * ld + 4 * j4) = v;
+    }
+  }
+  for (int k = 0; k < rd.n_lin; ++k) {
+    const int in = rd.in_dim[k], on = rd.out_dim[k], in4 = in >> 2;
+    const bool last = k == rd.n_lin - 1;
+    const float* W = params + rd.w_off[k];
+    const float* b = params + rd.b_off[k];
+    float* dst = last ? out : hp.h[k + 1];
+    for (int i = threadIdx.x; i < on * in4; i += 256) {
+      const int o = i / in4, j4 = i % in4;
+      *reinterpret_cast<float4*>(Ws + o * ld + 4 * j4) = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in) + j4);
+    }
+    __syncthreads();
+    for (int ob = 0; ob < on; ob += 64) {
+      float acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+      const float* hrow[4];
+      const float* wrow[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) hrow[a] = cur + (ty + 16 * a) * ld;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) wrow[c] = Ws + min(ob + tx + 16 * c, on - 1) * ld;
+      for (int j4 = 0; j4 < in4; ++j4) {
+        float4 h[4], w[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) h[a] = *reinterpret_cast<const float4*>(hrow[a] + 4 * j4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w[c] = *reinterpret_cast<const float4*>(wrow[c] + 4 * j4);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[a][c] = fmaf(h[a].x, w[c].x, acc[a][c]);
+            acc[a][c] = fmaf(h[a].y, w[c].y, acc[a][c]);
+            acc[a][c] = fmaf(h[a].z, w[c].z, acc[a][c]);
+            acc[a][c] = fmaf(h[a].w, w[c].w, acc[a][c]);
+          }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int o = ob + tx + 16 * c;
+        if (o >= on) continue;
+        const float bo = __ldg(b + o);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int g = ty + 16 * a;
+          float v = acc[a][c] + bo;
+          if (!last) {
+            v = act_fwd(v, act);
+            if (dr_base.p > 0.f) {
+              Drop dr = dr_base;
+              dr.tag += (uint32_t)(k + 1);
+              v = dropout_keep(dr.seed, dr.tag, (uint64_t)(g0 + g) * on + o, dr.p) ? v / (1.f - dr.p) : 0.f;
+            }
+            nxt[g * ld + o] = v;
+          }
+          if (dst && g < ng) dst[(size_t)(g0 + g) * on + o] = v;
+        }
+      }
+    }
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+readout2_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs hp, const float* __restrict__ d_out,
+                    float* __restrict__ partial, float* __restrict__ dPool, int G, int act, Drop dr_base) {
+  extern __shared__ __align__(16) float rs2[];
+  const int ld = readout2_ld(rd);
+  float* dz = rs2;                            // [GB][ld] gradient w.r.t. the current layer's output (0 for padded graphs)
+  float* hin = rs2 + kReadoutGB2 * ld;        // [GB][ld] the current layer's input H[k]
+  float* dh = rs2 + 2 * kReadoutGB2 * ld;     // [GB][ld] gradient w.r.t. the current layer's input
+  float* Ws = rs2 + 3 * kReadoutGB2 * ld;     // [on][ld]
+  const int g0 = blockIdx.x * kReadoutGB2;
+  const int ng = min(kReadoutGB2, G - g0);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float* my_partial = partial + (size_t)blockIdx.x * rd.partial_stride;
+  const int o_last = rd.out_dim[rd.n_lin - 1];
+  for (int i = threadIdx.x; i < kReadoutGB2 * o_last; i += 256) {
+    const int g = i / o_last, o = i % o_last;
+    dz[g * ld + o] = g < ng ? d_out[(size_t)(g0 + g) * o_last + o] : 0.f;
+  }
+  for (int k = rd.n_lin - 1; k >= 0; --k) {
+    const int in = rd.in_dim[k], on = rd.out_dim[k], in4 = in >> 2;
+    const float* W = params + rd.w_off[k];
+    for (int i = threadIdx.x; i < kReadoutGB2 * in4; i += 256) {
+      const int g = i / in4, j4 = i % in4;
+      const float4 v = g < ng ? __ldg(reinterpret_cast<const float4*>(hp.h[k] + (size_t)(g0 + g) * in) + j4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(hin + g * ld + 4 * j4) = v;
+    }
+    for (int i = threadIdx.x; i < on * in4; i += 256) {
+      const int o = i / in4, j4 = i % in4;
+      *reinterpret_cast<float4*>(Ws + o * ld + 4 * j4) = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in) + j4);
+    }
+    __syncthreads();
+    float* pw = my_partial + rd.p_off[k];
+    // ---- weight-gradient partial of this CTA's graphs: outputs o = ob + tx + 16 c, inputs j = jb + 8 ty .. + 7
+    for (int ob = 0; ob < on; ob += 64) {
+      for (int jb = 0; jb < in; jb += 128) {
+        const int j = jb + 8 * ty;
+        if (j >= in) continue;  // in % 8 may be 4: the last lane group handles the 4-wide remainder below
+        const bool wide = j + 8 <= in;
+        float acc[4][8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+        for (int g = 0; g < kReadoutGB2; ++g) {
+          const float4 h0 = *reinterpret_cast<const float4*>(hin + g * ld + j);
+          const float4 h1 = wide ? *reinterpret_cast<const float4*>(hin + g * ld + j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float d = dz[g * ld + min(ob + tx + 16 * c, on - 1)];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[c][e] = fmaf(d, hv[e], acc[c][e]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int o = ob + tx + 16 * c;
+          if (o >= on) continue;
+          float* q = pw + (size_t)o * in + j;
+          *reinterpret_cast<float4*>(q) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+          if (wide) *reinterpret_cast<float4*>(q + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+        }
+      }
+    }
+    for (int o = threadIdx.x; o < on; o += 256) {
+      float acc = 0.f;
+      for (int g = 0; g < kReadoutGB2; ++g) acc += dz[g * ld + o];
+      pw[(size_t)on * in + o] = acc;
+    }
+    // ---- gradient w.r.t. the layer input: graphs g = ty + 16 a, inputs j = jb + 8 tx .. + 7
+    for (int jb = 0; jb < in; jb += 128) {
+      const int j = jb + 8 * tx;
+      if (j >= in) continue;
+      const bool wide = j + 8 <= in;
+      float acc[4][8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+      for (int o = 0; o < on; ++o) {
+        const float4 w0 = *reinterpret_cast<const float4*>(Ws + o * ld + j);
+        const float4 w1 = wide ? *reinterpret_cast<const float4*>(Ws + o * ld + j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float d = dz[(ty + 16 * a) * ld + o];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[a][e] = fmaf(d, wv[e], acc[a][e]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int g = ty + 16 * a;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (!wide && e >= 4) continue;
+          float v = acc[a][e];
+          if (k > 0) {
+            float y = hin[g * ld + j + e], f = 1.f;
+            if (dr_base.p > 0.f) {
+              Drop dr = dr_base;
+              dr.tag += (uint32_t)k;
+              f = dropout_keep(dr.seed, dr.tag, (uint64_t)(g0 + g) * in + j + e, dr.p) ? 1.f / (1.f - dr.p) : 0.f;
+              y *= (1.f - dr.p);
+            }
+            dh[g * ld + j + e] = g < ng ? v * f * act_grad_from_out(y, act) : 0.f;
+          } else if (g < ng) {
+            dPool[(size_t)(g0 + g) * in + j + e] = v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    float* t = dz; dz = dh; dh = t;
+  }
+}
+
 }  // namespace gcb

@@ -98,3 +98,35 @@ def test_synthetic_generator_is_encoder_shaped():
     assert var.n_atoms.min() >= 6 and var.n_atoms.max() <= 38
     pb = var.collate_pack(np.arange(200), 4, 64, 32, pin=False)
     assert pb.G == 200 and pb.E >= pb.N
+
+
+def test_closed_row_tiles():
+    """tile_ptr: consecutive tiles of <= 128 rows that no edge leaves (molecules never split), matching the
+    numpy oracle; a component wider than a tile leaves n_tiles == 0 (untiled kernels)."""
+    from graphchem_b200 import _lib
+    data, graphs = random_batch(seed=9, n_graphs=300, max_atoms=30)
+    pb = pack_batch(data, 3, 12, 7, pin=False)
+    tp = pb.sections()["tile_ptr"].numpy()
+    assert pb.n_tiles == len(tp) - 1 > 1 and tp[0] == 0 and tp[-1] == pb.N
+    assert (np.diff(tp) > 0).all() and (np.diff(tp) <= _lib.TILE_ROWS).all()
+    tile_of = np.searchsorted(tp, np.arange(pb.N), side="right") - 1
+    ei = data.edge_index.numpy()
+    assert (tile_of[ei[0]] == tile_of[ei[1]]).all(), "an edge leaves its tile"
+    # greedy: two neighbouring tiles never fit into one
+    ptr = data.ptr.numpy()
+    assert set(tp.tolist()) <= set(ptr.tolist()), "tiles must end on molecule boundaries"
+    for a, b, c in zip(tp[:-2], tp[1:-1], tp[2:]):
+        nxt = ptr[np.searchsorted(ptr, b, side="right")]  # end of the first molecule of the next tile
+        assert nxt - a > _lib.TILE_ROWS
+    # a 200-atom ring: one component wider than a tile
+    n = 200
+    s = torch.arange(n)
+    ring = Data(x=torch.full((n,), 3), edge_index=torch.stack([torch.cat([s, (s + 1) % n]), torch.cat([(s + 1) % n, s])]),
+                edge_attr=torch.full((2 * n,), 2))
+    pr = pack_batch(ring, 2, 12, 7, pin=False)
+    assert pr.n_tiles == 0
+    _assert_matches_oracle(pr, ring, 1, 12, 7)
+    # ... next to small molecules it still poisons the whole batch (documented fallback)
+    both = ocollate([graphs[0], type(graphs[0])(x=ring.x.int(), edge_index=ring.edge_index, edge_attr=ring.edge_attr.int(),
+                                                y=torch.zeros(1, 1))])
+    assert pack_batch(both, 2, 12, 7, pin=False).n_tiles == 0

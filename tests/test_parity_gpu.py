@@ -331,3 +331,32 @@ def test_high_degree_random_graph_bf16_overflows_the_ell4_view():
     # ~8 candidates per max: bf16 rounding flips near-ties that fp32 resolves, which moves the bond
     # weight gradient by up to ~8% on this adversarial graph (every other parameter stays within 3%)
     _check_backward(oracle, model, data, 0.15)
+
+
+@pytest.mark.parametrize("n_readout,R,out_dim", [(2, 64, 1), (3, 128, 2), (1, 36, 3)])
+def test_large_batch_readout_fp32(n_readout, R, out_dim):
+    """More than 1024 graphs: the register-tiled readout kernels (readout.cuh) against the oracle, and
+    against the GEMM-per-layer path they replace."""
+    import os
+    data, _ = random_batch(seed=21, n_graphs=1300, max_atoms=6)
+    oracle, model = make_pair(12, 7, out_dim, embedding_dim=64, n_messages=1, n_readout=n_readout, readout_dim=R)
+    _retry_on_oracle_flake(_check_forward_once, oracle, model, data, FWD_F32)
+    _retry_on_oracle_flake(_check_backward_once, oracle, model, data, GRAD_F32)
+    dev = _to_dev(data)
+    model.train()
+
+    def grads():
+        out = model(dev)[0]
+        model.zero_grad()
+        (out ** 2).mean().backward()
+        return out.detach().clone(), [p.grad.clone() for p in model.parameters()]
+
+    o1, g1 = grads()
+    os.environ["GCB_NO_READOUT2"] = "1"
+    try:
+        o2, g2 = grads()
+    finally:
+        os.environ.pop("GCB_NO_READOUT2", None)
+    assert nerr(o1, o2) <= 1e-6
+    for a, b in zip(g1, g2):
+        assert nerr(a, b) <= 1e-5
