@@ -2,7 +2,7 @@
 // the row width is 8, 16 or 32 sixteen-byte chunks (D = 64/128/256 in bf16, 32/64/128 in fp32) and the
 // generic kernels of kernels.cuh otherwise.
 #pragma once
-#include "kernels_v3.cuh"
+#include "kernels_v2.cuh"
 
 namespace gcb {
 
@@ -29,37 +29,10 @@ namespace gcb {
 #define GCB_V2_GRID_FLAT(ROWS) v2::blocks_for<CH>(ROWS), v2::kThreads, 0, s
 #define GCB_V1_GRID(ROWS, DVAL) row_chunk_blocks(ROWS, DVAL, Vec<T>::N), 256, 0, s
 
-namespace tc { bool v3_enabled(); }
-inline unsigned v3_grid(int rows, int rows_per_block, int blocks_per_sm) {
-  const unsigned need = (unsigned)ceil_div(rows, rows_per_block), cap = (unsigned)(kNumSMs * blocks_per_sm);
-  return need < cap ? need : cap;
-}
-template <typename T, int CH>
-int launch_bond_update_v3(const T* PQ, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_src4, T* Bout, int M,
-                          int act, Drop dr, cudaStream_t s) {
-  constexpr int SM = v3::smem_bytes<5>();
-  static bool attr = false;
-  if (!attr) {
-    GCB_CUDA(cudaFuncSetAttribute(v3::bond_update_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
-    attr = true;
-  }
-  GCB_KERNEL("bond_update_kernel", s, (v3::bond_update_kernel<T, CH><<<v3_grid(M, v2::rows_per_block<CH>(), 3), v2::kThreads, SM, s>>>(
-      PQ, in_ptr, in_src, (const int4*)in_src4, Bout, M, act, dr)));
-  return GCB_OK;
-}
-
 template <typename T>
 int launch_bond_update(const T* PQ, const int32_t* in_ptr, const int32_t* in_src, const int32_t* in_eid,
                        const int32_t* in_src4, const int32_t* in_eid4, T* Bout, uint8_t* tiemask, uint8_t* tiecnt, int M,
                        int D, int act, Drop dr, int rev, cudaStream_t s) {
-  if (false && M > 0 && tc::v3_enabled()) {
-    switch (D / Vec<T>::N) {
-      case 8: return launch_bond_update_v3<T, 8>(PQ, in_ptr, in_src, in_src4, Bout, M, act, dr, s);
-      case 16: return launch_bond_update_v3<T, 16>(PQ, in_ptr, in_src, in_src4, Bout, M, act, dr, s);
-      case 32: return launch_bond_update_v3<T, 32>(PQ, in_ptr, in_src, in_src4, Bout, M, act, dr, s);
-      default: break;
-    }
-  }
   if (tiemask != nullptr) {
     GCB_ROW_DISPATCH("bond_update_kernel", M, D, dr.p > 0.f,
                      (v2::bond_update_kernel<T, CH, DROP, true><<<GCB_V2_GRID(M)>>>(PQ, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, Bout, tiemask, tiecnt, M, act, dr, rev)),

@@ -90,11 +90,6 @@ bool bond_bwd_merged_enabled() {
   return !(e && e[0] == '1');
 }
 
-bool v3_enabled() {
-  const char* e = std::getenv("GCB_NO_V3");
-  return !(e && e[0] == '1');
-}
-
 bool overlap_enabled() {
   const char* e = std::getenv("GCB_NO_OVERLAP");
   return !(e && e[0] == '1');

@@ -41,6 +41,8 @@ class TrainStep:
         self._pred: Optional[torch.Tensor] = None
         self._dpred: Optional[torch.Tensor] = None
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._keepalive: Dict[tuple, PackedBatch] = {}
+        self.max_graphs = 64
         self.launches_per_step = 0
         model.refresh_weights()
 
@@ -61,6 +63,7 @@ class TrainStep:
         if self._ws is None or self._ws.numel() < need:
             if self._graphs:
                 self._graphs.clear()
+                self._keepalive.clear()
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         out_cols = self.model._dims[2] if self.model._dims[4] > 0 else self.model._dims[3]
         if self._pred is None or self._pred.shape != (pb.G, out_cols):
@@ -123,7 +126,11 @@ class TrainStep:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._enqueue(pb)
+            if len(self._graphs) >= self.max_graphs:  # streaming callers with ever-changing batches: bound the cache
+                old = next(iter(self._graphs))
+                del self._graphs[old]
+                self._keepalive.pop(old, None)
             self._graphs[key] = g
-            self._keepalive = getattr(self, "_keepalive", []) + [pb]
+            self._keepalive[key] = pb
         g.replay()
         return self.loss

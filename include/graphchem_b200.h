@@ -134,7 +134,9 @@ int64_t gcb_workspace_bytes(const gcb_model_cfg* cfg, int32_t N, int32_t E, int3
 
 /* MoleculeGCN.forward, graphchem/nn/gcn.py:120-202 (embedding :152-157, EdgeConv :163-164,
  * GeneralConv :172-173, dropout :167-178, global_add_pool :181, readout :184-199).
- * packed: device packed batch.  out: float [G, out_dim] (or [G, D] when n_readout == 0);
+ * packed: device packed batch; packed_header_host: host copy of its first GCB_PACK_HEADER_INTS ints,
+ * taken AFTER packing (the packer writes the closed-tile count there; a header straight from
+ * gcb_pack_ints selects the untiled kernels).  out: float [G, out_dim] (or [G, D] when n_readout == 0);
  * out_atom: dtype [N, D]; out_bond: dtype [E, D] (either may be NULL to skip materialising). */
 int gcb_forward(const gcb_model_cfg* cfg, const int32_t* packed, const int32_t* packed_header_host,
                 const float* params, const void* derived, void* workspace, int64_t workspace_bytes,
