@@ -27,13 +27,14 @@ AGGR_ADD, AGGR_MEAN = 0, 1
 F32, BF16 = 0, 1
 TRAINING, SAVE_FOR_BWD = 1, 2
 
-PACK_HEADER_INTS = 32
+PACK_HEADER_INTS = 48
 (H_MAGIC, H_N, H_E, H_G, H_M, H_AV, H_BV, H_TOTAL_INTS, H_X_TOK, H_E_TOK, H_SRC, H_DST, H_IN_PTR, H_IN_EID,
  H_IN_SRC, H_OUT_PTR, H_OUT_EID, H_OUT_DST, H_GRAPH_PTR, H_GRAPH_NODE, H_ATOK_PTR, H_ATOK_NODE, H_BTOK_PTR,
  H_BTOK_ROW, H_NODE_GRAPH, H_IN_SRC4, H_IN_EID4, H_OUT_DST4, H_OUT_INPOS4, H_OUT_INPOS, H_TILE_PTR,
- H_NTILES) = range(32)
+ H_NTILES, H_FLAGS, H_BOND_POS) = range(34)
+PACK_EACH = 1
 TILE_ROWS = 128
-PACK_MAGIC = 0x47434231
+PACK_MAGIC = 0x47434232
 MAX_PARAM_TENSORS = 64
 
 
@@ -69,6 +70,8 @@ _cfgp = C.POINTER(ModelCfg)
 # name -> (restype, argtypes); one entry per declaration in include/graphchem_b200.h
 SIGNATURES = {
     "gcb_pack_ints": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "gcb_pack_ints_flags": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "gcb_collate_pack_each_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "gcb_pack_host": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64]),
     "gcb_collate_pack_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "gcb_param_layout": (C.c_int, [_cfgp, _vp]),

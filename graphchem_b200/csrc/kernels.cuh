@@ -177,6 +177,23 @@ __global__ void fill_const_rows_kernel(T* __restrict__ out, int row0, int rows, 
   store_vec(out + (size_t)(row0 + r) * D + c, v);
 }
 
+// out_bond of a GCB_PACK_EACH batch: out[e,:] = B[pos[e],:], or act(0) where pos[e] < 0.
+template <typename T>
+__global__ void gather_bond_rows_kernel(const T* __restrict__ B, const int32_t* __restrict__ pos, T* __restrict__ out,
+                                        int rows, int D, int act) {
+  GCB_ROW_CHUNK_PROLOGUE(rows)
+  const int p = __ldg(pos + r);
+  float v[V];
+  if (p >= 0) {
+    load_vec(B + (size_t)p * D + c, v);
+  } else {
+    const float z = act_fwd_t<T>(0.f, act);
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = z;
+  }
+  store_vec(out + (size_t)r * D + c, v);
+}
+
 // global_add_pool (gcn.py:181): out[g,:] = sum_{i in graph g} A[i,:], in node order.
 template <typename T>
 __global__ void pool_kernel(const T* __restrict__ A, const int32_t* __restrict__ graph_ptr,

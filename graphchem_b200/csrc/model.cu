@@ -391,8 +391,9 @@ struct Graph {
   int N, E, G, M;
   const int32_t *x_tok, *e_tok, *src, *dst, *in_ptr, *in_eid, *in_src, *out_ptr, *out_eid, *out_dst, *graph_ptr,
       *graph_node, *atok_ptr, *atok_node, *btok_ptr, *btok_row, *node_graph, *in_src4, *in_eid4, *out_dst4, *out_inpos4, *out_inpos,
-      *tile_ptr;
+      *tile_ptr, *bond_pos;
   int n_tiles;  // closed row tiles (0: none, use the unfused kernels)
+  int pack_flags;
 };
 static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32_t* h, Graph& g) {
   if (!packed || !h || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
@@ -408,6 +409,9 @@ static int make_graph(const gcb_model_cfg& c, const int32_t* packed, const int32
   g.atok_ptr = packed + h[GCB_H_ATOK_PTR]; g.atok_node = packed + h[GCB_H_ATOK_NODE];
   g.btok_ptr = packed + h[GCB_H_BTOK_PTR]; g.btok_row = packed + h[GCB_H_BTOK_ROW];
   g.node_graph = packed + h[GCB_H_NODE_GRAPH];
+  g.pack_flags = h[GCB_H_FLAGS];
+  g.bond_pos = (g.pack_flags & GCB_PACK_EACH) && h[GCB_H_BOND_POS] > 0 ? packed + h[GCB_H_BOND_POS] : nullptr;
+  if ((g.pack_flags & GCB_PACK_EACH) && !g.bond_pos) return GCB_ERR_INVALID_ARG;
   g.tile_ptr = packed + h[GCB_H_TILE_PTR];
   g.n_tiles = h[GCB_H_TILE_PTR] > 0 ? h[GCB_H_NTILES] : 0;
   g.in_src4 = packed + h[GCB_H_IN_SRC4]; g.in_eid4 = packed + h[GCB_H_IN_EID4]; g.out_dst4 = packed + h[GCB_H_OUT_DST4]; g.out_inpos4 = packed + h[GCB_H_OUT_INPOS4]; g.out_inpos = packed + h[GCB_H_OUT_INPOS];
@@ -560,7 +564,10 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
     }
   }
   if (out_atom && N > 0) GCB_CUDA(cudaMemcpyAsync(out_atom, p.A[L], (size_t)N * D * sizeof(T), cudaMemcpyDeviceToDevice, s));
-  if (out_bond && E > 0) {
+  if (out_bond && E > 0 && g.bond_pos) {
+    // "each molecule alone" layout: edge e's row lives at bond_pos[e] (or is the constant act(0) row)
+    GCB_KERNEL("gather_bond_rows_kernel", s, gather_bond_rows_kernel<T><<<row_chunk_blocks(E, D, V), 256, 0, s>>>((const T*)p.B[L], g.bond_pos, out_bond, E, D, c.act));
+  } else if (out_bond && E > 0) {
     if (M > 0) GCB_CUDA(cudaMemcpyAsync(out_bond, p.B[L], (size_t)M * D * sizeof(T), cudaMemcpyDeviceToDevice, s));
     if (E > M) {
       GCB_KERNEL("fill_const_rows_kernel", s, fill_const_rows_kernel<T><<<row_chunk_blocks(E - M, D, V), 256, 0, s>>>(out_bond, M, E - M, D, c.act,
@@ -861,6 +868,9 @@ extern "C" int gcb_forward(const gcb_model_cfg* cfg, const int32_t* packed, cons
   GCB_TRY(make_layout(*cfg, pl));
   Graph g;
   GCB_TRY(make_graph(*cfg, packed, packed_header_host, g));
+  // GCB_PACK_EACH batches are for prediction: no saved activations, no dropout
+  if ((g.pack_flags & GCB_PACK_EACH) && ((flags & GCB_SAVE_FOR_BWD) || ((flags & GCB_TRAINING) && cfg->p_dropout > 0.f)))
+    return GCB_ERR_INVALID_ARG;
   Plan p;
   GCB_TRY(make_plan(*cfg, pl, g.N, g.E, g.G, g.M, flags, workspace, p));
   if (p.total > workspace_bytes) return GCB_ERR_WORKSPACE;

@@ -15,7 +15,7 @@ namespace gcb {
 
 static inline int64_t pad4(int64_t n) { return (n + 3) & ~int64_t(3); }
 
-static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, int32_t bv, int32_t* h) {
+static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, int32_t bv, int32_t flags, int32_t* h) {
   int64_t off = GCB_PACK_HEADER_INTS;
   auto put = [&](int field, int64_t n) {
     if (h) h[field] = (int32_t)off;
@@ -25,6 +25,7 @@ static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, in
     std::memset(h, 0, sizeof(int32_t) * GCB_PACK_HEADER_INTS);
     h[GCB_H_MAGIC] = GCB_PACK_MAGIC;
     h[GCB_H_N] = N; h[GCB_H_E] = E; h[GCB_H_G] = G; h[GCB_H_M] = M; h[GCB_H_AV] = av; h[GCB_H_BV] = bv;
+    h[GCB_H_FLAGS] = flags;
   }
   put(GCB_H_X_TOK, N); put(GCB_H_E_TOK, E); put(GCB_H_SRC, E); put(GCB_H_DST, E);
   put(GCB_H_IN_PTR, (int64_t)N + 1); put(GCB_H_IN_EID, E); put(GCB_H_IN_SRC, E);
@@ -37,6 +38,7 @@ static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, in
   put(GCB_H_OUT_INPOS4, 4 * (int64_t)N);
   put(GCB_H_OUT_INPOS, E);
   put(GCB_H_TILE_PTR, (int64_t)N + 1);
+  if (flags & GCB_PACK_EACH) put(GCB_H_BOND_POS, E);
   if (off > INT32_MAX) return -1;
   if (h) h[GCB_H_TOTAL_INTS] = (int32_t)off;
   return off;
@@ -142,7 +144,14 @@ using namespace gcb;
 extern "C" int64_t gcb_pack_ints(int32_t N, int32_t E, int32_t G, int32_t M, int32_t atom_vocab,
                                  int32_t bond_vocab, int32_t* header) {
   if (N < 0 || E < 0 || G < 0 || M < 0 || M > E || atom_vocab < 0 || bond_vocab < 0) return GCB_ERR_INVALID_ARG;
-  return layout(N, E, G, M, atom_vocab, bond_vocab, header);
+  return layout(N, E, G, M, atom_vocab, bond_vocab, 0, header);
+}
+
+extern "C" int64_t gcb_pack_ints_flags(int32_t N, int32_t E, int32_t G, int32_t M, int32_t atom_vocab,
+                                       int32_t bond_vocab, int32_t flags, int32_t* header) {
+  if (N < 0 || E < 0 || G < 0 || M < 0 || M > E || atom_vocab < 0 || bond_vocab < 0 || (flags & ~GCB_PACK_EACH))
+    return GCB_ERR_INVALID_ARG;
+  return layout(N, E, G, M, atom_vocab, bond_vocab, flags, header);
 }
 
 extern "C" int gcb_pack_host(const void* x, const void* edge_attr, const void* edge_index, const void* batch,
@@ -242,4 +251,76 @@ extern "C" int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t*
     edge_off += ne;
   }
   return finish_pack(packed, h, b32.data());
+}
+
+// "Each molecule alone": bond row r of the packed batch = the molecule's own edge (r - its first atom).
+extern "C" int gcb_collate_pack_each_host(const int32_t* const* atoms, const int32_t* n_atoms,
+                                          const int32_t* const* bonds, const int64_t* const* conn,
+                                          const int32_t* n_edges, const float* const* y, int32_t n_targets,
+                                          int32_t n_graphs, int32_t n_messages, int32_t atom_vocab,
+                                          int32_t bond_vocab, int32_t* packed, int64_t packed_ints, float* y_out) {
+  if (n_graphs < 0 || !packed || (n_graphs > 0 && (!atoms || !n_atoms || !bonds || !conn || !n_edges)))
+    return GCB_ERR_INVALID_ARG;
+  if (n_messages < 1) return GCB_ERR_INVALID_ARG;  // without EdgeConv on the bond matrix batched == per molecule already
+  int64_t N64 = 0, E64 = 0;
+  for (int32_t g = 0; g < n_graphs; ++g) {
+    if (n_atoms[g] < 0 || n_edges[g] < 0) return GCB_ERR_INVALID_ARG;
+    N64 += n_atoms[g];
+    E64 += n_edges[g];
+  }
+  if (N64 > INT32_MAX || E64 > INT32_MAX) return GCB_ERR_INVALID_ARG;
+  if (E64 < N64) return GCB_ERR_UNSUPPORTED;  // the bond matrix must offer one row per atom
+  const int32_t N = (int32_t)N64, E = (int32_t)E64, G = n_graphs, M = N;
+  int32_t h[GCB_PACK_HEADER_INTS];
+  int64_t total = gcb_pack_ints_flags(N, E, G, M, atom_vocab, bond_vocab, GCB_PACK_EACH, h);
+  if (total < 0) return GCB_ERR_INVALID_ARG;
+  if (packed_ints < total) return GCB_ERR_WORKSPACE;
+  std::memset(packed, 0, sizeof(int32_t) * (size_t)total);
+  std::memcpy(packed, h, sizeof(h));
+  int32_t* x_tok = packed + h[GCB_H_X_TOK];
+  int32_t* e_tok = packed + h[GCB_H_E_TOK];
+  int32_t* src = packed + h[GCB_H_SRC];
+  int32_t* dst = packed + h[GCB_H_DST];
+  int32_t* bond_pos = packed + h[GCB_H_BOND_POS];
+  std::vector<int32_t> b32((size_t)N);
+  int64_t node_off = 0, edge_off = 0;
+  for (int32_t g = 0; g < G; ++g) {
+    const int32_t na = n_atoms[g], ne = n_edges[g];
+    for (int32_t i = 0; i < na; ++i) {
+      int32_t t = atoms[g][i];
+      if (t < 0 || t >= atom_vocab) return GCB_ERR_INDEX;
+      x_tok[node_off + i] = t;
+      b32[(size_t)(node_off + i)] = g;
+      // bond row of atom i = the molecule's edge i (rows past its last edge are never addressed: see the check below)
+      if (i < ne) {
+        int32_t bt = bonds[g][i];
+        if (bt < 0 || bt >= bond_vocab) return GCB_ERR_INDEX;
+        e_tok[node_off + i] = bt;
+      }
+    }
+    const int32_t lim = na < ne ? na : ne;  // live bond rows of this molecule alone: min(n_atoms, n_edges)
+    for (int32_t e = 0; e < ne; ++e) {
+      int32_t t = bonds[g][e];
+      if (t < 0 || t >= bond_vocab) return GCB_ERR_INDEX;
+      const int64_t s = conn[g][e], d = conn[g][(int64_t)ne + e];
+      if (s < 0 || d < 0 || s >= lim || d >= lim) return GCB_ERR_INDEX;  // PyG _lift IndexError for this molecule alone
+      src[edge_off + e] = (int32_t)(s + node_off);
+      dst[edge_off + e] = (int32_t)(d + node_off);
+      bond_pos[edge_off + e] = e < na ? (int32_t)(node_off + e) : -1;
+    }
+    if (y_out) {
+      for (int32_t t = 0; t < n_targets; ++t) y_out[(int64_t)g * n_targets + t] = y && y[g] ? y[g][t] : 0.f;
+    }
+    node_off += na;
+    edge_off += ne;
+  }
+  int rc = finish_pack(packed, h, b32.data());
+  if (rc != GCB_OK) return rc;
+  // the atom step reads the updated bond rows by EDGE id: send every CSR entry to the row that holds its edge
+  int32_t* in_eid = packed + h[GCB_H_IN_EID];
+  int32_t* e4 = packed + h[GCB_H_IN_EID4];
+  for (int64_t k = 0; k < E; ++k) in_eid[k] = bond_pos[in_eid[k]] >= 0 ? bond_pos[in_eid[k]] : M;
+  for (int64_t k = 0; k < 4 * (int64_t)N; ++k)
+    if (e4[k] >= 0) e4[k] = bond_pos[e4[k]] >= 0 ? bond_pos[e4[k]] : M;
+  return GCB_OK;
 }

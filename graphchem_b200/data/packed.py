@@ -74,7 +74,8 @@ class PackedBatch:
             node_graph=self.section(L.H_NODE_GRAPH, N), in_src4=self.section(L.H_IN_SRC4, 4 * N),
             in_eid4=self.section(L.H_IN_EID4, 4 * N), out_dst4=self.section(L.H_OUT_DST4, 4 * N),
             out_inpos4=self.section(L.H_OUT_INPOS4, 4 * N), out_inpos=self.section(L.H_OUT_INPOS, E),
-            tile_ptr=self.section(L.H_TILE_PTR, self.n_tiles + 1))
+            tile_ptr=self.section(L.H_TILE_PTR, self.n_tiles + 1),
+            **({"bond_pos": self.section(L.H_BOND_POS, E)} if int(self.header[L.H_FLAGS]) & L.PACK_EACH else {}))
 
 
 def _alloc_ints(n: int, pin: bool) -> Tensor:
@@ -82,9 +83,9 @@ def _alloc_ints(n: int, pin: bool) -> Tensor:
     return torch.empty(n, dtype=torch.int32, pin_memory=pin)
 
 
-def _header(N: int, E: int, G: int, M: int, av: int, bv: int):
+def _header(N: int, E: int, G: int, M: int, av: int, bv: int, flags: int = 0):
     header = np.zeros(_lib.PACK_HEADER_INTS, dtype=np.int32)
-    total = _lib.lib().gcb_pack_ints(N, E, G, M, av, bv, header.ctypes.data)
+    total = _lib.lib().gcb_pack_ints_flags(N, E, G, M, av, bv, flags, header.ctypes.data)
     _lib.check(int(total), "gcb_pack_ints")
     return header, int(total)
 
@@ -166,14 +167,18 @@ class MoleculeStore:
         return int(self.n_atoms.shape[0])
 
     def collate_pack(self, idx: Sequence[int], n_messages: int, atom_vocab: int, bond_vocab: int,
-                     pin: bool = True) -> PackedBatch:
-        """Collate molecules `idx` (in that order) and pack them: one C call, no Python per-graph loop."""
+                     pin: bool = True, each: bool = False) -> PackedBatch:
+        """Collate molecules `idx` (in that order) and pack them: one C call, no Python per-graph loop.
+        `each=True` lays the batch out so that every molecule is computed as if it were alone in the call
+        (include/graphchem_b200.h GCB_PACK_EACH; prediction only)."""
         idx = np.asarray(idx, dtype=np.int64)
         G = int(idx.shape[0])
         na, ne = self.n_atoms[idx], self.n_edges[idx]
         N, E = int(na.sum()), int(ne.sum())
-        M = live_bond_rows(N, E, n_messages)
-        header, total = _header(N, E, G, M, atom_vocab, bond_vocab)
+        if each and (n_messages < 1 or E < N):
+            raise NotImplementedError("each=True needs n_messages >= 1 and at least as many edges as atoms in the batch")
+        M = N if each else live_bond_rows(N, E, n_messages)
+        header, total = _header(N, E, G, M, atom_vocab, bond_vocab, _lib.PACK_EACH if each else 0)
         ints = _alloc_ints(total, pin)
         atoms_p = (self.atoms.data_ptr() + 4 * self.atom_off[idx]).astype(np.uint64)
         bonds_p = (self.bonds.data_ptr() + 4 * self.edge_off[idx]).astype(np.uint64)
@@ -188,9 +193,9 @@ class MoleculeStore:
             yo_p = y.data_ptr()
         na = np.ascontiguousarray(na)
         ne = np.ascontiguousarray(ne)
-        rc = _lib.lib().gcb_collate_pack_host(atoms_p.ctypes.data, na.ctypes.data, bonds_p.ctypes.data,
-                                              conn_p.ctypes.data, ne.ctypes.data, y_p, nt, G, n_messages, atom_vocab,
-                                              bond_vocab, ints.data_ptr(), total, yo_p)
+        fn = _lib.lib().gcb_collate_pack_each_host if each else _lib.lib().gcb_collate_pack_host
+        rc = fn(atoms_p.ctypes.data, na.ctypes.data, bonds_p.ctypes.data, conn_p.ctypes.data, ne.ctypes.data, y_p, nt, G,
+                n_messages, atom_vocab, bond_vocab, ints.data_ptr(), total, yo_p)
         _lib.check(rc, "gcb_collate_pack_host")
         header[:] = ints[:_lib.PACK_HEADER_INTS].numpy()
         return PackedBatch(ints, header, y)

@@ -275,6 +275,44 @@ class MoleculeGCN(nn.Module):
             _lib.check(rc, "gcb_backward")
         return [grad[off:off + p.numel()].view(p.shape) for p, off in zip(params, offs)]
 
+    # ---- batched per-molecule prediction ---------------------------------------------------------
+    @torch.no_grad()
+    def predict_each(self, molecules, batch_size: int = 4096, return_all: bool = False):
+        """What `[model(g) for g in molecules]` returns (the notebooks' evaluation loops, reference
+        examples/predict_cn.ipynb:258-263, 333-334), computed in batched launches.
+
+        A plain batched forward is NOT that: the reference indexes the bond matrix by atom id
+        (gcn.py:163), so molecules of one Batch see each other's bond rows.  Here the
+        batch is packed so that every molecule sees exactly the bond rows it would see alone
+        (GCB_PACK_EACH, include/graphchem_b200.h); dropout is off as under `model.eval()`.
+
+        `molecules`: a MoleculeStore, a MoleculeDataset or a sequence of Data/MoleculeGraph.  Returns the
+        predictions [n, out] (CPU), or with `return_all` also the per-molecule lists of out_atom / out_bond."""
+        from ..data.packed import MoleculeStore
+        dev = self._ensure_device()
+        store = molecules if isinstance(molecules, MoleculeStore) else MoleculeStore.from_graphs(list(molecules))
+        if int(self._n_messages) < 1:
+            raise NotImplementedError("predict_each needs n_messages >= 1 (without message passing a plain batch is already per-molecule)")
+        av, bv = self._dims[0], self._dims[1]
+        outs, atoms, bonds = [], [], []
+        n = len(store)
+        i = 0
+        while i < n:
+            # a chunk needs at least as many edges as atoms; single-atom molecules are appended to richer ones
+            j = min(n, i + batch_size)
+            idx = list(range(i, j))
+            pb = store.collate_pack(idx, int(self._n_messages), av, bv, each=True).to(dev, non_blocking=True)
+            out, out_atom, out_bond, _ = self._run_forward(pb, 0, 0)
+            outs.append(out.cpu())
+            if return_all:
+                na = store.n_atoms[i:j].tolist()
+                ne = store.n_edges[i:j].tolist()
+                atoms += list(torch.split(out_atom.cpu(), na))
+                bonds += list(torch.split(out_bond.cpu(), ne))
+            i = j
+        out = torch.cat(outs) if outs else torch.zeros(0, self._dims[2] if self._dims[4] > 0 else self._dims[3])
+        return (out, atoms, bonds) if return_all else out
+
     # ---- forward ---------------------------------------------------------------------------------
     def forward(self, data) -> Tuple[Tensor, Tensor, Tensor]:
         """`data`: PyG-style Data/Batch (x, edge_index, edge_attr, batch) or a `PackedBatch`.

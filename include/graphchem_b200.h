@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 1
+#define GCB_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define GCB_OK 0
@@ -65,8 +65,8 @@ typedef struct gcb_model_cfg {
  * the reference's scatter order), graph segments and token buckets.  GCB_PACK_HEADER_INTS header
  * ints are followed by the sections; offsets (in ints, from the buffer start) live in the header.
  */
-#define GCB_PACK_MAGIC 0x47434231 /* "GCB1" */
-#define GCB_PACK_HEADER_INTS 32
+#define GCB_PACK_MAGIC 0x47434232 /* "GCB2" */
+#define GCB_PACK_HEADER_INTS 48
 #define GCB_TILE_ROWS 128
 enum gcb_pack_field {
   GCB_H_MAGIC = 0, GCB_H_N, GCB_H_E, GCB_H_G, GCB_H_M, GCB_H_AV, GCB_H_BV, GCB_H_TOTAL_INTS,
@@ -84,14 +84,27 @@ enum gcb_pack_field {
    * split).  GCB_H_NTILES = 0 when some connected component spans more than GCB_TILE_ROWS rows
    * (the unfused kernels are used then).  Written by the packer, data dependent. */
   GCB_H_TILE_PTR, GCB_H_NTILES,
+  GCB_H_FLAGS,    /* GCB_PACK_* bits */
+  GCB_H_BOND_POS, /* GCB_PACK_EACH only: [E] bond-matrix row that holds edge e, or -1 (constant row) */
   GCB_H_FIELDS
 };
+
+/* GCB_PACK_EACH ("each molecule alone"): the batch is laid out so that every molecule sees the bond
+ * rows it would see if it were the only graph in the call.  The reference indexes the bond matrix by
+ * ATOM id (gcn.py:163), so a batched forward differs from per-molecule forwards; the
+ * notebooks predict one molecule per call (examples/predict_cn.ipynb:258-263, 333-334).  With this
+ * flag bond row r holds the molecule's OWN edge number (r - first atom of the molecule), so one
+ * batched launch reproduces the per-molecule results.  Inference only. */
+#define GCB_PACK_EACH 1
 
 /* Number of int32 elements a packed batch needs; fills header[GCB_PACK_HEADER_INTS] (host memory)
  * with sizes and section offsets.  M = number of live bond rows = min(N,E) when n_messages >= 1,
  * E when n_messages == 0. */
 int64_t gcb_pack_ints(int32_t N, int32_t E, int32_t G, int32_t M, int32_t atom_vocab, int32_t bond_vocab,
                       int32_t* header);
+/* Same with GCB_PACK_* flags (GCB_PACK_EACH adds the [E] bond-position section). */
+int64_t gcb_pack_ints_flags(int32_t N, int32_t E, int32_t G, int32_t M, int32_t atom_vocab, int32_t bond_vocab,
+                            int32_t flags, int32_t* header);
 
 /* Host packer (replaces nothing in the reference: it is the "prepacked into pinned CSR buffers"
  * step of the north star; the index semantics restate PyG's scatter order).
@@ -112,6 +125,17 @@ int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t* n_atoms, c
                           const int64_t* const* conn, const int32_t* n_edges, const float* const* y,
                           int32_t n_targets, int32_t n_graphs, int32_t n_messages, int32_t atom_vocab,
                           int32_t bond_vocab, int32_t* packed, int64_t packed_ints, float* y_out);
+
+/* Collate + pack in GCB_PACK_EACH layout (batched prediction that equals one forward per molecule:
+ * the `for g in dataset: model(g)` loops of examples/predict_cn.ipynb:258-263, 333-334 in one call).
+ * Same arguments as gcb_collate_pack_host; size the buffer with gcb_pack_ints_flags(GCB_PACK_EACH).
+ * Needs n_messages >= 1 and sum(n_edges) >= sum(n_atoms); returns GCB_ERR_INDEX when a molecule's
+ * connectivity addresses a bond row it does not have (the reference raises IndexError for it alone)
+ * and GCB_ERR_UNSUPPORTED when the batch has fewer edges than atoms. */
+int gcb_collate_pack_each_host(const int32_t* const* atoms, const int32_t* n_atoms, const int32_t* const* bonds,
+                               const int64_t* const* conn, const int32_t* n_edges, const float* const* y,
+                               int32_t n_targets, int32_t n_graphs, int32_t n_messages, int32_t atom_vocab,
+                               int32_t bond_vocab, int32_t* packed, int64_t packed_ints, float* y_out);
 
 /* ---- parameters -------------------------------------------------------------------------- */
 /* Flat fp32 parameter vector in the reference's state_dict order (gcn.py:78-114):

@@ -84,3 +84,25 @@ def build_index(x_tok, e_tok, edge_index, batch, n_graphs, atom_vocab, bond_voca
         node_graph=np.asarray(batch).astype(np.int32),
         tile_ptr=closed_tiles(src, dst, N),
     )
+
+
+def each_layout(n_atoms, n_edges, bond_tok_per_graph):
+    """GCB_PACK_EACH restated: molecule m with node offset a_m and edge offset e_m keeps, alone, the bond
+    matrix rows 0..n_edges[m]-1 indexed by its local atom ids (reference gcn.py:163).  In the batch the
+    bond row of global atom a_m + i is the molecule's edge i, so
+        bond_pos[e_m + k] = a_m + k if k < n_atoms[m] else -1      (row that holds edge e_m + k)
+        e_tok_each[a_m + i] = bond token of edge e_m + i if i < n_edges[m] else 0
+    Returns (bond_pos [E], e_tok_each [N])."""
+    n_atoms, n_edges = np.asarray(n_atoms), np.asarray(n_edges)
+    a_off = np.concatenate([[0], np.cumsum(n_atoms)])
+    N, E = int(a_off[-1]), int(n_edges.sum())
+    bond_pos = np.full(E, -1, dtype=np.int32)
+    e_tok = np.zeros(N, dtype=np.int32)
+    e = 0
+    for m, (na, ne) in enumerate(zip(n_atoms, n_edges)):
+        for k in range(ne):
+            if k < na:
+                bond_pos[e + k] = a_off[m] + k
+                e_tok[a_off[m] + k] = bond_tok_per_graph[m][k]
+        e += ne
+    return bond_pos, e_tok

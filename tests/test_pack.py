@@ -130,3 +130,32 @@ def test_closed_row_tiles():
     both = ocollate([graphs[0], type(graphs[0])(x=ring.x.int(), edge_index=ring.edge_index, edge_attr=ring.edge_attr.int(),
                                                 y=torch.zeros(1, 1))])
     assert pack_batch(both, 2, 12, 7, pin=False).n_tiles == 0
+
+
+def test_each_molecule_alone_layout():
+    """GCB_PACK_EACH (batched prediction == one forward per molecule): bond rows re-indexed per molecule,
+    CSR edge ids redirected to the rows that hold them; everything else as the plain collate."""
+    from graphchem_b200 import _lib
+    from oracle.csr_oracle import each_layout
+    data, graphs = random_batch(seed=13, n_graphs=40, max_atoms=9)
+    mgs = [MoleculeGraph(g.x, g.edge_attr, g.edge_index, g.y) for g in graphs]
+    store = MoleculeStore.from_graphs(mgs)
+    idx = np.arange(40)
+    plain = store.collate_pack(idx, 2, 12, 7, pin=False)
+    each = store.collate_pack(idx, 2, 12, 7, pin=False, each=True)
+    assert each.M == each.N == plain.N and int(each.header[_lib.H_FLAGS]) == _lib.PACK_EACH
+    sp, se = plain.sections(), each.sections()
+    bond_pos, e_tok_each = each_layout(store.n_atoms, store.n_edges, [g.edge_attr.numpy() for g in graphs])
+    assert np.array_equal(se["bond_pos"].numpy(), bond_pos)
+    assert np.array_equal(se["e_tok"].numpy()[:each.N], e_tok_each)
+    for k in ("x_tok", "src", "dst", "in_ptr", "in_src", "out_ptr", "out_dst", "graph_ptr", "tile_ptr", "in_src4", "out_dst4",
+              "out_inpos"):
+        assert torch.equal(sp[k], se[k]), k
+    redirect = lambda eid: np.where(eid >= 0, np.where(bond_pos[np.maximum(eid, 0)] >= 0, bond_pos[np.maximum(eid, 0)], each.M), -1)
+    assert np.array_equal(se["in_eid"].numpy(), redirect(sp["in_eid"].numpy()))
+    assert np.array_equal(se["in_eid4"].numpy(), redirect(sp["in_eid4"].numpy()))
+    # a molecule whose connectivity addresses a bond row it does not have alone: IndexError, as the reference
+    bad = MoleculeGraph(torch.tensor([2, 2, 2], dtype=torch.int32), torch.tensor([2, 2], dtype=torch.int32),
+                        torch.tensor([[1, 2], [2, 1]]))
+    with pytest.raises(IndexError):
+        MoleculeStore.from_graphs([mgs[0], bad]).collate_pack(np.arange(2), 2, 12, 7, pin=False, each=True)
