@@ -15,18 +15,11 @@ namespace gcb {
 
 static inline int64_t pad4(int64_t n) { return (n + 3) & ~int64_t(3); }
 
-static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, int32_t bv, int32_t flags, int32_t* h) {
-  int64_t off = GCB_PACK_HEADER_INTS;
-  auto put = [&](int field, int64_t n) {
-    if (h) h[field] = (int32_t)off;
-    off += pad4(n);
-  };
-  if (h) {
-    std::memset(h, 0, sizeof(int32_t) * GCB_PACK_HEADER_INTS);
-    h[GCB_H_MAGIC] = GCB_PACK_MAGIC;
-    h[GCB_H_N] = N; h[GCB_H_E] = E; h[GCB_H_G] = G; h[GCB_H_M] = M; h[GCB_H_AV] = av; h[GCB_H_BV] = bv;
-    h[GCB_H_FLAGS] = flags;
-  }
+// Section table of a packed batch: (header field, element count), in buffer order.
+struct Sec { int field; int64_t n; };
+static int section_table(int32_t N, int32_t E, int32_t G, int32_t av, int32_t bv, int32_t flags, Sec* t) {
+  int k = 0;
+  auto put = [&](int field, int64_t n) { t[k].field = field; t[k].n = n; ++k; };
   put(GCB_H_X_TOK, N); put(GCB_H_E_TOK, E); put(GCB_H_SRC, E); put(GCB_H_DST, E);
   put(GCB_H_IN_PTR, (int64_t)N + 1); put(GCB_H_IN_EID, E); put(GCB_H_IN_SRC, E);
   put(GCB_H_OUT_PTR, (int64_t)N + 1); put(GCB_H_OUT_EID, E); put(GCB_H_OUT_DST, E);
@@ -39,9 +32,43 @@ static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, in
   put(GCB_H_OUT_INPOS, E);
   put(GCB_H_TILE_PTR, (int64_t)N + 1);
   if (flags & GCB_PACK_EACH) put(GCB_H_BOND_POS, E);
+  return k;
+}
+
+static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, int32_t bv, int32_t flags, int32_t* h) {
+  int64_t off = GCB_PACK_HEADER_INTS;
+  if (h) {
+    std::memset(h, 0, sizeof(int32_t) * GCB_PACK_HEADER_INTS);
+    h[GCB_H_MAGIC] = GCB_PACK_MAGIC;
+    h[GCB_H_N] = N; h[GCB_H_E] = E; h[GCB_H_G] = G; h[GCB_H_M] = M; h[GCB_H_AV] = av; h[GCB_H_BV] = bv;
+    h[GCB_H_FLAGS] = flags;
+  }
+  Sec t[GCB_H_FIELDS];
+  const int k = section_table(N, E, G, av, bv, flags, t);
+  for (int i = 0; i < k; ++i) {
+    if (h) h[t[i].field] = (int32_t)off;
+    off += pad4(t[i].n);
+  }
   if (off > INT32_MAX) return -1;
   if (h) h[GCB_H_TOTAL_INTS] = (int32_t)off;
   return off;
+}
+
+// Every byte of a packed batch is defined (two packs of the same input compare equal) without clearing
+// the whole buffer first: only the alignment pads and the tails of the sections the packer fills
+// partially are zeroed.
+static void zero_unwritten(int32_t* packed, const int32_t* h, int64_t e_tok_written) {
+  const int32_t N = h[GCB_H_N], E = h[GCB_H_E], G = h[GCB_H_G], M = h[GCB_H_M];
+  Sec t[GCB_H_FIELDS];
+  const int k = section_table(N, E, G, h[GCB_H_AV], h[GCB_H_BV], h[GCB_H_FLAGS], t);
+  for (int i = 0; i < k; ++i)
+    for (int64_t j = t[i].n; j < pad4(t[i].n); ++j) packed[h[t[i].field] + j] = 0;
+  auto tail = [&](int field, int64_t written, int64_t n) {
+    if (written < n) std::memset(packed + h[field] + written, 0, sizeof(int32_t) * (size_t)(n - written));
+  };
+  tail(GCB_H_BTOK_ROW, M, E);
+  tail(GCB_H_TILE_PTR, (int64_t)packed[GCB_H_NTILES] + 1, (int64_t)N + 1);
+  tail(GCB_H_E_TOK, e_tok_written, E);
 }
 
 // Stable counting sort of ids 0..n-1 by key: ptr[nb+1], perm[n].
@@ -106,6 +133,7 @@ static int finish_pack(int32_t* packed, const int32_t* h, const int32_t* batch_i
     graph_ptr[0] = 0;
     for (int32_t g = 1; g <= G; ++g) graph_ptr[g] = N;
     for (int32_t i = 0; i < N; ++i) graph_node[i] = i;
+    std::memset(node_graph, 0, sizeof(int32_t) * (size_t)N);
   }
   bucket(x_tok, N, av, packed + h[GCB_H_ATOK_PTR], packed + h[GCB_H_ATOK_NODE]);
   bucket(e_tok, M, bv, packed + h[GCB_H_BTOK_PTR], packed + h[GCB_H_BTOK_ROW]);
@@ -163,7 +191,6 @@ extern "C" int gcb_pack_host(const void* x, const void* edge_attr, const void* e
   int64_t total = gcb_pack_ints(N, E, G, M, atom_vocab, bond_vocab, h);
   if (total < 0) return GCB_ERR_INVALID_ARG;
   if (packed_ints < total) return GCB_ERR_WORKSPACE;
-  std::memset(packed, 0, sizeof(int32_t) * (size_t)total);
   std::memcpy(packed, h, sizeof(h));
   int32_t* x_tok = packed + h[GCB_H_X_TOK];
   int32_t* e_tok = packed + h[GCB_H_E_TOK];
@@ -195,7 +222,9 @@ extern "C" int gcb_pack_host(const void* x, const void* edge_attr, const void* e
       b32[(size_t)i] = (int32_t)g;
     }
   }
-  return finish_pack(packed, h, batch ? b32.data() : nullptr);
+  const int rc = finish_pack(packed, h, batch ? b32.data() : nullptr);
+  if (rc == GCB_OK) zero_unwritten(packed, h, E);
+  return rc;
 }
 
 extern "C" int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t* n_atoms,
@@ -218,7 +247,6 @@ extern "C" int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t*
   int64_t total = gcb_pack_ints(N, E, G, M, atom_vocab, bond_vocab, h);
   if (total < 0) return GCB_ERR_INVALID_ARG;
   if (packed_ints < total) return GCB_ERR_WORKSPACE;
-  std::memset(packed, 0, sizeof(int32_t) * (size_t)total);
   std::memcpy(packed, h, sizeof(h));
   int32_t* x_tok = packed + h[GCB_H_X_TOK];
   int32_t* e_tok = packed + h[GCB_H_E_TOK];
@@ -250,7 +278,9 @@ extern "C" int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t*
     node_off += na;
     edge_off += ne;
   }
-  return finish_pack(packed, h, b32.data());
+  const int rc = finish_pack(packed, h, b32.data());
+  if (rc == GCB_OK) zero_unwritten(packed, h, E);
+  return rc;
 }
 
 // "Each molecule alone": bond row r of the packed batch = the molecule's own edge (r - its first atom).
@@ -275,13 +305,13 @@ extern "C" int gcb_collate_pack_each_host(const int32_t* const* atoms, const int
   int64_t total = gcb_pack_ints_flags(N, E, G, M, atom_vocab, bond_vocab, GCB_PACK_EACH, h);
   if (total < 0) return GCB_ERR_INVALID_ARG;
   if (packed_ints < total) return GCB_ERR_WORKSPACE;
-  std::memset(packed, 0, sizeof(int32_t) * (size_t)total);
   std::memcpy(packed, h, sizeof(h));
   int32_t* x_tok = packed + h[GCB_H_X_TOK];
   int32_t* e_tok = packed + h[GCB_H_E_TOK];
   int32_t* src = packed + h[GCB_H_SRC];
   int32_t* dst = packed + h[GCB_H_DST];
   int32_t* bond_pos = packed + h[GCB_H_BOND_POS];
+  std::memset(e_tok, 0, sizeof(int32_t) * (size_t)N);  // rows of atoms beyond a molecule's last edge keep token 0
   std::vector<int32_t> b32((size_t)N);
   int64_t node_off = 0, edge_off = 0;
   for (int32_t g = 0; g < G; ++g) {
@@ -322,5 +352,6 @@ extern "C" int gcb_collate_pack_each_host(const int32_t* const* atoms, const int
   for (int64_t k = 0; k < E; ++k) in_eid[k] = bond_pos[in_eid[k]] >= 0 ? bond_pos[in_eid[k]] : M;
   for (int64_t k = 0; k < 4 * (int64_t)N; ++k)
     if (e4[k] >= 0) e4[k] = bond_pos[e4[k]] >= 0 ? bond_pos[e4[k]] : M;
+  zero_unwritten(packed, h, N);
   return GCB_OK;
 }

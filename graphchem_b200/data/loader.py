@@ -4,7 +4,8 @@ The reference iterates a `torch_geometric.loader.DataLoader` whose collate is a 
 graph (examples/predict_cn.ipynb:212, 245).  At millions of molecules per second on the GPU that loop -- and
 even the one-C-call-per-batch packer, ~0.4 M molecules/s per host core -- is the bottleneck, so the loader
 
-* packs batches on a pool of host threads (the C-ABI packer releases the GIL) into pinned memory,
+* packs batches on a pool of host threads (the C-ABI packer releases the GIL) into RECYCLED pinned buffers
+  (a fresh 32 MB allocation per batch costs more in page faults / cudaHostAlloc than the packing itself),
 * ships them on a copy stream, `prefetch` batches ahead of the consumer,
 * and, with `cache=True`, keeps the packed batches resident (in HBM when `device` is CUDA) after the first
   epoch: later epochs replay them (optionally in shuffled ORDER; batch composition is then fixed), which is
@@ -14,6 +15,7 @@ even the one-C-call-per-batch packer, ~0.4 M molecules/s per host core -- is the
 """
 from __future__ import annotations
 
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Iterator, List, Optional, Sequence
 
@@ -36,6 +38,8 @@ class PackedLoader:
         self.epoch = 0
         self._cached: Optional[List[PackedBatch]] = None
         self._pin = self.device.type == "cuda"
+        self._pool: List[tuple] = []  # free (int32 buffer, float32 target buffer) pairs, pinned; CUDA devices only
+        self._pool_lock = threading.Lock()
 
     def __len__(self) -> int:
         n = len(self.indices)
@@ -50,8 +54,30 @@ class PackedLoader:
             out.pop()
         return out
 
-    def _pack(self, idx: np.ndarray) -> PackedBatch:
-        return self.store.collate_pack(idx, self.n_messages, self.av, self.bv, pin=self._pin, each=self.each)
+    def _pack(self, idx: np.ndarray):
+        """-> (host PackedBatch, pooled buffers or None).  On CUDA devices the batch is packed into a recycled
+        pinned buffer pair sized for this loader's largest batch."""
+        if not self._pin:
+            return self.store.collate_pack(idx, self.n_messages, self.av, self.bv, pin=False, each=self.each), None
+        with self._pool_lock:
+            bufs = self._pool.pop() if self._pool else None
+        if bufs is None:
+            nt = 0 if self.store.targets is None else int(self.store.targets.size(1))
+            bufs = (torch.empty(self._capacity(), dtype=torch.int32, pin_memory=True),
+                    torch.empty(max(1, self.batch_size * nt), dtype=torch.float32, pin_memory=True))
+        hb = self.store.collate_pack(idx, self.n_messages, self.av, self.bv, pin=True, each=self.each, out=bufs[0],
+                                     y_out=bufs[1])
+        return hb, bufs
+
+    def _capacity(self) -> int:
+        """int32 elements that hold any batch of this loader (packed size grows with atoms and edges)."""
+        from .. import _lib
+        from .packed import _header
+        na = np.sort(self.store.n_atoms[self.indices])[::-1][:self.batch_size].sum()
+        ne = np.sort(self.store.n_edges[self.indices])[::-1][:self.batch_size].sum()
+        N, E = int(na), int(max(ne, na if self.each else 0))
+        M = min(N, E) if self.n_messages >= 1 else E
+        return _header(N, E, self.batch_size, M, self.av, self.bv, _lib.PACK_EACH if self.each else 0)[1]
 
     def __iter__(self) -> Iterator[PackedBatch]:
         self.epoch += 1
@@ -80,19 +106,23 @@ class PackedLoader:
             submit()
             while pending or inflight:
                 while pending and len(inflight) < self.prefetch and (pending[0].done() or not inflight):
-                    hb = pending.pop(0).result()
+                    hb, bufs = pending.pop(0).result()
                     if cuda:
                         with torch.cuda.stream(copy_stream):
                             db = hb.to(self.device, non_blocking=True)
                             ev = torch.cuda.Event()
                             ev.record(copy_stream)
-                        inflight.append((db, ev, hb))  # hb kept alive until the copy has been consumed
+                        inflight.append((db, ev, bufs))
                     else:
                         inflight.append((hb, None, None))
                     submit()
-                db, ev, _hb = inflight.pop(0)
+                db, ev, bufs = inflight.pop(0)
                 if ev is not None:
                     torch.cuda.current_stream(self.device).wait_event(ev)
+                    if bufs is not None:  # the pinned pair is free again once its copy has left the host
+                        ev.synchronize()
+                        with self._pool_lock:
+                            self._pool.append(bufs)
                 if self.cache:
                     keep.append(db)
                 yield db

@@ -167,10 +167,12 @@ class MoleculeStore:
         return int(self.n_atoms.shape[0])
 
     def collate_pack(self, idx: Sequence[int], n_messages: int, atom_vocab: int, bond_vocab: int,
-                     pin: bool = True, each: bool = False) -> PackedBatch:
+                     pin: bool = True, each: bool = False, out: Optional[Tensor] = None,
+                     y_out: Optional[Tensor] = None) -> PackedBatch:
         """Collate molecules `idx` (in that order) and pack them: one C call, no Python per-graph loop.
         `each=True` lays the batch out so that every molecule is computed as if it were alone in the call
-        (include/graphchem_b200.h GCB_PACK_EACH; prediction only)."""
+        (include/graphchem_b200.h GCB_PACK_EACH; prediction only).  `out` / `y_out`: host buffers to pack into
+        (int32 / float32, large enough; a loader recycles pinned buffers through these) instead of fresh ones."""
         idx = np.asarray(idx, dtype=np.int64)
         G = int(idx.shape[0])
         na, ne = self.n_atoms[idx], self.n_edges[idx]
@@ -179,7 +181,9 @@ class MoleculeStore:
             raise NotImplementedError("each=True needs n_messages >= 1 and at least as many edges as atoms in the batch")
         M = N if each else live_bond_rows(N, E, n_messages)
         header, total = _header(N, E, G, M, atom_vocab, bond_vocab, _lib.PACK_EACH if each else 0)
-        ints = _alloc_ints(total, pin)
+        if out is not None and (out.dtype != torch.int32 or out.device.type != "cpu" or out.numel() < total):
+            raise ValueError("collate_pack: `out` must be a host int32 tensor with room for the packed batch")
+        ints = out[:total] if out is not None else _alloc_ints(total, pin)
         atoms_p = (self.atoms.data_ptr() + 4 * self.atom_off[idx]).astype(np.uint64)
         bonds_p = (self.bonds.data_ptr() + 4 * self.edge_off[idx]).astype(np.uint64)
         conn_p = (self.conn.data_ptr() + 16 * self.edge_off[idx]).astype(np.uint64)
@@ -187,7 +191,10 @@ class MoleculeStore:
         y = None
         y_p, yo_p, y_ptrs = None, None, None
         if nt:
-            y = torch.empty(G, nt, dtype=torch.float32, pin_memory=pin and torch.cuda.is_available())
+            if y_out is not None and y_out.numel() >= G * nt and y_out.dtype == torch.float32:
+                y = y_out.reshape(-1)[:G * nt].view(G, nt)
+            else:
+                y = torch.empty(G, nt, dtype=torch.float32, pin_memory=pin and torch.cuda.is_available())
             y_ptrs = (self.targets.data_ptr() + 4 * nt * idx).astype(np.uint64)  # kept alive across the call
             y_p = y_ptrs.ctypes.data
             yo_p = y.data_ptr()
