@@ -15,6 +15,8 @@
 // bit-identical (tests/test_fused_gpu.py).
 #pragma once
 #include "kernels_v2.cuh"
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace gcb {
@@ -114,25 +116,28 @@ __device__ __forceinline__ uint32_t tie_bits(const uint4& q, const uint4& m, uin
 }
 
 // ---- bond update: Bout[r] = act(P[r] + max_{e->r} Q[src e]);  staged: [P|Q] rows of the tile (512 B each) ----
-template <bool TIES>
-__global__ void __launch_bounds__(kThreads, 3)
-bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, bf16* __restrict__ Bout,
-                   uint8_t* __restrict__ tiemask, uint8_t* __restrict__ tiecnt, int act) {
-  GCB_TILE_PROLOGUE(2 * kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmPQ, &bar, 0, r0))
+// QONLY: stage only the Q half (32 KB, more CTAs per SM) and stream the row's own P chunk from global.
+template <bool TIES, bool QONLY>
+__global__ void __launch_bounds__(kThreads, QONLY ? 4 : 3)
+bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, const bf16* __restrict__ PQ,
+                   bf16* __restrict__ Bout, uint8_t* __restrict__ tiemask, uint8_t* __restrict__ tiecnt, int act) {
+  constexpr int kQRow = QONLY ? kRowBytes : 2 * kRowBytes;  // bytes per staged row
+  constexpr int kQOff = QONLY ? 0 : kRowBytes;              // offset of the Q half inside a staged row
+  GCB_TILE_PROLOGUE((QONLY ? 1 : 2) * kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmPQ, &bar, QONLY ? kD : 0, r0))
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
-    const uint4 praw = lds16(smem + rr * (2 * kRowBytes) + lig * 16);
+    const uint4 praw = QONLY ? R::load(PQ + (size_t)r * (2 * kD) + c) : lds16(smem + rr * kQRow + lig * 16);
     uint4 q[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) q[u] = lds16(smem + ((nidx[u] - r0) & 127) * (2 * kRowBytes) + kRowBytes + lig * 16);
+      if (nidx[u] >= 0) q[u] = lds16(smem + ((nidx[u] - r0) & 127) * kQRow + kQOff + lig * 16);
     uint4 mraw = R::neg_inf();
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (nidx[u] >= 0) mraw = R::vmax(mraw, q[u]);
     for (int e = e0 + 4; e < e1; ++e)
-      mraw = R::vmax(mraw, lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * (2 * kRowBytes) + kRowBytes + lig * 16));
+      mraw = R::vmax(mraw, lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kQRow + kQOff + lig * 16));
     if (TIES && e1 > e0) {
       // per in-edge: which of the 8 channels attain the max (one byte); per channel: how many edges tie
       uint32_t cnt_lo = 0u, cnt_hi = 0u;  // four byte counters each: channels 0-3 / 4-7
@@ -141,7 +146,7 @@ bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, bf16
         if (nidx[u] >= 0) tiemask[(size_t)(e0 + u) * 16 + lig] = (uint8_t)tie_bits(q[u], mraw, cnt_lo, cnt_hi);
       }
       for (int e = e0 + 4; e < e1; ++e) {
-        const uint4 qe = lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * (2 * kRowBytes) + kRowBytes + lig * 16);
+        const uint4 qe = lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kQRow + kQOff + lig * 16);
         tiemask[(size_t)e * 16 + lig] = (uint8_t)tie_bits(qe, mraw, cnt_lo, cnt_hi);
       }
       *reinterpret_cast<uint2*>(tiecnt + (size_t)r * kD + c) = make_uint2(cnt_lo, cnt_hi);
@@ -397,15 +402,24 @@ inline int set_smem(K kernel, int bytes) {
 
 inline int launch_bond_update(const bf16* PQ, const TileCommon& cm, int n_tiles, bf16* Bout, uint8_t* tiemask,
                               uint8_t* tiecnt, int act, cudaStream_t s) {
+  // Q-only staging makes this kernel ~6 % faster in isolation but the whole step 1 % slower on B200 (the P rows it
+  // then streams through L1 compete with the next kernel's operands in L2); opt-in.
+  static const bool qonly = std::getenv("GCB_TILE_Q_ONLY") && std::getenv("GCB_TILE_Q_ONLY")[0] == '1';
   CUtensorMap tm;
-  if (gcb::tc::make_tmap_bf16_plain(&tm, PQ, cm.rows, 2 * kD, 2 * kD, kRows, 2 * kD)) return GCB_ERR_CUDA;
-  const int smem = smem_for(2);
+  if (gcb::tc::make_tmap_bf16_plain(&tm, PQ, cm.rows, 2 * kD, 2 * kD, kRows, qonly ? kD : 2 * kD)) return GCB_ERR_CUDA;
+  const int smem = smem_for(qonly ? 1 : 2);
   static bool attr = false;
-  if (!attr) { GCB_TRY(set_smem(bond_update_kernel<true>, smem)); GCB_TRY(set_smem(bond_update_kernel<false>, smem)); attr = true; }
+  if (!attr) {
+    GCB_TRY(set_smem(bond_update_kernel<true, true>, smem_for(1))); GCB_TRY(set_smem(bond_update_kernel<false, true>, smem_for(1)));
+    GCB_TRY(set_smem(bond_update_kernel<true, false>, smem_for(2))); GCB_TRY(set_smem(bond_update_kernel<false, false>, smem_for(2)));
+    attr = true;
+  }
   if (tiemask) {
-    GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<true><<<n_tiles, kThreads, smem, s>>>(tm, cm, Bout, tiemask, tiecnt, act)));
+    if (qonly) GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<true, true><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
+    else GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<true, false><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
   } else {
-    GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<false><<<n_tiles, kThreads, smem, s>>>(tm, cm, Bout, tiemask, tiecnt, act)));
+    if (qonly) GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<false, true><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
+    else GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<false, false><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
   }
   return GCB_OK;
 }
