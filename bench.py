@@ -52,7 +52,7 @@ def kernel_alg_bytes(name, N, E, M, G, D, s):
     share a class name; the value is the per-layer message-passing shape, which dominates."""
     i4 = 4
     table = {
-        "embed_act_kernel": N * i4 + N * D * s,
+        "embed_rows_kernel": N * i4 + N * D * s,
         # forward row kernels (per launch)
         "bond_update_kernel": M * 2 * D * s + 4 * M * i4 + M * D * s + M * D + E * 16,   # PQ in, B' out, tie counts + masks
         "atom_gather_kernel": N * D * s + 4 * N * i4 + N * D * s,                          # one half per launch: rows in, half of S out

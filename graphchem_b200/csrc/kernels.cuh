@@ -32,20 +32,16 @@ struct Drop {  // dropout descriptor for one tensor (p == 0 -> inactive)
 
 inline unsigned row_chunk_blocks(int64_t rows, int D, int vec) { return (unsigned)ceil_div(rows * (D / vec), 256); }
 
-// out[r,:] = act(table[tok[r],:])                                            gcn.py:152-157
+// out[r,:] = tab[tok[r],:]: the embedding lookup + activation of gcn.py:152-157 as a row copy out of the
+// pre-activated table (prepare_weights_kernel); one 16-byte chunk per thread, 32-bit index math.
 template <typename T>
-__global__ void embed_act_kernel(const float* __restrict__ table, const int32_t* __restrict__ tok,
-                                 T* __restrict__ out, int rows, int D, int act) {
-  GCB_ROW_CHUNK_PROLOGUE(rows)
-  const float* src = table + (size_t)tok[r] * D + c;
-  float v[V];
-#pragma unroll
-  for (int i = 0; i < V; i += 4) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(src + i));
-    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
-  }
-  act_fwd_vec<T, V>(v, act);
-  store_vec(out + (size_t)r * D + c, v);
+__global__ void embed_rows_kernel(const T* __restrict__ tab, const int32_t* __restrict__ tok, T* __restrict__ out,
+                                  int rows, int CH) {
+  const unsigned gidx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned r = gidx / (unsigned)CH, ch = gidx - r * (unsigned)CH;
+  if (r >= (unsigned)rows) return;
+  const uint4* src = reinterpret_cast<const uint4*>(tab) + (size_t)__ldg(tok + r) * CH + ch;
+  reinterpret_cast<uint4*>(out)[(size_t)r * CH + ch] = __ldg(src);
 }
 
 template <typename T, int V>

@@ -175,7 +175,7 @@ static int check_cfg(const gcb_model_cfg& c) {
 // ---- derived weights ----------------------------------------------------------------------------
 struct Derived {
   char* base;
-  int64_t wpq, wat, watT, wpqT, bpq, bat, total;
+  int64_t wpq, wat, watT, wpqT, bpq, bat, tab_atom, tab_bond, total;
 };
 static Derived derived_layout(const gcb_model_cfg& c, void* base) {
   const int64_t D = c.D, es = c.dtype == GCB_BF16 ? 2 : 4;
@@ -185,6 +185,8 @@ static Derived derived_layout(const gcb_model_cfg& c, void* base) {
   auto add = [&](int64_t& slot, int64_t bytes) { slot = o; o += align_up(bytes, 256); };
   add(d.wpq, 2 * D * D * es); add(d.wat, 2 * D * D * es); add(d.watT, 2 * D * D * es); add(d.wpqT, 2 * D * D * es);
   add(d.bpq, 2 * D * 4); add(d.bat, D * 4);
+  // pre-activated embedding tables act(emb)[vocab, D] in the activation dtype: the forward lookup is a row copy
+  add(d.tab_atom, (int64_t)c.atom_vocab * D * es); add(d.tab_bond, (int64_t)c.bond_vocab * D * es);
   d.total = o;
   return d;
 }
@@ -194,8 +196,13 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w_msg, const fl
                                        const float* __restrict__ w_edge, const float* __restrict__ b_edge,
                                        const float* __restrict__ w_bond, const float* __restrict__ b_bond,
                                        T* __restrict__ wpq, T* __restrict__ wat, T* __restrict__ watT,
-                                       T* __restrict__ wpqT, float* __restrict__ bpq, float* __restrict__ bat, int D) {
+                                       T* __restrict__ wpqT, float* __restrict__ bpq, float* __restrict__ bat, int D,
+                                       const float* __restrict__ emb_atom, const float* __restrict__ emb_bond,
+                                       T* __restrict__ tab_atom, T* __restrict__ tab_bond, int n_atom, int n_bond, int act) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // act(embedding) rounded to the storage type, exactly what embed + act produced per row (gcn.py:152-157)
+  if (idx < n_atom) tab_atom[idx] = from_float<T>(act_fwd_t<T>(emb_atom[idx], act));
+  if (idx < n_bond) tab_bond[idx] = from_float<T>(act_fwd_t<T>(emb_bond[idx], act));
   const int DD2 = 2 * D * D;
   if (idx < DD2) {
     // Wpq[n][k], n in [0,2D), k in [0,D):  U = W1 - W2 (n < D), V = W2 (n >= D);  W_b = [W1 | W2], [D, 2D]
@@ -457,10 +464,10 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
   const float* bat = (const float*)(dv.base + dv.bat);
 
   if (N > 0) {
-    GCB_KERNEL("embed_act_kernel", s, embed_act_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>(params + pl.emb_atom, g.x_tok, (T*)p.A[0], N, D, c.act));
+    GCB_KERNEL("embed_rows_kernel", s, embed_rows_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((const T*)(dv.base + dv.tab_atom), g.x_tok, (T*)p.A[0], N, D / V));
   }
   if (M > 0) {
-    GCB_KERNEL("embed_act_kernel", s, embed_act_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>(params + pl.emb_bond, g.e_tok, (T*)p.B[0], M, D, c.act));
+    GCB_KERNEL("embed_rows_kernel", s, embed_rows_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>((const T*)(dv.base + dv.tab_bond), g.e_tok, (T*)p.B[0], M, D / V));
   }
   // Boustrophedon traversal: every large kernel walks its rows in the direction opposite to the
   // previous one, so it starts on the rows its producer wrote LAST (still L2 resident).
@@ -536,7 +543,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       static bool attr2 = false;
       if (!attr2) { GCB_CUDA(cudaFuncSetAttribute(readout2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr2 = true; }
       Drop drb = make_drop(c, flags, seed, tag_readout(0));
-      GCB_KERNEL("readout_fwd_kernel", s, readout2_fwd_kernel<<<(unsigned)ceil_div(G, kReadoutGB2), 256, readout2_fwd_smem(rd2), s>>>(rd2, params, hp, out, G, c.act, drb));
+      GCB_KERNEL("readout_fwd_kernel", s, readout2_fwd_kernel<<<(unsigned)ceil_div(G, kReadoutGB2), kReadout2Threads, readout2_fwd_smem(rd2), s>>>(rd2, params, hp, out, G, c.act, drb));
     } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
       ReadoutPtrs hp;
       for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
@@ -599,7 +606,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       if (!attr2) { GCB_CUDA(cudaFuncSetAttribute(readout2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr2 = true; }
       const int blocks = (int)ceil_div(G, kReadoutGB2);
       Drop drb = make_drop(c, flags, seed, tag_readout(0));
-      GCB_KERNEL("readout_bwd_kernel", s, readout2_bwd_kernel<<<blocks, 256, readout2_bwd_smem(rd2), s>>>(rd2, params, hp, d_out, p.partial, p.dPool, G, c.act, drb));
+      GCB_KERNEL("readout_bwd_kernel", s, readout2_bwd_kernel<<<blocks, kReadout2Threads, readout2_bwd_smem(rd2), s>>>(rd2, params, hp, d_out, p.partial, p.dPool, G, c.act, drb));
       GCB_TRY(launch_reduce_partials(p.partial, blocks, pl.total - pl.r_w[0], grad + pl.r_w[0], accumulate, s, rd2.partial_stride));
       dPool = p.dPool;
     } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
@@ -833,17 +840,23 @@ extern "C" int gcb_prepare_weights(const gcb_model_cfg* cfg, const float* params
   Derived d = derived_layout(*cfg, derived);
   cudaStream_t s = (cudaStream_t)stream;
   const int D = cfg->D;
-  const unsigned blocks = (unsigned)ceil_div(2 * D * D, 256);
+  const int n_atom = cfg->atom_vocab * D, n_bond = cfg->bond_vocab * D;
+  int most = 2 * D * D;
+  most = most > n_atom ? most : n_atom;
+  most = most > n_bond ? most : n_bond;
+  const unsigned blocks = (unsigned)ceil_div(most, 256);
   if (cfg->dtype == GCB_BF16) {
     GCB_KERNEL("prepare_weights_kernel", s, prepare_weights_kernel<bf16><<<blocks, 256, 0, s>>>(
         params + pl.w_msg, params + pl.b_msg, params + pl.w_edge, params + pl.b_edge, params + pl.w_bond,
         params + pl.b_bond, (bf16*)(d.base + d.wpq), (bf16*)(d.base + d.wat), (bf16*)(d.base + d.watT),
-        (bf16*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D));
+        (bf16*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D, params + pl.emb_atom,
+        params + pl.emb_bond, (bf16*)(d.base + d.tab_atom), (bf16*)(d.base + d.tab_bond), n_atom, n_bond, cfg->act));
   } else {
     GCB_KERNEL("prepare_weights_kernel", s, prepare_weights_kernel<float><<<blocks, 256, 0, s>>>(
         params + pl.w_msg, params + pl.b_msg, params + pl.w_edge, params + pl.b_edge, params + pl.w_bond,
         params + pl.b_bond, (float*)(d.base + d.wpq), (float*)(d.base + d.wat), (float*)(d.base + d.watT),
-        (float*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D));
+        (float*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D, params + pl.emb_atom,
+        params + pl.emb_bond, (float*)(d.base + d.tab_atom), (float*)(d.base + d.tab_bond), n_atom, n_bond, cfg->act));
   }
   return GCB_OK;
 }

@@ -167,7 +167,9 @@ inline size_t readout2_bwd_smem(const ReadoutDesc& rd) {
   return (size_t)(3 * kReadoutGB2 * readout2_ld(rd) + rd.max_dim * readout2_ld(rd)) * sizeof(float);
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kReadout2Threads = 512;  // 16 output lanes x 32 graph lanes
+
+__global__ void __launch_bounds__(kReadout2Threads)
 readout2_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs hp, float* __restrict__ out, int G,
                     int act, Drop dr_base) {
   extern __shared__ __align__(16) float rs2[];
@@ -180,7 +182,7 @@ readout2_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   {
     const int in4 = rd.in_dim[0] >> 2;
-    for (int i = threadIdx.x; i < kReadoutGB2 * in4; i += 256) {
+    for (int i = threadIdx.x; i < kReadoutGB2 * in4; i += kReadout2Threads) {
       const int g = i / in4, j4 = i % in4;
       const float4 v = g < ng ? __ldg(reinterpret_cast<const float4*>(hp.h[0] + (size_t)(g0 + g) * rd.in_dim[0]) + j4)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -193,31 +195,32 @@ readout2_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
     const float* W = params + rd.w_off[k];
     const float* b = params + rd.b_off[k];
     float* dst = last ? out : hp.h[k + 1];
-    for (int i = threadIdx.x; i < on * in4; i += 256) {
+    for (int i = threadIdx.x; i < on * in4; i += kReadout2Threads) {
       const int o = i / in4, j4 = i % in4;
       *reinterpret_cast<float4*>(Ws + o * ld + 4 * j4) = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in) + j4);
     }
     __syncthreads();
     for (int ob = 0; ob < on; ob += 64) {
-      float acc[4][4];
+      constexpr int GA = 2;  // graphs per thread: g = ty + 32 a
+      float acc[GA][4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < GA; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
-      const float* hrow[4];
+      const float* hrow[GA];
       const float* wrow[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) hrow[a] = cur + (ty + 16 * a) * ld;
+      for (int a = 0; a < GA; ++a) hrow[a] = cur + (ty + 32 * a) * ld;
 #pragma unroll
       for (int c = 0; c < 4; ++c) wrow[c] = Ws + min(ob + tx + 16 * c, on - 1) * ld;
       for (int j4 = 0; j4 < in4; ++j4) {
-        float4 h[4], w[4];
+        float4 h[GA], w[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) h[a] = *reinterpret_cast<const float4*>(hrow[a] + 4 * j4);
+        for (int a = 0; a < GA; ++a) h[a] = *reinterpret_cast<const float4*>(hrow[a] + 4 * j4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) w[c] = *reinterpret_cast<const float4*>(wrow[c] + 4 * j4);
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < GA; ++a)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             acc[a][c] = fmaf(h[a].x, w[c].x, acc[a][c]);
@@ -232,8 +235,8 @@ readout2_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
         if (o >= on) continue;
         const float bo = __ldg(b + o);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int g = ty + 16 * a;
+        for (int a = 0; a < GA; ++a) {
+          const int g = ty + 32 * a;
           float v = acc[a][c] + bo;
           if (!last) {
             v = act_fwd(v, act);
@@ -253,7 +256,7 @@ readout2_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kReadout2Threads)
 readout2_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs hp, const float* __restrict__ d_out,
                     float* __restrict__ partial, float* __restrict__ dPool, int G, int act, Drop dr_base) {
   extern __shared__ __align__(16) float rs2[];
@@ -267,34 +270,36 @@ readout2_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float* my_partial = partial + (size_t)blockIdx.x * rd.partial_stride;
   const int o_last = rd.out_dim[rd.n_lin - 1];
-  for (int i = threadIdx.x; i < kReadoutGB2 * o_last; i += 256) {
+  for (int i = threadIdx.x; i < kReadoutGB2 * o_last; i += kReadout2Threads) {
     const int g = i / o_last, o = i % o_last;
     dz[g * ld + o] = g < ng ? d_out[(size_t)(g0 + g) * o_last + o] : 0.f;
   }
   for (int k = rd.n_lin - 1; k >= 0; --k) {
     const int in = rd.in_dim[k], on = rd.out_dim[k], in4 = in >> 2;
     const float* W = params + rd.w_off[k];
-    for (int i = threadIdx.x; i < kReadoutGB2 * in4; i += 256) {
+    for (int i = threadIdx.x; i < kReadoutGB2 * in4; i += kReadout2Threads) {
       const int g = i / in4, j4 = i % in4;
       const float4 v = g < ng ? __ldg(reinterpret_cast<const float4*>(hp.h[k] + (size_t)(g0 + g) * in) + j4)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(hin + g * ld + 4 * j4) = v;
     }
-    for (int i = threadIdx.x; i < on * in4; i += 256) {
+    for (int i = threadIdx.x; i < on * in4; i += kReadout2Threads) {
       const int o = i / in4, j4 = i % in4;
       *reinterpret_cast<float4*>(Ws + o * ld + 4 * j4) = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * in) + j4);
     }
     __syncthreads();
     float* pw = my_partial + rd.p_off[k];
-    // ---- weight-gradient partial of this CTA's graphs: outputs o = ob + tx + 16 c, inputs j = jb + 8 ty .. + 7
+    // ---- weight-gradient partial of this CTA's graphs: outputs o = ob + tx + 16 (2 (ty >> 4) + c), c < 2,
+    //      inputs j = jb + 8 (ty & 15) .. + 7
     for (int ob = 0; ob < on; ob += 64) {
       for (int jb = 0; jb < in; jb += 128) {
-        const int j = jb + 8 * ty;
+        constexpr int CW = 2;
+        const int j = jb + 8 * (ty & 15), oh = ob + 32 * (ty >> 4);
         if (j >= in) continue;  // in % 8 may be 4: the last lane group handles the 4-wide remainder below
         const bool wide = j + 8 <= in;
-        float acc[4][8];
+        float acc[CW][8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < CW; ++c)
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
         for (int g = 0; g < kReadoutGB2; ++g) {
@@ -302,15 +307,15 @@ readout2_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
           const float4 h1 = wide ? *reinterpret_cast<const float4*>(hin + g * ld + j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float d = dz[g * ld + min(ob + tx + 16 * c, on - 1)];
+          for (int c = 0; c < CW; ++c) {
+            const float d = dz[g * ld + min(oh + tx + 16 * c, on - 1)];
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[c][e] = fmaf(d, hv[e], acc[c][e]);
           }
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int o = ob + tx + 16 * c;
+        for (int c = 0; c < CW; ++c) {
+          const int o = oh + tx + 16 * c;
           if (o >= on) continue;
           float* q = pw + (size_t)o * in + j;
           *reinterpret_cast<float4*>(q) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
@@ -318,19 +323,20 @@ readout2_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
         }
       }
     }
-    for (int o = threadIdx.x; o < on; o += 256) {
+    for (int o = threadIdx.x; o < on; o += kReadout2Threads) {
       float acc = 0.f;
       for (int g = 0; g < kReadoutGB2; ++g) acc += dz[g * ld + o];
       pw[(size_t)on * in + o] = acc;
     }
-    // ---- gradient w.r.t. the layer input: graphs g = ty + 16 a, inputs j = jb + 8 tx .. + 7
+    // ---- gradient w.r.t. the layer input: graphs g = ty + 32 a (a < 2), inputs j = jb + 8 tx .. + 7
     for (int jb = 0; jb < in; jb += 128) {
+      constexpr int GA = 2;
       const int j = jb + 8 * tx;
       if (j >= in) continue;
       const bool wide = j + 8 <= in;
-      float acc[4][8];
+      float acc[GA][8];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < GA; ++a)
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
       for (int o = 0; o < on; ++o) {
@@ -338,15 +344,15 @@ readout2_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
         const float4 w1 = wide ? *reinterpret_cast<const float4*>(Ws + o * ld + j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const float d = dz[(ty + 16 * a) * ld + o];
+        for (int a = 0; a < GA; ++a) {
+          const float d = dz[(ty + 32 * a) * ld + o];
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[a][e] = fmaf(d, wv[e], acc[a][e]);
         }
       }
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int g = ty + 16 * a;
+      for (int a = 0; a < GA; ++a) {
+        const int g = ty + 32 * a;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           if (!wide && e >= 4) continue;
