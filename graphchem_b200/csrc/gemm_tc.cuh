@@ -270,6 +270,209 @@ inline int launch_gemm_nt_tc_impl(const bf16* A, int lda, const bf16* W, bf16* C
                 : launch_gemm_nt_tc_res<K, N, false>(A, lda, W, C, ldc, rows, ep, s);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Streamed-weight variant for wide models (embedding_dim 256: [2D, D] weights are 256 KB and cannot stay
+// in shared memory).  Classic tiling: a CTA owns a [128 x 256] output tile at a time, A [128 x 64] and
+// W [256 x 64] K-slabs stream through a 3-stage TMA ring (weights come from L2, where all of W lives),
+// the accumulator is double-buffered in TMEM, the epilogue is the same as above (bias / degree-scaled
+// bias / residual / activation, swizzled staging, TMA store).  Persistent, tiles enumerated row-tile
+// major so that the column tiles of one row tile reuse its A slabs out of L2.
+struct NtStream {
+  static constexpr int BM = 128, BN = 256, BK = 64;
+  static constexpr int STAGES = 3;
+  static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + W_BYTES;  // 16 + 32 KB
+  static constexpr int OUT_BYTES = BM * BN * 2;
+  static constexpr int MAX_N = 1024;                               // bias vector kept in shared memory
+  static constexpr int BAR_BYTES = 256 + MAX_N * 4;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int EPI_WARPS = 8, COL_PARTS = 2;
+  static constexpr int THREADS = 64 + EPI_WARPS * 32;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+__global__ void __launch_bounds__(NtStream::THREADS, 1)
+gemm_nt_tcs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ CUtensorMap tmC, int rows, int N, int K, TcEpilogue ep) {
+  using S = NtStream;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sStage = smem;
+  uint8_t* sOut = sStage + S::STAGES * S::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + S::OUT_BYTES);
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + S::STAGES;     // [STAGES]
+  uint64_t* tfull = bars + 2 * S::STAGES; // [2]
+  uint64_t* tempty = tfull + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (rows + S::BM - 1) / S::BM, num_n = N / S::BN, num_tiles = num_m * num_n, ksteps = K / S::BK;
+
+  if (ep.bias) {
+    for (int i = threadIdx.x; i < N; i += S::THREADS) sBias[i] = __ldg(ep.bias + i);
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmW); prefetch_tmap(&tmC);
+    for (int i = 0; i < S::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], S::EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * S::BM, n0 = (tile % num_n) * S::BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
+          uint8_t* a = sStage + stage * S::STAGE_BYTES;
+          tma_load_2d(a, &tmA, &full[stage], ks * S::BK, m0);
+          tma_load_2d(a + S::A_BYTES, &tmW, &full[stage], ks * S::BK, n0);
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_bf16(S::BM, S::BN, 0, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sStage + stage * S::STAGE_BYTES);
+          const uint32_t w_base = a_base + S::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < S::BK / 16; ++kk) {
+            const uint64_t da = smem_desc_sw128(a_base + kk * 32, 16, 1024);
+            const uint64_t dw = smem_desc_sw128(w_base + kk * 32, 16, 1024);
+            umma_bf16(tmem_base + acc * S::BN, da, dw, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int row_in_tile = q * 32 + lane;
+    const int ep_tid = threadIdx.x - 64;
+    constexpr int COLS_PER_WARP = S::BN / S::COL_PARTS;  // 128
+    constexpr int NCHUNK = COLS_PER_WARP / 32;           // 4
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * S::BM, n0 = (tile % num_n) * S::BN;
+      const int r = m0 + row_in_tile;
+      const bool valid = r < rows;
+      float wrow = 1.f;
+      if (ep.rowptr) {
+        const int deg = valid ? __ldg(ep.rowptr + r + 1) - __ldg(ep.rowptr + r) : 0;
+        wrow = ep.aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      if (ep_tid == 0) tma_store_wait_read();  // the previous tile's store has finished reading the staging buffer
+      named_bar_sync(1, S::EPI_WARPS * 32);
+#pragma unroll
+      for (int ci = 0; ci < NCHUNK; ++ci) {
+        const int c0 = half * COLS_PER_WARP + ci * 32;  // column inside the tile
+        uint4 res_raw[4];
+        if (ep.res && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r * ep.ld_res + n0 + c0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) res_raw[j4] = __ldg(rp + j4);
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * S::BN + c0, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + n0 + c0 + j);
+            f[j] = fmaf(wrow, b4.x, f[j]); f[j + 1] = fmaf(wrow, b4.y, f[j + 1]);
+            f[j + 2] = fmaf(wrow, b4.z, f[j + 2]); f[j + 3] = fmaf(wrow, b4.w, f[j + 3]);
+          }
+        }
+        if (ep.res && valid) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint32_t w[4] = {res_raw[j4].x, res_raw[j4].y, res_raw[j4].z, res_raw[j4].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[j4 * 8 + 2 * i] += __uint_as_float(w[i] << 16);
+              f[j4 * 8 + 2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+            }
+          }
+        }
+        if (ep.act >= 0) act_fwd_vec_impl<true, 32>(f, ep.act);
+        uint8_t* slab = sOut + (c0 >> 6) * (S::BM * 128) + row_in_tile * 128;
+        const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint4 t;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[j4 * 8 + 2 * i], f[j4 * 8 + 2 * i + 1]);
+          *reinterpret_cast<uint4*>(slab + (((chunk0 + j4) ^ (row_in_tile & 7)) << 4)) = t;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      fence_proxy_async_smem();
+      named_bar_sync(1, S::EPI_WARPS * 32);
+      if (ep_tid == 0) {
+        for (int ns = 0; ns < S::BN / 64; ++ns) tma_store_2d(&tmC, sOut + ns * (S::BM * 128), n0 + ns * 64, m0);
+        tma_store_commit();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (ep_tid == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+inline int launch_gemm_nt_tcs(const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int rows, int N, int K,
+                              const TcEpilogue& ep, cudaStream_t s) {
+  using S = NtStream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCB_CUDA(cudaFuncSetAttribute(gemm_nt_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmW, tmC;
+  if (make_tmap_bf16(&tmA, A, rows, K, lda, S::BM) || make_tmap_bf16(&tmW, W, N, K, K, S::BN) ||
+      make_tmap_bf16(&tmC, C, rows, N, ldc, S::BM))
+    return GCB_ERR_CUDA;
+  const int num_tiles = ((rows + S::BM - 1) / S::BM) * (N / S::BN);
+  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  GCB_KERNEL("gemm_nt_tc_kernel", s, (gemm_nt_tcs_kernel<<<grid, S::THREADS, S::SMEM_BYTES, s>>>(tmA, tmW, tmC, rows, N, K, ep)));
+  return GCB_OK;
+}
+
 // Returns GCB_ERR_UNSUPPORTED when the shape has no tcgen05 instantiation (caller falls back to
 // the CUDA-core GEMM).
 inline int launch_gemm_nt_tc(const bf16* A, int lda, const bf16* W, bf16* C, int ldc, int rows, int N, int K,
@@ -281,6 +484,9 @@ inline int launch_gemm_nt_tc(const bf16* A, int lda, const bf16* W, bf16* C, int
   if (K == 256 && N == 128) return launch_gemm_nt_tc_impl<256, 128>(A, lda, W, C, ldc, rows, ep, s);
   if (K == 64 && N == 128) return launch_gemm_nt_tc_impl<64, 128>(A, lda, W, C, ldc, rows, ep, s);
   if (K == 128 && N == 64) return launch_gemm_nt_tc_impl<128, 64>(A, lda, W, C, ldc, rows, ep, s);
+  // wide models: weights streamed from L2 (any K that is a multiple of 64, any N that is a multiple of 256)
+  if (K % NtStream::BK == 0 && N % NtStream::BN == 0 && N <= NtStream::MAX_N && K >= NtStream::BK)
+    return launch_gemm_nt_tcs(A, lda, W, C, ldc, rows, N, K, ep, s);
   return GCB_ERR_UNSUPPORTED;
 }
 

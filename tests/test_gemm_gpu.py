@@ -54,6 +54,16 @@ def test_tc_gemm_plain(rows, K, N):
     _run(rows, N, K)
 
 
+@pytest.mark.parametrize("K,N", [(256, 512), (512, 256), (192, 768)])
+@pytest.mark.parametrize("rows", [1, 129, 3000, 40000])
+def test_tc_gemm_streamed_weights(rows, K, N):
+    """Wide models (embedding_dim 256): weights do not fit shared memory and stream through the TMA ring."""
+    _run(rows, N, K)
+    if rows == 3000:
+        _run(rows, N, K, bias=True)
+        _run(rows, N, K, bias=True, deg=True, res=True, act="softplus")
+
+
 @pytest.mark.parametrize("K,N", [(128, 256), (256, 128)])
 def test_tc_gemm_epilogues(K, N):
     _run(5000, N, K, bias=True)
