@@ -124,3 +124,52 @@ def test_wide_component_falls_back_to_unfused():
         ro = oracle(d)
         rm = model(_dev(d))
     assert nerr(rm[0].float(), ro[0]) <= 2e-2 and nerr(rm[1].float(), ro[1]) <= 2e-2
+
+
+@pytest.mark.parametrize("chain", [127, 128, 129])
+def test_tile_boundary_molecule_sizes(chain):
+    """A molecule that exactly fills a 128-row tile (and its neighbours 127 / 129: the latter has no closed
+    tiling and runs untiled) next to small molecules: forward and gradients against the oracle."""
+    from graphchem_b200.data import pack_batch
+    from oracle.pyg_restated import Data as OData, collate as ocollate
+    g = torch.Generator().manual_seed(chain)
+    src = torch.arange(chain - 1)
+    big = OData(x=torch.randint(2, 12, (chain,), generator=g).int(),
+                edge_index=torch.stack([torch.cat([src, src + 1]), torch.cat([src + 1, src])]),
+                edge_attr=torch.randint(2, 7, (2 * (chain - 1),), generator=g).int(), y=torch.randn(1, 1, generator=g))
+    _, small = random_batch(seed=chain, n_graphs=20, max_atoms=9)
+    data = ocollate(small[:10] + [big] + small[10:])
+    pb = pack_batch(data, 2, 12, 7, pin=False)
+    assert (pb.n_tiles > 0) == (chain <= 128)
+    oracle, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=2)
+    dev = _dev(data)
+    oracle.eval(); model.eval()
+    with torch.no_grad():
+        ro, rm = oracle(data), model(dev)
+    for a, b in zip(rm, ro):
+        assert nerr(a.float(), b) <= 2e-2
+    oracle.train(); model.train()
+    lo = F.mse_loss(oracle(data)[0], data.y)
+    oracle.zero_grad(); lo.backward()
+    lm = F.mse_loss(model(dev)[0], dev.y)
+    model.zero_grad(); lm.backward()
+    for (name, po), (_, pm) in zip(oracle.named_parameters(), model.named_parameters()):
+        if po.grad is not None and float(po.grad.abs().max()) > 0:
+            assert nerr(pm.grad, po.grad) <= 6e-2, name
+
+
+def test_single_atom_molecules_force_the_untiled_path():
+    """More atoms than edges (single-atom molecules): not every atom row is a live bond row, the tile
+    kernels decline, results still match the oracle."""
+    from oracle.pyg_restated import Data as OData, collate as ocollate
+    _, small = random_batch(seed=3, n_graphs=4, max_atoms=4)
+    lone = [OData(x=torch.tensor([3], dtype=torch.int32), edge_index=torch.zeros(2, 0, dtype=torch.long),
+                  edge_attr=torch.zeros(0, dtype=torch.int32), y=torch.zeros(1, 1)) for _ in range(40)]
+    data = ocollate(small + lone)
+    assert data.edge_index.size(1) < data.x.numel()
+    oracle, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=2)
+    oracle.eval(); model.eval()
+    with torch.no_grad():
+        ro, rm = oracle(data), model(_dev(data))
+    for a, b in zip(rm, ro):
+        assert nerr(a.float(), b) <= 2e-2
