@@ -447,7 +447,7 @@ static bool fused_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
 template <typename T>
 static bool tiles_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
   if constexpr (sizeof(T) != 2) return false;
-  return tc::tile_enabled() && c.D == 128 && g.n_tiles > 0 && g.N > 0 && g.M == g.N &&
+  return tc::tile_enabled() && tile::width_ok(c.D) && g.n_tiles > 0 && g.N > 0 && g.M == g.N &&
          !((flags & GCB_TRAINING) && c.p_dropout > 0.f);
 }
 
@@ -501,7 +501,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
         if (tiles_ok<T>(c, g, flags)) {
           const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
           const tile::TileCommon cm{g.tile_ptr, M, g.in_ptr, g.in_src, (const int4*)g.in_src4, nullptr, nullptr};
-          GCB_TRY(tile::launch_bond_update((const bf16*)p.PQ[l], cm, g.n_tiles, (bf16*)p.B[l], save ? p.tiemask[l] : nullptr,
+          GCB_TRY(tile::launch_bond_update(D, (const bf16*)p.PQ[l], cm, g.n_tiles, (bf16*)p.B[l], save ? p.tiemask[l] : nullptr,
                                            save ? p.tiecnt[l] : nullptr, c.act, s));
           tiled = true;
         }
@@ -516,7 +516,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       if constexpr (sizeof(T) == 2) {
         if (c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags)) {
           const tile::TileCommon cm{g.tile_ptr, N, g.in_ptr, g.in_src, (const int4*)g.in_src4, (const int4*)g.in_eid4, g.in_eid};
-          GCB_TRY(tile::launch_atom_gather((const bf16*)p.A[l - 1], (const bf16*)p.B[l], M, cm, g.n_tiles, (bf16*)p.S[l], c.act, s));
+          GCB_TRY(tile::launch_atom_gather(D, (const bf16*)p.A[l - 1], (const bf16*)p.B[l], M, cm, g.n_tiles, (bf16*)p.S[l], c.act, s));
           a_tiled = true;
         }
       }
@@ -727,7 +727,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       if constexpr (sizeof(T) == 2) {
         if (N > 0 && c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags)) {
           const tile::TileCommon cm{g.tile_ptr, N, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, nullptr, nullptr};
-          GCB_TRY(tile::launch_atom_bwd((const bf16*)p.dS, (const bf16*)p.dZA[cur], (const bf16*)p.A[l - 1], cm, g.n_tiles,
+          GCB_TRY(tile::launch_atom_bwd(D, (const bf16*)p.dS, (const bf16*)p.dZA[cur], (const bf16*)p.A[l - 1], cm, g.n_tiles,
                                         (bf16*)p.dZA[cur ^ 1], c.act, s));
           tiled = true;
         }
@@ -743,7 +743,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     if constexpr (sizeof(T) == 2) {
       if (M > 0 && c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags) && tc::bond_bwd_merged_enabled()) {
         const tile::TileCommon cm{g.tile_ptr, M, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, (const int4*)g.out_inpos4, g.out_inpos};
-        GCB_TRY(tile::launch_bond_bwd(cm, g.n_tiles, g.in_ptr, g.dst, (const bf16*)p.dS, (const bf16*)dBnext,
+        GCB_TRY(tile::launch_bond_bwd(D, cm, g.n_tiles, g.in_ptr, g.dst, (const bf16*)p.dS, (const bf16*)dBnext,
                                       l == L ? (const bf16*)d_out_bond : nullptr, (const bf16*)p.B[l], p.tiecnt[l], p.tiemask[l],
                                       (bf16*)dPQ_l, c.act, s));
         bond_tiled = true;
@@ -758,7 +758,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       if constexpr (sizeof(T) == 2) {
         if (tiles_ok<T>(c, g, flags)) {
           const tile::TileCommon cm{g.tile_ptr, M, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, (const int4*)g.out_inpos4, g.out_inpos};
-          GCB_TRY(tile::launch_bond_scatter((const bf16*)p.gsplit, cm, g.n_tiles, p.tiemask[l], (bf16*)dPQ_l, s));
+          GCB_TRY(tile::launch_bond_scatter(D, (const bf16*)p.gsplit, cm, g.n_tiles, p.tiemask[l], (bf16*)dPQ_l, s));
           tiled = true;
         }
       }

@@ -1,4 +1,4 @@
-// Tile-staged row kernels (bf16, D = 128): the message-passing gathers out of shared memory.
+// Tile-staged row kernels (bf16, D = 128 or 256): the message-passing gathers out of shared memory.
 //
 // The unfused row kernels (kernels_v2.cuh) chase  index -> neighbour row  through global memory and
 // are bound by that dependent latency at the occupancy their registers allow (25-35 % of HBM
@@ -28,14 +28,20 @@ int make_tmap_bf16_plain(CUtensorMap* out, const void* base, int64_t rows, int64
 
 namespace tile {
 
-constexpr int kD = 128;
 constexpr int kRows = GCB_TILE_ROWS;              // 128
-constexpr int kThreads = 256;                     // 16 row slots x 16 lanes
-constexpr int kSlots = kThreads / 16;             // rows per pass
-constexpr int kPasses = kRows / kSlots;           // 8
-constexpr int kRowBytes = kD * 2;                 // 256
-constexpr int kBoxBytes = kRows * kRowBytes;      // 32 KB: one staged [128 x 128] bf16 box
+constexpr int kThreads = 256;
 constexpr int kIdxBytes = 2 * kRows * 16 + 544;   // two ELL-4 arrays + 129 row pointers (padded)
+
+// CH = 16-byte chunks (= lanes) per row: 16 for D = 128, 32 for D = 256.
+template <int CH>
+struct Cfg {
+  static constexpr int D = CH * 8;
+  static constexpr int kSlots = kThreads / CH;        // rows per pass: 16 / 8
+  static constexpr int kPasses = kRows / kSlots;      // 8 / 16
+  static constexpr int kRowBytes = D * 2;             // 256 / 512
+  static constexpr int kBoxBytes = kRows * kRowBytes; // one staged [128 x D] bf16 box: 32 / 64 KB
+  static constexpr int kCtas = CH == 16 ? 4 : 3;      // CTAs per SM the launch bounds aim for
+};
 
 using R = v2::Raw<bf16>;
 
@@ -60,6 +66,9 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
 // Tile prologue: [r0, r1) of this CTA's tile; one thread issues the TMA boxes (ISSUE, BOX_BYTES in
 // total, 0 = none) while all threads stage the indices; ends with everything visible.
 #define GCB_TILE_PROLOGUE(BOX_BYTES, ISSUE)                                                         \
+  constexpr int kD = Cfg<CH>::D, kSlots = Cfg<CH>::kSlots, kPasses = Cfg<CH>::kPasses;              \
+  constexpr int kRowBytes = Cfg<CH>::kRowBytes, kBoxBytes = Cfg<CH>::kBoxBytes;                     \
+  (void)kD; (void)kSlots; (void)kPasses; (void)kRowBytes; (void)kBoxBytes;                          \
   extern __shared__ uint8_t smem_raw[];                                                             \
   const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u; /* 32-bit shared address */   \
   const uint32_t s_n4 = smem + (BOX_BYTES), s_a4 = s_n4 + kRows * 16, s_ptr = s_a4 + kRows * 16;    \
@@ -85,7 +94,7 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
     }                                                                                               \
     sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);                                          \
   }                                                                                                 \
-  const int grp = threadIdx.x >> 4, lig = threadIdx.x & 15, c = lig * 8;                            \
+  const int grp = threadIdx.x / CH, lig = threadIdx.x % CH, c = lig * 8;                            \
   (void)c; (void)s_a4;                                                                              \
   __syncthreads(); /* indices staged, barrier initialised */                                        \
   if ((BOX_BYTES) > 0) gcb::tc::mbar_wait(&bar, 0);
@@ -117,13 +126,13 @@ __device__ __forceinline__ uint32_t tie_bits(const uint4& q, const uint4& m, uin
 
 // ---- bond update: Bout[r] = act(P[r] + max_{e->r} Q[src e]);  staged: [P|Q] rows of the tile (512 B each) ----
 // QONLY: stage only the Q half (32 KB, more CTAs per SM) and stream the row's own P chunk from global.
-template <bool TIES, bool QONLY>
-__global__ void __launch_bounds__(kThreads, QONLY ? 4 : 3)
+template <int CH, bool TIES, bool QONLY>
+__global__ void __launch_bounds__(kThreads, (QONLY && CH == 16) ? 4 : 3)
 bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, const bf16* __restrict__ PQ,
                    bf16* __restrict__ Bout, uint8_t* __restrict__ tiemask, uint8_t* __restrict__ tiecnt, int act) {
-  constexpr int kQRow = QONLY ? kRowBytes : 2 * kRowBytes;  // bytes per staged row
-  constexpr int kQOff = QONLY ? 0 : kRowBytes;              // offset of the Q half inside a staged row
-  GCB_TILE_PROLOGUE((QONLY ? 1 : 2) * kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmPQ, &bar, QONLY ? kD : 0, r0))
+  constexpr int kQRow = QONLY ? Cfg<CH>::kRowBytes : 2 * Cfg<CH>::kRowBytes;  // bytes per staged row
+  constexpr int kQOff = QONLY ? 0 : Cfg<CH>::kRowBytes;                        // offset of the Q half inside a staged row
+  GCB_TILE_PROLOGUE((QONLY ? 1 : 2) * Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmPQ, &bar, QONLY ? Cfg<CH>::D : 0, r0))
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
@@ -143,11 +152,11 @@ bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, cons
       uint32_t cnt_lo = 0u, cnt_hi = 0u;  // four byte counters each: channels 0-3 / 4-7
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (nidx[u] >= 0) tiemask[(size_t)(e0 + u) * 16 + lig] = (uint8_t)tie_bits(q[u], mraw, cnt_lo, cnt_hi);
+        if (nidx[u] >= 0) tiemask[(size_t)(e0 + u) * CH + lig] = (uint8_t)tie_bits(q[u], mraw, cnt_lo, cnt_hi);
       }
       for (int e = e0 + 4; e < e1; ++e) {
         const uint4 qe = lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kQRow + kQOff + lig * 16);
-        tiemask[(size_t)e * 16 + lig] = (uint8_t)tie_bits(qe, mraw, cnt_lo, cnt_hi);
+        tiemask[(size_t)e * CH + lig] = (uint8_t)tie_bits(qe, mraw, cnt_lo, cnt_hi);
       }
       *reinterpret_cast<uint2*>(tiecnt + (size_t)r * kD + c) = make_uint2(cnt_lo, cnt_hi);
     }
@@ -171,10 +180,11 @@ bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, cons
 // ---- atom aggregation: S[i] = [ sum_{e->i} A[src e] | sum_{e->i} Bnew[eid e] ]  (Bnew[e >= M] = act(0)) ----
 // staged: A rows of the tile (neighbours are tile-local); the bond rows are addressed by EDGE id and
 // live in other tiles, so they are gathered from global memory, issued before the shared-memory half.
-__global__ void __launch_bounds__(kThreads, 4)
+template <int CH>
+__global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 atom_gather_kernel(const __grid_constant__ CUtensorMap tmA, TileCommon cm, const bf16* __restrict__ Bnew, int M,
                    bf16* __restrict__ S, int act) {
-  GCB_TILE_PROLOGUE(kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmA, &bar, 0, r0))
+  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmA, &bar, 0, r0))
   const float cst = round_to(act_fwd_t<bf16>(0.f, act), (const bf16*)nullptr);
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
@@ -219,10 +229,11 @@ atom_gather_kernel(const __grid_constant__ CUtensorMap tmA, TileCommon cm, const
 
 // ---- atom backward: dZA_prev[j] = (dZA[j] + sum_{e: src e = j} dS[dst e, :D]) * act'(A_prev[j]) ----
 // staged: dS[:, :D] rows of the tile (neighbours); the row's own dZA / A_prev chunks stream from global.
-__global__ void __launch_bounds__(kThreads, 4)
+template <int CH>
+__global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 atom_bwd_kernel(const __grid_constant__ CUtensorMap tmdS, TileCommon cm, const bf16* __restrict__ dZA,
                 const bf16* __restrict__ A_prev, bf16* __restrict__ dZA_prev, int act) {
-  GCB_TILE_PROLOGUE(kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmdS, &bar, 0, r0))
+  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmdS, &bar, 0, r0))
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
@@ -247,10 +258,11 @@ atom_bwd_kernel(const __grid_constant__ CUtensorMap tmdS, TileCommon cm, const b
 
 // ---- bond backward, source side: dQ[j] = sum_{e: src e = j} tie(e) * gsplit[dst e];  staged: gsplit rows ----
 // tie bits come from tiemask[dst-CSR position of e] (global; 16 contiguous bytes per edge).
-__global__ void __launch_bounds__(kThreads, 4)
+template <int CH>
+__global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 bond_scatter_kernel(const __grid_constant__ CUtensorMap tmG, TileCommon cm, const uint8_t* __restrict__ tiemask,
                     bf16* __restrict__ dPQ) {
-  GCB_TILE_PROLOGUE(kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmG, &bar, 0, r0))
+  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmG, &bar, 0, r0))
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
@@ -261,7 +273,7 @@ bond_scatter_kernel(const __grid_constant__ CUtensorMap tmG, TileCommon cm, cons
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (nidx[u] >= 0) {
-        bits[u] = __ldg(tiemask + (size_t)oidx[u] * 16 + lig);
+        bits[u] = __ldg(tiemask + (size_t)oidx[u] * CH + lig);
         g[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
       }
     }
@@ -278,7 +290,7 @@ bond_scatter_kernel(const __grid_constant__ CUtensorMap tmG, TileCommon cm, cons
       if (nidx[u] >= 0) consume(g[u], bits[u]);
     for (int e = e0 + 4; e < e1; ++e)
       consume(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16),
-              __ldg(tiemask + (size_t)__ldg(cm.aux + e) * 16 + lig));
+              __ldg(tiemask + (size_t)__ldg(cm.aux + e) * CH + lig));
     store_vec(dPQ + (size_t)r * (2 * kD) + kD + c, acc);
   }
 }
@@ -291,13 +303,16 @@ bond_scatter_kernel(const __grid_constant__ CUtensorMap tmG, TileCommon cm, cons
 //       dPQ[j, D:] = sum_{e: src e = j} tie(e) * g[dst e]          (dst e is tile-local)
 // The split gradient never goes to HBM.  `dst` is the edge list's destination array: bond row r is
 // EDGE r, and it collects the gradient of the atom it points to (gcn.py:163 quirk).
-__global__ void __launch_bounds__(kThreads, 4)
+template <int CH>
+__global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ dst,
                 const bf16* __restrict__ dS, const bf16* __restrict__ dBnext, const bf16* __restrict__ d_out_bond,
                 const bf16* __restrict__ B_l, const uint8_t* __restrict__ tiecnt, const uint8_t* __restrict__ tiemask,
                 bf16* __restrict__ dPQ, int act) {
+  constexpr int kD = Cfg<CH>::D, kSlots = Cfg<CH>::kSlots, kPasses = Cfg<CH>::kPasses;
+  constexpr int kRowBytes = Cfg<CH>::kRowBytes, kBoxBytes = Cfg<CH>::kBoxBytes;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u;  // g tile [128][256 B]
+  const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u;  // g tile [128][2 D bytes]
   const uint32_t s_n4 = smem + kBoxBytes, s_a4 = s_n4 + kRows * 16, s_ptr = s_a4 + kRows * 16;
   const uint32_t s_dst = s_ptr + 544;  // [128] destination atom of bond row r, or -1 when r has no in-edge
   const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
@@ -318,7 +333,7 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
     }
     sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);
   }
-  const int grp = threadIdx.x >> 4, lig = threadIdx.x & 15, c = lig * 8;
+  const int grp = threadIdx.x / CH, lig = threadIdx.x % CH, c = lig * 8;
   __syncthreads();
   // ---- phase 1 ----
 #pragma unroll 2
@@ -369,7 +384,7 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (nidx[u] >= 0) {
-        bits[u] = __ldg(tiemask + (size_t)oidx[u] * 16 + lig);
+        bits[u] = __ldg(tiemask + (size_t)oidx[u] * CH + lig);
         gq[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
       }
     }
@@ -386,13 +401,16 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
       if (nidx[u] >= 0) consume(gq[u], bits[u]);
     for (int e = e0 + 4; e < e1; ++e)
       consume(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16),
-              __ldg(tiemask + (size_t)__ldg(cm.aux + e) * 16 + lig));
+              __ldg(tiemask + (size_t)__ldg(cm.aux + e) * CH + lig));
     store_vec(dPQ + (size_t)r * (2 * kD) + kD + c, acc);
   }
 }
 
-// ---- launchers ----------------------------------------------------------------------------------
-inline int smem_for(int boxes) { return boxes * kBoxBytes + kIdxBytes + 128; }
+// ---- launchers (D = 128 -> CH 16, D = 256 -> CH 32) ------------------------------------------------
+inline bool width_ok(int D) { return D == 128 || D == 256; }
+
+template <int CH>
+inline int smem_for(int boxes) { return boxes * Cfg<CH>::kBoxBytes + kIdxBytes + 128; }
 
 template <typename K>
 inline int set_smem(K kernel, int bytes) {
@@ -400,72 +418,111 @@ inline int set_smem(K kernel, int bytes) {
   return GCB_OK;
 }
 
-inline int launch_bond_update(const bf16* PQ, const TileCommon& cm, int n_tiles, bf16* Bout, uint8_t* tiemask,
-                              uint8_t* tiecnt, int act, cudaStream_t s) {
-  // Q-only staging makes this kernel ~6 % faster in isolation but the whole step 1 % slower on B200 (the P rows it
-  // then streams through L1 compete with the next kernel's operands in L2); opt-in.
-  static const bool qonly = std::getenv("GCB_TILE_Q_ONLY") && std::getenv("GCB_TILE_Q_ONLY")[0] == '1';
+template <int CH>
+inline int launch_bond_update_w(const bf16* PQ, const TileCommon& cm, int n_tiles, bf16* Bout, uint8_t* tiemask,
+                                uint8_t* tiecnt, int act, cudaStream_t s) {
+  constexpr int D = Cfg<CH>::D;
+  // Q-only staging makes this kernel ~6 % faster in isolation but the whole step 1 % slower on B200 at D = 128 (the P
+  // rows it then streams through L1 compete with the next kernel's operands in L2): opt-in there.  At D = 256 the
+  // [P|Q] box (512 columns) exceeds a TMA box, so Q-only is the only form.
+  static const bool q_env = std::getenv("GCB_TILE_Q_ONLY") && std::getenv("GCB_TILE_Q_ONLY")[0] == '1';
+  const bool qonly = q_env || CH == 32;
   CUtensorMap tm;
-  if (gcb::tc::make_tmap_bf16_plain(&tm, PQ, cm.rows, 2 * kD, 2 * kD, kRows, qonly ? kD : 2 * kD)) return GCB_ERR_CUDA;
-  const int smem = smem_for(qonly ? 1 : 2);
+  if (gcb::tc::make_tmap_bf16_plain(&tm, PQ, cm.rows, 2 * D, 2 * D, kRows, qonly ? D : 2 * D)) return GCB_ERR_CUDA;
+  const int smem = smem_for<CH>(qonly ? 1 : 2);
   static bool attr = false;
   if (!attr) {
-    GCB_TRY(set_smem(bond_update_kernel<true, true>, smem_for(1))); GCB_TRY(set_smem(bond_update_kernel<false, true>, smem_for(1)));
-    GCB_TRY(set_smem(bond_update_kernel<true, false>, smem_for(2))); GCB_TRY(set_smem(bond_update_kernel<false, false>, smem_for(2)));
+    GCB_TRY(set_smem(bond_update_kernel<CH, true, true>, smem_for<CH>(1))); GCB_TRY(set_smem(bond_update_kernel<CH, false, true>, smem_for<CH>(1)));
+    if constexpr (CH == 16) {
+      GCB_TRY(set_smem(bond_update_kernel<CH, true, false>, smem_for<CH>(2))); GCB_TRY(set_smem(bond_update_kernel<CH, false, false>, smem_for<CH>(2)));
+    }
     attr = true;
   }
-  if (tiemask) {
-    if (qonly) GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<true, true><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
-    else GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<true, false><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
-  } else {
-    if (qonly) GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<false, true><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
-    else GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<false, false><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
+  if (qonly) {
+    if (tiemask) GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<CH, true, true><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
+    else GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<CH, false, true><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
+  } else if constexpr (CH == 16) {
+    if (tiemask) GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<CH, true, false><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
+    else GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<CH, false, false><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
   }
   return GCB_OK;
 }
+inline int launch_bond_update(int D, const bf16* PQ, const TileCommon& cm, int n_tiles, bf16* Bout, uint8_t* tiemask,
+                              uint8_t* tiecnt, int act, cudaStream_t s) {
+  return D == 128 ? launch_bond_update_w<16>(PQ, cm, n_tiles, Bout, tiemask, tiecnt, act, s)
+                  : launch_bond_update_w<32>(PQ, cm, n_tiles, Bout, tiemask, tiecnt, act, s);
+}
 
-inline int launch_atom_gather(const bf16* A, const bf16* Bnew, int M, const TileCommon& cm, int n_tiles, bf16* S, int act,
+template <int CH>
+inline int launch_atom_gather_w(const bf16* A, const bf16* Bnew, int M, const TileCommon& cm, int n_tiles, bf16* S, int act,
+                                cudaStream_t s) {
+  constexpr int D = Cfg<CH>::D;
+  CUtensorMap tm;
+  if (gcb::tc::make_tmap_bf16_plain(&tm, A, cm.rows, D, D, kRows, D)) return GCB_ERR_CUDA;
+  const int smem = smem_for<CH>(1);
+  static bool attr = false;
+  if (!attr) { GCB_TRY(set_smem(atom_gather_kernel<CH>, smem)); attr = true; }
+  GCB_KERNEL("tile_atom_gather_kernel", s, (atom_gather_kernel<CH><<<n_tiles, kThreads, smem, s>>>(tm, cm, Bnew, M, S, act)));
+  return GCB_OK;
+}
+inline int launch_atom_gather(int D, const bf16* A, const bf16* Bnew, int M, const TileCommon& cm, int n_tiles, bf16* S, int act,
                               cudaStream_t s) {
-  CUtensorMap tm;
-  if (gcb::tc::make_tmap_bf16_plain(&tm, A, cm.rows, kD, kD, kRows, kD)) return GCB_ERR_CUDA;
-  const int smem = smem_for(1);
-  static bool attr = false;
-  if (!attr) { GCB_TRY(set_smem(atom_gather_kernel, smem)); attr = true; }
-  GCB_KERNEL("tile_atom_gather_kernel", s, (atom_gather_kernel<<<n_tiles, kThreads, smem, s>>>(tm, cm, Bnew, M, S, act)));
-  return GCB_OK;
+  return D == 128 ? launch_atom_gather_w<16>(A, Bnew, M, cm, n_tiles, S, act, s)
+                  : launch_atom_gather_w<32>(A, Bnew, M, cm, n_tiles, S, act, s);
 }
 
-inline int launch_atom_bwd(const bf16* dS, const bf16* dZA, const bf16* A_prev, const TileCommon& cm, int n_tiles,
-                           bf16* dZA_prev, int act, cudaStream_t s) {
+template <int CH>
+inline int launch_atom_bwd_w(const bf16* dS, const bf16* dZA, const bf16* A_prev, const TileCommon& cm, int n_tiles,
+                             bf16* dZA_prev, int act, cudaStream_t s) {
+  constexpr int D = Cfg<CH>::D;
   CUtensorMap tmS;
-  if (gcb::tc::make_tmap_bf16_plain(&tmS, dS, cm.rows, kD, 2 * kD, kRows, kD)) return GCB_ERR_CUDA;
-  const int smem = smem_for(1);
+  if (gcb::tc::make_tmap_bf16_plain(&tmS, dS, cm.rows, D, 2 * D, kRows, D)) return GCB_ERR_CUDA;
+  const int smem = smem_for<CH>(1);
   static bool attr = false;
-  if (!attr) { GCB_TRY(set_smem(atom_bwd_kernel, smem)); attr = true; }
-  GCB_KERNEL("tile_atom_bwd_kernel", s, (atom_bwd_kernel<<<n_tiles, kThreads, smem, s>>>(tmS, cm, dZA, A_prev, dZA_prev, act)));
+  if (!attr) { GCB_TRY(set_smem(atom_bwd_kernel<CH>, smem)); attr = true; }
+  GCB_KERNEL("tile_atom_bwd_kernel", s, (atom_bwd_kernel<CH><<<n_tiles, kThreads, smem, s>>>(tmS, cm, dZA, A_prev, dZA_prev, act)));
   return GCB_OK;
 }
+inline int launch_atom_bwd(int D, const bf16* dS, const bf16* dZA, const bf16* A_prev, const TileCommon& cm, int n_tiles,
+                           bf16* dZA_prev, int act, cudaStream_t s) {
+  return D == 128 ? launch_atom_bwd_w<16>(dS, dZA, A_prev, cm, n_tiles, dZA_prev, act, s)
+                  : launch_atom_bwd_w<32>(dS, dZA, A_prev, cm, n_tiles, dZA_prev, act, s);
+}
 
-inline int launch_bond_scatter(const bf16* gsplit, const TileCommon& cm, int n_tiles, const uint8_t* tiemask, bf16* dPQ,
-                               cudaStream_t s) {
+template <int CH>
+inline int launch_bond_scatter_w(const bf16* gsplit, const TileCommon& cm, int n_tiles, const uint8_t* tiemask, bf16* dPQ,
+                                 cudaStream_t s) {
+  constexpr int D = Cfg<CH>::D;
   CUtensorMap tm;
-  if (gcb::tc::make_tmap_bf16_plain(&tm, gsplit, cm.rows, kD, kD, kRows, kD)) return GCB_ERR_CUDA;
-  const int smem = smem_for(1);
+  if (gcb::tc::make_tmap_bf16_plain(&tm, gsplit, cm.rows, D, D, kRows, D)) return GCB_ERR_CUDA;
+  const int smem = smem_for<CH>(1);
   static bool attr = false;
-  if (!attr) { GCB_TRY(set_smem(bond_scatter_kernel, smem)); attr = true; }
-  GCB_KERNEL("tile_bond_scatter_kernel", s, (bond_scatter_kernel<<<n_tiles, kThreads, smem, s>>>(tm, cm, tiemask, dPQ)));
+  if (!attr) { GCB_TRY(set_smem(bond_scatter_kernel<CH>, smem)); attr = true; }
+  GCB_KERNEL("tile_bond_scatter_kernel", s, (bond_scatter_kernel<CH><<<n_tiles, kThreads, smem, s>>>(tm, cm, tiemask, dPQ)));
   return GCB_OK;
 }
+inline int launch_bond_scatter(int D, const bf16* gsplit, const TileCommon& cm, int n_tiles, const uint8_t* tiemask, bf16* dPQ,
+                               cudaStream_t s) {
+  return D == 128 ? launch_bond_scatter_w<16>(gsplit, cm, n_tiles, tiemask, dPQ, s)
+                  : launch_bond_scatter_w<32>(gsplit, cm, n_tiles, tiemask, dPQ, s);
+}
 
-inline int launch_bond_bwd(const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
+template <int CH>
+inline int launch_bond_bwd_w(const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
+                             const bf16* dBnext, const bf16* d_out_bond, const bf16* B_l, const uint8_t* tiecnt,
+                             const uint8_t* tiemask, bf16* dPQ, int act, cudaStream_t s) {
+  const int smem = smem_for<CH>(1) + kRows * 4;
+  static bool attr = false;
+  if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel<CH>, smem)); attr = true; }
+  GCB_KERNEL("tile_bond_bwd_kernel", s, (bond_bwd_kernel<CH><<<n_tiles, kThreads, smem, s>>>(cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
+                                                                                            tiecnt, tiemask, dPQ, act)));
+  return GCB_OK;
+}
+inline int launch_bond_bwd(int D, const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
                            const bf16* dBnext, const bf16* d_out_bond, const bf16* B_l, const uint8_t* tiecnt,
                            const uint8_t* tiemask, bf16* dPQ, int act, cudaStream_t s) {
-  const int smem = smem_for(1) + kRows * 4;
-  static bool attr = false;
-  if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel, smem)); attr = true; }
-  GCB_KERNEL("tile_bond_bwd_kernel", s, (bond_bwd_kernel<<<n_tiles, kThreads, smem, s>>>(cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
-                                                                                         tiecnt, tiemask, dPQ, act)));
-  return GCB_OK;
+  return D == 128 ? launch_bond_bwd_w<16>(cm, n_tiles, in_ptr, dst, dS, dBnext, d_out_bond, B_l, tiecnt, tiemask, dPQ, act, s)
+                  : launch_bond_bwd_w<32>(cm, n_tiles, in_ptr, dst, dS, dBnext, d_out_bond, B_l, tiecnt, tiemask, dPQ, act, s);
 }
 
 }  // namespace tile

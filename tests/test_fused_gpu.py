@@ -47,12 +47,15 @@ def _run(model, dev, train, mode):
             os.environ.pop(k, None)
 
 
-@pytest.mark.parametrize("n_graphs,max_atoms,L", [(1, 12, 1), (7, 12, 2), (64, 30, 3), (700, 40, 4)])
+@pytest.mark.parametrize("n_graphs,max_atoms,L,D", [(1, 12, 1, 128), (7, 12, 2, 128), (64, 30, 3, 128), (700, 40, 4, 128),
+                                                      (5, 12, 1, 256), (300, 30, 2, 256)])
 @pytest.mark.parametrize("act", [F.softplus, F.relu])
 @pytest.mark.parametrize("mode", ["tile", "tile_split", "fused"])
-def test_fused_equals_unfused_bitwise(n_graphs, max_atoms, L, act, mode):
+def test_fused_equals_unfused_bitwise(n_graphs, max_atoms, L, D, act, mode):
+    if mode == "fused" and D != 128:
+        pytest.skip("the fused tcgen05 kernels are D = 128 only")
     data, _ = random_batch(seed=n_graphs, n_graphs=n_graphs, max_atoms=max_atoms)
-    _, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=L, act_fn=act)
+    _, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=D, n_messages=L, act_fn=act)
     dev = _dev(data)
     from graphchem_b200.data import pack_batch
     assert pack_batch(data, L, 12, 7, pin=False).n_tiles > 0
