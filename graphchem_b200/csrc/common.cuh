@@ -53,6 +53,25 @@ struct KernelTimer {
     GCB_LAUNCH_CHECK();                        \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// Kernels launched through launch_pdl() may begin while the previous kernel of the stream is still draining:
+// their set-up (barrier / TMEM initialisation, staging of the immutable batch indices) overlaps its tail, and
+// pdl_wait() blocks until that kernel has completed and its writes are visible.  Everything that reads or
+// writes activations must come after pdl_wait(); both calls are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // GCB_NO_PDL=1 turns the launch attribute off
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

@@ -84,12 +84,16 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // set-up done (barriers, TMEM, bias).  The weights are immutable while a step runs, so their load may still
+  // overlap the previous kernel's tail; everything that touches activations comes after pdl_wait().
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(wfull, S::W_BYTES);
       for (int ks = 0; ks < S::KS; ++ks) tma_load_2d(sW + ks * (N * 128), &tmW, wfull, ks * 64, 0);
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -130,6 +134,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===================== epilogue (EPI_WARPS warps) =====================
+    pdl_wait();
     const int ew = warp - 2;              // 0..EPI_WARPS-1
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int half = ew >> 2;             // column part handled by this warp
@@ -258,7 +263,7 @@ inline int launch_gemm_nt_tc_res(const bf16* A, int lda, const bf16* W, bf16* C,
     return GCB_ERR_CUDA;
   const int num_tiles = (rows + S::BM - 1) / S::BM;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  GCB_KERNEL("gemm_nt_tc_kernel", s, (gemm_nt_tc_kernel<K, N, RES><<<grid, S::THREADS, S::SMEM_BYTES, s>>>(tmA, tmW, tmC, rows, ep)));
+  GCB_KERNEL("gemm_nt_tc_kernel", s, launch_pdl(gemm_nt_tc_kernel<K, N, RES>, grid, S::THREADS, S::SMEM_BYTES, s, tmA, tmW, tmC, rows, ep));
   return GCB_OK;
 }
 
@@ -324,6 +329,9 @@ gemm_nt_tcs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // set-up done (barriers, TMEM, bias): from here on the kernel touches activations of the previous kernel
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -469,7 +477,7 @@ inline int launch_gemm_nt_tcs(const bf16* A, int lda, const bf16* W, bf16* C, in
     return GCB_ERR_CUDA;
   const int num_tiles = ((rows + S::BM - 1) / S::BM) * (N / S::BN);
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  GCB_KERNEL("gemm_nt_tc_kernel", s, (gemm_nt_tcs_kernel<<<grid, S::THREADS, S::SMEM_BYTES, s>>>(tmA, tmW, tmC, rows, N, K, ep)));
+  GCB_KERNEL("gemm_nt_tc_kernel", s, launch_pdl(gemm_nt_tcs_kernel, grid, S::THREADS, S::SMEM_BYTES, s, tmA, tmW, tmC, rows, N, K, ep));
   return GCB_OK;
 }
 
@@ -558,6 +566,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // set-up done (barriers, TMEM, bias): from here on the kernel touches activations of the previous kernel
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -706,7 +717,7 @@ inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb
   const int per = (num_tiles + grid - 1) / grid;
   grid = (num_tiles + per - 1) / per;  // every CTA owns at least one tile
   *grid_out = grid;
-  GCB_KERNEL("gemm_tn_tc_kernel", s, gemm_tn_tc_kernel<NN, KK><<<grid, S::THREADS, S::SMEM_BYTES, s>>>(
+  GCB_KERNEL("gemm_tn_tc_kernel", s, launch_pdl(gemm_tn_tc_kernel<NN, KK>, grid, S::THREADS, S::SMEM_BYTES, s,
       tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr, rev, acc_partial));
   return GCB_OK;
 }

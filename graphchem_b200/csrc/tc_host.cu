@@ -6,6 +6,12 @@
 #include "tc_common.cuh"
 
 namespace gcb {
+
+bool pdl_enabled() {
+  static const bool off = std::getenv("GCB_NO_PDL") && std::getenv("GCB_NO_PDL")[0] == '1';
+  return !off;
+}
+
 namespace tc {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -75,9 +75,11 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
   __shared__ uint64_t bar;                                                                          \
   const int r0 = __ldg(cm.tile_ptr + blockIdx.x);                                                   \
   const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);                                 \
+  pdl_launch_dependents();                                                                          \
   if ((BOX_BYTES) > 0 && threadIdx.x == 0) {                                                        \
     gcb::tc::mbar_init(&bar, 1);                                                                    \
     gcb::tc::fence_barrier_init();                                                                  \
+    pdl_wait(); /* the boxes hold activations of the previous kernel */                             \
     gcb::tc::mbar_arrive_expect_tx(&bar, (BOX_BYTES));                                              \
     ISSUE;                                                                                          \
   }                                                                                                 \
@@ -96,6 +98,7 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
   }                                                                                                 \
   const int grp = threadIdx.x / CH, lig = threadIdx.x % CH, c = lig * 8;                            \
   (void)c; (void)s_a4;                                                                              \
+  pdl_wait(); /* indices are immutable batch data and were staged above; activations come after this */ \
   __syncthreads(); /* indices staged, barrier initialised */                                        \
   if ((BOX_BYTES) > 0) gcb::tc::mbar_wait(&bar, 0);
 
@@ -317,6 +320,7 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   const uint32_t s_dst = s_ptr + 544;  // [128] destination atom of bond row r, or -1 when r has no in-edge
   const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
   const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i <= kRows; i += kThreads) {
     const int r = r0 + i;
     if (i < kRows) {
@@ -334,6 +338,7 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
     sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);
   }
   const int grp = threadIdx.x / CH, lig = threadIdx.x % CH, c = lig * 8;
+  pdl_wait();
   __syncthreads();
   // ---- phase 1 ----
 #pragma unroll 2
@@ -439,11 +444,11 @@ inline int launch_bond_update_w(const bf16* PQ, const TileCommon& cm, int n_tile
     attr = true;
   }
   if (qonly) {
-    if (tiemask) GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<CH, true, true><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
-    else GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<CH, false, true><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
+    if (tiemask) GCB_KERNEL("tile_bond_update_kernel", s, launch_pdl(bond_update_kernel<CH, true, true>, n_tiles, kThreads, smem, s, tm, cm, PQ, Bout, tiemask, tiecnt, act));
+    else GCB_KERNEL("tile_bond_update_kernel", s, launch_pdl(bond_update_kernel<CH, false, true>, n_tiles, kThreads, smem, s, tm, cm, PQ, Bout, tiemask, tiecnt, act));
   } else if constexpr (CH == 16) {
-    if (tiemask) GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<CH, true, false><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
-    else GCB_KERNEL("tile_bond_update_kernel", s, (bond_update_kernel<CH, false, false><<<n_tiles, kThreads, smem, s>>>(tm, cm, PQ, Bout, tiemask, tiecnt, act)));
+    if (tiemask) GCB_KERNEL("tile_bond_update_kernel", s, launch_pdl(bond_update_kernel<CH, true, false>, n_tiles, kThreads, smem, s, tm, cm, PQ, Bout, tiemask, tiecnt, act));
+    else GCB_KERNEL("tile_bond_update_kernel", s, launch_pdl(bond_update_kernel<CH, false, false>, n_tiles, kThreads, smem, s, tm, cm, PQ, Bout, tiemask, tiecnt, act));
   }
   return GCB_OK;
 }
@@ -462,7 +467,7 @@ inline int launch_atom_gather_w(const bf16* A, const bf16* Bnew, int M, const Ti
   const int smem = smem_for<CH>(1);
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(atom_gather_kernel<CH>, smem)); attr = true; }
-  GCB_KERNEL("tile_atom_gather_kernel", s, (atom_gather_kernel<CH><<<n_tiles, kThreads, smem, s>>>(tm, cm, Bnew, M, S, act)));
+  GCB_KERNEL("tile_atom_gather_kernel", s, launch_pdl(atom_gather_kernel<CH>, n_tiles, kThreads, smem, s, tm, cm, Bnew, M, S, act));
   return GCB_OK;
 }
 inline int launch_atom_gather(int D, const bf16* A, const bf16* Bnew, int M, const TileCommon& cm, int n_tiles, bf16* S, int act,
@@ -480,7 +485,7 @@ inline int launch_atom_bwd_w(const bf16* dS, const bf16* dZA, const bf16* A_prev
   const int smem = smem_for<CH>(1);
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(atom_bwd_kernel<CH>, smem)); attr = true; }
-  GCB_KERNEL("tile_atom_bwd_kernel", s, (atom_bwd_kernel<CH><<<n_tiles, kThreads, smem, s>>>(tmS, cm, dZA, A_prev, dZA_prev, act)));
+  GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, dZA_prev, act));
   return GCB_OK;
 }
 inline int launch_atom_bwd(int D, const bf16* dS, const bf16* dZA, const bf16* A_prev, const TileCommon& cm, int n_tiles,
@@ -498,7 +503,7 @@ inline int launch_bond_scatter_w(const bf16* gsplit, const TileCommon& cm, int n
   const int smem = smem_for<CH>(1);
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(bond_scatter_kernel<CH>, smem)); attr = true; }
-  GCB_KERNEL("tile_bond_scatter_kernel", s, (bond_scatter_kernel<CH><<<n_tiles, kThreads, smem, s>>>(tm, cm, tiemask, dPQ)));
+  GCB_KERNEL("tile_bond_scatter_kernel", s, launch_pdl(bond_scatter_kernel<CH>, n_tiles, kThreads, smem, s, tm, cm, tiemask, dPQ));
   return GCB_OK;
 }
 inline int launch_bond_scatter(int D, const bf16* gsplit, const TileCommon& cm, int n_tiles, const uint8_t* tiemask, bf16* dPQ,
@@ -514,8 +519,8 @@ inline int launch_bond_bwd_w(const TileCommon& cm, int n_tiles, const int32_t* i
   const int smem = smem_for<CH>(1) + kRows * 4;
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel<CH>, smem)); attr = true; }
-  GCB_KERNEL("tile_bond_bwd_kernel", s, (bond_bwd_kernel<CH><<<n_tiles, kThreads, smem, s>>>(cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
-                                                                                            tiecnt, tiemask, dPQ, act)));
+  GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
+                                                     tiecnt, tiemask, dPQ, act));
   return GCB_OK;
 }
 inline int launch_bond_bwd(int D, const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
