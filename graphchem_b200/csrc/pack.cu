@@ -165,6 +165,110 @@ static int finish_pack(int32_t* packed, const int32_t* h, const int32_t* batch_i
   return GCB_OK;
 }
 
+// Collated molecules: every edge stays inside its molecule, atoms and edges of a molecule are contiguous, and
+// graph ids increase -- so all index structures except the token buckets are per-molecule problems whose
+// working set (tens of atoms / edges) lives in L1.  One sequential pass over the molecules instead of a dozen
+// passes over the whole batch; the result is identical to finish_pack() (stable order inside every row).
+// src / dst / tokens are already written; n_atoms / n_edges describe the molecules in batch order.
+static int finish_pack_local(int32_t* packed, const int32_t* h, const int32_t* n_atoms, const int32_t* n_edges) {
+  const int32_t N = h[GCB_H_N], E = h[GCB_H_E], G = h[GCB_H_G], M = h[GCB_H_M];
+  const int32_t av = h[GCB_H_AV], bv = h[GCB_H_BV];
+  const int32_t* src = packed + h[GCB_H_SRC];
+  const int32_t* dst = packed + h[GCB_H_DST];
+  int32_t* in_ptr = packed + h[GCB_H_IN_PTR];
+  int32_t* in_eid = packed + h[GCB_H_IN_EID];
+  int32_t* in_src = packed + h[GCB_H_IN_SRC];
+  int32_t* out_ptr = packed + h[GCB_H_OUT_PTR];
+  int32_t* out_eid = packed + h[GCB_H_OUT_EID];
+  int32_t* out_dst = packed + h[GCB_H_OUT_DST];
+  int32_t* s4 = packed + h[GCB_H_IN_SRC4];
+  int32_t* e4 = packed + h[GCB_H_IN_EID4];
+  int32_t* d4 = packed + h[GCB_H_OUT_DST4];
+  int32_t* o4 = packed + h[GCB_H_OUT_INPOS4];
+  int32_t* out_inpos = packed + h[GCB_H_OUT_INPOS];
+  int32_t* graph_ptr = packed + h[GCB_H_GRAPH_PTR];
+  int32_t* graph_node = packed + h[GCB_H_GRAPH_NODE];
+  int32_t* node_graph = packed + h[GCB_H_NODE_GRAPH];
+  int32_t* tile_ptr = packed + h[GCB_H_TILE_PTR];
+  int32_t max_a = 0, max_e = 0;
+  for (int32_t g = 0; g < G; ++g) { max_a = n_atoms[g] > max_a ? n_atoms[g] : max_a; max_e = n_edges[g] > max_e ? n_edges[g] : max_e; }
+  std::vector<int32_t> pin((size_t)max_a + 2), pout((size_t)max_a + 2), cin((size_t)max_a + 1), cout((size_t)max_a + 1),
+      pos((size_t)max_e + 1), span((size_t)max_a + 2);
+  // closed row tiles: greedy over the cut positions, in order (same walk as finish_pack)
+  int32_t nt = 0, start = 0, last_cut = 0;
+  bool tiles_ok = true;
+  tile_ptr[0] = 0;
+  auto cut_at = [&](int32_t p) {
+    if (!tiles_ok) return;
+    if (p - start > GCB_TILE_ROWS) {
+      if (last_cut == start) { tiles_ok = false; return; }
+      tile_ptr[++nt] = last_cut;
+      start = last_cut;
+      if (p - start > GCB_TILE_ROWS) { tiles_ok = false; return; }
+    }
+    last_cut = p;
+  };
+  int32_t a0 = 0, e0 = 0;
+  for (int32_t g = 0; g < G; ++g) {
+    const int32_t na = n_atoms[g], ne = n_edges[g];
+    graph_ptr[g] = a0;
+    for (int32_t i = 0; i <= na + 1; ++i) { pin[i] = 0; pout[i] = 0; span[i] = 0; }
+    for (int32_t e = 0; e < ne; ++e) {
+      const int32_t sl = src[e0 + e] - a0, dl = dst[e0 + e] - a0;
+      pin[dl + 1]++;
+      pout[sl + 1]++;
+      const int32_t lo = sl < dl ? sl : dl, hi = sl < dl ? dl : sl;
+      if (lo < hi) { span[lo + 1]++; span[hi + 1]--; }
+    }
+    for (int32_t i = 0; i < na; ++i) { pin[i + 1] += pin[i]; pout[i + 1] += pout[i]; cin[i] = pin[i]; cout[i] = pout[i]; }
+    for (int32_t i = 0; i < na; ++i) {
+      in_ptr[a0 + i] = e0 + pin[i];
+      out_ptr[a0 + i] = e0 + pout[i];
+      graph_node[a0 + i] = a0 + i;
+      node_graph[a0 + i] = g;
+    }
+    for (int32_t e = 0; e < ne; ++e) {  // stable: edge-id order inside every row
+      const int32_t k = cin[dst[e0 + e] - a0]++;
+      in_eid[e0 + k] = e0 + e;
+      in_src[e0 + k] = src[e0 + e];
+      pos[e] = k;
+    }
+    for (int32_t e = 0; e < ne; ++e) {
+      const int32_t k = cout[src[e0 + e] - a0]++;
+      out_eid[e0 + k] = e0 + e;
+      out_dst[e0 + k] = dst[e0 + e];
+      out_inpos[e0 + k] = e0 + pos[e];
+    }
+    for (int32_t i = 0; i < na; ++i) {  // ELL-4 views
+      const int64_t a = (int64_t)(a0 + i) * 4;
+      for (int u = 0; u < 4; ++u) {
+        const int32_t ki = pin[i] + u, ko = pout[i] + u;
+        const bool hi_ = ki < pin[i + 1], ho_ = ko < pout[i + 1];
+        s4[a + u] = hi_ ? in_src[e0 + ki] : -1;
+        e4[a + u] = hi_ ? in_eid[e0 + ki] : -1;
+        d4[a + u] = ho_ ? out_dst[e0 + ko] : -1;
+        o4[a + u] = ho_ ? out_inpos[e0 + ko] : -1;
+      }
+    }
+    int32_t cover = 0;  // cuts inside the molecule (it may be disconnected) and at its end
+    for (int32_t p = 1; p <= na; ++p) {
+      cover += span[p];
+      if (p == na || cover == 0) cut_at(a0 + p);
+    }
+    a0 += na;
+    e0 += ne;
+  }
+  graph_ptr[G] = N;
+  in_ptr[N] = E;
+  out_ptr[N] = E;
+  if (tiles_ok && N > 0 && last_cut != N) tiles_ok = false;  // (cannot happen: the last molecule ends at N)
+  if (tiles_ok && N > 0) tile_ptr[++nt] = N;
+  packed[GCB_H_NTILES] = tiles_ok ? nt : 0;
+  bucket(packed + h[GCB_H_X_TOK], N, av, packed + h[GCB_H_ATOK_PTR], packed + h[GCB_H_ATOK_NODE]);
+  bucket(packed + h[GCB_H_E_TOK], M, bv, packed + h[GCB_H_BTOK_PTR], packed + h[GCB_H_BTOK_ROW]);
+  return GCB_OK;
+}
+
 }  // namespace gcb
 
 using namespace gcb;
@@ -252,16 +356,15 @@ extern "C" int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t*
   int32_t* e_tok = packed + h[GCB_H_E_TOK];
   int32_t* src = packed + h[GCB_H_SRC];
   int32_t* dst = packed + h[GCB_H_DST];
-  std::vector<int32_t> b32((size_t)N);
   const int64_t lim = n_messages >= 1 ? M : N;
   int64_t node_off = 0, edge_off = 0;
+  bool local = true;  // every edge stays inside its molecule (always, for encoder output)
   for (int32_t g = 0; g < G; ++g) {
     const int32_t na = n_atoms[g], ne = n_edges[g];
     for (int32_t i = 0; i < na; ++i) {
       int32_t t = atoms[g][i];
       if (t < 0 || t >= atom_vocab) return GCB_ERR_INDEX;
       x_tok[node_off + i] = t;
-      b32[(size_t)(node_off + i)] = g;
     }
     for (int32_t e = 0; e < ne; ++e) {
       int32_t t = bonds[g][e];
@@ -269,6 +372,7 @@ extern "C" int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t*
       e_tok[edge_off + e] = t;
       int64_t s = conn[g][e] + node_off, d = conn[g][(int64_t)ne + e] + node_off;  // [2,e] row-major
       if (conn[g][e] < 0 || conn[g][(int64_t)ne + e] < 0 || s >= lim || d >= lim) return GCB_ERR_INDEX;
+      local = local && conn[g][e] < na && conn[g][(int64_t)ne + e] < na;
       src[edge_off + e] = (int32_t)s;
       dst[edge_off + e] = (int32_t)d;
     }
@@ -278,7 +382,15 @@ extern "C" int gcb_collate_pack_host(const int32_t* const* atoms, const int32_t*
     node_off += na;
     edge_off += ne;
   }
-  const int rc = finish_pack(packed, h, b32.data());
+  int rc;
+  if (local) {
+    rc = finish_pack_local(packed, h, n_atoms, n_edges);
+  } else {  // an edge into another molecule's atoms (what PyG's collate would also produce): the general builder
+    std::vector<int32_t> b32((size_t)N);
+    int64_t off = 0;
+    for (int32_t g = 0; g < G; ++g) { for (int32_t i = 0; i < n_atoms[g]; ++i) b32[(size_t)(off + i)] = g; off += n_atoms[g]; }
+    rc = finish_pack(packed, h, b32.data());
+  }
   if (rc == GCB_OK) zero_unwritten(packed, h, E);
   return rc;
 }

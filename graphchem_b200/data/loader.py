@@ -40,6 +40,7 @@ class PackedLoader:
         self._pin = self.device.type == "cuda"
         self._pool: List[tuple] = []  # free (int32 buffer, float32 target buffer) pairs, pinned; CUDA devices only
         self._pool_lock = threading.Lock()
+        self._pool_ready = False
 
     def __len__(self) -> int:
         n = len(self.indices)
@@ -92,6 +93,16 @@ class PackedLoader:
         keep: List[PackedBatch] = []
         cuda = self.device.type == "cuda"
         copy_stream = torch.cuda.Stream(self.device) if cuda else None
+        if cuda and not self._pool_ready:
+            # all pinned buffers up front: cudaHostAlloc is slow and synchronises the device, it must not happen
+            # in the middle of an epoch
+            nt = 0 if self.store.targets is None else int(self.store.targets.size(1))
+            cap = self._capacity()
+            with self._pool_lock:
+                for _ in range(min(len(batches), self.prefetch + self.workers)):
+                    self._pool.append((torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                                       torch.empty(max(1, self.batch_size * nt), dtype=torch.float32, pin_memory=True)))
+            self._pool_ready = True
         with ThreadPoolExecutor(self.workers) as pool:
             pending = []   # futures of host batches, in order
             inflight = []  # (device batch, copy-done event)

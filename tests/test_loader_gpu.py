@@ -20,7 +20,7 @@ def test_cuda_loader_batches_are_exact_and_recycled():
             assert (b.header == ref.header).all()
             n += 1
         assert n == 8
-    assert 1 <= len(loader._pool) <= 4 + 2 + 2
+    assert 1 <= len(loader._pool) <= 4 + 2 + 2 and loader._pool_ready
 
 
 def test_trainstep_over_loader_learns():
