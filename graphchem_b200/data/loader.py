@@ -28,12 +28,18 @@ from .packed import MoleculeStore, PackedBatch
 class PackedLoader:
     def __init__(self, store: MoleculeStore, batch_size: int, n_messages: int, atom_vocab: int, bond_vocab: int,
                  device="cuda", shuffle: bool = False, drop_last: bool = False, seed: int = 0, workers: int = 8,
-                 prefetch: int = 4, cache: bool = False, indices: Optional[Sequence[int]] = None, each: bool = False):
+                 prefetch: int = 4, cache: bool = False, indices: Optional[Sequence[int]] = None, each: bool = False,
+                 device_slots: int = 0):
         self.store, self.batch_size = store, int(batch_size)
         self.n_messages, self.av, self.bv = int(n_messages), int(atom_vocab), int(bond_vocab)
         self.device = torch.device(device)
         self.shuffle, self.drop_last, self.seed = shuffle, drop_last, seed
         self.workers, self.prefetch, self.cache, self.each = max(1, workers), max(1, prefetch), cache, each
+        # device_slots > 0: batches land in a fixed ring of device buffers (instead of a fresh allocation each), so
+        # consumers that key CUDA graphs on buffer addresses (TrainStep) replay instead of re-capturing; a yielded
+        # batch is valid until `device_slots - 1` further batches have been requested.  Not combinable with cache.
+        self.device_slots = 0 if cache else max(0, int(device_slots))
+        self._slots: List[tuple] = []
         self.indices = np.arange(len(store), dtype=np.int64) if indices is None else np.asarray(indices, dtype=np.int64)
         self.epoch = 0
         self._cached: Optional[List[PackedBatch]] = None
@@ -103,6 +109,15 @@ class PackedLoader:
                     self._pool.append((torch.empty(cap, dtype=torch.int32, pin_memory=True),
                                        torch.empty(max(1, self.batch_size * nt), dtype=torch.float32, pin_memory=True)))
             self._pool_ready = True
+        if cuda and self.device_slots and not self._slots:
+            nt = 0 if self.store.targets is None else int(self.store.targets.size(1))
+            cap = self._capacity()
+            self._slots = [(torch.empty(cap, dtype=torch.int32, device=self.device),
+                            torch.empty(max(1, self.batch_size * nt), dtype=torch.float32, device=self.device),
+                            torch.cuda.Event()) for _ in range(self.device_slots)]
+            for _, _, ev0 in self._slots:
+                ev0.record(torch.cuda.current_stream(self.device))
+        slot_i = 0
         with ThreadPoolExecutor(self.workers) as pool:
             pending = []   # futures of host batches, in order
             inflight = []  # (device batch, copy-done event)
@@ -116,11 +131,26 @@ class PackedLoader:
 
             submit()
             while pending or inflight:
-                while pending and len(inflight) < self.prefetch and (pending[0].done() or not inflight):
+                # with a slot ring, a slot may only be refilled after its previous batch was consumed: at most
+                # device_slots - 1 copies ahead of the consumer
+                ahead = min(self.prefetch, len(self._slots) - 1) if self._slots else self.prefetch
+                while pending and len(inflight) < max(1, ahead) and (pending[0].done() or not inflight):
                     hb, bufs = pending.pop(0).result()
                     if cuda:
                         with torch.cuda.stream(copy_stream):
-                            db = hb.to(self.device, non_blocking=True)
+                            if self._slots:
+                                d_ints, d_y, free_ev = self._slots[slot_i % len(self._slots)]
+                                slot_i += 1
+                                copy_stream.wait_event(free_ev)  # the consumer is done with this slot's previous batch
+                                n = hb.ints.numel()
+                                d_ints[:n].copy_(hb.ints, non_blocking=True)
+                                y = None
+                                if hb.y is not None:
+                                    y = d_y[:hb.y.numel()].view(hb.y.shape)
+                                    y.copy_(hb.y, non_blocking=True)
+                                db = PackedBatch(d_ints[:n], hb.header, y)
+                            else:
+                                db = hb.to(self.device, non_blocking=True)
                             ev = torch.cuda.Event()
                             ev.record(copy_stream)
                         inflight.append((db, ev, bufs))
@@ -137,6 +167,9 @@ class PackedLoader:
                 if self.cache:
                     keep.append(db)
                 yield db
+                if self._slots:  # whatever the consumer enqueued on its stream for this batch frees the slot
+                    k = (slot_i - len(inflight) - 1) % len(self._slots)
+                    self._slots[k][2].record(torch.cuda.current_stream(self.device))
                 submit()
         if self.cache:
             self._cached = keep
