@@ -134,3 +134,80 @@ class TrainStep:
             self._keepalive[key] = pb
         g.replay()
         return self.loss
+
+
+class InferStep:
+    """Forward-only counterpart of `TrainStep` for screening (BASELINE.json configs[4]): `model.eval()`
+    semantics (no dropout), no saved activations, workspace and outputs allocated once, one CUDA graph per
+    resident batch buffer.  `step(pb)` returns the predictions [G, out] as a device tensor that is OVERWRITTEN
+    by the next call with a batch of the same shape (clone it, or pass `out=`)."""
+
+    def __init__(self, model, use_cuda_graph: bool = True, want_atom_bond: bool = False):
+        self.model = model
+        self.device = model._ensure_device()
+        self.use_cuda_graph = use_cuda_graph
+        self.want_atom_bond = want_atom_bond
+        self._ws: Optional[torch.Tensor] = None
+        self._out: Dict[tuple, tuple] = {}
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._keepalive: Dict[tuple, PackedBatch] = {}
+        self.max_graphs = 64
+        model.refresh_weights()
+
+    def refresh_weights(self) -> None:
+        """Call after the parameters changed (the kernel-side weight copies are derived from them)."""
+        self.model.refresh_weights()
+
+    def _buffers(self, pb: PackedBatch):
+        model = self.model
+        cfg = model._cfg()
+        need = int(_lib.check(int(_lib.lib().gcb_workspace_bytes(C.byref(cfg), pb.N, pb.E, pb.G, 0)), "gcb_workspace_bytes"))
+        if self._ws is None or self._ws.numel() < need:
+            self._graphs.clear(); self._keepalive.clear()
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        key = (pb.N, pb.E, pb.G)
+        if key not in self._out:
+            av, bv, out_dim, D, n_readout, R = model._dims
+            cols = int(out_dim) if n_readout > 0 else D
+            out = torch.empty(pb.G, cols, dtype=torch.float32, device=self.device)
+            oa = torch.empty(pb.N, D, dtype=model._compute_dtype, device=self.device) if self.want_atom_bond else None
+            ob = torch.empty(pb.E, D, dtype=model._compute_dtype, device=self.device) if self.want_atom_bond else None
+            self._out[key] = (out, oa, ob)
+        return self._out[key]
+
+    def _enqueue(self, pb: PackedBatch, bufs) -> None:
+        model = self.model
+        out, oa, ob = bufs
+        flat = model.flat_parameters()
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.lib().gcb_forward(C.byref(model._cfg()), pb.ints.data_ptr(), pb.header.ctypes.data, flat.data_ptr(),
+                                          model._derived.data_ptr(), self._ws.data_ptr(), self._ws.numel(), 0, 0,
+                                          out.data_ptr(), None if oa is None else oa.data_ptr(),
+                                          None if ob is None else ob.data_ptr(), s), "gcb_forward")
+
+    def __call__(self, pb: PackedBatch):
+        if pb.device != self.device:
+            raise RuntimeError("InferStep needs a device-resident PackedBatch (use .to(device) / PackedLoader)")
+        bufs = self._buffers(pb)
+        if not self.use_cuda_graph:
+            self._enqueue(pb, bufs)
+        else:
+            key = (pb.ints.data_ptr(), pb.header.tobytes())
+            g = self._graphs.get(key)
+            if g is None:
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    self._enqueue(pb, bufs)  # warm-up before capture
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(pb, bufs)
+                if len(self._graphs) >= self.max_graphs:
+                    old = next(iter(self._graphs))
+                    del self._graphs[old]
+                    self._keepalive.pop(old, None)
+                self._graphs[key] = g
+                self._keepalive[key] = pb
+            g.replay()
+        return bufs if self.want_atom_bond else bufs[0]

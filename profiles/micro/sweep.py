@@ -11,7 +11,7 @@ import torch
 
 from graphchem_b200.nn import MoleculeGCN
 from graphchem_b200.synthetic import make_molecules
-from graphchem_b200.train import TrainStep
+from graphchem_b200.train import InferStep, TrainStep
 
 dev = torch.device("cuda", 0)
 
@@ -37,6 +37,9 @@ def case(mode, B, D, L, dtype):
     if mode == "train":
         step = TrainStep(model, lr=1e-3)
         ms = timed(lambda i: step(batches[i % 4]), 8, 20)
+    elif mode == "infer":  # CUDA-graphed forward on resident batches
+        step = InferStep(model)
+        ms = timed(lambda i: step(batches[i % 4]), 8, 20)
     else:
         model.eval()
         with torch.no_grad():
@@ -47,5 +50,7 @@ def case(mode, B, D, L, dtype):
 
 for args in [("train", 4096, 128, 4, torch.bfloat16), ("train", 16384, 128, 4, torch.bfloat16),
              ("train", 8192, 128, 4, torch.float32), ("forward", 8192, 128, 4, torch.bfloat16),
-             ("forward", 8192, 256, 6, torch.bfloat16), ("forward", 32768, 128, 4, torch.bfloat16)]:
+             ("forward", 8192, 256, 6, torch.bfloat16), ("forward", 32768, 128, 4, torch.bfloat16),
+             ("infer", 8192, 128, 4, torch.bfloat16), ("infer", 32768, 128, 4, torch.bfloat16),
+             ("infer", 8192, 256, 6, torch.bfloat16), ("infer", 32768, 256, 6, torch.bfloat16)]:
     case(*args)

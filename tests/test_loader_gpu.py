@@ -74,3 +74,22 @@ def test_device_slot_ring_lets_trainstep_replay_graphs():
     l_plain, _ = run(False)
     assert n_graphs == 3
     assert torch.equal(l_graph, l_plain)
+
+
+def test_inferstep_matches_module_forward():
+    """InferStep (graphed forward, no saved activations) returns exactly what model.eval()(batch) returns."""
+    from graphchem_b200.nn import MoleculeGCN
+    from graphchem_b200.synthetic import make_molecules
+    from graphchem_b200.train import InferStep
+    store = make_molecules(600, seed=9, variable=True)
+    torch.manual_seed(1)
+    model = MoleculeGCN(64, 32, 2, embedding_dim=128, n_messages=3, compute_dtype=torch.bfloat16).cuda().eval()
+    pbs = [store.collate_pack(np.arange(i, i + 200), 3, 64, 32).to("cuda") for i in (0, 200, 400)]
+    step = InferStep(model, want_atom_bond=True)
+    for rep in range(2):  # second round replays the graphs
+        for pb in pbs:
+            out, oa, ob = (t.clone() for t in step(pb))
+            with torch.no_grad():
+                ref = model(pb)
+            assert torch.equal(out, ref[0]) and torch.equal(oa, ref[1]) and torch.equal(ob, ref[2])
+    assert len(step._graphs) == 3
