@@ -318,9 +318,12 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u;  // g tile [128][2 D bytes]
   const uint32_t s_n4 = smem + kBoxBytes, s_a4 = s_n4 + kRows * 16, s_ptr = s_a4 + kRows * 16;
   const uint32_t s_dst = s_ptr + 544;  // [128] destination atom of bond row r, or -1 when r has no in-edge
+  const uint32_t s_inv = s_dst + kRows * 4;  // [256] 1 / tie count (1 for counts 0 and 1), the factor of the even tie split
   const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
   const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
   pdl_launch_dependents();
+  // x / cnt of the tie split as x * (1 / cnt): the same MUFU reciprocal __fdividef() uses, looked up instead of recomputed
+  for (int i = threadIdx.x; i < 256; i += kThreads) sts32(s_inv + i * 4, __float_as_int(i <= 1 ? 1.f : __fdividef(1.f, (float)i)));
   for (int i = threadIdx.x; i <= kRows; i += kThreads) {
     const int r = r0 + i;
     if (i < kRows) {
@@ -367,7 +370,7 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t cnt = (cwv[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-        g[i] = cnt <= 1u ? d[i] : __fdividef(d[i], (float)cnt);
+        g[i] = d[i] * __int_as_float(lds32(s_inv + cnt * 4));
       }
     }
     store_vec(dPQ + (size_t)r * (2 * kD) + c, d);
@@ -516,7 +519,7 @@ template <int CH>
 inline int launch_bond_bwd_w(const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
                              const bf16* dBnext, const bf16* d_out_bond, const bf16* B_l, const uint8_t* tiecnt,
                              const uint8_t* tiemask, bf16* dPQ, int act, cudaStream_t s) {
-  const int smem = smem_for<CH>(1) + kRows * 4;
+  const int smem = smem_for<CH>(1) + kRows * 4 + 256 * 4;
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel<CH>, smem)); attr = true; }
   GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
