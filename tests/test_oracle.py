@@ -134,3 +134,20 @@ def test_oracle_matches_real_pyg():
     xa = torch.randn(data.x.numel(), 16)
     assert torch.equal(real_g(xa, data.edge_index, xb), mine_g(xa, data.edge_index, xb))
     assert torch.equal(global_add_pool(xa, data.batch), R.global_add_pool(xa, data.batch))
+
+
+def test_oracle_reproduces_committed_golden_vectors():
+    """tests/golden/gcn_small.pt (made by tests/golden/make_gcn_golden.py): the oracle must keep producing the
+    committed forward outputs, gradients and Adam trajectory (guards against drift of the checker itself)."""
+    from tests.golden.make_gcn_golden import build
+    gold = torch.load(os.path.join(HERE, "golden", "gcn_small.pt"), weights_only=False)
+    now = build()
+    for k in ("x", "edge_index", "edge_attr", "batch"):
+        assert torch.equal(gold[k], now[k]), k
+    for k in ("out", "out_atom", "out_bond"):
+        assert torch.allclose(gold[k], now[k], rtol=1e-5, atol=1e-6), k
+    assert abs(gold["loss"] - now["loss"]) <= 1e-5 * max(1.0, abs(gold["loss"]))
+    for k, v in gold["grads"].items():
+        assert torch.allclose(v, now["grads"][k], rtol=1e-4, atol=1e-6), k
+    for k, v in gold["state_after_3_adam_steps"].items():
+        assert torch.allclose(v, now["state_after_3_adam_steps"][k], rtol=1e-4, atol=1e-6), k

@@ -360,3 +360,35 @@ def test_large_batch_readout_fp32(n_readout, R, out_dim):
     assert nerr(o1, o2) <= 1e-6
     for a, b in zip(g1, g2):
         assert nerr(a, b) <= 1e-5
+
+
+def test_cuda_path_matches_committed_golden_vectors():
+    """The committed oracle outputs (tests/golden/gcn_small.pt): forward, gradients and three Adam steps of the
+    fused TrainStep, fp32, through the C-ABI."""
+    import os
+    from graphchem_b200.data import Data
+    from graphchem_b200.nn import MoleculeGCN
+    from graphchem_b200.train import TrainStep
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gcn_small.pt"), weights_only=False)
+    d = gold["dims"]
+    model = MoleculeGCN(d["av"], d["bv"], d["out"], embedding_dim=d["embedding_dim"], n_messages=d["n_messages"],
+                        n_readout=d["n_readout"], readout_dim=d["readout_dim"])
+    model.load_state_dict(gold["state"])
+    model = model.cuda().train()
+    dev = Data(x=gold["x"].cuda(), edge_index=gold["edge_index"].cuda(), edge_attr=gold["edge_attr"].cuda(),
+               batch=gold["batch"].cuda(), y=gold["y"].cuda(), num_graphs=int(gold["batch"].max()) + 1)
+    out, out_atom, out_bond = model(dev)
+    assert nerr(out, gold["out"]) <= FWD_F32 and nerr(out_atom, gold["out_atom"]) <= FWD_F32
+    assert nerr(out_bond, gold["out_bond"]) <= FWD_F32
+    loss = F.mse_loss(out, dev.y)
+    assert abs(float(loss) - gold["loss"]) <= 1e-5 * max(1.0, abs(gold["loss"]))
+    model.zero_grad(); loss.backward()
+    for name, p in model.named_parameters():
+        assert nerr(p.grad, gold["grads"][name]) <= GRAD_F32, name
+    step = TrainStep(model, lr=1e-3, use_cuda_graph=False)
+    pb = model.pack(dev).to("cuda")
+    losses = [float(step(pb).item()) for _ in range(3)]
+    for a, b in zip(losses, gold["adam_losses"]):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(b))
+    for name, v in model.state_dict().items():
+        assert nerr(v, gold["state_after_3_adam_steps"][name]) <= 2e-4, name
