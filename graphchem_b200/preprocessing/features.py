@@ -1,9 +1,11 @@
-"""Host-side featurisation contract (reference `graphchem/preprocessing/features.py:10-384`).
+"""Host-side featurisation (reference `graphchem/preprocessing/features.py:10-384`).
 
-Out of scope for the GPU work (north star: "RDKit featurisation stays on host cores"); kept so that
-user code written against graphchem keeps importing.  RDKit is imported lazily -- it is not a
-dependency of the CUDA path and is absent from the build image.  The OUTPUT LAYOUT is part of the
-data contract: int32 atom tokens [n_atoms], int32 bond tokens [2*n_bonds] (both directions of a
+Stays on host cores (north star) and is not timed as GPU work.  The molecule perception behind the
+property tuples comes from RDKit when it is importable and from the built-in restatement
+`graphchem_b200.preprocessing.smiles` otherwise (RDKit is absent from the build image); both yield the
+same strings, hence the same first-seen token ids (pinned by tests/test_smiles.py on the reference's
+test strings, the four notebook encodings and the eight notebook vocabulary sizes).  `backend=` on
+`MoleculeEncoder` forces one of them.  The OUTPUT LAYOUT is part of the data contract: int32 atom tokens [n_atoms], int32 bond tokens [2*n_bonds] (both directions of a
 bond share one token), int64 connectivity [2, 2*n_bonds] in source-atom-major order
 (features.py:294-319); tokens start at 2, `unk` is 1, vocab_size = num_classes + 1 (:148-193).
 """
@@ -16,13 +18,19 @@ import numpy as np
 import torch
 
 
-def _chem():
-    try:
-        from rdkit import Chem
-    except ImportError as e:  # pragma: no cover - RDKit is not installed in the build image
-        raise ImportError("MoleculeEncoder needs RDKit (rdkit-pypi==2022.9.5 in the reference's pins); "
-                          "pre-tokenised molecules can be fed through graphchem_b200.data.MoleculeStore") from e
-    return Chem
+def _chem(backend: str = "auto"):
+    """The object whose `MolFromSmiles` the encoder calls: `rdkit.Chem`, or the built-in perception."""
+    if backend not in ("auto", "rdkit", "builtin"):
+        raise ValueError(f"backend must be 'auto', 'rdkit' or 'builtin', not {backend!r}")
+    if backend != "builtin":
+        try:
+            from rdkit import Chem
+            return Chem
+        except ImportError:
+            if backend == "rdkit":
+                raise ImportError("backend='rdkit' needs RDKit (rdkit-pypi==2022.9.5 in the reference's pins)")
+    from . import smiles
+    return smiles
 
 
 def get_ring_size(obj, max_size: int = 12) -> int:
@@ -74,8 +82,9 @@ class Tokenizer:
 
 
 class MoleculeEncoder:
-    def __init__(self, smiles: List[str]):
-        Chem = _chem()
+    def __init__(self, smiles: List[str], backend: str = "auto"):
+        Chem = _chem(backend)
+        self._backend = backend
         self._atom_tokenizer, self._bond_tokenizer = Tokenizer(), Tokenizer()
         mols = []
         for smi in smiles:
@@ -98,7 +107,7 @@ class MoleculeEncoder:
         return self._atom_tokenizer.vocab_size, self._bond_tokenizer.vocab_size
 
     def encode(self, smiles: str) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        mol = _chem().MolFromSmiles(smiles)
+        mol = _chem(getattr(self, "_backend", "auto")).MolFromSmiles(smiles)
         if mol is None:
             raise ValueError(f"Unable to parse SMILES string: {smiles}")
         atoms, bonds, src, dst = [], [], [], []

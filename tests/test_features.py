@@ -1,5 +1,5 @@
-"""-m "not gpu": tokenizer contract of reference features.py:122-193 (tests/test_features.py:105-116);
-the RDKit-backed encoder tests run only where RDKit is importable (not in the build image)."""
+"""-m "not gpu": tokenizer contract of reference features.py:122-193 (tests/test_features.py:105-116) and the
+encoder's perception back ends; the RDKit-vs-built-in comparison runs only where RDKit is importable."""
 import pickle
 
 import pytest
@@ -24,16 +24,29 @@ def test_import_paths_of_the_reference_resolve():
     assert MoleculeGCN is nn2.MoleculeGCN and E2 is MoleculeEncoder and MoleculeGraph and MoleculeDataset
 
 
-def test_encoder_needs_rdkit_or_matches_golden(tmp_path):
+def test_encoder_backends(tmp_path):
+    """Default: RDKit when importable, the built-in perception otherwise (same strings, tests/test_smiles.py);
+    backend='rdkit' without RDKit is an ImportError, an unknown backend a ValueError."""
     try:
         import rdkit  # noqa: F401
+        have = True
     except ImportError:
+        have = False
+    if not have:
         with pytest.raises(ImportError):
-            MoleculeEncoder(["CC"])
-        return
-    import json, os
-    enc = MoleculeEncoder(["C=C"])
+            MoleculeEncoder(["CC"], backend="rdkit")
+    with pytest.raises(ValueError):
+        MoleculeEncoder(["CC"], backend="openbabel")
+    enc = MoleculeEncoder(["C=C", "CCO"])
     a, b, c = enc.encode("C=C")
     assert a.shape == (2,) and b.shape == (2,) and c.shape == (2, 2) and min(enc.vocab_sizes) > 1
     enc.save(str(tmp_path / "e.pkl"))
     assert load_encoder(str(tmp_path / "e.pkl")).vocab_sizes == enc.vocab_sizes
+    if have:  # both perceptions must number a data set identically
+        from tests.util import load_fuel_set
+        smiles = load_fuel_set("ysi")[0]
+        e1, e2 = MoleculeEncoder(smiles, backend="rdkit"), MoleculeEncoder(smiles, backend="builtin")
+        assert e1.vocab_sizes == e2.vocab_sizes
+        for s in smiles:
+            for t1, t2 in zip(e1.encode(s), e2.encode(s)):
+                assert (t1 == t2).all()

@@ -74,3 +74,26 @@ def nerr(a: torch.Tensor, b: torch.Tensor) -> float:
     if b.numel() == 0:
         return 0.0
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+def load_fuel_set(name: str):
+    """(smiles, targets [n,1] fp32, train_idx, test_idx, notebook vocab sizes) of one bundled property data set
+    from the committed fixture tests/golden/fuel_sets.json (made by tests/golden/make_fuel_sets.py)."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuel_sets.json")
+    with open(path) as f:
+        d = json.load(f)[name]
+    y = torch.tensor(d["target"], dtype=torch.float32).reshape(-1, 1)
+    return d["smiles"], y, d["train_idx"], d["test_idx"], tuple(d["notebook_vocab_sizes"])
+
+
+def encoded_fuel_set(name: str):
+    """The notebook pipeline on one data set with the built-in perception (predict_cn.ipynb cells 0-1):
+    encoder on the training split, MoleculeGraph lists for train and test."""
+    from graphchem_b200.data import MoleculeGraph
+    from graphchem_b200.preprocessing import MoleculeEncoder
+    smiles, y, tr, te, _ = load_fuel_set(name)
+    enc = MoleculeEncoder([smiles[i] for i in tr], backend="builtin")
+    mk = lambda idx: [MoleculeGraph(*enc.encode(smiles[i]), y[i]) for i in idx]  # noqa: E731
+    return enc, mk(tr), mk(te)
