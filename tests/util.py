@@ -97,3 +97,16 @@ def encoded_fuel_set(name: str):
     enc = MoleculeEncoder([smiles[i] for i in tr], backend="builtin")
     mk = lambda idx: [MoleculeGraph(*enc.encode(smiles[i]), y[i]) for i in idx]  # noqa: E731
     return enc, mk(tr), mk(te)
+
+
+def assert_adam_states_close(got: torch.Tensor, want: torch.Tensor, lr: float, steps: int, name: str = "") -> None:
+    """Parameters after a few Adam steps, two implementations.  Adam's first update is lr * sign(g): an entry whose
+    gradient is zero to within the rounding noise of the two backward passes can move by +lr in one and -lr in the
+    other, so a few entries may differ by up to 2 * lr * steps; everything else must agree to a fraction of lr."""
+    d = (got.detach().double().cpu() - want.detach().double().cpu()).abs()
+    assert d.shape == want.shape, name
+    if d.numel() == 0:
+        return
+    assert float(d.max()) <= 2.02 * lr * steps + 1e-6, (name, float(d.max()))
+    outliers = int((d > 0.05 * lr).sum())
+    assert outliers <= max(1, int(2e-3 * d.numel() + 0.5)), (name, outliers, d.numel())
