@@ -159,7 +159,15 @@ class PackedLoader:
                     submit()
                 db, ev, bufs = inflight.pop(0)
                 if ev is not None:
-                    torch.cuda.current_stream(self.device).wait_event(ev)
+                    consumer = torch.cuda.current_stream(self.device)
+                    consumer.wait_event(ev)
+                    if not self._slots:
+                        # the batch was allocated on the copy stream but is read on the consumer's stream: without
+                        # this the caching allocator hands its memory to a later copy as soon as the consumer drops
+                        # the batch, while the consumer's kernels may still be reading it (garbage indices)
+                        db.ints.record_stream(consumer)
+                        if db.y is not None:
+                            db.y.record_stream(consumer)
                     if bufs is not None:  # the pinned pair is free again once its copy has left the host
                         ev.synchronize()
                         with self._pool_lock:

@@ -11,7 +11,10 @@ Prints one JSON line per data set with the loss curve, the test metrics beside t
 (the notebooks are unseeded, so agreement is distributional), the training throughput, and
 the first-steps parity of the loss trajectory against the CPU oracle on identical batches and weights.
 
-    python profiles/micro/fuel_property.py [--sets cn ysi] [--epochs 400]"""
+Initial weights and batch order are those of the CPU twin profiles/micro/fuel_property_oracle.py (same seed), so the
+two loss curves start together and then drift apart the way any two fp32 runs of a chaotic optimisation do.
+
+    python profiles/micro/fuel_property.py [--sets cn ysi ron mon lhv] [--epochs 400] [--seeds 0 1 2]"""
 import argparse
 import json
 import os
@@ -62,13 +65,17 @@ def oracle_trajectory(name, enc, train, steps=5):
     return out
 
 
-def run(name: str, epochs: int, seed: int = 0):
+def run(name: str, epochs: int, seed: int = 0, oracle_steps: bool = True):
     t0 = time.perf_counter()
     enc, train, test = encoded_fuel_set(name)
     t_feat = time.perf_counter() - t0
     av, bv = enc.vocab_sizes
-    torch.manual_seed(seed)
-    model = MoleculeGCN(av, bv, 1, **KW).cuda().train()
+    from oracle.gcn_oracle import OracleMoleculeGCN
+    torch.manual_seed(seed)                      # same initial weights as the CPU twin (fuel_property_oracle.py)
+    init = OracleMoleculeGCN(av, bv, 1, **KW).state_dict()
+    model = MoleculeGCN(av, bv, 1, **KW)
+    model.load_state_dict(init)
+    model = model.cuda().train()
     store = MoleculeStore.from_graphs(train)
     loader = PackedLoader(store, 16, KW["n_messages"], av, bv, device="cuda", shuffle=True, seed=seed, workers=2, prefetch=4)
     step = TrainStep(model, lr=1e-3, use_cuda_graph=False)   # every shuffled batch has its own (N, E): nothing to replay
@@ -87,18 +94,21 @@ def run(name: str, epochs: int, seed: int = 0):
     y_train = torch.cat([g.y for g in train])
     mae, r2 = median_ae_r2(model.predict_each(test), y_test)
     mae_tr, r2_tr = median_ae_r2(model.predict_each(train), y_train)
-    return {"set": name, "molecules_train": len(train), "molecules_test": len(test), "vocab_sizes": [av, bv],
+    return {"set": name, "impl": "cuda", "seed": seed, "molecules_train": len(train), "molecules_test": len(test), "vocab_sizes": [av, bv],
             "epochs": epochs, "featurise_s": round(t_feat, 3), "train_s": round(t_train, 3),
             "train_molecules_per_s": round(epochs * len(train) / t_train, 1), "loss_per_molecule": curve,
             "test_median_ae": round(mae, 4), "test_r2": round(r2, 4), "train_median_ae": round(mae_tr, 4),
             "train_r2": round(r2_tr, 4), "notebook_test_median_ae_r2": NOTEBOOK[name],
-            "oracle_first_steps": oracle_trajectory(name, enc, train)}
+            "oracle_first_steps": oracle_trajectory(name, enc, train) if oracle_steps else None}
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--sets", nargs="+", default=["cn", "ysi"])
     ap.add_argument("--epochs", type=int, default=400)
+    ap.add_argument("--seeds", nargs="+", type=int, default=[0])
+    ap.add_argument("--no-oracle-steps", action="store_true", help="skip the first-steps comparison with the CPU oracle")
     a = ap.parse_args()
     for s in a.sets:
-        print(json.dumps(run(s, a.epochs)), flush=True)
+        for seed in a.seeds:
+            print(json.dumps(run(s, a.epochs, seed, not a.no_oracle_steps)), flush=True)

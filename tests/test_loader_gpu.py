@@ -93,3 +93,41 @@ def test_inferstep_matches_module_forward():
                 ref = model(pb)
             assert torch.equal(out, ref[0]) and torch.equal(oa, ref[1]) and torch.equal(ob, ref[2])
     assert len(step._graphs) == 3
+
+
+def test_streamed_variable_shape_batches_are_not_recycled_under_the_consumer():
+    """Real CN molecules (every shuffled batch of 16 has its own N and E) streamed through the loader WITHOUT a
+    slot ring: a batch is allocated on the copy stream and read on the consumer's stream, so it must stay alive
+    until the consumer's kernels are done with it (record_stream).  Losses of the streamed run must equal, bit for
+    bit, those of the same batches packed and stepped one at a time."""
+    from graphchem_b200.data import MoleculeStore, PackedLoader
+    from graphchem_b200.nn import MoleculeGCN
+    from graphchem_b200.train import TrainStep
+    from tests.util import encoded_fuel_set
+    enc, train, _ = encoded_fuel_set("cn")
+    av, bv = enc.vocab_sizes
+    store = MoleculeStore.from_graphs(train)
+    kw = dict(embedding_dim=128, n_messages=3, n_readout=3, readout_dim=128)
+
+    def run(streamed):
+        torch.manual_seed(0)
+        model = MoleculeGCN(av, bv, 1, **kw).cuda().train()
+        step = TrainStep(model, lr=1e-3, use_cuda_graph=False)
+        loader = PackedLoader(store, 16, 3, av, bv, device="cuda", shuffle=True, seed=3, workers=2, prefetch=4)
+        losses = []
+        for epoch in range(6):
+            if streamed:
+                losses += [step(pb).clone() for pb in loader]
+            else:
+                loader.epoch += 1
+                for idx in loader._batches():
+                    pb = store.collate_pack(idx, 3, av, bv).to("cuda")
+                    losses.append(step(pb).clone())
+                    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return torch.stack(losses).cpu()
+
+    a, b = run(True), run(False)
+    assert a.numel() == 6 * 23
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b)
