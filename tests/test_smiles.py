@@ -184,3 +184,108 @@ def test_tetrahedral_tags():
 @pytest.mark.parametrize("bad", ["", "C(", "C)", "C1CC", "C=", "C(C)(C)(C)(C)C", "[C", "c1cccc1", "C%1CC", "Xx"])
 def test_unparsable_smiles_give_none(bad):
     assert Chem.MolFromSmiles(bad) is None
+
+
+def test_azulene_keeps_its_fusion_bond_single():
+    """RDKit writes azulene as c1ccc2cccc-2cc1: neither ring is aromatic alone (5 and 7 electrons), the 10-electron
+    envelope is, and only envelope bonds are marked."""
+    mol = Chem.MolFromSmiles("C1=CC2=CC=CC=CC2=C1")
+    assert all(a.GetIsAromatic() for a in mol.GetAtoms())
+    kinds = [str(b.GetBondType()) for b in mol.GetBonds()]
+    assert kinds.count("AROMATIC") == 10 and kinds.count("SINGLE") == 1
+    assert _strings("C1=CC2=CC=CC=CC2=C1") == _strings("c1ccc2cccc-2cc1")
+
+
+def _write_random_smiles(mol, rng):
+    """A SMILES of `mol` from a random start atom with random branch order, aromatic atoms in lower case (no stereo)."""
+    n = mol.GetNumAtoms()
+    nbrs = {a.GetIdx(): [(b.GetEndAtomIdx() if b.GetBeginAtomIdx() == a.GetIdx() else b.GetBeginAtomIdx(), b)
+                         for b in a.GetBonds()] for a in mol.GetAtoms()}
+    for v in nbrs.values():
+        rng.shuffle(v)
+    start = int(rng.integers(n))
+    # pass 1: DFS tree + ring-closure bonds
+    seen, tree, order = {start}, set(), []
+    closures = {i: [] for i in range(n)}
+    stack = [(start, None)]
+    parent_bond = {start: None}
+
+    def visit(u):
+        order.append(u)
+        for v, b in nbrs[u]:
+            if b.GetIdx() == (parent_bond[u].GetIdx() if parent_bond[u] is not None else -1):
+                continue
+            if v in seen:
+                if b.GetIdx() not in tree and all(b.GetIdx() != c.GetIdx() for c in closures[u]):
+                    closures[u].append(b)
+                    closures[v].append(b)
+            else:
+                seen.add(v); tree.add(b.GetIdx()); parent_bond[v] = b
+                visit(v)
+
+    visit(start)
+    assert len(seen) == n
+    digit = {}
+
+    def bond_symbol(b):
+        a1, a2 = b.GetBeginAtom(), b.GetEndAtom()
+        kind = str(b.GetBondType())
+        if kind == "AROMATIC":
+            return ""
+        if kind == "SINGLE":
+            return "-" if (a1.GetIsAromatic() and a2.GetIsAromatic()) else ""
+        return {"DOUBLE": "=", "TRIPLE": "#"}[kind]
+
+    def atom_symbol(a):
+        sym = a.GetSymbol().lower() if a.GetIsAromatic() else a.GetSymbol()
+        if a.GetNoImplicit() or a.GetFormalCharge():
+            h = a.GetNumExplicitHs()
+            c = a.GetFormalCharge()
+            return "[" + sym + ("H" + (str(h) if h > 1 else "") if h else "") + ("+" * c if c > 0 else "-" * -c) + "]"
+        return sym
+
+    out = []
+
+    def emit(u):
+        out.append(atom_symbol(mol.GetAtomWithIdx(u)))
+        for b in closures[u]:
+            if b.GetIdx() not in digit:
+                digit[b.GetIdx()] = len(digit) + 1
+                out.append(bond_symbol(b))
+            k = digit[b.GetIdx()]
+            out.append(str(k) if k < 10 else f"%{k}")
+        kids = [(v, b) for v, b in nbrs[u] if parent_bond.get(v) is b and v != start]
+        for i, (v, b) in enumerate(kids):
+            last = i == len(kids) - 1
+            if not last:
+                out.append("(")
+            out.append(bond_symbol(b))
+            emit(v)
+            if not last:
+                out.append(")")
+
+    emit(start)
+    return "".join(out)
+
+
+@pytest.mark.parametrize("name", ["cn", "ysi", "lhv"])
+def test_perception_does_not_depend_on_how_the_smiles_is_written(name):
+    """Every stereo-free molecule of a data set, rewritten from a random atom with random branch order and aromatic
+    rings in lower case (so the rewritten string goes through kekulisation), must give the same multiset of atom and
+    bond strings: valence, rings, aromaticity, conjugation and hybridisation are properties of the graph."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    smiles = load_fuel_set(name)[0]
+    checked = 0
+    for smi in smiles:
+        if any(c in smi for c in "@/\\"):
+            continue
+        mol = Chem.MolFromSmiles(smi)
+        if any(a.GetIsAromatic() and a.GetSymbol() == "N" and a.GetTotalNumHs() for a in mol.GetAtoms()):
+            continue                              # [nH] must be written in brackets: explicit-H fields differ by design
+        want = _strings(smi)
+        for _ in range(2):
+            again = _write_random_smiles(mol, rng)
+            assert _strings(again) == want, (smi, again)
+        checked += 1
+    assert checked > 250
