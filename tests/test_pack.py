@@ -179,3 +179,38 @@ def test_packed_loader_matches_direct_packing():
     sh = PackedLoader(store, 64, 4, 64, 32, device="cpu", shuffle=True, drop_last=True, seed=1, indices=np.arange(0, 300, 2))
     e1 = [b.G for b in sh]
     assert e1 == [64, 64] and len(sh) == 2
+
+
+def test_packed_loader_host_side_logic_on_cpu():
+    """PackedLoader with device='cpu' (no CUDA involved): batch composition, shuffle per epoch, drop_last, shards
+    (`indices`), the resident cache and the each-molecule layout all equal direct collate_pack calls."""
+    from graphchem_b200.data import PackedLoader
+    from tests.util import encoded_fuel_set
+    enc, train, _ = encoded_fuel_set("lhv")
+    av, bv = enc.vocab_sizes
+    store = MoleculeStore.from_graphs(train)
+    n = len(store)
+    loader = PackedLoader(store, 32, 3, av, bv, device="cpu", workers=3, prefetch=2)
+    assert len(loader) == -(-n // 32)
+    got = list(loader)
+    assert sum(b.G for b in got) == n
+    for k, b in enumerate(got):
+        ref = store.collate_pack(np.arange(32 * k, min(n, 32 * k + 32)), 3, av, bv, pin=False)
+        assert torch.equal(b.ints, ref.ints) and torch.equal(b.y, ref.y)
+    # shuffle: a permutation of the data set per epoch, different between epochs, reproducible from the seed
+    sh = PackedLoader(store, 32, 3, av, bv, device="cpu", shuffle=True, seed=5, drop_last=True, workers=2)
+    assert len(sh) == n // 32
+    e1 = torch.cat([b.y for b in sh]); e2 = torch.cat([b.y for b in sh])
+    sh2 = PackedLoader(store, 32, 3, av, bv, device="cpu", shuffle=True, seed=5, drop_last=True, workers=1)
+    assert torch.equal(e1, torch.cat([b.y for b in sh2])) and not torch.equal(e1, e2)
+    assert e1.numel() == (n // 32) * 32
+    # shard + cache: the second epoch replays the very same packed batches
+    shard = PackedLoader(store, 16, 3, av, bv, device="cpu", indices=np.arange(1, n, 2), cache=True)
+    first = list(shard); again = list(shard)
+    assert sum(b.G for b in first) == len(range(1, n, 2)) and all(a is b for a, b in zip(first, again))
+    ref = store.collate_pack(np.arange(1, n, 2)[:16], 3, av, bv, pin=False)
+    assert torch.equal(first[0].ints, ref.ints)
+    # each-molecule layout (predict_each)
+    each = next(iter(PackedLoader(store, 8, 3, av, bv, device="cpu", each=True)))
+    ref = store.collate_pack(np.arange(8), 3, av, bv, pin=False, each=True)
+    assert torch.equal(each.ints, ref.ints) and each.M == each.N
