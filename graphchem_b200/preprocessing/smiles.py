@@ -254,6 +254,7 @@ def _parse(smiles: str) -> Mol:
     s = smiles.strip()
     if not s:
         raise SmilesError("empty SMILES")
+    s = s.split()[0]                        # RDKit reads "SMILES name": everything after white space is a title
     prev: Optional[Atom] = None
     stack: List[Optional[Atom]] = []
     pending = ""                            # bond symbol waiting for its second atom
@@ -352,6 +353,10 @@ def _parse(smiles: str) -> Mol:
         atom._ring_closures = [made[key] for key in atom._ring_closures]
     if not mol._atoms:
         raise SmilesError("no atoms")
+    if len(mol._atoms) > 1 and any(a._symbol == "H" for a in mol._atoms):
+        # RDKit folds [H] atoms into their neighbours (removeHs, with its own rules for isotopes, chirality and
+        # bridging hydrogens); not restated here, so refuse instead of numbering a different graph
+        raise SmilesError("explicit hydrogen atoms need RDKit")
     return mol
 
 
@@ -373,6 +378,8 @@ def _kekulize(mol: Mol) -> None:
             wants = a._charge == 0
         elif a._symbol in ("N", "P"):
             wants = (sigma == 2 and a._charge == 0) or (sigma == 3 and a._charge == 1)
+        elif a._symbol in ("O", "S", "Se"):
+            wants = sigma == 2 and a._charge == 1          # pyrylium / thiopyrylium
         else:
             wants = False
         if wants and not any(b._order >= 2.0 for b in a._bonds):
@@ -759,6 +766,8 @@ def _stereo(mol: Mol) -> None:
         for a in tagged:
             total = a.GetTotalDegree()
             legal = 3 <= total <= 4 and len(a._bonds) >= 3 and a.GetTotalNumHs() <= 1
+            if a._z == 7 and total == 3 and a._ring_size != 3:
+                legal = False                  # a three-coordinate nitrogen inverts (RDKit keeps it only in 3-rings / bridgeheads)
             nbr_ranks = [ranks[x._idx] for x in a._neighbors()]
             dupes = len(set(nbr_ranks)) != len(nbr_ranks)
             if legal and not dupes:

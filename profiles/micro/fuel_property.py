@@ -65,7 +65,7 @@ def oracle_trajectory(name, enc, train, steps=5):
     return out
 
 
-def run(name: str, epochs: int, seed: int = 0, oracle_steps: bool = True):
+def run(name: str, epochs: int, seed: int = 0, oracle_steps: bool = True, dtype=torch.float32):
     t0 = time.perf_counter()
     enc, train, test = encoded_fuel_set(name)
     t_feat = time.perf_counter() - t0
@@ -73,7 +73,7 @@ def run(name: str, epochs: int, seed: int = 0, oracle_steps: bool = True):
     from oracle.gcn_oracle import OracleMoleculeGCN
     torch.manual_seed(seed)                      # same initial weights as the CPU twin (fuel_property_oracle.py)
     init = OracleMoleculeGCN(av, bv, 1, **KW).state_dict()
-    model = MoleculeGCN(av, bv, 1, **KW)
+    model = MoleculeGCN(av, bv, 1, compute_dtype=dtype, **KW)
     model.load_state_dict(init)
     model = model.cuda().train()
     store = MoleculeStore.from_graphs(train)
@@ -94,7 +94,7 @@ def run(name: str, epochs: int, seed: int = 0, oracle_steps: bool = True):
     y_train = torch.cat([g.y for g in train])
     mae, r2 = median_ae_r2(model.predict_each(test), y_test)
     mae_tr, r2_tr = median_ae_r2(model.predict_each(train), y_train)
-    return {"set": name, "impl": "cuda", "seed": seed, "molecules_train": len(train), "molecules_test": len(test), "vocab_sizes": [av, bv],
+    return {"set": name, "impl": "cuda", "dtype": str(dtype).replace("torch.", ""), "seed": seed, "molecules_train": len(train), "molecules_test": len(test), "vocab_sizes": [av, bv],
             "epochs": epochs, "featurise_s": round(t_feat, 3), "train_s": round(t_train, 3),
             "train_molecules_per_s": round(epochs * len(train) / t_train, 1), "loss_per_molecule": curve,
             "test_median_ae": round(mae, 4), "test_r2": round(r2, 4), "train_median_ae": round(mae_tr, 4),
@@ -108,7 +108,9 @@ if __name__ == "__main__":
     ap.add_argument("--epochs", type=int, default=400)
     ap.add_argument("--seeds", nargs="+", type=int, default=[0])
     ap.add_argument("--no-oracle-steps", action="store_true", help="skip the first-steps comparison with the CPU oracle")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"], help="activation dtype (bf16: tile kernels + tcgen05 GEMMs)")
     a = ap.parse_args()
     for s in a.sets:
         for seed in a.seeds:
-            print(json.dumps(run(s, a.epochs, seed, not a.no_oracle_steps)), flush=True)
+            print(json.dumps(run(s, a.epochs, seed, not a.no_oracle_steps and a.dtype == "fp32",
+                                 torch.bfloat16 if a.dtype == "bf16" else torch.float32)), flush=True)

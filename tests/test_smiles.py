@@ -289,3 +289,15 @@ def test_perception_does_not_depend_on_how_the_smiles_is_written(name):
             assert _strings(again) == want, (smi, again)
         checked += 1
     assert checked > 250
+
+
+def test_inputs_outside_the_restated_rules_fail_loudly_or_follow_rdkit():
+    assert Chem.MolFromSmiles("[H]C([H])([H])O") is None          # explicit H atoms: RDKit's removeHs is not restated
+    assert Chem.MolFromSmiles("[H][H]") is None and Chem.MolFromSmiles("[Fe]") is None
+    assert Chem.MolFromSmiles("CCO ethanol").GetNumAtoms() == 3   # "SMILES title"
+    pyr = Chem.MolFromSmiles("c1cc[o+]cc1")                       # pyrylium kekulises and is aromatic again
+    assert pyr is not None and all(a.GetIsAromatic() for a in pyr.GetAtoms())
+    assert [a.GetFormalCharge() for a in pyr.GetAtoms()].count(1) == 1
+    assert str(Chem.MolFromSmiles("C[N@](CC)CCC").GetAtomWithIdx(1).GetChiralTag()) == "CHI_UNSPECIFIED"
+    with pytest.raises(ValueError):
+        MoleculeEncoder(["[H]C"], backend="builtin")
