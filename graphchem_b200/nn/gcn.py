@@ -31,6 +31,27 @@ _ACT_IDS = {
     F.tanh: _lib.ACT_TANH, torch.tanh: _lib.ACT_TANH,
     F.leaky_relu: _lib.ACT_LEAKY_RELU,
 }
+
+
+def _act_id(act_fn) -> Optional[int]:
+    """Kernel id of `act_fn`: one of the five functional activations above, or the `nn.Module` form of
+    the same function with its default hyper-parameters (`nn.Softplus()`, `nn.LeakyReLU()` ...).  The
+    reference takes any callable (gcn.py:66-68); here the activation is compiled into the kernels."""
+    try:
+        if act_fn in _ACT_IDS:
+            return _ACT_IDS[act_fn]
+    except TypeError:  # unhashable callable
+        return None
+    if isinstance(act_fn, nn.Softplus) and act_fn.beta == 1 and act_fn.threshold == 20:
+        return _lib.ACT_SOFTPLUS
+    if isinstance(act_fn, nn.LeakyReLU) and act_fn.negative_slope == 0.01:
+        return _lib.ACT_LEAKY_RELU
+    for cls, aid in ((nn.Sigmoid, _lib.ACT_SIGMOID), (nn.ReLU, _lib.ACT_RELU), (nn.Tanh, _lib.ACT_TANH)):
+        if isinstance(act_fn, cls):
+            return aid
+    return None
+
+
 _POISON = os.environ.get("GCB_DEBUG_POISON", "0") == "1"
 _AGGR_IDS = {"add": _lib.AGGR_ADD, "sum": _lib.AGGR_ADD, "mean": _lib.AGGR_MEAN}
 
@@ -107,8 +128,10 @@ class MoleculeGCN(nn.Module):
         self._p_dropout = p_dropout
         self._n_messages = n_messages
         self.act_fn = act_fn
-        if act_fn not in _ACT_IDS:
-            raise ValueError("act_fn must be one of torch.nn.functional.{softplus, sigmoid, relu, tanh, leaky_relu}: "
+        self._act_id = _act_id(act_fn)
+        if self._act_id is None:
+            raise ValueError("act_fn must be one of torch.nn.functional.{softplus, sigmoid, relu, tanh, leaky_relu} "
+                             "(or the nn.Module of the same function with default arguments): "
                              "the activation is fused into the CUDA kernels")
         if aggr not in _AGGR_IDS:
             raise NotImplementedError(f"aggr={aggr!r} is not implemented by the CUDA kernels (use 'add' or 'mean')")
@@ -142,7 +165,7 @@ class MoleculeGCN(nn.Module):
         key = (self._compute_dtype, float(self._p_dropout), int(self._n_messages))
         if self._cfg_cache is None or self._cfg_cache[0] != key:
             cfg = _lib.ModelCfg(av, bv, int(out_dim) if (n_readout > 0 and out_dim is not None) else 0, D,
-                                int(self._n_messages), n_readout, R, _ACT_IDS[self.act_fn], _AGGR_IDS[self._aggr],
+                                int(self._n_messages), n_readout, R, self._act_id, _AGGR_IDS[self._aggr],
                                 _lib.BF16 if self._compute_dtype == torch.bfloat16 else _lib.F32,
                                 float(self._p_dropout), 0)
             offs = (C.c_int64 * (_lib.MAX_PARAM_TENSORS + 1))()
