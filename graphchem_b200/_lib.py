@@ -35,6 +35,7 @@ PACK_HEADER_INTS = 48
 PACK_EACH = 1
 TILE_ROWS = 128
 PACK_MAGIC = 0x47434232
+RAW_HEADER_INTS = 16
 MAX_PARAM_TENSORS = 64
 
 
@@ -74,6 +75,11 @@ SIGNATURES = {
     "gcb_collate_pack_each_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "gcb_pack_host": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64]),
     "gcb_collate_pack_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "gcb_raw_ints": (_i64, [_i32, _i32, _i32]),
+    "gcb_collate_raw_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "gcb_pack_device_scratch_ints": (_i64, [_vp]),
+    "gcb_pack_device": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "gcb_debug_pack_emulate_host": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32]),
     "gcb_param_layout": (C.c_int, [_cfgp, _vp]),
     "gcb_derived_bytes": (_i64, [_cfgp]),
     "gcb_prepare_weights": (C.c_int, [_cfgp, _vp, _vp, _vp]),

@@ -165,6 +165,31 @@ static int finish_pack(int32_t* packed, const int32_t* h, const int32_t* batch_i
   return GCB_OK;
 }
 
+// Greedy closed-tile walk over cut positions given in increasing order (rows no edge spans): a tile is closed at
+// the last cut that keeps it within GCB_TILE_ROWS rows.  Shared by the collate packer and the raw collate of the
+// device packer, so both produce the same tile_ptr.
+struct TileWalker {
+  int32_t* tile_ptr;
+  int32_t nt = 0, start = 0, last_cut = 0;
+  bool ok = true;
+  explicit TileWalker(int32_t* tp) : tile_ptr(tp) { tile_ptr[0] = 0; }
+  void cut_at(int32_t p) {
+    if (!ok) return;
+    if (p - start > GCB_TILE_ROWS) {
+      if (last_cut == start) { ok = false; return; }
+      tile_ptr[++nt] = last_cut;
+      start = last_cut;
+      if (p - start > GCB_TILE_ROWS) { ok = false; return; }
+    }
+    last_cut = p;
+  }
+  int32_t finish(int32_t N) {  // number of tiles, 0 = no closed tiling (a component wider than a tile)
+    if (ok && N > 0 && last_cut != N) ok = false;  // (cannot happen: the last molecule ends at N)
+    if (ok && N > 0) tile_ptr[++nt] = N;
+    return ok ? nt : 0;
+  }
+};
+
 // Collated molecules: every edge stays inside its molecule, atoms and edges of a molecule are contiguous, and
 // graph ids increase -- so all index structures except the token buckets are per-molecule problems whose
 // working set (tens of atoms / edges) lives in L1.  One sequential pass over the molecules instead of a dozen
@@ -194,20 +219,8 @@ static int finish_pack_local(int32_t* packed, const int32_t* h, const int32_t* n
   for (int32_t g = 0; g < G; ++g) { max_a = n_atoms[g] > max_a ? n_atoms[g] : max_a; max_e = n_edges[g] > max_e ? n_edges[g] : max_e; }
   std::vector<int32_t> pin((size_t)max_a + 2), pout((size_t)max_a + 2), cin((size_t)max_a + 1), cout((size_t)max_a + 1),
       pos((size_t)max_e + 1), span((size_t)max_a + 2);
-  // closed row tiles: greedy over the cut positions, in order (same walk as finish_pack)
-  int32_t nt = 0, start = 0, last_cut = 0;
-  bool tiles_ok = true;
-  tile_ptr[0] = 0;
-  auto cut_at = [&](int32_t p) {
-    if (!tiles_ok) return;
-    if (p - start > GCB_TILE_ROWS) {
-      if (last_cut == start) { tiles_ok = false; return; }
-      tile_ptr[++nt] = last_cut;
-      start = last_cut;
-      if (p - start > GCB_TILE_ROWS) { tiles_ok = false; return; }
-    }
-    last_cut = p;
-  };
+  TileWalker tw(tile_ptr);  // closed row tiles: greedy over the cut positions, in order (same walk as finish_pack)
+  auto cut_at = [&](int32_t p) { tw.cut_at(p); };
   int32_t a0 = 0, e0 = 0;
   for (int32_t g = 0; g < G; ++g) {
     const int32_t na = n_atoms[g], ne = n_edges[g];
@@ -261,9 +274,7 @@ static int finish_pack_local(int32_t* packed, const int32_t* h, const int32_t* n
   graph_ptr[G] = N;
   in_ptr[N] = E;
   out_ptr[N] = E;
-  if (tiles_ok && N > 0 && last_cut != N) tiles_ok = false;  // (cannot happen: the last molecule ends at N)
-  if (tiles_ok && N > 0) tile_ptr[++nt] = N;
-  packed[GCB_H_NTILES] = tiles_ok ? nt : 0;
+  packed[GCB_H_NTILES] = tw.finish(N);
   bucket(packed + h[GCB_H_X_TOK], N, av, packed + h[GCB_H_ATOK_PTR], packed + h[GCB_H_ATOK_NODE]);
   bucket(packed + h[GCB_H_E_TOK], M, bv, packed + h[GCB_H_BTOK_PTR], packed + h[GCB_H_BTOK_ROW]);
   return GCB_OK;
@@ -465,5 +476,415 @@ extern "C" int gcb_collate_pack_each_host(const int32_t* const* atoms, const int
   for (int64_t k = 0; k < 4 * (int64_t)N; ++k)
     if (e4[k] >= 0) e4[k] = bond_pos[e4[k]] >= 0 ? bond_pos[e4[k]] : M;
   zero_unwritten(packed, h, N);
+  return GCB_OK;
+}
+
+// =====================================================================================================
+// Device-side packer (SURVEY.md 8 d config 5: batches "packed on device"; 8 f1).  The host only gathers the
+// molecules of a batch into a RAW buffer -- molecule offsets, tokens, edge list with batch-global atom ids and
+// the closed-tile table (0.7 kB per molecule instead of 3.9 kB) -- and the device derives every other
+// section of the packed batch.  The result is bit-identical to gcb_collate_pack_host on the same molecules.
+//
+// The per-molecule and per-chunk routines are __host__ __device__: gcb_debug_pack_emulate_host runs exactly the
+// code of the kernels serially on the CPU (a test hook like gcb_debug_gemm_*, not a product path), so the index
+// logic is pinned against the host packer without a GPU.
+// =====================================================================================================
+namespace gcb {
+
+enum {
+  RAW_MAGIC = 0, RAW_N, RAW_E, RAW_G, RAW_M, RAW_AV, RAW_BV, RAW_NTILES, RAW_ATOM_OFF, RAW_EDGE_OFF, RAW_X_TOK,
+  RAW_E_TOK, RAW_SRC, RAW_DST, RAW_TILE_PTR, RAW_TOTAL_INTS
+};
+static_assert(RAW_TOTAL_INTS < GCB_RAW_HEADER_INTS, "raw header too small");
+
+static inline int64_t raw_tile_cap(int32_t N) { return (int64_t)N / (GCB_TILE_ROWS / 2) + 3; }  // > tiles + 1 of any greedy walk
+
+static int64_t raw_layout(int32_t N, int32_t E, int32_t G, int32_t* rh) {
+  int64_t off = GCB_RAW_HEADER_INTS;
+  const int64_t n[7] = {(int64_t)G + 1, (int64_t)G + 1, N, E, E, E, raw_tile_cap(N)};
+  for (int i = 0; i < 7; ++i) {
+    if (rh) rh[RAW_ATOM_OFF + i] = (int32_t)off;
+    off += pad4(n[i]);
+  }
+  if (off > INT32_MAX) return -1;
+  if (rh) rh[RAW_TOTAL_INTS] = (int32_t)off;
+  return off;
+}
+
+struct PackPtrs {
+  const int32_t *src, *dst;
+  int32_t *in_ptr, *in_eid, *in_src, *out_ptr, *out_eid, *out_dst, *s4, *e4, *d4, *o4, *out_inpos, *graph_ptr,
+      *graph_node, *node_graph;
+};
+
+static PackPtrs pack_ptrs(int32_t* packed, const int32_t* h) {
+  PackPtrs p;
+  p.src = packed + h[GCB_H_SRC]; p.dst = packed + h[GCB_H_DST];
+  p.in_ptr = packed + h[GCB_H_IN_PTR]; p.in_eid = packed + h[GCB_H_IN_EID]; p.in_src = packed + h[GCB_H_IN_SRC];
+  p.out_ptr = packed + h[GCB_H_OUT_PTR]; p.out_eid = packed + h[GCB_H_OUT_EID]; p.out_dst = packed + h[GCB_H_OUT_DST];
+  p.s4 = packed + h[GCB_H_IN_SRC4]; p.e4 = packed + h[GCB_H_IN_EID4]; p.d4 = packed + h[GCB_H_OUT_DST4];
+  p.o4 = packed + h[GCB_H_OUT_INPOS4]; p.out_inpos = packed + h[GCB_H_OUT_INPOS];
+  p.graph_ptr = packed + h[GCB_H_GRAPH_PTR]; p.graph_node = packed + h[GCB_H_GRAPH_NODE];
+  p.node_graph = packed + h[GCB_H_NODE_GRAPH];
+  return p;
+}
+
+// One molecule (atoms [a0, a0+na), edges [e0, e0+ne), every edge inside the molecule): both CSRs in stable
+// edge-id order, the cross index, the ELL-4 views, graph segment entries.  pin / pout: na + 1 ints, pos: ne ints.
+__host__ __device__ inline void pack_one_molecule(const PackPtrs& p, int32_t g, int32_t a0, int32_t na, int32_t e0,
+                                                  int32_t ne, int32_t* pin, int32_t* pout, int32_t* pos) {
+  p.graph_ptr[g] = a0;
+  for (int32_t i = 0; i <= na; ++i) { pin[i] = 0; pout[i] = 0; }
+  for (int32_t e = 0; e < ne; ++e) {  // counts of row i at index i + 1
+    pin[p.dst[e0 + e] - a0 + 1]++;
+    pout[p.src[e0 + e] - a0 + 1]++;
+  }
+  for (int32_t i = 0; i < na; ++i) { pin[i + 1] += pin[i]; pout[i + 1] += pout[i]; }  // pin[i] = first entry of row i
+  for (int32_t i = 0; i < na; ++i) {
+    p.in_ptr[a0 + i] = e0 + pin[i];
+    p.out_ptr[a0 + i] = e0 + pout[i];
+    p.graph_node[a0 + i] = a0 + i;
+    p.node_graph[a0 + i] = g;
+  }
+  for (int32_t e = 0; e < ne; ++e) {  // pin[] turns into the row cursors: afterwards pin[i] = end of row i
+    const int32_t k = pin[p.dst[e0 + e] - a0]++;
+    p.in_eid[e0 + k] = e0 + e;
+    p.in_src[e0 + k] = p.src[e0 + e];
+    pos[e] = k;
+  }
+  for (int32_t e = 0; e < ne; ++e) {
+    const int32_t k = pout[p.src[e0 + e] - a0]++;
+    p.out_eid[e0 + k] = e0 + e;
+    p.out_dst[e0 + k] = p.dst[e0 + e];
+    p.out_inpos[e0 + k] = e0 + pos[e];
+  }
+  for (int32_t i = 0; i < na; ++i) {  // ELL-4 views: first four entries of every row, -1 padded
+    const int32_t bi = i ? pin[i - 1] : 0, ei = pin[i], bo = i ? pout[i - 1] : 0, eo = pout[i];
+    const int64_t a = (int64_t)(a0 + i) * 4;
+    for (int u = 0; u < 4; ++u) {
+      const int32_t ki = bi + u, ko = bo + u;
+      p.s4[a + u] = ki < ei ? p.in_src[e0 + ki] : -1;
+      p.e4[a + u] = ki < ei ? p.in_eid[e0 + ki] : -1;
+      p.d4[a + u] = ko < eo ? p.out_dst[e0 + ko] : -1;
+      p.o4[a + u] = ko < eo ? p.out_inpos[e0 + ko] : -1;
+    }
+  }
+}
+
+// Stable counting sort of ids 0..n-1 by key in three passes over chunks of kBucketChunk consecutive ids:
+// (A) per-chunk histogram, (B) per-bucket exclusive scan over the chunks + bucket pointers, (C) placement in id order.
+constexpr int kBucketChunk = 64;
+__host__ __device__ inline void bucket_hist_chunk(const int32_t* key, int64_t n, int32_t nb, int64_t c, int32_t* hist) {
+  int32_t* h = hist + c * nb;
+  for (int32_t b = 0; b < nb; ++b) h[b] = 0;
+  const int64_t i1 = (c + 1) * kBucketChunk < n ? (c + 1) * kBucketChunk : n;
+  for (int64_t i = c * kBucketChunk; i < i1; ++i) h[key[i]]++;
+}
+__host__ __device__ inline void bucket_scan_bucket(int32_t nb, int64_t chunks, int32_t b, int32_t* hist, int32_t* ptr) {
+  int32_t run = 0;
+  for (int64_t c = 0; c < chunks; ++c) {
+    const int32_t t = hist[c * nb + b];
+    hist[c * nb + b] = run;
+    run += t;
+  }
+  ptr[b + 1] = run;  // bucket size; bucket_ptr_scan turns the sizes into offsets
+}
+__host__ __device__ inline void bucket_ptr_scan(int32_t nb, int32_t* ptr) {
+  ptr[0] = 0;
+  for (int32_t b = 0; b < nb; ++b) ptr[b + 1] += ptr[b];
+}
+__host__ __device__ inline void bucket_place_chunk(const int32_t* key, int64_t n, int32_t nb, int64_t c, int32_t* hist,
+                                                   const int32_t* ptr, int32_t* perm) {
+  int32_t* h = hist + c * nb;
+  const int64_t i1 = (c + 1) * kBucketChunk < n ? (c + 1) * kBucketChunk : n;
+  for (int64_t i = c * kBucketChunk; i < i1; ++i) {
+    const int32_t k = key[i];
+    perm[ptr[k] + h[k]++] = (int32_t)i;
+  }
+}
+static inline int64_t bucket_chunks(int64_t n) { return (n + kBucketChunk - 1) / kBucketChunk; }
+
+// Copies (raw -> packed) and zero fills that complete a packed batch around the derived sections.
+constexpr int kMaxSegs = 48;
+struct PackSegs {
+  int32_t header[GCB_PACK_HEADER_INTS];
+  int32_t n;
+  int32_t dst_off[kMaxSegs], src_off[kMaxSegs] /* -1: zero fill */, count[kMaxSegs];
+  int32_t in_ptr_end, out_ptr_end, graph_ptr_end;  // positions of in_ptr[N], out_ptr[N], graph_ptr[G]
+};
+static int build_segs(const int32_t* h, const int32_t* rh, PackSegs* sg) {
+  const int32_t N = h[GCB_H_N], E = h[GCB_H_E], G = h[GCB_H_G], M = h[GCB_H_M], nt = h[GCB_H_NTILES];
+  std::memcpy(sg->header, h, sizeof(sg->header));
+  sg->n = 0;
+  auto put = [&](int64_t dst, int64_t src, int64_t count) {
+    if (count <= 0) return true;
+    if (sg->n >= kMaxSegs) return false;
+    sg->dst_off[sg->n] = (int32_t)dst; sg->src_off[sg->n] = (int32_t)src; sg->count[sg->n] = (int32_t)count;
+    ++sg->n;
+    return true;
+  };
+  bool ok = put(h[GCB_H_X_TOK], rh[RAW_X_TOK], N) && put(h[GCB_H_E_TOK], rh[RAW_E_TOK], E) &&
+            put(h[GCB_H_SRC], rh[RAW_SRC], E) && put(h[GCB_H_DST], rh[RAW_DST], E) &&
+            put(h[GCB_H_TILE_PTR], rh[RAW_TILE_PTR], (int64_t)nt + 1);
+  Sec t[GCB_H_FIELDS];  // same fills as zero_unwritten()
+  const int k = section_table(N, E, G, h[GCB_H_AV], h[GCB_H_BV], h[GCB_H_FLAGS], t);
+  for (int i = 0; i < k; ++i) ok = ok && put(h[t[i].field] + t[i].n, -1, pad4(t[i].n) - t[i].n);
+  ok = ok && put((int64_t)h[GCB_H_BTOK_ROW] + M, -1, (int64_t)E - M);
+  ok = ok && put((int64_t)h[GCB_H_TILE_PTR] + nt + 1, -1, (int64_t)N + 1 - (nt + 1));
+  sg->in_ptr_end = h[GCB_H_IN_PTR] + N;
+  sg->out_ptr_end = h[GCB_H_OUT_PTR] + N;
+  sg->graph_ptr_end = h[GCB_H_GRAPH_PTR] + G;
+  return ok ? GCB_OK : GCB_ERR_INVALID_ARG;
+}
+__host__ __device__ inline void seg_element(const PackSegs& sg, int s, int64_t i, const int32_t* raw, int32_t* packed) {
+  packed[(int64_t)sg.dst_off[s] + i] = sg.src_off[s] >= 0 ? raw[(int64_t)sg.src_off[s] + i] : 0;
+}
+__host__ __device__ inline void seg_fixed(const PackSegs& sg, int32_t* packed) {  // header and the three end sentinels
+  for (int i = 0; i < GCB_PACK_HEADER_INTS; ++i) packed[i] = sg.header[i];
+  packed[sg.in_ptr_end] = sg.header[GCB_H_E];
+  packed[sg.out_ptr_end] = sg.header[GCB_H_E];
+  packed[sg.graph_ptr_end] = sg.header[GCB_H_N];
+}
+
+// ---- kernels: one thread per unit of the routines above -------------------------------------------------
+constexpr int kPackMaxA = 64, kPackMaxE = 160;  // molecules up to this size use thread-local arrays, larger ones scratch
+__global__ void pack_segments_kernel(const __grid_constant__ PackSegs sg, const int32_t* __restrict__ raw, int32_t* __restrict__ packed) {
+  const int s = blockIdx.y;
+  if (s == sg.n) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) seg_fixed(sg, packed);
+    return;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.count[s]; i += (int64_t)gridDim.x * blockDim.x)
+    seg_element(sg, s, i, raw, packed);
+}
+__global__ void pack_molecules_kernel(const PackPtrs p, const int32_t* __restrict__ atom_off, const int32_t* __restrict__ edge_off,
+                                      int32_t G, int32_t* scr_pin, int32_t* scr_pout, int32_t* scr_pos) {
+  const int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int32_t a0 = atom_off[g], na = atom_off[g + 1] - a0, e0 = edge_off[g], ne = edge_off[g + 1] - e0;
+  if (na <= kPackMaxA && ne <= kPackMaxE) {
+    int32_t pin[kPackMaxA + 1], pout[kPackMaxA + 1], pos[kPackMaxE];
+    pack_one_molecule(p, g, a0, na, e0, ne, pin, pout, pos);
+  } else {
+    pack_one_molecule(p, g, a0, na, e0, ne, scr_pin + a0 + g, scr_pout + a0 + g, scr_pos + e0);
+  }
+}
+__global__ void bucket_hist_kernel(const int32_t* __restrict__ key, int64_t n, int32_t nb, int64_t chunks, int32_t* hist) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < chunks) bucket_hist_chunk(key, n, nb, c, hist);
+}
+__global__ void bucket_scan_kernel(int32_t nb, int64_t chunks, int32_t* hist, int32_t* ptr) {  // ONE block
+  for (int32_t b = threadIdx.x; b < nb; b += blockDim.x) bucket_scan_bucket(nb, chunks, b, hist, ptr);
+  __syncthreads();
+  if (threadIdx.x == 0) bucket_ptr_scan(nb, ptr);
+}
+__global__ void bucket_place_kernel(const int32_t* __restrict__ key, int64_t n, int32_t nb, int64_t chunks, int32_t* hist,
+                                    const int32_t* __restrict__ ptr, int32_t* perm) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < chunks) bucket_place_chunk(key, n, nb, c, hist, ptr, perm);
+}
+
+static int bucket_device(const int32_t* key, int64_t n, int32_t nb, int32_t* ptr, int32_t* perm, int32_t* hist, cudaStream_t s) {
+  const int64_t chunks = bucket_chunks(n);
+  const int bt = 64;
+  if (chunks > 0)
+    GCB_KERNEL("pack_bucket_hist_kernel", s, bucket_hist_kernel<<<(unsigned)((chunks + bt - 1) / bt), bt, 0, s>>>(key, n, nb, chunks, hist));
+  GCB_KERNEL("pack_bucket_scan_kernel", s, bucket_scan_kernel<<<1, 256, 0, s>>>(nb, chunks, hist, ptr));
+  if (chunks > 0)
+    GCB_KERNEL("pack_bucket_place_kernel", s, bucket_place_kernel<<<(unsigned)((chunks + bt - 1) / bt), bt, 0, s>>>(key, n, nb, chunks, hist, ptr, perm));
+  return GCB_OK;
+}
+
+struct Scratch { int64_t pin, pout, pos, hist_a, hist_b, total; };
+static Scratch scratch_layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, int32_t bv) {
+  Scratch sc;
+  int64_t off = 0;
+  sc.pin = off; off += pad4((int64_t)N + G);
+  sc.pout = off; off += pad4((int64_t)N + G);
+  sc.pos = off; off += pad4(E);
+  sc.hist_a = off; off += pad4(bucket_chunks(N) * av);
+  sc.hist_b = off; off += pad4(bucket_chunks(M) * bv);
+  sc.total = off > 0 ? off : 4;
+  return sc;
+}
+
+static int check_raw_against_header(const int32_t* rh, const int32_t* h) {
+  if (rh[RAW_MAGIC] != GCB_RAW_MAGIC || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
+  if (rh[RAW_N] != h[GCB_H_N] || rh[RAW_E] != h[GCB_H_E] || rh[RAW_G] != h[GCB_H_G] || rh[RAW_M] != h[GCB_H_M] ||
+      rh[RAW_AV] != h[GCB_H_AV] || rh[RAW_BV] != h[GCB_H_BV] || rh[RAW_NTILES] != h[GCB_H_NTILES] || h[GCB_H_FLAGS] != 0)
+    return GCB_ERR_INVALID_ARG;
+  return GCB_OK;
+}
+
+}  // namespace gcb
+
+extern "C" int64_t gcb_raw_ints(int32_t N, int32_t E, int32_t G) {
+  if (N < 0 || E < 0 || G < 0) return GCB_ERR_INVALID_ARG;
+  const int64_t t = raw_layout(N, E, G, nullptr);
+  return t < 0 ? GCB_ERR_INVALID_ARG : t;
+}
+
+extern "C" int gcb_collate_raw_host(const int32_t* const* atoms, const int32_t* n_atoms, const int32_t* const* bonds,
+                                    const int64_t* const* conn, const int32_t* n_edges, const float* const* y,
+                                    int32_t n_targets, int32_t n_graphs, int32_t n_messages, int32_t atom_vocab,
+                                    int32_t bond_vocab, int32_t* raw, int64_t raw_ints, float* y_out, int32_t* packed_header) {
+  if (n_graphs < 0 || !raw || !packed_header || (n_graphs > 0 && (!atoms || !n_atoms || !bonds || !conn || !n_edges)))
+    return GCB_ERR_INVALID_ARG;
+  int64_t N64 = 0, E64 = 0;
+  int32_t max_a = 0;
+  for (int32_t g = 0; g < n_graphs; ++g) {
+    if (n_atoms[g] < 0 || n_edges[g] < 0) return GCB_ERR_INVALID_ARG;
+    N64 += n_atoms[g];
+    E64 += n_edges[g];
+    max_a = n_atoms[g] > max_a ? n_atoms[g] : max_a;
+  }
+  if (N64 > INT32_MAX || E64 > INT32_MAX) return GCB_ERR_INVALID_ARG;
+  const int32_t N = (int32_t)N64, E = (int32_t)E64, G = n_graphs;
+  const int32_t M = n_messages >= 1 ? (N < E ? N : E) : E;
+  if (layout(N, E, G, M, atom_vocab, bond_vocab, 0, packed_header) < 0) return GCB_ERR_INVALID_ARG;
+  int32_t rh[GCB_RAW_HEADER_INTS];
+  std::memset(rh, 0, sizeof(rh));
+  const int64_t total = raw_layout(N, E, G, rh);
+  if (total < 0) return GCB_ERR_INVALID_ARG;
+  if (raw_ints < total) return GCB_ERR_WORKSPACE;
+  int32_t* atom_off = raw + rh[RAW_ATOM_OFF];
+  int32_t* edge_off = raw + rh[RAW_EDGE_OFF];
+  int32_t* x_tok = raw + rh[RAW_X_TOK];
+  int32_t* e_tok = raw + rh[RAW_E_TOK];
+  int32_t* src = raw + rh[RAW_SRC];
+  int32_t* dst = raw + rh[RAW_DST];
+  int32_t* tile_ptr = raw + rh[RAW_TILE_PTR];
+  const int64_t lim = n_messages >= 1 ? M : N;
+  std::vector<int32_t> span((size_t)max_a + 2);
+  std::vector<int32_t> tiles((size_t)N + 2);  // the walk may write up to N + 1 entries before it gives up
+  TileWalker tw(tiles.data());
+  int32_t node_off = 0, edge_off_ = 0;
+  for (int32_t g = 0; g < G; ++g) {
+    const int32_t na = n_atoms[g], ne = n_edges[g];
+    atom_off[g] = node_off;
+    edge_off[g] = edge_off_;
+    for (int32_t i = 0; i < na; ++i) {
+      const int32_t t = atoms[g][i];
+      if (t < 0 || t >= atom_vocab) return GCB_ERR_INDEX;
+      x_tok[node_off + i] = t;
+    }
+    for (int32_t i = 0; i <= na + 1; ++i) span[i] = 0;
+    for (int32_t e = 0; e < ne; ++e) {
+      const int32_t t = bonds[g][e];
+      if (t < 0 || t >= bond_vocab) return GCB_ERR_INDEX;
+      e_tok[edge_off_ + e] = t;
+      const int64_t sl = conn[g][e], dl = conn[g][(int64_t)ne + e];  // [2,e] row-major
+      if (sl < 0 || dl < 0 || sl + node_off >= lim || dl + node_off >= lim) return GCB_ERR_INDEX;  // PyG _lift IndexError
+      if (sl >= na || dl >= na) return GCB_ERR_UNSUPPORTED;  // an edge into another molecule: the host packer's general path
+      src[edge_off_ + e] = (int32_t)sl + node_off;
+      dst[edge_off_ + e] = (int32_t)dl + node_off;
+      const int32_t lo = (int32_t)(sl < dl ? sl : dl), hi = (int32_t)(sl < dl ? dl : sl);
+      if (lo < hi) { span[lo + 1]++; span[hi + 1]--; }
+    }
+    int32_t cover = 0;  // cuts inside the molecule (it may be disconnected) and at its end, as in finish_pack_local
+    for (int32_t p = 1; p <= na; ++p) {
+      cover += span[p];
+      if (p == na || cover == 0) tw.cut_at(node_off + p);
+    }
+    if (y_out) {
+      for (int32_t t = 0; t < n_targets; ++t) y_out[(int64_t)g * n_targets + t] = y && y[g] ? y[g][t] : 0.f;
+    }
+    node_off += na;
+    edge_off_ += ne;
+  }
+  atom_off[G] = N;
+  edge_off[G] = E;
+  const int32_t nt = tw.finish(N);
+  if ((int64_t)nt + 1 > raw_tile_cap(N)) return GCB_ERR_INVALID_ARG;  // (cannot happen: two consecutive tiles span > GCB_TILE_ROWS rows)
+  std::memcpy(tile_ptr, tiles.data(), sizeof(int32_t) * ((size_t)nt + 1));
+  for (int64_t j = (int64_t)nt + 1; j < pad4(raw_tile_cap(N)); ++j) tile_ptr[j] = 0;
+  {  // define every byte: alignment pads of the other sections
+    const int64_t n[6] = {(int64_t)G + 1, (int64_t)G + 1, N, E, E, E};
+    for (int i = 0; i < 6; ++i)
+      for (int64_t j = n[i]; j < pad4(n[i]); ++j) raw[rh[RAW_ATOM_OFF + i] + j] = 0;
+  }
+  packed_header[GCB_H_NTILES] = nt;
+  rh[RAW_MAGIC] = GCB_RAW_MAGIC;
+  rh[RAW_N] = N; rh[RAW_E] = E; rh[RAW_G] = G; rh[RAW_M] = M; rh[RAW_AV] = atom_vocab; rh[RAW_BV] = bond_vocab;
+  rh[RAW_NTILES] = nt;
+  std::memcpy(raw, rh, sizeof(rh));
+  return GCB_OK;
+}
+
+extern "C" int64_t gcb_pack_device_scratch_ints(const int32_t* packed_header) {
+  if (!packed_header || packed_header[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
+  const int32_t* h = packed_header;
+  return scratch_layout(h[GCB_H_N], h[GCB_H_E], h[GCB_H_G], h[GCB_H_M], h[GCB_H_AV], h[GCB_H_BV]).total;
+}
+
+extern "C" int gcb_pack_device(const int32_t* raw_dev, const int32_t* raw_header_host, const int32_t* packed_header_host,
+                               int32_t* packed_dev, int64_t packed_ints, int32_t* scratch_dev, int64_t scratch_ints,
+                               void* stream) {
+  if (!raw_dev || !raw_header_host || !packed_header_host || !packed_dev || !scratch_dev) return GCB_ERR_INVALID_ARG;
+  const int32_t* h = packed_header_host;
+  const int32_t* rh = raw_header_host;
+  GCB_TRY(check_raw_against_header(rh, h));
+  const int32_t N = h[GCB_H_N], E = h[GCB_H_E], G = h[GCB_H_G], M = h[GCB_H_M], av = h[GCB_H_AV], bv = h[GCB_H_BV];
+  const Scratch sc = scratch_layout(N, E, G, M, av, bv);
+  if (packed_ints < h[GCB_H_TOTAL_INTS] || scratch_ints < sc.total) return GCB_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  PackSegs sg;
+  GCB_TRY(build_segs(h, rh, &sg));
+  int32_t maxc = 1;
+  for (int i = 0; i < sg.n; ++i) maxc = sg.count[i] > maxc ? sg.count[i] : maxc;
+  int gx = (maxc + 256 * 4 - 1) / (256 * 4);
+  gx = gx < 1 ? 1 : (gx > 4 * kNumSMs ? 4 * kNumSMs : gx);
+  GCB_KERNEL("pack_segments_kernel", s, pack_segments_kernel<<<dim3((unsigned)gx, (unsigned)sg.n + 1), 256, 0, s>>>(sg, raw_dev, packed_dev));
+  if (G > 0) {
+    const PackPtrs p = pack_ptrs(packed_dev, h);
+    GCB_KERNEL("pack_molecules_kernel", s,
+               pack_molecules_kernel<<<(unsigned)((G + 31) / 32), 32, 0, s>>>(p, raw_dev + rh[RAW_ATOM_OFF], raw_dev + rh[RAW_EDGE_OFF], G,
+                                                                             scratch_dev + sc.pin, scratch_dev + sc.pout, scratch_dev + sc.pos));
+  }
+  // token buckets read the packed token sections (written by the segment copies, same stream)
+  GCB_TRY(bucket_device(packed_dev + h[GCB_H_X_TOK], N, av, packed_dev + h[GCB_H_ATOK_PTR], packed_dev + h[GCB_H_ATOK_NODE],
+                        scratch_dev + sc.hist_a, s));
+  GCB_TRY(bucket_device(packed_dev + h[GCB_H_E_TOK], M, bv, packed_dev + h[GCB_H_BTOK_PTR], packed_dev + h[GCB_H_BTOK_ROW],
+                        scratch_dev + sc.hist_b, s));
+  return GCB_OK;
+}
+
+// Test hook: the routines of the kernels above, run serially on the CPU over host buffers (raw, packed and scratch
+// in host memory).  Pins the device packer's index logic against gcb_collate_pack_host without a GPU.
+extern "C" int gcb_debug_pack_emulate_host(const int32_t* raw, const int32_t* packed_header, int32_t* packed,
+                                           int64_t packed_ints, int32_t* scratch, int64_t scratch_ints, int32_t force_scratch) {
+  if (!raw || !packed_header || !packed || !scratch) return GCB_ERR_INVALID_ARG;
+  const int32_t* h = packed_header;
+  const int32_t* rh = raw;
+  GCB_TRY(check_raw_against_header(rh, h));
+  const int32_t N = h[GCB_H_N], E = h[GCB_H_E], G = h[GCB_H_G], M = h[GCB_H_M], av = h[GCB_H_AV], bv = h[GCB_H_BV];
+  const Scratch sc = scratch_layout(N, E, G, M, av, bv);
+  if (packed_ints < h[GCB_H_TOTAL_INTS] || scratch_ints < sc.total) return GCB_ERR_WORKSPACE;
+  PackSegs sg;
+  GCB_TRY(build_segs(h, rh, &sg));
+  for (int s = 0; s < sg.n; ++s)
+    for (int64_t i = 0; i < sg.count[s]; ++i) seg_element(sg, s, i, raw, packed);
+  seg_fixed(sg, packed);
+  const PackPtrs p = pack_ptrs(packed, h);
+  const int32_t* atom_off = raw + rh[RAW_ATOM_OFF];
+  const int32_t* edge_off = raw + rh[RAW_EDGE_OFF];
+  for (int32_t g = 0; g < G; ++g) {
+    const int32_t a0 = atom_off[g], na = atom_off[g + 1] - a0, e0 = edge_off[g], ne = edge_off[g + 1] - e0;
+    if (!force_scratch && na <= kPackMaxA && ne <= kPackMaxE) {
+      int32_t pin[kPackMaxA + 1], pout[kPackMaxA + 1], pos[kPackMaxE];
+      pack_one_molecule(p, g, a0, na, e0, ne, pin, pout, pos);
+    } else {
+      pack_one_molecule(p, g, a0, na, e0, ne, scratch + sc.pin + a0 + g, scratch + sc.pout + a0 + g, scratch + sc.pos + e0);
+    }
+  }
+  auto bucket_emulated = [&](const int32_t* key, int64_t n, int32_t nb, int32_t* ptr, int32_t* perm, int32_t* hist) {
+    const int64_t chunks = bucket_chunks(n);
+    for (int64_t c = 0; c < chunks; ++c) bucket_hist_chunk(key, n, nb, c, hist);
+    for (int32_t b = 0; b < nb; ++b) bucket_scan_bucket(nb, chunks, b, hist, ptr);
+    bucket_ptr_scan(nb, ptr);
+    for (int64_t c = 0; c < chunks; ++c) bucket_place_chunk(key, n, nb, c, hist, ptr, perm);
+  };
+  bucket_emulated(packed + h[GCB_H_X_TOK], N, av, packed + h[GCB_H_ATOK_PTR], packed + h[GCB_H_ATOK_NODE], scratch + sc.hist_a);
+  bucket_emulated(packed + h[GCB_H_E_TOK], M, bv, packed + h[GCB_H_BTOK_PTR], packed + h[GCB_H_BTOK_ROW], scratch + sc.hist_b);
   return GCB_OK;
 }

@@ -22,14 +22,14 @@ from typing import Iterator, List, Optional, Sequence
 import numpy as np
 import torch
 
-from .packed import MoleculeStore, PackedBatch
+from .packed import MoleculeStore, PackedBatch, RawBatch
 
 
 class PackedLoader:
     def __init__(self, store: MoleculeStore, batch_size: int, n_messages: int, atom_vocab: int, bond_vocab: int,
                  device="cuda", shuffle: bool = False, drop_last: bool = False, seed: int = 0, workers: int = 8,
                  prefetch: int = 4, cache: bool = False, indices: Optional[Sequence[int]] = None, each: bool = False,
-                 device_slots: int = 0):
+                 device_slots: int = 0, device_pack: bool = False):
         self.store, self.batch_size = store, int(batch_size)
         self.n_messages, self.av, self.bv = int(n_messages), int(atom_vocab), int(bond_vocab)
         self.device = torch.device(device)
@@ -40,6 +40,12 @@ class PackedLoader:
         # batch is valid until `device_slots - 1` further batches have been requested.  Not combinable with cache.
         self.device_slots = 0 if cache else max(0, int(device_slots))
         self._slots: List[tuple] = []
+        # device_pack: host threads only gather each batch into a raw buffer (`MoleculeStore.collate_raw`, a fifth
+        # of the packing work and of the H2D bytes); the packed batch is derived on the GPU by `gcb_pack_device`
+        # on the copy stream, bit-identical to the host packer's.  CUDA devices only, not with `each`.
+        self.device_pack = bool(device_pack)
+        if self.device_pack and (each or torch.device(device).type != "cuda"):
+            raise ValueError("device_pack needs a CUDA device and is not available for each=True batches")
         self.indices = np.arange(len(store), dtype=np.int64) if indices is None else np.asarray(indices, dtype=np.int64)
         self.epoch = 0
         self._cached: Optional[List[PackedBatch]] = None
@@ -72,8 +78,11 @@ class PackedLoader:
             nt = 0 if self.store.targets is None else int(self.store.targets.size(1))
             bufs = (torch.empty(self._capacity(), dtype=torch.int32, pin_memory=True),
                     torch.empty(max(1, self.batch_size * nt), dtype=torch.float32, pin_memory=True))
-        hb = self.store.collate_pack(idx, self.n_messages, self.av, self.bv, pin=True, each=self.each, out=bufs[0],
-                                     y_out=bufs[1])
+        if self.device_pack:
+            hb = self.store.collate_raw(idx, self.n_messages, self.av, self.bv, pin=True, out=bufs[0], y_out=bufs[1])
+        else:
+            hb = self.store.collate_pack(idx, self.n_messages, self.av, self.bv, pin=True, each=self.each, out=bufs[0],
+                                         y_out=bufs[1])
         return hb, bufs
 
     def _capacity(self) -> int:
@@ -142,15 +151,21 @@ class PackedLoader:
                                 d_ints, d_y, free_ev = self._slots[slot_i % len(self._slots)]
                                 slot_i += 1
                                 copy_stream.wait_event(free_ev)  # the consumer is done with this slot's previous batch
-                                n = hb.ints.numel()
-                                d_ints[:n].copy_(hb.ints, non_blocking=True)
                                 y = None
                                 if hb.y is not None:
                                     y = d_y[:hb.y.numel()].view(hb.y.shape)
                                     y.copy_(hb.y, non_blocking=True)
-                                db = PackedBatch(d_ints[:n], hb.header, y)
+                                if self.device_pack:  # raw H2D, then the packer kernels, both on the copy stream
+                                    db = RawBatch(hb.ints.to(self.device, non_blocking=True), hb.raw_header, hb.header,
+                                                  y).pack(out=d_ints)
+                                else:
+                                    n = hb.ints.numel()
+                                    d_ints[:n].copy_(hb.ints, non_blocking=True)
+                                    db = PackedBatch(d_ints[:n], hb.header, y)
                             else:
                                 db = hb.to(self.device, non_blocking=True)
+                                if self.device_pack:
+                                    db = db.pack()
                             ev = torch.cuda.Event()
                             ev.record(copy_stream)
                         inflight.append((db, ev, bufs))

@@ -78,6 +78,53 @@ class PackedBatch:
             **({"bond_pos": self.section(L.H_BOND_POS, E)} if int(self.header[L.H_FLAGS]) & L.PACK_EACH else {}))
 
 
+class RawBatch:
+    """Collated but not yet packed batch (include/graphchem_b200.h "device-side packer"): molecule offsets,
+    tokens, edge list and tile table in ONE int32 buffer of ~0.7 kB per molecule, plus the header the packed
+    batch will have.  `pack()` derives the packed batch on the device (`gcb_pack_device`), bit-identical
+    to what `MoleculeStore.collate_pack` builds on host cores."""
+
+    __slots__ = ("ints", "raw_header", "header", "y")
+
+    def __init__(self, ints: Tensor, raw_header: np.ndarray, header: np.ndarray, y: Optional[Tensor]):
+        self.ints, self.raw_header, self.header, self.y = ints, raw_header, header, y
+
+    @property
+    def device(self) -> torch.device:
+        return self.ints.device
+
+    @property
+    def nbytes(self) -> int:
+        return self.ints.numel() * 4 + (0 if self.y is None else self.y.numel() * self.y.element_size())
+
+    def to(self, device, non_blocking: bool = False) -> "RawBatch":
+        y = None if self.y is None else self.y.to(device, non_blocking=non_blocking)
+        return RawBatch(self.ints.to(device, non_blocking=non_blocking), self.raw_header, self.header, y)
+
+    def pack(self, out: Optional[Tensor] = None, scratch: Optional[Tensor] = None) -> PackedBatch:
+        """Packed batch on this batch's CUDA device, built by kernels on torch's current stream.  `out` /
+        `scratch`: device int32 buffers to reuse (large enough), else fresh ones.  No CPU fallback."""
+        if self.ints.device.type != "cuda":
+            raise RuntimeError("RawBatch.pack runs on the GPU: move the batch with .to('cuda') first "
+                               "(on host cores use MoleculeStore.collate_pack)")
+        dev = self.ints.device
+        total = int(self.header[_lib.H_TOTAL_INTS])
+        n_scr = int(_lib.check(int(_lib.lib().gcb_pack_device_scratch_ints(self.header.ctypes.data)),
+                               "gcb_pack_device_scratch_ints"))
+        with torch.cuda.device(dev):
+            if out is None:
+                out = torch.empty(total, dtype=torch.int32, device=dev)
+            if scratch is None:
+                scratch = torch.empty(n_scr, dtype=torch.int32, device=dev)
+            if out.numel() < total or scratch.numel() < n_scr or out.dtype != torch.int32 or scratch.dtype != torch.int32:
+                raise ValueError("RawBatch.pack: `out` / `scratch` must be int32 device buffers with room for the batch")
+            rc = _lib.lib().gcb_pack_device(self.ints.data_ptr(), self.raw_header.ctypes.data, self.header.ctypes.data,
+                                            out.data_ptr(), out.numel(), scratch.data_ptr(), scratch.numel(),
+                                            torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "gcb_pack_device")
+        return PackedBatch(out[:total], self.header.copy(), self.y)
+
+
 def _alloc_ints(n: int, pin: bool) -> Tensor:
     pin = pin and torch.cuda.is_available()
     return torch.empty(n, dtype=torch.int32, pin_memory=pin)
@@ -165,6 +212,43 @@ class MoleculeStore:
 
     def __len__(self) -> int:
         return int(self.n_atoms.shape[0])
+
+    def _pointer_tables(self, idx: np.ndarray):
+        atoms_p = (self.atoms.data_ptr() + 4 * self.atom_off[idx]).astype(np.uint64)
+        bonds_p = (self.bonds.data_ptr() + 4 * self.edge_off[idx]).astype(np.uint64)
+        conn_p = (self.conn.data_ptr() + 16 * self.edge_off[idx]).astype(np.uint64)
+        return atoms_p, bonds_p, conn_p
+
+    def collate_raw(self, idx: Sequence[int], n_messages: int, atom_vocab: int, bond_vocab: int,
+                    pin: bool = True, out: Optional[Tensor] = None, y_out: Optional[Tensor] = None) -> RawBatch:
+        """Collate molecules `idx` into a `RawBatch` (one C call: validation, gather, tile table); the device
+        derives the packed batch from it (`RawBatch.to(device).pack()`).  A fifth of the host work and of the
+        H2D bytes of `collate_pack`.  `out` / `y_out` as in `collate_pack`."""
+        idx = np.asarray(idx, dtype=np.int64)
+        G = int(idx.shape[0])
+        na, ne = np.ascontiguousarray(self.n_atoms[idx]), np.ascontiguousarray(self.n_edges[idx])
+        N, E = int(na.sum()), int(ne.sum())
+        total = int(_lib.check(int(_lib.lib().gcb_raw_ints(N, E, G)), "gcb_raw_ints"))
+        if out is not None and (out.dtype != torch.int32 or out.device.type != "cpu" or out.numel() < total):
+            raise ValueError("collate_raw: `out` must be a host int32 tensor with room for the raw batch")
+        ints = out[:total] if out is not None else _alloc_ints(total, pin)
+        atoms_p, bonds_p, conn_p = self._pointer_tables(idx)
+        nt = 0 if self.targets is None else int(self.targets.size(1))
+        y, y_p, yo_p, y_ptrs = None, None, None, None
+        if nt:
+            if y_out is not None and y_out.numel() >= G * nt and y_out.dtype == torch.float32:
+                y = y_out.reshape(-1)[:G * nt].view(G, nt)
+            else:
+                y = torch.empty(G, nt, dtype=torch.float32, pin_memory=pin and torch.cuda.is_available())
+            y_ptrs = (self.targets.data_ptr() + 4 * nt * idx).astype(np.uint64)  # kept alive across the call
+            y_p, yo_p = y_ptrs.ctypes.data, y.data_ptr()
+        header = np.zeros(_lib.PACK_HEADER_INTS, dtype=np.int32)
+        rc = _lib.lib().gcb_collate_raw_host(atoms_p.ctypes.data, na.ctypes.data, bonds_p.ctypes.data, conn_p.ctypes.data,
+                                             ne.ctypes.data, y_p, nt, G, n_messages, atom_vocab, bond_vocab,
+                                             ints.data_ptr(), total, yo_p, header.ctypes.data)
+        _lib.check(rc, "gcb_collate_raw_host")
+        raw_header = ints[:_lib.RAW_HEADER_INTS].numpy().copy()
+        return RawBatch(ints, raw_header, header, y)
 
     def collate_pack(self, idx: Sequence[int], n_messages: int, atom_vocab: int, bond_vocab: int,
                      pin: bool = True, each: bool = False, out: Optional[Tensor] = None,

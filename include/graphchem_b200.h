@@ -137,6 +137,37 @@ int gcb_collate_pack_each_host(const int32_t* const* atoms, const int32_t* n_ato
                                int32_t n_targets, int32_t n_graphs, int32_t n_messages, int32_t atom_vocab,
                                int32_t bond_vocab, int32_t* packed, int64_t packed_ints, float* y_out);
 
+/* ---- device-side packer (SURVEY.md 8 d config 5 "packed on device"; 8 f1) ------------------- */
+/* The host gathers a batch into a RAW buffer (0.7 kB per molecule instead of 3.9 kB): header, molecule
+ * atom / edge offsets [G+1], atom tokens [N], bond tokens [E], src / dst [E] with batch-global atom ids,
+ * closed-tile table; the device derives every other section.  The packed batch is bit-identical to
+ * gcb_collate_pack_host on the same molecules (same collate semantics: Collater -> Batch.from_data_list,
+ * examples/predict_cn.ipynb:212,245; same scatter order). */
+#define GCB_RAW_MAGIC 0x47435231 /* "GCR1" */
+#define GCB_RAW_HEADER_INTS 16
+/* int32 elements of the raw buffer of a batch with N atoms, E directed edges, G molecules. */
+int64_t gcb_raw_ints(int32_t N, int32_t E, int32_t G);
+/* Host half: validate (same GCB_ERR_INDEX cases as gcb_collate_pack_host), gather into raw (host, normally
+ * pinned), concatenate targets into y_out, and fill packed_header[GCB_PACK_HEADER_INTS] (host) with the
+ * layout of the packed batch including its tile count.  GCB_ERR_UNSUPPORTED when an edge leaves its
+ * molecule (use gcb_collate_pack_host for such input). */
+int gcb_collate_raw_host(const int32_t* const* atoms, const int32_t* n_atoms, const int32_t* const* bonds,
+                         const int64_t* const* conn, const int32_t* n_edges, const float* const* y,
+                         int32_t n_targets, int32_t n_graphs, int32_t n_messages, int32_t atom_vocab,
+                         int32_t bond_vocab, int32_t* raw, int64_t raw_ints, float* y_out, int32_t* packed_header);
+/* int32 elements of device scratch gcb_pack_device needs for the batch described by packed_header. */
+int64_t gcb_pack_device_scratch_ints(const int32_t* packed_header);
+/* Device half: raw_dev (device copy of raw) -> packed_dev (device, packed_header[GCB_H_TOTAL_INTS] ints).
+ * raw_header_host = the first GCB_RAW_HEADER_INTS ints of raw, packed_header_host from gcb_collate_raw_host
+ * (both host memory).  Enqueues its kernels on `stream`; no allocation, no synchronisation. */
+int gcb_pack_device(const int32_t* raw_dev, const int32_t* raw_header_host, const int32_t* packed_header_host,
+                    int32_t* packed_dev, int64_t packed_ints, int32_t* scratch_dev, int64_t scratch_ints, void* stream);
+/* Test hook (like gcb_debug_gemm_*): the per-molecule / per-chunk routines of gcb_pack_device's kernels run
+ * serially on the CPU over HOST buffers, so the index logic is pinned without a GPU.  force_scratch != 0 takes
+ * the large-molecule path (scratch instead of thread-local arrays) for every molecule.  Not a product path. */
+int gcb_debug_pack_emulate_host(const int32_t* raw, const int32_t* packed_header, int32_t* packed, int64_t packed_ints,
+                                int32_t* scratch, int64_t scratch_ints, int32_t force_scratch);
+
 /* ---- parameters -------------------------------------------------------------------------- */
 /* Flat fp32 parameter vector in the reference's state_dict order (gcn.py:78-114):
  * emb_atom.weight, emb_bond.weight, atom_conv.lin_msg.{weight,bias}, atom_conv.lin_edge.{weight,
