@@ -485,9 +485,10 @@ extern "C" int gcb_collate_pack_each_host(const int32_t* const* atoms, const int
 // the closed-tile table (0.7 kB per molecule instead of 3.9 kB) -- and the device derives every other
 // section of the packed batch.  The result is bit-identical to gcb_collate_pack_host on the same molecules.
 //
-// The per-molecule and per-chunk routines are __host__ __device__: gcb_debug_pack_emulate_host runs exactly the
-// code of the kernels serially on the CPU (a test hook like gcb_debug_gemm_*, not a product path), so the index
-// logic is pinned against the host packer without a GPU.
+// The per-molecule and per-chunk routines are __host__ __device__: gcb_debug_pack_emulate_host runs the code of
+// the kernels serially on the CPU (a test hook like gcb_debug_gemm_*, not a product path), so the index logic is
+// pinned against the host packer without a GPU.  Only the scan over the chunk histograms differs on the device
+// (block-parallel instead of a serial walk); the -m gpu tests pin that one.
 // =====================================================================================================
 namespace gcb {
 
@@ -673,10 +674,53 @@ __global__ void bucket_hist_kernel(const int32_t* __restrict__ key, int64_t n, i
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c < chunks) bucket_hist_chunk(key, n, nb, c, hist);
 }
-__global__ void bucket_scan_kernel(int32_t nb, int64_t chunks, int32_t* hist, int32_t* ptr) {  // ONE block
-  for (int32_t b = threadIdx.x; b < nb; b += blockDim.x) bucket_scan_bucket(nb, chunks, b, hist, ptr);
+// Pass B on the device: one block per bucket scans that bucket's column of the chunk histograms (a serial walk
+// over thousands of chunks is pure memory latency -- 400 us alone and milliseconds next to a running train step),
+// then one block turns the bucket sizes into offsets.  Same results as bucket_scan_bucket / bucket_ptr_scan.
+constexpr int kScanThreads = 256;
+__global__ void __launch_bounds__(kScanThreads) bucket_scan_kernel(int32_t nb, int64_t chunks, int32_t* hist, int32_t* ptr) {
+  __shared__ int32_t part[kScanThreads];
+  const int32_t b = blockIdx.x;
+  const int t = threadIdx.x;
+  const int64_t per = (chunks + kScanThreads - 1) / kScanThreads;
+  const int64_t c0 = t * per < chunks ? t * per : chunks, c1 = c0 + per < chunks ? c0 + per : chunks;
+  int32_t sum = 0;
+  for (int64_t c = c0; c < c1; ++c) sum += hist[c * nb + b];
+  part[t] = sum;
   __syncthreads();
-  if (threadIdx.x == 0) bucket_ptr_scan(nb, ptr);
+  for (int off = 1; off < kScanThreads; off <<= 1) {  // inclusive scan of the per-thread sums
+    const int32_t v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int32_t run = part[t] - sum;  // chunks before this thread's segment
+  for (int64_t c = c0; c < c1; ++c) {
+    const int32_t v = hist[c * nb + b];
+    hist[c * nb + b] = run;
+    run += v;
+  }
+  if (t == kScanThreads - 1) ptr[b + 1] = part[t];  // bucket size
+}
+__global__ void __launch_bounds__(kScanThreads) bucket_ptr_kernel(int32_t nb, int32_t* ptr) {  // ONE block
+  __shared__ int32_t sm[1024];
+  __shared__ int32_t carry;
+  const int t = threadIdx.x;
+  if (t == 0) { carry = 0; ptr[0] = 0; }
+  __syncthreads();
+  for (int32_t base = 0; base < nb; base += 1024) {
+    const int32_t n = nb - base < 1024 ? nb - base : 1024;
+    for (int32_t i = t; i < n; i += kScanThreads) sm[i] = ptr[base + 1 + i];
+    __syncthreads();
+    if (t == 0) {
+      int32_t run = carry;
+      for (int32_t i = 0; i < n; ++i) { run += sm[i]; sm[i] = run; }
+      carry = run;
+    }
+    __syncthreads();
+    for (int32_t i = t; i < n; i += kScanThreads) ptr[base + 1 + i] = sm[i];
+    __syncthreads();
+  }
 }
 __global__ void bucket_place_kernel(const int32_t* __restrict__ key, int64_t n, int32_t nb, int64_t chunks, int32_t* hist,
                                     const int32_t* __restrict__ ptr, int32_t* perm) {
@@ -689,7 +733,8 @@ static int bucket_device(const int32_t* key, int64_t n, int32_t nb, int32_t* ptr
   const int bt = 64;
   if (chunks > 0)
     GCB_KERNEL("pack_bucket_hist_kernel", s, bucket_hist_kernel<<<(unsigned)((chunks + bt - 1) / bt), bt, 0, s>>>(key, n, nb, chunks, hist));
-  GCB_KERNEL("pack_bucket_scan_kernel", s, bucket_scan_kernel<<<1, 256, 0, s>>>(nb, chunks, hist, ptr));
+  if (nb > 0) GCB_KERNEL("pack_bucket_scan_kernel", s, bucket_scan_kernel<<<(unsigned)nb, kScanThreads, 0, s>>>(nb, chunks, hist, ptr));
+  GCB_KERNEL("pack_bucket_ptr_kernel", s, bucket_ptr_kernel<<<1, kScanThreads, 0, s>>>(nb, ptr));
   if (chunks > 0)
     GCB_KERNEL("pack_bucket_place_kernel", s, bucket_place_kernel<<<(unsigned)((chunks + bt - 1) / bt), bt, 0, s>>>(key, n, nb, chunks, hist, ptr, perm));
   return GCB_OK;

@@ -42,7 +42,8 @@ class PackedLoader:
         self._slots: List[tuple] = []
         # device_pack: host threads only gather each batch into a raw buffer (`MoleculeStore.collate_raw`, a fifth
         # of the packing work and of the H2D bytes); the packed batch is derived on the GPU by `gcb_pack_device`
-        # on the copy stream, bit-identical to the host packer's.  CUDA devices only, not with `each`.
+        # on the consumer's stream when the batch is handed out, bit-identical to the host packer's.  CUDA devices
+        # only, not with `each`.
         self.device_pack = bool(device_pack)
         if self.device_pack and (each or torch.device(device).type != "cuda"):
             raise ValueError("device_pack needs a CUDA device and is not available for each=True batches")
@@ -155,9 +156,9 @@ class PackedLoader:
                                 if hb.y is not None:
                                     y = d_y[:hb.y.numel()].view(hb.y.shape)
                                     y.copy_(hb.y, non_blocking=True)
-                                if self.device_pack:  # raw H2D, then the packer kernels, both on the copy stream
-                                    db = RawBatch(hb.ints.to(self.device, non_blocking=True), hb.raw_header, hb.header,
-                                                  y).pack(out=d_ints)
+                                if self.device_pack:  # raw H2D here; packed into the slot on the consumer's stream
+                                    db = (RawBatch(hb.ints.to(self.device, non_blocking=True), hb.raw_header, hb.header,
+                                                   y), d_ints)
                                 else:
                                     n = hb.ints.numel()
                                     d_ints[:n].copy_(hb.ints, non_blocking=True)
@@ -165,7 +166,7 @@ class PackedLoader:
                             else:
                                 db = hb.to(self.device, non_blocking=True)
                                 if self.device_pack:
-                                    db = db.pack()
+                                    db = (db, None)
                             ev = torch.cuda.Event()
                             ev.record(copy_stream)
                         inflight.append((db, ev, bufs))
@@ -176,6 +177,15 @@ class PackedLoader:
                 if ev is not None:
                     consumer = torch.cuda.current_stream(self.device)
                     consumer.wait_event(ev)
+                    if self.device_pack:
+                        # The pack kernels run on the CONSUMER's stream, in front of its step, not on the copy stream:
+                        # running next to a train step they cost more than they hide (measured: 2.68 ms per batch with
+                        # the packer on the copy stream vs 2.12 ms with the host packer, profiles/micro/stream_modes.py;
+                        # presumably their blocks hold SM resources that the persistent one-CTA-per-SM GEMMs need, and
+                        # a GEMM waits for its slowest SM).
+                        raw, slot_ints = db
+                        raw.ints.record_stream(consumer)  # allocated on the copy stream, read by the pack kernels here
+                        db = raw.pack(out=slot_ints)
                     if not self._slots:
                         # the batch was allocated on the copy stream but is read on the consumer's stream: without
                         # this the caching allocator hands its memory to a later copy as soon as the consumer drops
