@@ -815,7 +815,7 @@ using namespace gcb;
 extern "C" int gcb_abi_version(void) { return GCB_ABI_VERSION; }
 extern "C" const char* gcb_last_cuda_error(void) { return g_err; }
 extern "C" const char* gcb_build_info(void) {
-  return "graphchem_b200 sm_100a; kernels: tcgen05/TMEM/TMA GEMMs (bf16), TMA-staged tile row kernels, CSR row kernels + CUDA-core GEMMs (fp32); built " __DATE__ " " __TIME__;
+  return "graphchem_b200 sm_100a; kernels: tcgen05/TMEM/TMA GEMMs (bf16), TMA-staged tile row kernels, CSR row kernels + CUDA-core GEMMs (fp32), device-side batch packer; built " __DATE__ " " __TIME__;
 }
 
 extern "C" int gcb_param_layout(const gcb_model_cfg* cfg, int64_t* offsets) {

@@ -211,3 +211,58 @@ class InferStep:
                 self._keepalive[key] = pb
             g.replay()
         return bufs if self.want_atom_bond else bufs[0]
+
+
+def screening_shard(n_items: int, rank: int, world: int):
+    """Contiguous block of molecule indices that `rank` of `world` screens (BASELINE.json configs[4]: independent
+    molecules, replicas only, no collective; blocks differ in size by at most one)."""
+    import numpy as np
+    if not 0 <= rank < world:
+        raise ValueError("rank must be in [0, world)")
+    lo = (n_items * rank) // world
+    hi = (n_items * (rank + 1)) // world
+    return np.arange(lo, hi, dtype=np.int64)
+
+
+@torch.no_grad()
+def screen(model, store, batch_size: int = 32768, indices=None, rank: int = 0, world: int = 1, workers: int = 8,
+           prefetch: int = 4, device_pack: bool = True, use_cuda_graph: Optional[bool] = None) -> torch.Tensor:
+    """Inference-only screening (BASELINE.json configs[4]): predictions [n, out] (host tensor) of the molecules
+    `indices` of a `MoleculeStore` (all of them by default; with `world > 1` this rank's `screening_shard` of
+    them), in order.  Host threads gather raw batches, the GPU packs them (`device_pack`) and runs the forward
+    pass only, `model.eval()` semantics (no dropout); no collective is involved, predictions stay with the rank.
+
+    As with any batched forward of the reference, molecules of one batch see each other's bond rows
+    (gcn.py:163): results equal `model(batch)` on the same batches, not `predict_each`.
+    CUDA graphs are used when every batch has the same shape (`use_cuda_graph=None`: decided from the store)."""
+    import numpy as np
+    from .data.loader import PackedLoader
+    dev = model._ensure_device()
+    idx = np.arange(len(store), dtype=np.int64) if indices is None else np.asarray(indices, dtype=np.int64)
+    if world > 1:
+        idx = idx[screening_shard(len(idx), rank, world)]
+    n = int(idx.shape[0])
+    av, bv, out_dim, D, n_readout, R = model._dims
+    cols = int(out_dim) if n_readout > 0 else D
+    preds = torch.empty(n, cols, dtype=torch.float32, device=dev)
+    if n == 0:
+        return preds.cpu()
+    L = int(model._n_messages)
+    if use_cuda_graph is None:  # one graph per device slot pays only when all (full) batches share one shape
+        na, ne = store.n_atoms[idx], store.n_edges[idx]
+        use_cuda_graph = bool((na == na[0]).all() and (ne == ne[0]).all()) and n >= batch_size
+    slots = 3 if use_cuda_graph else 0
+    loader = PackedLoader(store, batch_size, L, av, bv, device=dev, workers=workers, prefetch=prefetch, indices=idx,
+                          device_slots=slots, device_pack=device_pack)
+    step = InferStep(model, use_cuda_graph=True) if use_cuda_graph else None
+    was_training = model.training
+    model.eval()
+    try:
+        k = 0
+        for pb in loader:
+            out = step(pb) if step is not None else model._run_forward(pb, 0, 0)[0]
+            preds[k:k + pb.G].copy_(out)
+            k += pb.G
+    finally:
+        model.train(was_training)
+    return preds.cpu()

@@ -131,3 +131,29 @@ def test_streamed_variable_shape_batches_are_not_recycled_under_the_consumer():
     assert a.numel() == 6 * 23
     assert torch.isfinite(a).all()
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("variable", [False, True])
+def test_screen_streams_the_batched_forward(variable):
+    """train.screen (BASELINE configs[4]: forward only, device-packed batches, graphed when the shapes repeat) returns,
+    in order, what model.eval()(batch) returns on the same batches; with world=2 every rank screens its own block."""
+    from graphchem_b200.nn import MoleculeGCN
+    from graphchem_b200.synthetic import make_molecules
+    from graphchem_b200.train import screen, screening_shard
+    store = make_molecules(700, seed=9, variable=variable)
+    torch.manual_seed(1)
+    model = MoleculeGCN(64, 32, 2, embedding_dim=128, n_messages=3, compute_dtype=torch.bfloat16).cuda()
+
+    def reference(idx, bs):
+        model.eval()
+        with torch.no_grad():
+            outs = [model(store.collate_pack(idx[i:i + bs], 3, 64, 32).to("cuda"))[0].cpu() for i in range(0, len(idx), bs)]
+        model.train()
+        return torch.cat(outs)
+
+    got = screen(model, store, batch_size=256, workers=2)
+    assert model.training and got.shape == (700, 2) and not got.is_cuda
+    assert torch.equal(got, reference(np.arange(700), 256))
+    for r in range(2):
+        part = screen(model, store, batch_size=128, rank=r, world=2, workers=2, device_pack=bool(r))
+        assert torch.equal(part, reference(screening_shard(700, r, 2), 128))
