@@ -73,3 +73,21 @@ def test_shards_partition_each_epoch():
     assert sorted(allidx.tolist()) == list(range(64))
     nxt = shard_indices(64, 0, 2, 8, 4, seed=3)  # next epoch reshuffles
     assert not np.array_equal(nxt, seen[0])
+
+
+def test_screening_shards_are_contiguous_blocks_that_partition_the_set():
+    """configs[4] (inference sharded across GPUs, no collective): rank blocks are contiguous, ordered, differ in size
+    by at most one and together cover every molecule exactly once."""
+    import numpy as np
+    import pytest
+    from graphchem_b200.train import screening_shard
+    for n, world in ((100_000_000, 8), (10, 3), (7, 8), (0, 2), (1, 1)):
+        parts = [screening_shard(n, r, world) for r in range(world)] if n <= 1000 else None
+        if parts is None:  # sizes only, without materialising 1e8 indices per rank
+            sizes = [(n * (r + 1)) // world - (n * r) // world for r in range(world)]
+            assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+            continue
+        assert np.array_equal(np.concatenate(parts), np.arange(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    with pytest.raises(ValueError):
+        screening_shard(10, 2, 2)
