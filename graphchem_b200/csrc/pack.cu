@@ -6,6 +6,7 @@
 // edge_index[1], collate concatenates graphs with cumulative node offsets
 // (call site examples/predict_cn.ipynb:212,245), MoleculeEncoder.encode emits
 // int32 tokens and an int64 [2,e] connectivity (graphchem/preprocessing/features.py:294-319).
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -572,6 +573,89 @@ __host__ __device__ inline void pack_one_molecule(const PackPtrs& p, int32_t g, 
   }
 }
 
+// The same molecule packed by the 32 lanes of a warp, as a sequence of phases that only communicate through memory:
+// the kernel runs phase, __syncwarp(), phase, ...; the emulation hook runs every phase for lanes 0..31 in turn, which is
+// equivalent.  w: per-warp work area of kWarpWork ints (pin | pout | pos | local src | local dst); the molecule must
+// satisfy na <= kPackMaxA and ne <= kPackMaxE.  Results are identical to pack_one_molecule (experimental, GCB_PACK_WARP=1).
+constexpr int kPackMaxA = 64, kPackMaxE = 160;  // molecules up to this size use thread-local / per-warp arrays, larger ones scratch
+constexpr int kWarpWork = 2 * (kPackMaxA + 1) + 3 * kPackMaxE;
+constexpr int kWarpPhases = 6;
+__host__ __device__ inline void warp_count_inc(int32_t* p) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, 1);
+#else
+  ++*p;
+#endif
+}
+__host__ __device__ inline void pack_warp_phase(int phase, int lane, const PackPtrs& p, int32_t g, int32_t a0, int32_t na,
+                                                int32_t e0, int32_t ne, int32_t* w) {
+  int32_t* pin = w;
+  int32_t* pout = w + (kPackMaxA + 1);
+  int32_t* pos = w + 2 * (kPackMaxA + 1);
+  int32_t* ls = pos + kPackMaxE;  // molecule-local source / destination atom of every edge
+  int32_t* ld = ls + kPackMaxE;
+  switch (phase) {
+    case 0:  // clear the counters, fetch the edge list
+      for (int32_t i = lane; i <= na; i += 32) { pin[i] = 0; pout[i] = 0; }
+      for (int32_t e = lane; e < ne; e += 32) { ls[e] = p.src[e0 + e] - a0; ld[e] = p.dst[e0 + e] - a0; }
+      if (lane == 0) p.graph_ptr[g] = a0;
+      break;
+    case 1:  // degree counts of row i at index i + 1 (integer atomics: the result does not depend on their order)
+      for (int32_t e = lane; e < ne; e += 32) { warp_count_inc(&pin[ld[e] + 1]); warp_count_inc(&pout[ls[e] + 1]); }
+      break;
+    case 2:  // prefix sums: pin[i] = first entry of row i (two lanes, one array each)
+      if (lane < 2) {
+        int32_t* c = lane ? pout : pin;
+        for (int32_t i = 0; i < na; ++i) c[i + 1] += c[i];
+      }
+      break;
+    case 3:  // row pointers, graph segments
+      for (int32_t i = lane; i < na; i += 32) {
+        p.in_ptr[a0 + i] = e0 + pin[i];
+        p.out_ptr[a0 + i] = e0 + pout[i];
+        p.graph_node[a0 + i] = a0 + i;
+        p.node_graph[a0 + i] = g;
+      }
+      break;
+    case 4:  // stable placement: edge-id order inside every row, so one lane walks each CSR; cursors end at the row ends
+      if (lane == 0) {
+        for (int32_t e = 0; e < ne; ++e) {
+          const int32_t k = pin[ld[e]]++;
+          p.in_eid[e0 + k] = e0 + e;
+          p.in_src[e0 + k] = a0 + ls[e];
+          pos[e] = k;
+        }
+      } else if (lane == 1) {
+        for (int32_t e = 0; e < ne; ++e) {
+          const int32_t k = pout[ls[e]]++;
+          p.out_eid[e0 + k] = e0 + e;
+          p.out_dst[e0 + k] = a0 + ld[e];
+        }
+      }
+      break;
+    case 5:  // cross index and ELL-4 views
+      for (int32_t k = lane; k < ne; k += 32) p.out_inpos[e0 + k] = e0 + pos[p.out_eid[e0 + k] - e0];
+      break;
+    default: break;
+  }
+}
+// Last phase, separate because it reads out_inpos written by other lanes in phase 5.
+__host__ __device__ inline void pack_warp_ell(int lane, const PackPtrs& p, int32_t a0, int32_t na, int32_t e0, const int32_t* w) {
+  const int32_t* pin = w;
+  const int32_t* pout = w + (kPackMaxA + 1);
+  for (int32_t i = lane; i < na; i += 32) {
+    const int32_t bi = i ? pin[i - 1] : 0, ei = pin[i], bo = i ? pout[i - 1] : 0, eo = pout[i];
+    const int64_t a = (int64_t)(a0 + i) * 4;
+    for (int u = 0; u < 4; ++u) {
+      const int32_t ki = bi + u, ko = bo + u;
+      p.s4[a + u] = ki < ei ? p.in_src[e0 + ki] : -1;
+      p.e4[a + u] = ki < ei ? p.in_eid[e0 + ki] : -1;
+      p.d4[a + u] = ko < eo ? p.out_dst[e0 + ko] : -1;
+      p.o4[a + u] = ko < eo ? p.out_inpos[e0 + ko] : -1;
+    }
+  }
+}
+
 // Stable counting sort of ids 0..n-1 by key in three passes over chunks of kBucketChunk consecutive ids:
 // (A) per-chunk histogram, (B) per-bucket exclusive scan over the chunks + bucket pointers, (C) placement in id order.
 constexpr int kBucketChunk = 64;
@@ -648,7 +732,6 @@ __host__ __device__ inline void seg_fixed(const PackSegs& sg, int32_t* packed) {
 }
 
 // ---- kernels: one thread per unit of the routines above -------------------------------------------------
-constexpr int kPackMaxA = 64, kPackMaxE = 160;  // molecules up to this size use thread-local arrays, larger ones scratch
 __global__ void pack_segments_kernel(const __grid_constant__ PackSegs sg, const int32_t* __restrict__ raw, int32_t* __restrict__ packed) {
   const int s = blockIdx.y;
   if (s == sg.n) {
@@ -669,6 +752,28 @@ __global__ void pack_molecules_kernel(const PackPtrs p, const int32_t* __restric
   } else {
     pack_one_molecule(p, g, a0, na, e0, ne, scr_pin + a0 + g, scr_pout + a0 + g, scr_pos + e0);
   }
+}
+// Warp per molecule (experimental, GCB_PACK_WARP=1): the phases of pack_warp_phase with a __syncwarp() between them, the
+// work area in shared memory; a molecule beyond the per-warp limits is packed by lane 0 alone out of global scratch.
+constexpr int kPackWarps = 8;
+__global__ void __launch_bounds__(kPackWarps * 32)
+pack_molecules_warp_kernel(const PackPtrs p, const int32_t* __restrict__ atom_off, const int32_t* __restrict__ edge_off,
+                           int32_t G, int32_t* scr_pin, int32_t* scr_pout, int32_t* scr_pos) {
+  __shared__ int32_t work[kPackWarps][kWarpWork];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int32_t g = blockIdx.x * kPackWarps + wid;
+  if (g >= G) return;  // whole warps leave together
+  const int32_t a0 = atom_off[g], na = atom_off[g + 1] - a0, e0 = edge_off[g], ne = edge_off[g + 1] - e0;
+  if (na > kPackMaxA || ne > kPackMaxE) {
+    if (lane == 0) pack_one_molecule(p, g, a0, na, e0, ne, scr_pin + a0 + g, scr_pout + a0 + g, scr_pos + e0);
+    return;
+  }
+  int32_t* w = work[wid];
+  for (int phase = 0; phase < kWarpPhases; ++phase) {
+    pack_warp_phase(phase, lane, p, g, a0, na, e0, ne, w);
+    __syncwarp();
+  }
+  pack_warp_ell(lane, p, a0, na, e0, w);
 }
 __global__ void bucket_hist_kernel(const int32_t* __restrict__ key, int64_t n, int32_t nb, int64_t chunks, int32_t* hist) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -882,9 +987,17 @@ extern "C" int gcb_pack_device(const int32_t* raw_dev, const int32_t* raw_header
   GCB_KERNEL("pack_segments_kernel", s, pack_segments_kernel<<<dim3((unsigned)gx, (unsigned)sg.n + 1), 256, 0, s>>>(sg, raw_dev, packed_dev));
   if (G > 0) {
     const PackPtrs p = pack_ptrs(packed_dev, h);
-    GCB_KERNEL("pack_molecules_kernel", s,
-               pack_molecules_kernel<<<(unsigned)((G + 31) / 32), 32, 0, s>>>(p, raw_dev + rh[RAW_ATOM_OFF], raw_dev + rh[RAW_EDGE_OFF], G,
-                                                                             scratch_dev + sc.pin, scratch_dev + sc.pout, scratch_dev + sc.pos));
+    static const bool warp_path = [] { const char* e = getenv("GCB_PACK_WARP"); return e && e[0] == '1'; }();
+    if (warp_path) {
+      GCB_KERNEL("pack_molecules_warp_kernel", s,
+                 pack_molecules_warp_kernel<<<(unsigned)((G + kPackWarps - 1) / kPackWarps), kPackWarps * 32, 0, s>>>(
+                     p, raw_dev + rh[RAW_ATOM_OFF], raw_dev + rh[RAW_EDGE_OFF], G, scratch_dev + sc.pin, scratch_dev + sc.pout,
+                     scratch_dev + sc.pos));
+    } else {
+      GCB_KERNEL("pack_molecules_kernel", s,
+                 pack_molecules_kernel<<<(unsigned)((G + 31) / 32), 32, 0, s>>>(p, raw_dev + rh[RAW_ATOM_OFF], raw_dev + rh[RAW_EDGE_OFF], G,
+                                                                               scratch_dev + sc.pin, scratch_dev + sc.pout, scratch_dev + sc.pos));
+    }
   }
   // token buckets read the packed token sections (written by the segment copies, same stream)
   GCB_TRY(bucket_device(packed_dev + h[GCB_H_X_TOK], N, av, packed_dev + h[GCB_H_ATOK_PTR], packed_dev + h[GCB_H_ATOK_NODE],
@@ -915,7 +1028,13 @@ extern "C" int gcb_debug_pack_emulate_host(const int32_t* raw, const int32_t* pa
   const int32_t* edge_off = raw + rh[RAW_EDGE_OFF];
   for (int32_t g = 0; g < G; ++g) {
     const int32_t a0 = atom_off[g], na = atom_off[g + 1] - a0, e0 = edge_off[g], ne = edge_off[g + 1] - e0;
-    if (!force_scratch && na <= kPackMaxA && ne <= kPackMaxE) {
+    if (force_scratch == 2 && na <= kPackMaxA && ne <= kPackMaxE) {  // the warp-per-molecule phases, lane by lane
+      int32_t w[kWarpWork];
+      for (int i = 0; i < kWarpWork; ++i) w[i] = -9;
+      for (int phase = 0; phase < kWarpPhases; ++phase)
+        for (int lane = 0; lane < 32; ++lane) pack_warp_phase(phase, lane, p, g, a0, na, e0, ne, w);
+      for (int lane = 0; lane < 32; ++lane) pack_warp_ell(lane, p, a0, na, e0, w);
+    } else if (!force_scratch && na <= kPackMaxA && ne <= kPackMaxE) {
       int32_t pin[kPackMaxA + 1], pout[kPackMaxA + 1], pos[kPackMaxE];
       pack_one_molecule(p, g, a0, na, e0, ne, pin, pout, pos);
     } else {

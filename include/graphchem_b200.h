@@ -163,8 +163,9 @@ int64_t gcb_pack_device_scratch_ints(const int32_t* packed_header);
 int gcb_pack_device(const int32_t* raw_dev, const int32_t* raw_header_host, const int32_t* packed_header_host,
                     int32_t* packed_dev, int64_t packed_ints, int32_t* scratch_dev, int64_t scratch_ints, void* stream);
 /* Test hook (like gcb_debug_gemm_*): the per-molecule / per-chunk routines of gcb_pack_device's kernels run
- * serially on the CPU over HOST buffers, so the index logic is pinned without a GPU.  force_scratch != 0 takes
- * the large-molecule path (scratch instead of thread-local arrays) for every molecule.  Not a product path. */
+ * serially on the CPU over HOST buffers, so the index logic is pinned without a GPU.  force_scratch = 1 takes
+ * the large-molecule path (scratch instead of thread-local arrays) for every molecule, 2 the phases of the
+ * experimental warp-per-molecule kernel (GCB_PACK_WARP=1), lane by lane.  Not a product path. */
 int gcb_debug_pack_emulate_host(const int32_t* raw, const int32_t* packed_header, int32_t* packed, int64_t packed_ints,
                                 int32_t* scratch, int64_t scratch_ints, int32_t force_scratch);
 

@@ -92,7 +92,7 @@ def test_raw_collate_and_emulated_device_pack_equal_host_pack(name, L):
         assert raw.nbytes < ref.nbytes
         if ref.y is not None:
             assert torch.equal(raw.y, ref.y)
-        for force in (0, 1):
+        for force in (0, 1, 2):
             got = _emulate(raw, force)
             assert torch.equal(got, ref.ints), f"{name}: first difference at int {int((got != ref.ints).nonzero()[0])}"
 
@@ -188,3 +188,26 @@ def test_loader_device_pack_argument_checks():
         PackedLoader(CASES["small"], 8, 2, AV, BV, device="cpu", device_pack=True)
     with pytest.raises(ValueError):
         PackedLoader(CASES["small"], 8, 2, AV, BV, device="cuda", device_pack=True, each=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("GCB_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental warp-per-molecule pack kernel (GCB_PACK_WARP=1): pinned on the CPU lane by lane "
+                           "(force_scratch=2 above), not yet run on a GPU; set GCB_TEST_EXPERIMENTAL=1 to include it")
+def test_warp_per_molecule_kernel_in_a_subprocess():
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch\n"
+        "from tests.test_pack_device import CASES, _orders, AV, BV\n"
+        "for name, store in CASES.items():\n"
+        "    for idx in _orders(store):\n"
+        "        ref = store.collate_pack(idx, 2, AV, BV)\n"
+        "        got = store.collate_raw(idx, 2, AV, BV).to('cuda').pack().ints.cpu()\n"
+        "        assert torch.equal(got, ref.ints), name\n"
+        "print('warp pack ok')\n")
+    env = dict(os.environ, GCB_PACK_WARP="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "warp pack ok" in res.stdout, res.stdout + res.stderr
