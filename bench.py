@@ -332,7 +332,7 @@ def run_ours(args):
 
     note(f"e2e: {e2e_value:.0f} mol/s")
     # ---- (3) per-kernel timing with CUDA events (un-graphed pass, rank 0, N == 1 only) -------------
-    roofline, kernels, cpu_baseline, stream = None, None, None, None
+    roofline, kernels, cpu_baseline, stream, stream_dev = None, None, None, None, None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
