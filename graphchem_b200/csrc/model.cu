@@ -13,8 +13,8 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
-#include "fused_tc.cuh"
 #include "tile_rows.cuh"
+#include "fused_rows.cuh"
 #include "kernels.cuh"
 #include "readout.cuh"
 #include "rowops.cuh"
@@ -49,7 +49,7 @@ void KernelTimer::stop() {
 }
 
 // ---- GEMM dispatch: tcgen05 kernel for bf16 hot shapes, CUDA-core kernel otherwise ---------------
-namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(); bool tile_enabled(); bool bond_bwd_merged_enabled(); }
+namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(int which); bool fused_exact(); bool tile_enabled(); bool bond_bwd_merged_enabled(); }
 template <typename T>
 static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                         const Epilogue& ep, cudaStream_t s) {
@@ -434,12 +434,16 @@ static inline uint32_t tag_bond(int l) { return 4u * (uint32_t)l; }
 static inline uint32_t tag_atom(int l) { return 4u * (uint32_t)l + 1u; }
 static inline uint32_t tag_readout(int k) { return 100000u + (uint32_t)k; }
 
-// The fused GEMM + message kernels (fused_tc.cuh) take bf16, D = 128, closed row tiles, every atom
-// row a live bond row, and no active dropout; anything else runs on the unfused kernels.
+// The fused GEMM + message kernels (fused_rows.cuh) take bf16, D = 128, add aggregation, closed row tiles, every
+// atom row a live bond row, and no active dropout; anything else runs on the unfused kernels.  `which`: 0 bond
+// forward, 1 atom forward, 2 atom backward (GCB_NO_FUSED=1 / GCB_NO_FUSED_BOND / _ATOM / _ABWD switch them off).
+// The fused bond forward records tie bits only (no tie counts) and the fused atom backward emits dS[:, D:] as
+// planes: both are understood by tile::bond_bwd_kernel only, hence the merged-bond-backward condition.
 template <typename T>
-static bool fused_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
+static bool fused_ok(const gcb_model_cfg& c, const Graph& g, int flags, int which) {
   if constexpr (sizeof(T) != 2) return false;
-  return tc::tc_enabled() && tc::fused_enabled() && c.D == 128 && g.n_tiles > 0 && g.N > 0 && g.M == g.N &&
+  return tc::tc_enabled() && tc::tile_enabled() && tc::fused_enabled(which) && c.D == 128 && c.aggr == GCB_AGGR_ADD &&
+         g.n_tiles > 0 && g.N > 0 && g.M == g.N && tc::bond_bwd_merged_enabled() &&
          !((flags & GCB_TRAINING) && c.p_dropout > 0.f);
 }
 
@@ -479,15 +483,19 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
     const Drop da = make_drop(c, flags, seed, tag_atom(l));
     bool bond_done = false;
     if constexpr (sizeof(T) == 2) {
-      if (M > 0 && fused_ok<T>(c, g, flags)) {
+      if (M > 0 && fused_ok<T>(c, g, flags, 0)) {
         const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
-        tc::FusedArgs fa;
-        fa.tile_ptr = g.tile_ptr; fa.n_tiles = g.n_tiles; fa.rows = M; fa.act = c.act;
-        fa.ptr = g.in_ptr; fa.nbr = g.in_src; fa.nbr4 = (const int4*)g.in_src4;
-        fa.bias = bpq; fa.Bout = (bf16*)p.B[l];
-        fa.tiemask = save ? p.tiemask[l] : nullptr; fa.tiecnt = save ? p.tiecnt[l] : nullptr;
-        const int rc = save ? tc::launch_fused_rows_tc<tc::FUSED_BOND_FWD, true>("fused_bond_fwd_kernel", (const bf16*)p.B[l - 1], (const bf16*)wpq, fa, s)
-                            : tc::launch_fused_rows_tc<tc::FUSED_BOND_FWD, false>("fused_bond_fwd_kernel", (const bf16*)p.B[l - 1], (const bf16*)wpq, fa, s);
+        fr::RowArgs ra;
+        ra.tile_ptr = g.tile_ptr; ra.n_tiles = g.n_tiles; ra.rows = M; ra.act = c.act;
+        ra.ptr = g.in_ptr; ra.nbr = g.in_src; ra.nbr4 = (const int4*)g.in_src4;
+        ra.bias = bpq; ra.out = (bf16*)p.B[l];
+        ra.tiemask = save ? reinterpret_cast<uint32_t*>(p.tiemask[l]) : nullptr;
+        const bool exact = tc::fused_exact();
+        int rc;
+        if (save) rc = exact ? fr::launch_rows<fr::BOND_FWD, true, true>("fused_bond_fwd_kernel", (const bf16*)p.B[l - 1], (const bf16*)wpq, nullptr, ra, s)
+                             : fr::launch_rows<fr::BOND_FWD, true, false>("fused_bond_fwd_kernel", (const bf16*)p.B[l - 1], (const bf16*)wpq, nullptr, ra, s);
+        else rc = exact ? fr::launch_rows<fr::BOND_FWD, false, true>("fused_bond_fwd_kernel", (const bf16*)p.B[l - 1], (const bf16*)wpq, nullptr, ra, s)
+                        : fr::launch_rows<fr::BOND_FWD, false, false>("fused_bond_fwd_kernel", (const bf16*)p.B[l - 1], (const bf16*)wpq, nullptr, ra, s);
         if (rc == GCB_OK) bond_done = true;
         else if (rc != GCB_ERR_UNSUPPORTED) return rc;
       }
@@ -511,7 +519,22 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
                                     (flags & GCB_SAVE_FOR_BWD) ? p.tiemask[l] : nullptr,
                                     (flags & GCB_SAVE_FOR_BWD) ? p.tiecnt[l] : nullptr, M, D, c.act, db, flip(), s));
     }
-    if (N > 0) {
+    bool atom_done = false;
+    if constexpr (sizeof(T) == 2) {
+      if (N > 0 && fused_ok<T>(c, g, flags, 1)) {
+        const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
+        fr::AtomArgs aa;
+        aa.tile_ptr = g.tile_ptr; aa.n_tiles = g.n_tiles; aa.rows = N; aa.M = M; aa.act = c.act;
+        aa.in_ptr = g.in_ptr; aa.in_src = g.in_src; aa.in_src4 = (const int4*)g.in_src4;
+        aa.in_eid = g.in_eid; aa.in_eid4 = (const int4*)g.in_eid4;
+        aa.Bnew = (const bf16*)p.B[l]; aa.bias = bat; aa.Aout = (bf16*)p.A[l]; aa.S = save ? (bf16*)p.S[l] : nullptr;
+        const int rc = save ? fr::launch_atom_fwd<true>((const bf16*)p.A[l - 1], (const bf16*)wat, aa, s)
+                            : fr::launch_atom_fwd<false>((const bf16*)p.A[l - 1], (const bf16*)wat, aa, s);
+        if (rc == GCB_OK) atom_done = true;
+        else if (rc != GCB_ERR_UNSUPPORTED) return rc;
+      }
+    }
+    if (N > 0 && !atom_done) {
       bool a_tiled = false;
       if constexpr (sizeof(T) == 2) {
         if (c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags)) {
@@ -695,14 +718,14 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     T* dPQ_l = (T*)p.dPQ2[l & 1];
     bool atom_done = false;
     if constexpr (sizeof(T) == 2) {
-      if (N > 0 && c.aggr == GCB_AGGR_ADD && fused_ok<T>(c, g, flags)) {
+      if (N > 0 && M > 0 && fused_ok<T>(c, g, flags, 2)) {
         GCB_TRY(join(done_at[l + 1]));  // W_at(l+1) read the buffer this layer's dZA_{l-1} goes to
-        tc::FusedArgs fa;
-        fa.tile_ptr = g.tile_ptr; fa.n_tiles = g.n_tiles; fa.rows = N; fa.act = c.act;
-        fa.ptr = g.out_ptr; fa.nbr = g.out_dst; fa.nbr4 = (const int4*)g.out_dst4;
-        fa.dZA = (const bf16*)p.dZA[cur]; fa.A_prev = (const bf16*)p.A[l - 1]; fa.dZA_prev = (bf16*)p.dZA[cur ^ 1];
-        fa.dS = (bf16*)p.dS;
-        const int rc = tc::launch_fused_rows_tc<tc::FUSED_ATOM_BWD, false>("fused_atom_bwd_kernel", (const bf16*)p.dZA[cur], (const bf16*)watT, fa, s);
+        fr::RowArgs ra;
+        ra.tile_ptr = g.tile_ptr; ra.n_tiles = g.n_tiles; ra.rows = N; ra.act = c.act;
+        ra.ptr = g.out_ptr; ra.nbr = g.out_dst; ra.nbr4 = (const int4*)g.out_dst4;
+        ra.out = (bf16*)p.dZA[cur ^ 1]; ra.dS2p = (bf16*)p.dS;
+        const int rc = fr::launch_rows<fr::ATOM_BWD, false, false>("fused_atom_bwd_kernel", (const bf16*)p.dZA[cur], (const bf16*)watT,
+                                                                   (const bf16*)p.A[l - 1], ra, s);
         if (rc == GCB_OK) atom_done = true;
         else if (rc != GCB_ERR_UNSUPPORTED) return rc;
       }
@@ -744,8 +767,9 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       if (M > 0 && c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags) && tc::bond_bwd_merged_enabled()) {
         const tile::TileCommon cm{g.tile_ptr, M, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, (const int4*)g.out_inpos4, g.out_inpos};
         GCB_TRY(tile::launch_bond_bwd(D, cm, g.n_tiles, g.in_ptr, g.dst, (const bf16*)p.dS, (const bf16*)dBnext,
-                                      l == L ? (const bf16*)d_out_bond : nullptr, (const bf16*)p.B[l], p.tiecnt[l], p.tiemask[l],
-                                      (bf16*)dPQ_l, c.act, s));
+                                      l == L ? (const bf16*)d_out_bond : nullptr, (const bf16*)p.B[l],
+                                      fused_ok<T>(c, g, flags, 0) ? nullptr : p.tiecnt[l], p.tiemask[l],
+                                      (bf16*)dPQ_l, c.act, atom_done ? N : 0, s));
         bond_tiled = true;
       }
     }

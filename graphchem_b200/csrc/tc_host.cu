@@ -77,10 +77,19 @@ bool tc_enabled() {
   return !(e && e[0] == '1');
 }
 
-// Fused tcgen05 GEMM + message kernels: correct (bit-identical) but, with one CTA per SM, slower than
-// GEMM + tile-staged row kernels on B200; opt-in.
-bool fused_enabled() {
-  const char* e = std::getenv("GCB_FUSED_TC");
+// Fused tcgen05 GEMM + message kernels (fused_rows.cuh), on by default.  GCB_NO_FUSED=1 switches all of them off,
+// GCB_NO_FUSED_BOND / GCB_NO_FUSED_ATOM / GCB_NO_FUSED_ABWD one of them (which = 0 / 1 / 2): A/B switches.
+bool fused_enabled(int which) {
+  static const char* names[3] = {"GCB_NO_FUSED_BOND", "GCB_NO_FUSED_ATOM", "GCB_NO_FUSED_ABWD"};
+  const char* all = std::getenv("GCB_NO_FUSED");
+  if (all && all[0] == '1') return false;
+  const char* e = std::getenv(names[which]);
+  return !(e && e[0] == '1');
+}
+// GCB_FUSED_EXACT=1: the fused bond forward rounds P to bf16 as the unfused pipeline stores it (bit-identical
+// results, tests/test_fused_gpu.py); by default P stays in fp32 (closer to the reference, fewer instructions).
+bool fused_exact() {
+  const char* e = std::getenv("GCB_FUSED_EXACT");
   return e && e[0] == '1';
 }
 

@@ -311,7 +311,10 @@ __global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ dst,
                 const bf16* __restrict__ dS, const bf16* __restrict__ dBnext, const bf16* __restrict__ d_out_bond,
                 const bf16* __restrict__ B_l, const uint8_t* __restrict__ tiecnt, const uint8_t* __restrict__ tiemask,
-                bf16* __restrict__ dPQ, int act) {
+                bf16* __restrict__ dPQ, int act, int ds_plane_rows) {
+  // tiecnt == nullptr: the tie counts are derived from the per-edge tie bits (the fused forward records only those);
+  // ds_plane_rows > 0: dS[:, D:] arrives as D/32 planes of [ds_plane_rows x 32] (fused atom backward), else as the
+  // second half of the [rows, 2D] matrix.
   constexpr int kD = Cfg<CH>::D, kSlots = Cfg<CH>::kSlots, kPasses = Cfg<CH>::kPasses;
   constexpr int kRowBytes = Cfg<CH>::kRowBytes, kBoxBytes = Cfg<CH>::kBoxBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -319,6 +322,7 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   const uint32_t s_n4 = smem + kBoxBytes, s_a4 = s_n4 + kRows * 16, s_ptr = s_a4 + kRows * 16;
   const uint32_t s_dst = s_ptr + 544;  // [128] destination atom of bond row r, or -1 when r has no in-edge
   const uint32_t s_inv = s_dst + kRows * 4;  // [256] 1 / tie count (1 for counts 0 and 1), the factor of the even tie split
+  const uint32_t s_ie = s_inv + 256 * 4;     // [129] dst-CSR row pointers of the tile's rows (tie bits of a row's in-edges)
   const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
   const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
   pdl_launch_dependents();
@@ -339,6 +343,7 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
       sts32(s_dst + i * 4, t);
     }
     sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);
+    sts32(s_ie + i * 4, r <= r1 ? __ldg(in_ptr + r) : 0);
   }
   const int grp = threadIdx.x / CH, lig = threadIdx.x % CH, c = lig * 8;
   pdl_wait();
@@ -354,9 +359,36 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = g[i] = 0.f;
     if (t >= 0) {
-      const uint4 sraw = R::load(dS + (size_t)t * (2 * kD) + kD + c);
+      const uint4 sraw = ds_plane_rows > 0 ? R::load(dS + ((size_t)(c >> 5) * ds_plane_rows + t) * 32 + (c & 31))
+                                           : R::load(dS + (size_t)t * (2 * kD) + kD + c);
       const uint4 yraw = R::load(B_l + (size_t)r * kD + c);
-      const uint2 cw = __ldg(reinterpret_cast<const uint2*>(tiecnt + (size_t)r * kD + c));
+      uint2 cw = make_uint2(0x01010101u, 0x01010101u);
+      if (tiecnt) {
+        cw = __ldg(reinterpret_cast<const uint2*>(tiecnt + (size_t)r * kD + c));
+      } else {
+        // count per channel how many in-edges tie for the max: channels seen twice are rare after the first layer
+        const int ie0 = lds32(s_ie + rr * 4), ie1 = lds32(s_ie + rr * 4 + 4);
+        uint32_t seen = 0u, twice = 0u;
+        for (int e = ie0; e < ie1; ++e) {
+          const uint32_t b = __ldg(tiemask + (size_t)e * CH + lig);
+          twice |= seen & b;
+          seen |= b;
+        }
+        if (twice) {
+          uint32_t cnt[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cnt[i] = 0u;
+          for (int e = ie0; e < ie1; ++e) {
+            const uint32_t b = __ldg(tiemask + (size_t)e * CH + lig);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cnt[i] += (b >> i) & 1u;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cnt[i] = cnt[i] > 255u ? 255u : cnt[i];
+          cw.x = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16) | (cnt[3] << 24);
+          cw.y = cnt[4] | (cnt[5] << 8) | (cnt[6] << 16) | (cnt[7] << 24);
+        }
+      }
       uint4 nraw = R::zero(), oraw = R::zero();
       if (dBnext) nraw = R::load(dBnext + (size_t)r * kD + c);
       if (d_out_bond) oraw = R::load(d_out_bond + (size_t)r * kD + c);
@@ -518,19 +550,19 @@ inline int launch_bond_scatter(int D, const bf16* gsplit, const TileCommon& cm, 
 template <int CH>
 inline int launch_bond_bwd_w(const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
                              const bf16* dBnext, const bf16* d_out_bond, const bf16* B_l, const uint8_t* tiecnt,
-                             const uint8_t* tiemask, bf16* dPQ, int act, cudaStream_t s) {
-  const int smem = smem_for<CH>(1) + kRows * 4 + 256 * 4;
+                             const uint8_t* tiemask, bf16* dPQ, int act, int ds_plane_rows, cudaStream_t s) {
+  const int smem = smem_for<CH>(1) + kRows * 4 + 256 * 4 + 544;
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel<CH>, smem)); attr = true; }
   GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
-                                                     tiecnt, tiemask, dPQ, act));
+                                                     tiecnt, tiemask, dPQ, act, ds_plane_rows));
   return GCB_OK;
 }
 inline int launch_bond_bwd(int D, const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
                            const bf16* dBnext, const bf16* d_out_bond, const bf16* B_l, const uint8_t* tiecnt,
-                           const uint8_t* tiemask, bf16* dPQ, int act, cudaStream_t s) {
-  return D == 128 ? launch_bond_bwd_w<16>(cm, n_tiles, in_ptr, dst, dS, dBnext, d_out_bond, B_l, tiecnt, tiemask, dPQ, act, s)
-                  : launch_bond_bwd_w<32>(cm, n_tiles, in_ptr, dst, dS, dBnext, d_out_bond, B_l, tiecnt, tiemask, dPQ, act, s);
+                           const uint8_t* tiemask, bf16* dPQ, int act, int ds_plane_rows, cudaStream_t s) {
+  return D == 128 ? launch_bond_bwd_w<16>(cm, n_tiles, in_ptr, dst, dS, dBnext, d_out_bond, B_l, tiecnt, tiemask, dPQ, act, ds_plane_rows, s)
+                  : launch_bond_bwd_w<32>(cm, n_tiles, in_ptr, dst, dS, dBnext, d_out_bond, B_l, tiecnt, tiemask, dPQ, act, ds_plane_rows, s);
 }
 
 }  // namespace tile

@@ -8,7 +8,10 @@ required; real PyG `Data`/`Batch` objects are accepted everywhere by duck typing
 """
 from __future__ import annotations
 
+import numbers
 from typing import Any, Iterable, Iterator, List, Optional, Sequence, Union
+
+import numpy as np
 
 import torch
 from torch import Tensor
@@ -143,10 +146,12 @@ class MoleculeDataset(torch.utils.data.Dataset):
         return self.len()
 
     def __getitem__(self, idx: Union[int, slice, Sequence[int], Tensor]):
-        if isinstance(idx, (int,)) or (isinstance(idx, Tensor) and idx.dim() == 0):
+        if isinstance(idx, numbers.Integral) or (isinstance(idx, (Tensor, np.ndarray)) and idx.ndim == 0):
             return self.get(int(idx))
         if isinstance(idx, slice):
             return MoleculeDataset(self._graphs[idx])
+        if isinstance(idx, np.ndarray):
+            idx = torch.from_numpy(idx)
         if isinstance(idx, Tensor):
             idx = idx.nonzero().flatten().tolist() if idx.dtype == torch.bool else idx.tolist()
         return MoleculeDataset([self._graphs[int(i)] for i in idx])

@@ -41,6 +41,14 @@ def shard_indices(n_items: int, rank: int, world: int, per_rank_batch: int, step
     return order[lo:lo + per_rank_batch]
 
 
+def allreduce_sum_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum-all-reduce the flat gradient in place (`TrainStep` folds 1/world into its Adam kernel, so the captured
+    step has no extra scaling launch).  NCCL on CUDA tensors (captured into the step's CUDA graph), gloo on CPU."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad
+
+
 def allreduce_mean_(flat_grad: torch.Tensor, world: int, group=None) -> torch.Tensor:
     """Sum-all-reduce the flat gradient in place and scale by 1/world (mean of per-rank means)."""
     if world > 1:

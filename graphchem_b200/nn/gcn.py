@@ -16,6 +16,7 @@ import os
 import warnings
 from typing import Callable, List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -317,23 +318,34 @@ class MoleculeGCN(nn.Module):
         if int(self._n_messages) < 1:
             raise NotImplementedError("predict_each needs n_messages >= 1 (without message passing a plain batch is already per-molecule)")
         av, bv = self._dims[0], self._dims[1]
-        outs, atoms, bonds = [], [], []
         n = len(store)
-        i = 0
-        while i < n:
-            # a chunk needs at least as many edges as atoms; single-atom molecules are appended to richer ones
-            j = min(n, i + batch_size)
-            idx = list(range(i, j))
+        cols = self._dims[2] if self._dims[4] > 0 else self._dims[3]
+        D = self._dims[3]
+        out = torch.zeros(n, cols)
+        atoms: List[Optional[Tensor]] = [None] * n
+        bonds: List[Optional[Tensor]] = [None] * n
+        na_all, ne_all = np.asarray(store.n_atoms), np.asarray(store.n_edges)
+        # The "each alone" layout gives atom i of a molecule the molecule's bond row i, so it needs at least as many
+        # edges as atoms per molecule.  Molecules with fewer (a lone atom, salts / mixtures with unbonded atoms) are
+        # rare: each of them runs as its own plain one-molecule batch, which IS the reference's `model(g)`
+        # (including its IndexError when an edge addresses a bond row that does not exist, gcn.py:163).
+        odd = np.nonzero(ne_all < na_all)[0]
+        regular = np.nonzero(ne_all >= na_all)[0]
+        for i in range(0, len(regular), batch_size):
+            idx = regular[i:i + batch_size]
             pb = store.collate_pack(idx, int(self._n_messages), av, bv, each=True).to(dev, non_blocking=True)
-            out, out_atom, out_bond, _ = self._run_forward(pb, 0, 0)
-            outs.append(out.cpu())
+            o, out_atom, out_bond, _ = self._run_forward(pb, 0, 0)
+            out[torch.from_numpy(idx)] = o.cpu()
             if return_all:
-                na = store.n_atoms[i:j].tolist()
-                ne = store.n_edges[i:j].tolist()
-                atoms += list(torch.split(out_atom.cpu(), na))
-                bonds += list(torch.split(out_bond.cpu(), ne))
-            i = j
-        out = torch.cat(outs) if outs else torch.zeros(0, self._dims[2] if self._dims[4] > 0 else self._dims[3])
+                for k, a, b in zip(idx.tolist(), torch.split(out_atom.cpu(), na_all[idx].tolist()),
+                                   torch.split(out_bond.cpu(), ne_all[idx].tolist())):
+                    atoms[k], bonds[k] = a, b
+        for k in odd.tolist():
+            pb = store.collate_pack([k], int(self._n_messages), av, bv).to(dev, non_blocking=True)
+            o, out_atom, out_bond, _ = self._run_forward(pb, 0, 0)
+            out[k] = o.cpu()[0]
+            if return_all:
+                atoms[k], bonds[k] = out_atom.cpu(), out_bond.cpu().reshape(-1, D)
         return (out, atoms, bonds) if return_all else out
 
     # ---- forward ---------------------------------------------------------------------------------

@@ -9,22 +9,38 @@ predict_cn.ipynb:252, is replaced by a device-side loss scalar the caller reads 
 from __future__ import annotations
 
 import ctypes as C
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
 import torch
 
 from . import _lib
 from .data.packed import PackedBatch
+from .distributed import allreduce_sum_
 
 
 class TrainStep:
+    """One fused training step per call (see module docstring).
+
+    Device state: the model's flat fp32 parameter vector, Adam's `exp_avg` / `exp_avg_sq`, the step counter and
+    the learning rate all live in device memory at fixed addresses, so captured CUDA graphs stay valid across
+    `lr` changes, `load_state_dict` and `restore`.  `state_dict()` / `load_state_dict()` carry everything a resume
+    needs (the reference keeps `deepcopy(model.state_dict())` of the best epoch,
+    examples/comparison/train_cn.ipynb:220-226; optimiser state is added here so that a resumed run continues
+    bit-identically); `snapshot()` / `restore()` are the device-side form of that best-epoch copy.
+
+    CUDA graphs: a batch buffer is run eagerly the first `capture_after - 1` times it is seen and captured on the
+    next sighting, so streaming loaders whose batches never repeat pay no capture cost; the cache is LRU with
+    `max_graphs` entries (raise it to the number of resident batches)."""
+
     def __init__(self, model, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 use_cuda_graph: bool = True, process_group=None):
+                 use_cuda_graph: bool = True, process_group=None, capture_after: int = 2, max_graphs: int = 64):
         self.model = model
         self.betas, self.eps = betas, eps
         dev = model._ensure_device()
         self.device = dev
         flat = model.flat_parameters()
+        self._flat_ptr = flat.data_ptr()
         self.grad = torch.zeros_like(flat)
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
@@ -37,12 +53,17 @@ class TrainStep:
         self._lr = lr
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.use_cuda_graph = use_cuda_graph
+        self.capture_after = max(1, int(capture_after))
         self._ws: Optional[torch.Tensor] = None
+        self._pred_buf: Optional[torch.Tensor] = None   # [G_max, out]; `_pred` / `_dpred` are its leading rows
+        self._dpred_buf: Optional[torch.Tensor] = None
         self._pred: Optional[torch.Tensor] = None
         self._dpred: Optional[torch.Tensor] = None
-        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._graphs: "OrderedDict[tuple, torch.cuda.CUDAGraph]" = OrderedDict()
         self._keepalive: Dict[tuple, PackedBatch] = {}
-        self.max_graphs = 64
+        self._seen: "OrderedDict[tuple, int]" = OrderedDict()
+        self._warm = False
+        self.max_graphs = max_graphs
         self.launches_per_step = 0
         model.refresh_weights()
 
@@ -56,19 +77,74 @@ class TrainStep:
         self._lr = float(value)
         self.hyper[0:1].fill_(self._lr)
 
+    # ---- checkpoint / resume ----------------------------------------------------
+    def state_dict(self) -> dict:
+        """Everything a bit-identical resume needs, as host tensors: model parameters (reference keys), Adam
+        moments over the flat parameter vector, step counter, learning rate and the Adam constants."""
+        return {
+            "model": {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
+            "exp_avg": self.exp_avg.detach().cpu().clone(),
+            "exp_avg_sq": self.exp_avg_sq.detach().cpu().clone(),
+            "step_count": int(self.step_count.item()),
+            "lr": float(self._lr), "betas": tuple(self.betas), "eps": float(self.eps),
+        }
+
+    def load_state_dict(self, state: dict) -> None:
+        self.model.load_state_dict(state["model"])
+        self._rebind()
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        self.step_count.fill_(int(state["step_count"]))
+        self.betas, self.eps = tuple(state["betas"]), float(state["eps"])
+        self.lr = float(state["lr"])
+        self.model.refresh_weights()
+
+    def snapshot(self) -> dict:
+        """Device-side copy of the training state (one D2D copy per tensor, no host sync): the best-epoch
+        `deepcopy(model.state_dict())` of examples/comparison/train_cn.ipynb:220."""
+        return {"flat": self.model.flat_parameters().clone(), "exp_avg": self.exp_avg.clone(),
+                "exp_avg_sq": self.exp_avg_sq.clone(), "step_count": self.step_count.clone(), "lr": self._lr}
+
+    def restore(self, snap: dict, optimizer_state: bool = True) -> None:
+        """Back to a `snapshot()` (train_cn.ipynb:226 `model.load_state_dict(best_state)`); addresses are kept,
+        captured graphs stay valid."""
+        self._rebind()
+        self.model.flat_parameters().copy_(snap["flat"])
+        if optimizer_state:
+            self.exp_avg.copy_(snap["exp_avg"])
+            self.exp_avg_sq.copy_(snap["exp_avg_sq"])
+            self.step_count.copy_(snap["step_count"])
+            self.lr = snap["lr"]
+        self.model.refresh_weights()
+
+    def _rebind(self) -> None:
+        """The captured graphs hold the address of the flat parameter vector: if the model re-flattened its
+        parameters (`.to()`, externally replaced `.data`), drop them."""
+        flat = self.model.flat_parameters()
+        if flat.data_ptr() != self._flat_ptr:
+            self._flat_ptr = flat.data_ptr()
+            self._drop_graphs()
+
+    def _drop_graphs(self) -> None:
+        self._graphs.clear()
+        self._keepalive.clear()
+        self._seen.clear()
+
     def _buffers(self, pb: PackedBatch, flags: int):
         cfg = self.model._cfg()
         need = int(_lib.check(int(_lib.lib().gcb_workspace_bytes(C.byref(cfg), pb.N, pb.E, pb.G, flags)),
                               "gcb_workspace_bytes"))
         if self._ws is None or self._ws.numel() < need:
-            if self._graphs:
-                self._graphs.clear()
-                self._keepalive.clear()
+            self._drop_graphs()
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         out_cols = self.model._dims[2] if self.model._dims[4] > 0 else self.model._dims[3]
-        if self._pred is None or self._pred.shape != (pb.G, out_cols):
-            self._pred = torch.empty(pb.G, out_cols, dtype=torch.float32, device=self.device)
-            self._dpred = torch.empty_like(self._pred)
+        if self._pred_buf is None or self._pred_buf.shape[0] < pb.G or self._pred_buf.shape[1] != out_cols:
+            # graphs captured earlier hold the old buffers' addresses: they go with them
+            self._drop_graphs()
+            self._pred_buf = torch.empty(pb.G, out_cols, dtype=torch.float32, device=self.device)
+            self._dpred_buf = torch.empty_like(self._pred_buf)
+        # leading rows of the capacity buffers: the same base address for every batch size
+        self._pred, self._dpred = self._pred_buf[:pb.G], self._dpred_buf[:pb.G]
 
     def _enqueue(self, pb: PackedBatch) -> None:
         """Enqueue one full training step on the current stream."""
@@ -90,7 +166,7 @@ class TrainStep:
                                     self._ws.data_ptr(), self._ws.numel(), flags, seed, self._dpred.data_ptr(), None,
                                     None, self.grad.data_ptr(), 0, s), "gcb_backward")
         if self.world > 1:
-            torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            allreduce_sum_(self.grad, group=self.pg)  # 1/world is folded into the Adam kernel (hyper[1])
         b1, b2 = self.betas
         _lib.check(lib.gcb_adam_step(flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                      self.exp_avg_sq.data_ptr(), flat.numel(), self.hyper.data_ptr(),
@@ -98,40 +174,61 @@ class TrainStep:
         _lib.check(lib.gcb_prepare_weights(C.byref(cfg), flat.data_ptr(), model._derived.data_ptr(), s),
                    "gcb_prepare_weights")
 
+    def _capture(self, pb: PackedBatch) -> torch.cuda.CUDAGraph:
+        if not self._warm:
+            # one eager step on a side stream before the first capture (lazy one-time initialisation inside the
+            # library must not happen under capture), undone so that it does not change the training trajectory
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            tensors = (self.model.flat_parameters(), self.exp_avg, self.exp_avg_sq, self.step_count)
+            state = [t.clone() for t in tensors]
+            with torch.cuda.stream(side):
+                self._enqueue(pb)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            for t, s0 in zip(tensors, state):
+                t.copy_(s0)
+            self.model.refresh_weights()
+            self._warm = True
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue(pb)
+        return g
+
     def __call__(self, pb: PackedBatch) -> torch.Tensor:
         """Run one step on a device-resident PackedBatch; returns the device loss scalar (no sync)."""
         if pb.device != self.device:
             raise RuntimeError("TrainStep needs a device-resident PackedBatch (use .to(device) / a prefetcher)")
         if pb.y is None:
             raise ValueError("PackedBatch has no targets")
+        self._rebind()
         self._buffers(pb, _lib.TRAINING | _lib.SAVE_FOR_BWD)
         graphable = self.use_cuda_graph and self.model._p_dropout == 0
         if not graphable:
             self._enqueue(pb)
+            self._warm = True
             return self.loss
         key = (pb.ints.data_ptr(), pb.y.data_ptr(), pb.header.tobytes())
         g = self._graphs.get(key)
-        if g is None:
-            # warm-up on a side stream (required before capture), then capture
-            side = torch.cuda.Stream(self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            state = [t.clone() for t in (self.model.flat_parameters(), self.exp_avg, self.exp_avg_sq, self.step_count)]
-            with torch.cuda.stream(side):
-                self._enqueue(pb)
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            # undo the warm-up step so that capture does not change the training trajectory
-            for t, s0 in zip((self.model.flat_parameters(), self.exp_avg, self.exp_avg_sq, self.step_count), state):
-                t.copy_(s0)
-            self.model.refresh_weights()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._enqueue(pb)
-            if len(self._graphs) >= self.max_graphs:  # streaming callers with ever-changing batches: bound the cache
-                old = next(iter(self._graphs))
-                del self._graphs[old]
-                self._keepalive.pop(old, None)
-            self._graphs[key] = g
-            self._keepalive[key] = pb
+        if g is not None:
+            self._graphs.move_to_end(key)
+            g.replay()
+            return self.loss
+        seen = self._seen.get(key, 0) + 1
+        if seen < self.capture_after:  # not yet worth a capture: run eagerly
+            self._seen[key] = seen
+            self._seen.move_to_end(key)
+            while len(self._seen) > 4 * max(self.max_graphs, 1):
+                self._seen.popitem(last=False)
+            self._enqueue(pb)
+            self._warm = True
+            return self.loss
+        self._seen.pop(key, None)
+        g = self._capture(pb)
+        while len(self._graphs) >= max(self.max_graphs, 1):  # least recently used graph goes
+            old, _ = self._graphs.popitem(last=False)
+            self._keepalive.pop(old, None)
+        self._graphs[key] = g
+        self._keepalive[key] = pb
         g.replay()
         return self.loss
 
