@@ -242,7 +242,7 @@ def run_ours(args):
     dev_batches = [hb.to(dev) for hb in host_batches]
     torch.cuda.synchronize()
 
-    step = TrainStep(model, lr=1e-3)
+    step = TrainStep(model, lr=1e-3, capture_after=1)  # resident batches repeat: capture on first sight
 
     def barrier():
         if world > 1:

@@ -436,7 +436,7 @@ static inline uint32_t tag_readout(int k) { return 100000u + (uint32_t)k; }
 
 // The fused GEMM + message kernels (fused_rows.cuh) take bf16, D = 128, add aggregation, closed row tiles, every
 // atom row a live bond row, and no active dropout; anything else runs on the unfused kernels.  `which`: 0 bond
-// forward, 1 atom forward, 2 atom backward (GCB_NO_FUSED=1 / GCB_NO_FUSED_BOND / _ATOM / _ABWD switch them off).
+// forward, 1 atom forward, 2 atom backward (opt-in: GCB_FUSED=1 / GCB_FUSED_BOND / _ATOM / _ABWD, see tc_host.cu).
 // The fused bond forward records tie bits only (no tie counts) and the fused atom backward emits dS[:, D:] as
 // planes: both are understood by tile::bond_bwd_kernel only, hence the merged-bond-backward condition.
 template <typename T>

@@ -77,14 +77,17 @@ bool tc_enabled() {
   return !(e && e[0] == '1');
 }
 
-// Fused tcgen05 GEMM + message kernels (fused_rows.cuh), on by default.  GCB_NO_FUSED=1 switches all of them off,
-// GCB_NO_FUSED_BOND / GCB_NO_FUSED_ATOM / GCB_NO_FUSED_ABWD one of them (which = 0 / 1 / 2): A/B switches.
+// Fused tcgen05 GEMM + message kernels (fused_rows.cuh): OPT-IN.  Measured on B200 (batch 8192, D = 128, 4 steps,
+// profiles/r2_fused_ab.jsonl) they lose to the tile kernels + stand-alone GEMMs (2.15 vs 1.77 ms per train step):
+// their 16 row warps run drain -> gather -> activation -> copy-out in lock-step at 28 % issue utilisation.
+// GCB_FUSED=1 switches all three on, GCB_FUSED_BOND / GCB_FUSED_ATOM / GCB_FUSED_ABWD one of them (which = 0 / 1 / 2);
+// GCB_NO_FUSED=1 and GCB_NO_FUSED_BOND / _ATOM / _ABWD veto (A/B switches).
 bool fused_enabled(int which) {
-  static const char* names[3] = {"GCB_NO_FUSED_BOND", "GCB_NO_FUSED_ATOM", "GCB_NO_FUSED_ABWD"};
-  const char* all = std::getenv("GCB_NO_FUSED");
-  if (all && all[0] == '1') return false;
-  const char* e = std::getenv(names[which]);
-  return !(e && e[0] == '1');
+  static const char* on_names[3] = {"GCB_FUSED_BOND", "GCB_FUSED_ATOM", "GCB_FUSED_ABWD"};
+  static const char* off_names[3] = {"GCB_NO_FUSED_BOND", "GCB_NO_FUSED_ATOM", "GCB_NO_FUSED_ABWD"};
+  auto set = [](const char* name) { const char* e = std::getenv(name); return e && e[0] == '1'; };
+  if (set("GCB_NO_FUSED") || set(off_names[which])) return false;
+  return set("GCB_FUSED") || set(on_names[which]);
 }
 // GCB_FUSED_EXACT=1: the fused bond forward rounds P to bf16 as the unfused pipeline stores it (bit-identical
 // results, tests/test_fused_gpu.py); by default P stays in fp32 (closer to the reference, fewer instructions).

@@ -205,6 +205,28 @@ class MoleculeStore:
         self.targets = None if targets is None else targets.to(torch.float32).reshape(n, -1).contiguous()
 
     @classmethod
+    def from_flat(cls, atoms: Tensor, bonds: Tensor, conn: Tensor, n_atoms: np.ndarray, n_edges: np.ndarray,
+                  targets: Optional[Tensor] = None) -> "MoleculeStore":
+        """Store over already-concatenated arrays: `atoms` int32 [sum n_atoms], `bonds` int32 [sum n_edges],
+        `conn` int64 [2 * sum n_edges] (per molecule: its e sources, then its e destinations, molecule-local ids,
+        i.e. each molecule's [2, e] connectivity flattened).  No per-molecule Python objects: the form a
+        10 M-molecule shard is built in."""
+        self = cls.__new__(cls)
+        self.n_atoms = np.ascontiguousarray(n_atoms, dtype=np.int32)
+        self.n_edges = np.ascontiguousarray(n_edges, dtype=np.int32)
+        n = int(self.n_atoms.shape[0])
+        self.atoms = atoms.reshape(-1).to(torch.int32).contiguous()
+        self.bonds = bonds.reshape(-1).to(torch.int32).contiguous()
+        self.conn = conn.reshape(-1).to(torch.int64).contiguous()
+        self.atom_off = np.concatenate([[0], np.cumsum(self.n_atoms, dtype=np.int64)])
+        self.edge_off = np.concatenate([[0], np.cumsum(self.n_edges, dtype=np.int64)])
+        if (int(self.atom_off[-1]) != self.atoms.numel() or int(self.edge_off[-1]) != self.bonds.numel()
+                or 2 * int(self.edge_off[-1]) != self.conn.numel() or self.n_edges.shape[0] != n):
+            raise ValueError("MoleculeStore.from_flat: array lengths disagree with the per-molecule counts")
+        self.targets = None if targets is None else targets.to(torch.float32).reshape(n, -1).contiguous()
+        return self
+
+    @classmethod
     def from_graphs(cls, graphs: Sequence) -> "MoleculeStore":
         ys = [g.y for g in graphs]
         targets = torch.cat(ys, dim=0) if all(y is not None for y in ys) and len(ys) else None

@@ -59,10 +59,18 @@ def make_molecules(n_molecules: int, seed: int = 1234, atom_vocab: int = 64, bon
     """Generate `n_molecules` synthetic molecules as a flat host `MoleculeStore`."""
     rng = np.random.default_rng(seed)
     if not variable:
-        atoms, bonds, conn = _gen_class(rng, n_molecules, 23, 3, atom_vocab, bond_vocab)
-        atoms_l = list(torch.from_numpy(atoms))
-        bonds_l = list(torch.from_numpy(bonds))
-        conn_l = list(torch.from_numpy(conn))
+        # flat arrays, generated in chunks (the [G, 23, 23] adjacency scratch of a 10 M-molecule shard would not fit)
+        chunk = 1 << 18
+        parts = [_gen_class(rng, min(chunk, n_molecules - lo), 23, 3, atom_vocab, bond_vocab)
+                 for lo in range(0, n_molecules, chunk)]
+        targets = torch.from_numpy(rng.standard_normal((n_molecules, 1)).astype(np.float32))
+        cat = lambda k: (np.concatenate([p[k] for p in parts]) if len(parts) > 1 else parts[0][k]) if parts else None  # noqa: E731
+        if n_molecules == 0:
+            return MoleculeStore([], [], [], targets)
+        return MoleculeStore.from_flat(torch.from_numpy(cat(0).reshape(-1)), torch.from_numpy(cat(1).reshape(-1)),
+                                       torch.from_numpy(cat(2).reshape(-1)),
+                                       np.full(n_molecules, 23, dtype=np.int32), np.full(n_molecules, 50, dtype=np.int32),
+                                       targets)
     else:
         na = np.clip(np.rint(rng.normal(23, 4.5, size=n_molecules)), 6, 38).astype(np.int64)
         nr = rng.binomial(4, 0.6, size=n_molecules)

@@ -126,9 +126,9 @@ class TrainStep:
             self._drop_graphs()
 
     def _drop_graphs(self) -> None:
+        # captured graphs hold stale addresses; the sighting counts stay valid (a batch seen before is still a repeat)
         self._graphs.clear()
         self._keepalive.clear()
-        self._seen.clear()
 
     def _buffers(self, pb: PackedBatch, flags: int):
         cfg = self.model._cfg()
@@ -146,8 +146,8 @@ class TrainStep:
         # leading rows of the capacity buffers: the same base address for every batch size
         self._pred, self._dpred = self._pred_buf[:pb.G], self._dpred_buf[:pb.G]
 
-    def _enqueue(self, pb: PackedBatch) -> None:
-        """Enqueue one full training step on the current stream."""
+    def _enqueue_grad(self, pb: PackedBatch) -> None:
+        """Forward, MSE and backward of one batch on the current stream: `self.loss`, `self.grad` (this rank's)."""
         lib, model = _lib.lib(), self.model
         cfg = model._cfg()
         flat = model.flat_parameters()
@@ -165,6 +165,13 @@ class TrainStep:
         _lib.check(lib.gcb_backward(C.byref(cfg), pb.ints.data_ptr(), hdr, flat.data_ptr(), model._derived.data_ptr(),
                                     self._ws.data_ptr(), self._ws.numel(), flags, seed, self._dpred.data_ptr(), None,
                                     None, self.grad.data_ptr(), 0, s), "gcb_backward")
+
+    def _enqueue_update(self) -> None:
+        """Data-parallel gradient sum, Adam on the flat parameter vector, refresh of the derived weights."""
+        lib, model = _lib.lib(), self.model
+        cfg = model._cfg()
+        flat = model.flat_parameters()
+        s = torch.cuda.current_stream(self.device).cuda_stream
         if self.world > 1:
             allreduce_sum_(self.grad, group=self.pg)  # 1/world is folded into the Adam kernel (hyper[1])
         b1, b2 = self.betas
@@ -173,6 +180,20 @@ class TrainStep:
                                      self.step_count.data_ptr(), b1, b2, self.eps, s), "gcb_adam_step")
         _lib.check(lib.gcb_prepare_weights(C.byref(cfg), flat.data_ptr(), model._derived.data_ptr(), s),
                    "gcb_prepare_weights")
+
+    def _enqueue(self, pb: PackedBatch) -> None:
+        """Enqueue one full training step on the current stream."""
+        self._enqueue_grad(pb)
+        self._enqueue_update()
+
+    def local_gradient(self, pb: PackedBatch) -> torch.Tensor:
+        """This rank's flat gradient of the batch's MSE loss (no collective, no parameter update); the building
+        block of the data-parallel parity check (tests/dist_trainstep_check.py)."""
+        self._rebind()
+        self._buffers(pb, _lib.TRAINING | _lib.SAVE_FOR_BWD)
+        self._enqueue_grad(pb)
+        self._warm = True
+        return self.grad
 
     def _capture(self, pb: PackedBatch) -> torch.cuda.CUDAGraph:
         if not self._warm:

@@ -61,7 +61,7 @@ res["dropin_autograd_mol_per_s"] = EPOCHS * len(ds) / (time.perf_counter() - t0)
 # (b) TrainStep on pre-packed device batches
 store = MoleculeStore.from_graphs(list(ds))
 packed = [store.collate_pack(np.arange(i, min(i + B, len(ds))), 2, AV, BV).to("cuda") for i in range(0, len(ds), B)]
-step = TrainStep(model, lr=1e-3)
+step = TrainStep(model, lr=1e-3, capture_after=1)
 for pb in packed:
     step(pb)
 torch.cuda.synchronize()

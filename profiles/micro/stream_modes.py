@@ -19,7 +19,7 @@ B, NB = 8192, int(sys.argv[1]) if len(sys.argv) > 1 else 32
 store = make_molecules(B * NB, seed=1234)
 torch.manual_seed(0)
 model = MoleculeGCN(64, 32, 1, embedding_dim=128, n_messages=4, compute_dtype=torch.bfloat16).cuda()
-step = TrainStep(model, lr=1e-3)
+step = TrainStep(model, lr=1e-3, capture_after=1)
 
 t_pack = [0.0, 0]
 _orig = packed_mod.RawBatch.pack

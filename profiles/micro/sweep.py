@@ -35,7 +35,7 @@ def case(mode, B, D, L, dtype):
     store = make_molecules(4 * B, seed=7)
     batches = [store.collate_pack(np.arange(i * B, (i + 1) * B), L, 64, 32).to(dev) for i in range(4)]
     if mode == "train":
-        step = TrainStep(model, lr=1e-3)
+        step = TrainStep(model, lr=1e-3, capture_after=1)
         ms = timed(lambda i: step(batches[i % 4]), 8, 20)
     elif mode == "infer":  # CUDA-graphed forward on resident batches
         step = InferStep(model)

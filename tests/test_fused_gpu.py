@@ -1,5 +1,5 @@
-"""-m gpu: the fused tcgen05 GEMM + message kernels (csrc/fused_rows.cuh, default when the batch has
-closed row tiles) and the tile-staged row kernels (csrc/tile_rows.cuh, GCB_NO_FUSED=1) against the
+"""-m gpu: the tile-staged row kernels (csrc/tile_rows.cuh, the default when the batch has closed row
+tiles) and the opt-in fused tcgen05 GEMM + message kernels (csrc/fused_rows.cuh, GCB_FUSED=1) against the
 plain row kernels (kernels_v2.cuh, GCB_NO_TILE=1).
 
 The tile kernels, the fused atom backward and the fused bond forward in its GCB_FUSED_EXACT=1 form
@@ -27,7 +27,7 @@ def _dev(data):
 
 
 ENV = {"tile": {"GCB_NO_FUSED": "1"}, "tile_split": {"GCB_NO_BOND_MERGE": "1"},
-       "fused_exact": {"GCB_FUSED_EXACT": "1", "GCB_NO_FUSED_ATOM": "1"}, "fused": {}, "v2": {"GCB_NO_TILE": "1"}}
+       "fused_exact": {"GCB_FUSED": "1", "GCB_FUSED_EXACT": "1", "GCB_NO_FUSED_ATOM": "1"}, "fused": {"GCB_FUSED": "1"}, "v2": {"GCB_NO_TILE": "1"}}
 
 
 def _run(model, dev, train, mode):
@@ -73,7 +73,7 @@ def test_fused_equals_unfused_bitwise(n_graphs, max_atoms, L, D, act, mode):
 
 
 @pytest.mark.parametrize("n_graphs,max_atoms,L", [(1, 12, 1), (7, 12, 2), (64, 30, 3), (700, 40, 4), (3000, 30, 4)])
-@pytest.mark.parametrize("act", [F.softplus, F.relu, F.tanh])
+@pytest.mark.parametrize("act", [F.softplus, F.tanh])  # smooth activations: relu's kink makes two roundings of the same value disagree on 0/1 derivatives
 def test_default_fused_path_close_to_unfused(n_graphs, max_atoms, L, act):
     """Default fused kernels (fp32 P, accumulator pre-loaded with residual + deg * bias) against the plain row
     kernels: a different but equally valid set of bf16 rounding points (two bf16 paths that are each within the
@@ -119,12 +119,12 @@ def test_fused_kernels_are_launched_and_relu_ties_match():
         lib.gcb_timing_report(buf, len(buf))
         return buf.value.decode()
 
-    names = kernels_of_a_step({})
+    names = kernels_of_a_step({"GCB_FUSED": "1"})
     for k in ("fused_bond_fwd_kernel", "fused_atom_fwd_kernel", "fused_atom_bwd_kernel", "tile_bond_bwd_kernel"):
         assert k in names, (k, names)
     for k in ("tile_bond_update_kernel", "tile_atom_gather_kernel", "tile_atom_bwd_kernel"):
         assert k not in names, (k, names)
-    names = kernels_of_a_step({"GCB_NO_FUSED": "1"})
+    names = kernels_of_a_step({})  # the default: tile kernels + stand-alone tcgen05 GEMMs
     for k in ("tile_bond_update_kernel", "tile_atom_gather_kernel", "tile_atom_bwd_kernel", "tile_bond_bwd_kernel"):
         assert k in names, (k, names)
     for k in ('"bond_update_kernel"', '"atom_gather_kernel"', "atom_bwd_gather_kernel", "bond_bwd_scatter_kernel", "bond_bwd_tie_kernel"):

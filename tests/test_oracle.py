@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from oracle.gcn_oracle import OracleMoleculeGCN, train_step
 from oracle.pyg_restated import Data, collate
-from tests.util import random_batch
+from tests.util import nerr, random_batch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -151,3 +151,23 @@ def test_oracle_reproduces_committed_golden_vectors():
         assert torch.allclose(v, now["grads"][k], rtol=1e-4, atol=1e-6), k
     for k, v in gold["state_after_3_adam_steps"].items():
         assert torch.allclose(v, now["state_after_3_adam_steps"][k], rtol=1e-4, atol=1e-6), k
+
+
+@pytest.mark.parametrize("act", [F.softplus, F.tanh, F.relu])
+def test_fp32_oracle_is_within_its_noise_floor_of_the_fp64_oracle(act):
+    """the float64 evaluation of the restatement separates algorithmic from rounding error.
+    The fp32 restatement (the reference's own arithmetic) must sit within a few 1e-6 of it -- which is why the
+    -m gpu parity tests compare the CUDA path with the fp64 evaluation at the north star's 1e-5 / 1e-4 bars."""
+    from tests.util import oracle_fp64
+    data, _ = random_batch(seed=11, n_graphs=8)
+    torch.manual_seed(0)
+    o32 = OracleMoleculeGCN(12, 7, 2, embedding_dim=128, n_messages=4, act_fn=act)
+    o64 = oracle_fp64(o32)
+    r32, r64 = o32(data), o64(data)
+    assert all(t.dtype == torch.float64 for t in r64)
+    for a, b in zip(r32, r64):
+        assert nerr(a, b) <= 5e-6
+    F.mse_loss(r32[0], data.y.expand_as(r32[0])).backward()
+    F.mse_loss(r64[0], data.y.double().expand_as(r64[0])).backward()
+    for (name, p), q in zip(o32.named_parameters(), o64.parameters()):
+        assert nerr(p.grad, q.grad) <= 2e-5, name

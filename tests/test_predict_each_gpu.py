@@ -49,3 +49,28 @@ def test_each_batches_are_inference_only():
     model.eval()
     with torch.no_grad():
         assert model(pb)[0].shape == (8, 1)
+
+
+def test_predict_each_with_lone_atoms_and_unbonded_fragments():
+    """'C' (one atom, no bond, tests/test_features.py:146-155 shape) and a salt-like molecule with unbonded atoms
+    have fewer edges than atoms; the reference's `model(g)` handles each of them alone, so must predict_each."""
+    from graphchem_b200.data import MoleculeGraph
+    _, graphs = random_batch(seed=9, n_graphs=6, max_atoms=9)
+    lone = MoleculeGraph(torch.tensor([3], dtype=torch.int32), torch.zeros(0, dtype=torch.int32),
+                         torch.zeros(2, 0, dtype=torch.long), torch.zeros(1, 1))
+    # three atoms, one bond between atoms 0 and 1 (edge ids 0, 1 < E = 2), atom 2 unbonded
+    salt = MoleculeGraph(torch.tensor([2, 4, 5], dtype=torch.int32), torch.tensor([3, 3], dtype=torch.int32),
+                         torch.tensor([[0, 1], [1, 0]]), torch.zeros(1, 1))
+    mgs = [MoleculeGraph(g.x, g.edge_attr, g.edge_index, g.y) for g in graphs]
+    mols = mgs[:2] + [lone] + mgs[2:4] + [salt, lone] + mgs[4:]
+    oracle, model = make_pair(12, 7, 1, embedding_dim=64, n_messages=2)
+    oracle.eval(); model.eval()
+    out, atoms, bonds = model.predict_each(mols, batch_size=4, return_all=True)
+    assert out.shape == (len(mols), 1)
+    with torch.no_grad():
+        for i, g in enumerate(mols):
+            po, ao, bo = oracle(g)
+            assert atoms[i].shape == ao.shape and bonds[i].shape == bo.shape, i
+            assert nerr(out[i:i + 1], po) <= 1e-5 and nerr(atoms[i], ao) <= 1e-5 and nerr(bonds[i], bo) <= 1e-5, i
+    # only lone atoms: the chunk that round 1 rejected with NotImplementedError
+    assert model.predict_each([lone, lone, lone]).shape == (3, 1)

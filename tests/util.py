@@ -66,6 +66,26 @@ def make_pair(av, bv, out_dim, seed=0, dtype=torch.float32, device="cuda", **kw)
     return oracle, model
 
 
+def oracle_fp64(oracle: OracleMoleculeGCN) -> OracleMoleculeGCN:
+    """The same restatement evaluated in float64: its rounding noise (~1e-16) is far below every
+    tolerance, so |CUDA - oracle64| is the CUDA path's OWN error, and |oracle32 - oracle64| is the rounding noise of
+    the reference's fp32 arithmetic.  Comparing against it makes the parity tests independent of how torch's CPU
+    kernels happen to block their fp32 sums on a given box / thread count."""
+    import copy
+    o = copy.deepcopy(oracle).double()
+    o.train(oracle.training)
+    return o
+
+
+def data_fp64(data):
+    """Shallow copy of a batch with float64 targets (integer tensors are shared)."""
+    import copy
+    d = copy.copy(data)
+    if getattr(data, "y", None) is not None:
+        d.y = data.y.double()
+    return d
+
+
 def nerr(a: torch.Tensor, b: torch.Tensor) -> float:
     """Norm-wise relative error max|a-b| / max|b| (b = oracle)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
