@@ -43,6 +43,15 @@ struct NtShape {
   static constexpr int EPI_WARPS = (N == 128 || (N == 256 && !RES)) ? 16 : 8;
   static constexpr int COL_PARTS = EPI_WARPS / 4;
   static constexpr int THREADS = 64 + EPI_WARPS * 32;
+  // Store groups: the warps whose columns fall into the same 64-column output slab(s) stage, publish and TMA-store
+  // those slabs on their own (named barrier per group, bulk group per leader thread), so that one group's store
+  // overlaps the other groups' TMEM drains instead of all 16 warps marching through two CTA-wide barriers per tile.
+  static constexpr int COLS_PER_PART = N / COL_PARTS;
+  static constexpr int PARTS_PER_GROUP = COLS_PER_PART >= 64 ? 1 : 64 / COLS_PER_PART;
+  static constexpr int SLABS_PER_GROUP = COLS_PER_PART >= 64 ? COLS_PER_PART / 64 : 1;
+  static constexpr int GROUPS = COL_PARTS / PARTS_PER_GROUP;
+  static constexpr int GROUP_THREADS = PARTS_PER_GROUP * 128;
+  static_assert(GROUPS * SLABS_PER_GROUP == NS && GROUPS >= 1 && GROUPS <= 8, "store groups must tile the output slabs");
   static_assert(K % 64 == 0 && N % 64 == 0 && N <= 256, "unsupported GEMM shape");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
@@ -142,16 +151,18 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ep_tid = threadIdx.x - 64;
     constexpr int COLS_PER_WARP = N / S::COL_PARTS;
     constexpr int NCHUNK = COLS_PER_WARP / 32;
+    const int group = half / S::PARTS_PER_GROUP;               // store group of this warp
+    const bool leader = ep_tid == group * S::GROUP_THREADS;    // first thread of the group's first warp
     // Software pipeline across tiles: the residual row chunk and the row degree of the NEXT tile are
     // loaded into registers while the current tile is being finished, so that no global-memory latency
     // sits between "accumulator ready" and "tile staged".
     uint4 res_raw[RES ? NCHUNK : 1][4];
-    int deg_pref = 0;
+    int rp_lo = 0, rp_hi = 0;  // row pointers of the NEXT tile's row: subtracted when used, a tile later
     const int res_col0 = half * COLS_PER_WARP;
     if ((int)blockIdx.x < num_tiles) {
       const int r0 = (ep.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * S::BM + row_in_tile;
       if (r0 < rows) {
-        if (ep.rowptr) deg_pref = __ldg(ep.rowptr + r0 + 1) - __ldg(ep.rowptr + r0);
+        if (ep.rowptr) { rp_hi = __ldg(ep.rowptr + r0 + 1); rp_lo = __ldg(ep.rowptr + r0); }
         if constexpr (RES) {
           const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r0 * ep.ld_res + res_col0);
 #pragma unroll
@@ -171,24 +182,28 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool next_valid = (tile + (int)gridDim.x < num_tiles) && r_next < rows;
       float wrow = 1.f;
       if (ep.rowptr) {
-        wrow = ep.aggr == GCB_AGGR_MEAN ? (deg_pref > 0 ? 1.f : 0.f) : (float)deg_pref;
-        if (next_valid) deg_pref = __ldg(ep.rowptr + r_next + 1) - __ldg(ep.rowptr + r_next);
+        const int deg = rp_hi - rp_lo;
+        wrow = ep.aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+        if (next_valid) { rp_hi = __ldg(ep.rowptr + r_next + 1); rp_lo = __ldg(ep.rowptr + r_next); }
       }
       const uint4* rp_next = RES ? reinterpret_cast<const uint4*>(ep.res + (size_t)(next_valid ? r_next : 0) * ep.ld_res + res_col0) : nullptr;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      // the previous tile's TMA store must have finished reading the staging buffer
-      if (ep_tid == 0) tma_store_wait_read();
-      named_bar_sync(1, S::EPI_WARPS * 32);
+      // this group's previous TMA store must have finished reading the group's staging slabs
+      if (leader) tma_store_wait_read();
+      named_bar_sync(1 + group, S::GROUP_THREADS);
+      // TMEM loads run one 32-column chunk ahead of the arithmetic (tcgen05.wait::ld covers all outstanding loads)
+      uint32_t v[2][32];
+      const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + res_col0;
+      tmem_ld_32x32(tsrc, v[0]);
 #pragma unroll
       for (int ci = 0; ci < NCHUNK; ++ci) {
         const int c0 = res_col0 + ci * 32;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + c0, v);
         tmem_ld_wait();
+        if (ci + 1 < NCHUNK) tmem_ld_32x32(tsrc + (ci + 1) * 32, v[(ci + 1) & 1]);
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[ci & 1][j]);
         if (ep.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -231,17 +246,21 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      // publish the staged tile to the async proxy, then one thread issues the store
+      // publish the group's staged slabs to the async proxy, then the group leader issues their store
       fence_proxy_async_smem();
-      named_bar_sync(1, S::EPI_WARPS * 32);
-      if (ep_tid == 0) {
-        for (int ns = 0; ns < S::NS; ++ns) tma_store_2d(&tmC, sOut + ns * (S::BM * 128), ns * 64, ptile * S::BM);
+      named_bar_sync(1 + group, S::GROUP_THREADS);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < S::SLABS_PER_GROUP; ++k) {
+          const int ns = group * S::SLABS_PER_GROUP + k;
+          tma_store_2d(&tmC, sOut + ns * (S::BM * 128), ns * 64, ptile * S::BM);
+        }
         tma_store_commit();
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (ep_tid == 0) tma_store_wait_all();
+    if (leader) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -263,7 +282,12 @@ inline int launch_gemm_nt_tc_res(const bf16* A, int lda, const bf16* W, bf16* C,
     return GCB_ERR_CUDA;
   const int num_tiles = (rows + S::BM - 1) / S::BM;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  GCB_KERNEL("gemm_nt_tc_kernel", s, launch_pdl(gemm_nt_tc_kernel<K, N, RES>, grid, S::THREADS, S::SMEM_BYTES, s, tmA, tmW, tmC, rows, ep));
+  // one timing name per template instance (bench.py's roofline names ONE kernel, with that shape's bytes)
+  static constexpr const char* kName = (K == 128 && N == 256) ? (RES ? "gemm_nt_tc_k128n256_res" : "gemm_nt_tc_k128n256")
+                                       : (K == 256 && N == 128) ? (RES ? "gemm_nt_tc_k256n128_res" : "gemm_nt_tc_k256n128")
+                                       : (K == 64 && N == 128) ? (RES ? "gemm_nt_tc_k64n128_res" : "gemm_nt_tc_k64n128")
+                                                                : (RES ? "gemm_nt_tc_k128n64_res" : "gemm_nt_tc_k128n64");
+  GCB_KERNEL(kName, s, launch_pdl(gemm_nt_tc_kernel<K, N, RES>, grid, S::THREADS, S::SMEM_BYTES, s, tmA, tmW, tmC, rows, ep));
   return GCB_OK;
 }
 
@@ -383,6 +407,9 @@ gemm_nt_tcs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int ep_tid = threadIdx.x - 64;
     constexpr int COLS_PER_WARP = S::BN / S::COL_PARTS;  // 128
     constexpr int NCHUNK = COLS_PER_WARP / 32;           // 4
+    // two store groups (the four warps of a column part own two 64-column slabs): see NtShape
+    const int group = half;
+    const bool leader = ep_tid == group * 128;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -396,8 +423,8 @@ gemm_nt_tcs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      if (ep_tid == 0) tma_store_wait_read();  // the previous tile's store has finished reading the staging buffer
-      named_bar_sync(1, S::EPI_WARPS * 32);
+      if (leader) tma_store_wait_read();  // the group's previous store has finished reading its staging slabs
+      named_bar_sync(1 + group, 128);
 #pragma unroll
       for (int ci = 0; ci < NCHUNK; ++ci) {
         const int c0 = half * COLS_PER_WARP + ci * 32;  // column inside the tile
@@ -448,15 +475,19 @@ gemm_nt_tcs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       fence_proxy_async_smem();
-      named_bar_sync(1, S::EPI_WARPS * 32);
-      if (ep_tid == 0) {
-        for (int ns = 0; ns < S::BN / 64; ++ns) tma_store_2d(&tmC, sOut + ns * (S::BM * 128), n0 + ns * 64, m0);
+      named_bar_sync(1 + group, 128);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int ns = group * 2 + k;
+          tma_store_2d(&tmC, sOut + ns * (S::BM * 128), n0 + ns * 64, m0);
+        }
         tma_store_commit();
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (ep_tid == 0) tma_store_wait_all();
+    if (leader) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -477,7 +508,7 @@ inline int launch_gemm_nt_tcs(const bf16* A, int lda, const bf16* W, bf16* C, in
     return GCB_ERR_CUDA;
   const int num_tiles = ((rows + S::BM - 1) / S::BM) * (N / S::BN);
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  GCB_KERNEL("gemm_nt_tc_kernel", s, launch_pdl(gemm_nt_tcs_kernel, grid, S::THREADS, S::SMEM_BYTES, s, tmA, tmW, tmC, rows, N, K, ep));
+  GCB_KERNEL("gemm_nt_tcs_kernel", s, launch_pdl(gemm_nt_tcs_kernel, grid, S::THREADS, S::SMEM_BYTES, s, tmA, tmW, tmC, rows, N, K, ep));
   return GCB_OK;
 }
 
@@ -717,7 +748,7 @@ inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb
   const int per = (num_tiles + grid - 1) / grid;
   grid = (num_tiles + per - 1) / per;  // every CTA owns at least one tile
   *grid_out = grid;
-  GCB_KERNEL("gemm_tn_tc_kernel", s, launch_pdl(gemm_tn_tc_kernel<NN, KK>, grid, S::THREADS, S::SMEM_BYTES, s,
+  GCB_KERNEL(NN == 128 ? "gemm_tn_tc_n128k256" : "gemm_tn_tc_n256k128", s, launch_pdl(gemm_tn_tc_kernel<NN, KK>, grid, S::THREADS, S::SMEM_BYTES, s,
       tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr, rev, acc_partial));
   return GCB_OK;
 }

@@ -29,7 +29,7 @@ class PackedLoader:
     def __init__(self, store: MoleculeStore, batch_size: int, n_messages: int, atom_vocab: int, bond_vocab: int,
                  device="cuda", shuffle: bool = False, drop_last: bool = False, seed: int = 0, workers: int = 8,
                  prefetch: int = 4, cache: bool = False, indices: Optional[Sequence[int]] = None, each: bool = False,
-                 device_slots: int = 0, device_pack: bool = False):
+                 device_slots: int = 0, device_pack: bool = False, buffers: Optional[dict] = None):
         self.store, self.batch_size = store, int(batch_size)
         self.n_messages, self.av, self.bv = int(n_messages), int(atom_vocab), int(bond_vocab)
         self.device = torch.device(device)
@@ -54,6 +54,30 @@ class PackedLoader:
         self._pool: List[tuple] = []  # free (int32 buffer, float32 target buffer) pairs, pinned; CUDA devices only
         self._pool_lock = threading.Lock()
         self._pool_ready = False
+        self._scratch: Optional[torch.Tensor] = None   # device scratch of the pack kernels, reused across batches
+        if buffers:  # pinned pool / device slots of an earlier loader of the same geometry (`export_buffers`)
+            self.adopt_buffers(buffers)
+
+    def export_buffers(self) -> dict:
+        """Pinned host buffers, device slots and pack scratch of this loader, for a later loader over another store
+        with the same batch geometry (`buffers=`): cudaHostAlloc of the pool costs more than a whole epoch."""
+        with self._pool_lock:
+            return {"pool": list(self._pool), "slots": list(self._slots), "scratch": self._scratch,
+                    "host_cap": self._capacity_host() if self._pool else 0,
+                    "slot_cap": self._capacity() if self._slots else 0, "device": self.device,
+                    "device_pack": self.device_pack, "n_pool": len(self._pool)}
+
+    def adopt_buffers(self, b: dict) -> None:
+        if b.get("device") != self.device or b.get("device_pack") != self.device_pack:
+            return
+        nt = 0 if self.store.targets is None else int(self.store.targets.size(1))
+        y_cap = max(1, self.batch_size * nt)
+        if b.get("pool") and b["host_cap"] >= self._capacity_host() and b["pool"][0][1].numel() >= y_cap:
+            self._pool = list(b["pool"])
+        if (b.get("slots") and self.device_slots and len(b["slots"]) == self.device_slots
+                and b["slot_cap"] >= self._capacity() and b["slots"][0][1].numel() >= y_cap):
+            self._slots = list(b["slots"])
+        self._scratch = b.get("scratch")
 
     def __len__(self) -> int:
         n = len(self.indices)
@@ -77,7 +101,7 @@ class PackedLoader:
             bufs = self._pool.pop() if self._pool else None
         if bufs is None:
             nt = 0 if self.store.targets is None else int(self.store.targets.size(1))
-            bufs = (torch.empty(self._capacity(), dtype=torch.int32, pin_memory=True),
+            bufs = (torch.empty(self._capacity_host(), dtype=torch.int32, pin_memory=True),
                     torch.empty(max(1, self.batch_size * nt), dtype=torch.float32, pin_memory=True))
         if self.device_pack:
             hb = self.store.collate_raw(idx, self.n_messages, self.av, self.bv, pin=True, out=bufs[0], y_out=bufs[1])
@@ -96,6 +120,15 @@ class PackedLoader:
         M = min(N, E) if self.n_messages >= 1 else E
         return _header(N, E, self.batch_size, M, self.av, self.bv, _lib.PACK_EACH if self.each else 0)[1]
 
+    def _capacity_host(self) -> int:
+        """int32 elements of a pinned host buffer: the raw batch when the device packs (a sixth of the packed size)."""
+        if not self.device_pack:
+            return self._capacity()
+        from .. import _lib
+        na = np.sort(self.store.n_atoms[self.indices])[::-1][:self.batch_size].sum()
+        ne = np.sort(self.store.n_edges[self.indices])[::-1][:self.batch_size].sum()
+        return int(_lib.check(int(_lib.lib().gcb_raw_ints(int(na), int(ne), self.batch_size)), "gcb_raw_ints"))
+
     def __iter__(self) -> Iterator[PackedBatch]:
         self.epoch += 1
         if self._cached is not None:  # resident batches: replay, in shuffled order if asked
@@ -109,15 +142,17 @@ class PackedLoader:
         keep: List[PackedBatch] = []
         cuda = self.device.type == "cuda"
         copy_stream = torch.cuda.Stream(self.device) if cuda else None
-        if cuda and not self._pool_ready:
-            # all pinned buffers up front: cudaHostAlloc is slow and synchronises the device, it must not happen
-            # in the middle of an epoch
+        if cuda:
+            # all pinned buffers up front (topping up an adopted pool): cudaHostAlloc is slow and synchronises the
+            # device, it must not happen in the middle of an epoch
             nt = 0 if self.store.targets is None else int(self.store.targets.size(1))
-            cap = self._capacity()
             with self._pool_lock:
-                for _ in range(min(len(batches), self.prefetch + self.workers)):
-                    self._pool.append((torch.empty(cap, dtype=torch.int32, pin_memory=True),
-                                       torch.empty(max(1, self.batch_size * nt), dtype=torch.float32, pin_memory=True)))
+                missing = min(len(batches), self.prefetch + self.workers) - len(self._pool)
+                if missing > 0:
+                    cap = self._capacity_host()
+                    for _ in range(missing):
+                        self._pool.append((torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                                           torch.empty(max(1, self.batch_size * nt), dtype=torch.float32, pin_memory=True)))
             self._pool_ready = True
         if cuda and self.device_slots and not self._slots:
             nt = 0 if self.store.targets is None else int(self.store.targets.size(1))
@@ -185,7 +220,16 @@ class PackedLoader:
                         # a GEMM waits for its slowest SM).
                         raw, slot_ints = db
                         raw.ints.record_stream(consumer)  # allocated on the copy stream, read by the pack kernels here
-                        db = raw.pack(out=slot_ints)
+                        if self._scratch is None:
+                            from .. import _lib
+                            n_scr = int(_lib.check(int(_lib.lib().gcb_pack_device_scratch_ints(raw.header.ctypes.data)),
+                                                   "gcb_pack_device_scratch_ints"))
+                            self._scratch = torch.empty(int(n_scr * 1.25) + 1024, dtype=torch.int32, device=self.device)
+                        try:
+                            db = raw.pack(out=slot_ints, scratch=self._scratch)
+                        except ValueError:  # a larger batch than the scratch was sized for
+                            self._scratch = None
+                            db = raw.pack(out=slot_ints)
                     if not self._slots:
                         # the batch was allocated on the copy stream but is read on the consumer's stream: without
                         # this the caching allocator hands its memory to a later copy as soon as the consumer drops

@@ -342,45 +342,72 @@ def screening_shard(n_items: int, rank: int, world: int):
     return np.arange(lo, hi, dtype=np.int64)
 
 
-@torch.no_grad()
+class Screener:
+    """Inference-only screening (BASELINE.json configs[4]) with its set-up kept between calls: the pinned host
+    pool, the ring of device slots, the pack scratch, the forward workspace and one CUDA graph per slot are built
+    by the first call and reused by every later call with the same batch geometry (cudaHostAlloc of the pool and
+    the graph captures cost more than screening a million molecules).  `screen()` is the one-shot form.
+
+    `screener(store, indices=None, rank=0, world=1)` returns the predictions [n, out] (host tensor) of the molecules
+    `indices` of a `MoleculeStore` (all of them by default; with `world > 1` this rank's `screening_shard` of them),
+    in order.  Host threads gather raw batches, the GPU packs them (`device_pack`) and runs the forward pass only,
+    `model.eval()` semantics (no dropout); no collective is involved, predictions stay with the rank.
+
+    As with any batched forward of the reference, molecules of one batch see each other's bond rows (gcn.py:163,
+    SURVEY.md 3.3): results equal `model(batch)` on the same batches, not `predict_each`.  CUDA graphs are used when
+    every batch has the same shape (`use_cuda_graph=None`: decided per call from the store)."""
+
+    def __init__(self, model, batch_size: int = 32768, workers: int = 8, prefetch: int = 4, device_pack: bool = True,
+                 use_cuda_graph: Optional[bool] = None):
+        self.model, self.batch_size = model, int(batch_size)
+        self.workers, self.prefetch, self.device_pack = workers, prefetch, device_pack
+        self.use_cuda_graph = use_cuda_graph
+        self._buffers: Dict[bool, dict] = {}      # graphed? -> loader buffer set
+        self._step: Optional[InferStep] = None
+
+    @torch.no_grad()
+    def __call__(self, store, indices=None, rank: int = 0, world: int = 1) -> torch.Tensor:
+        import numpy as np
+        from .data.loader import PackedLoader
+        model = self.model
+        dev = model._ensure_device()
+        idx = np.arange(len(store), dtype=np.int64) if indices is None else np.asarray(indices, dtype=np.int64)
+        if world > 1:
+            idx = idx[screening_shard(len(idx), rank, world)]
+        n = int(idx.shape[0])
+        av, bv, out_dim, D, n_readout, R = model._dims
+        cols = int(out_dim) if n_readout > 0 else D
+        preds = torch.empty(n, cols, dtype=torch.float32, device=dev)
+        if n == 0:
+            return preds.cpu()
+        L = int(model._n_messages)
+        graphed = self.use_cuda_graph
+        if graphed is None:  # one graph per device slot pays only when all (full) batches share one shape
+            na, ne = store.n_atoms[idx], store.n_edges[idx]
+            graphed = bool((na == na[0]).all() and (ne == ne[0]).all()) and n >= self.batch_size
+        loader = PackedLoader(store, self.batch_size, L, av, bv, device=dev, workers=self.workers, prefetch=self.prefetch,
+                              indices=idx, device_slots=3 if graphed else 0, device_pack=self.device_pack,
+                              buffers=self._buffers.get(graphed))
+        if graphed and self._step is None:
+            self._step = InferStep(model, use_cuda_graph=True)
+        step = self._step if graphed else None
+        if step is not None:
+            step.refresh_weights()
+        was_training = model.training
+        model.eval()
+        try:
+            k = 0
+            for pb in loader:
+                out = step(pb) if step is not None else model._run_forward(pb, 0, 0)[0]
+                preds[k:k + pb.G].copy_(out)
+                k += pb.G
+        finally:
+            model.train(was_training)
+            self._buffers[graphed] = loader.export_buffers()
+        return preds.cpu()
+
+
 def screen(model, store, batch_size: int = 32768, indices=None, rank: int = 0, world: int = 1, workers: int = 8,
            prefetch: int = 4, device_pack: bool = True, use_cuda_graph: Optional[bool] = None) -> torch.Tensor:
-    """Inference-only screening (BASELINE.json configs[4]): predictions [n, out] (host tensor) of the molecules
-    `indices` of a `MoleculeStore` (all of them by default; with `world > 1` this rank's `screening_shard` of
-    them), in order.  Host threads gather raw batches, the GPU packs them (`device_pack`) and runs the forward
-    pass only, `model.eval()` semantics (no dropout); no collective is involved, predictions stay with the rank.
-
-    As with any batched forward of the reference, molecules of one batch see each other's bond rows
-    (gcn.py:163): results equal `model(batch)` on the same batches, not `predict_each`.
-    CUDA graphs are used when every batch has the same shape (`use_cuda_graph=None`: decided from the store)."""
-    import numpy as np
-    from .data.loader import PackedLoader
-    dev = model._ensure_device()
-    idx = np.arange(len(store), dtype=np.int64) if indices is None else np.asarray(indices, dtype=np.int64)
-    if world > 1:
-        idx = idx[screening_shard(len(idx), rank, world)]
-    n = int(idx.shape[0])
-    av, bv, out_dim, D, n_readout, R = model._dims
-    cols = int(out_dim) if n_readout > 0 else D
-    preds = torch.empty(n, cols, dtype=torch.float32, device=dev)
-    if n == 0:
-        return preds.cpu()
-    L = int(model._n_messages)
-    if use_cuda_graph is None:  # one graph per device slot pays only when all (full) batches share one shape
-        na, ne = store.n_atoms[idx], store.n_edges[idx]
-        use_cuda_graph = bool((na == na[0]).all() and (ne == ne[0]).all()) and n >= batch_size
-    slots = 3 if use_cuda_graph else 0
-    loader = PackedLoader(store, batch_size, L, av, bv, device=dev, workers=workers, prefetch=prefetch, indices=idx,
-                          device_slots=slots, device_pack=device_pack)
-    step = InferStep(model, use_cuda_graph=True) if use_cuda_graph else None
-    was_training = model.training
-    model.eval()
-    try:
-        k = 0
-        for pb in loader:
-            out = step(pb) if step is not None else model._run_forward(pb, 0, 0)[0]
-            preds[k:k + pb.G].copy_(out)
-            k += pb.G
-    finally:
-        model.train(was_training)
-    return preds.cpu()
+    """One-shot `Screener` (see there): predictions [n, out] (host tensor) of the molecules `indices` of `store`."""
+    return Screener(model, batch_size, workers, prefetch, device_pack, use_cuda_graph)(store, indices, rank, world)
