@@ -68,6 +68,7 @@ def kernel_alg_bytes(name, N, E, M, G, D, s):
         "atom_gather_kernel": N * D * s + 4 * N * i4 + N * D * s,
         # tile-staged row kernels (closed row tiles; indices = ELL-4 views + row pointers)
         "tile_bond_update_kernel": M * 2 * D * s + M * D * s + M * D + E * 16 + 5 * M * i4,   # PQ in; B', tie counts, tie masks out
+        "tile_bond_update_tok_kernel": M * D * s + M * D + E * 16 + 6 * M * i4,                   # tokens in (table in smem); B', tie data out
         "tile_atom_gather_kernel": N * D * s + M * D * s + N * 2 * D * s + 9 * N * i4,           # A tile + B' rows (by edge id) in; S out
         "tile_atom_bwd_kernel": 3 * N * D * s + N * D * s + 5 * N * i4,                           # dS half, dZA, A_prev in; dZA_prev out
         "tile_bond_bwd_kernel": 3 * M * D * s + M * D + E * 16 + M * 2 * D * s + 12 * M * i4,   # dS half, dBnext, B_l, counts, masks in; [dP|dQ] out

@@ -159,11 +159,30 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint4 res_raw[RES ? NCHUNK : 1][4];
     int rp_lo = 0, rp_hi = 0;  // row pointers of the NEXT tile's row: subtracted when used, a tile later
     const int res_col0 = half * COLS_PER_WARP;
+    // COAL (the forward atom transform, N = 128): the residual tile is fetched with COALESCED loads -- the group's
+    // 256 threads walk its [128 rows x 128 B] slab 16 bytes per lane, a warp covering four full 128-byte row
+    // segments -- one tile ahead into registers, parked in the group's (idle) staging slab in the swizzled layout,
+    // and every thread then picks up its own row's 64 bytes from shared memory and overwrites them in place with the
+    // result.  The thread = TMEM lane = row mapping made the direct loads a 256-byte-stride gather (32 lines per
+    // instruction, half of every sector unused): 39 us instead of 25 us for the plain GEMM (profiles/r2_gemm_epilogue.jsonl).
+    constexpr bool COAL = RES && N == 128 && S::GROUP_THREADS == 256 && S::SLABS_PER_GROUP == 1;
+    const int gtid = ep_tid - group * S::GROUP_THREADS;  // thread index inside the store group
+    auto coal_prefetch = [&](int tile_row0) {
+      if constexpr (COAL) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int qd = gtid + 256 * k, rr = qd >> 3, cc = qd & 7;  // 16-byte chunk cc of slab row rr
+          const int gr = tile_row0 + rr;
+          res_raw[0][k] = gr < rows ? __ldg(reinterpret_cast<const uint4*>(ep.res + (size_t)gr * ep.ld_res + group * 64 + cc * 8))
+                                    : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    };
     if ((int)blockIdx.x < num_tiles) {
       const int r0 = (ep.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * S::BM + row_in_tile;
       if (r0 < rows) {
         if (ep.rowptr) { rp_hi = __ldg(ep.rowptr + r0 + 1); rp_lo = __ldg(ep.rowptr + r0); }
-        if constexpr (RES) {
+        if constexpr (RES && !COAL) {
           const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r0 * ep.ld_res + res_col0);
 #pragma unroll
           for (int ci = 0; ci < NCHUNK; ++ci)
@@ -171,6 +190,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j4 = 0; j4 < 4; ++j4) res_raw[ci][j4] = __ldg(rp + ci * 4 + j4);
         }
       }
+      if constexpr (COAL) coal_prefetch((ep.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * S::BM);
     }
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -196,6 +216,16 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t v[2][32];
       const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + res_col0;
       tmem_ld_32x32(tsrc, v[0]);
+      if constexpr (COAL) {
+        uint8_t* gslab = sOut + group * (S::BM * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int qd = gtid + 256 * k, rr = qd >> 3, cc = qd & 7;
+          *reinterpret_cast<uint4*>(gslab + rr * 128 + ((cc ^ (rr & 7)) << 4)) = res_raw[0][k];
+        }
+        named_bar_sync(1 + group, S::GROUP_THREADS);  // the group's residual slab is complete
+        if (tile + (int)gridDim.x < num_tiles) coal_prefetch((ep.rev ? num_tiles - 1 - (tile + (int)gridDim.x) : tile + (int)gridDim.x) * S::BM);
+      }
 #pragma unroll
       for (int ci = 0; ci < NCHUNK; ++ci) {
         const int c0 = res_col0 + ci * 32;
@@ -212,7 +242,20 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             f[j + 2] = fmaf(wrow, b4.z, f[j + 2]); f[j + 3] = fmaf(wrow, b4.w, f[j + 3]);
           }
         }
-        if constexpr (RES) {
+        if constexpr (COAL) {
+          const uint8_t* rs = sOut + (c0 >> 6) * (S::BM * 128) + row_in_tile * 128;
+          const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 rw = *reinterpret_cast<const uint4*>(rs + (((ch0 + j4) ^ (row_in_tile & 7)) << 4));
+            const uint32_t w[4] = {rw.x, rw.y, rw.z, rw.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[j4 * 8 + 2 * i] += __uint_as_float(w[i] << 16);
+              f[j4 * 8 + 2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+            }
+          }
+        } else if constexpr (RES) {
           if (valid) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {

@@ -444,7 +444,27 @@ embed_bwd_partial_kernel(const T* __restrict__ dZ, const T* __restrict__ Y, cons
   float acc[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
-  for (int k = lo + rl; k < hi; k += RL) {
+  // four rows in flight per thread (index loads first, then the row loads): the walk is a dependent
+  // index -> row chain and was latency bound with one row at a time; the summation order is unchanged
+  int k = lo + rl;
+  for (; k + 3 * RL < hi; k += 4 * RL) {
+    int row[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) row[j] = __ldg(tok_row + k + j * RL);
+    float d[4][V], y[4][V];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      load_vec(dZ + (size_t)row[j] * D + c, d[j]);
+      if (Y) load_vec(Y + (size_t)row[j] * D + c, y[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (Y) act_grad_mul_vec<T, V>(d[j], y[j], act);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += d[j][i];
+    }
+  }
+  for (; k < hi; k += RL) {
     const int row = __ldg(tok_row + k);
     float d[V];
     load_vec(dZ + (size_t)row * D + c, d);

@@ -175,7 +175,7 @@ static int check_cfg(const gcb_model_cfg& c) {
 // ---- derived weights ----------------------------------------------------------------------------
 struct Derived {
   char* base;
-  int64_t wpq, wat, watT, wpqT, bpq, bat, tab_atom, tab_bond, total;
+  int64_t wpq, wat, watT, wpqT, bpq, bat, tab_atom, tab_bond, tab_pq, total;
 };
 static Derived derived_layout(const gcb_model_cfg& c, void* base) {
   const int64_t D = c.D, es = c.dtype == GCB_BF16 ? 2 : 4;
@@ -187,6 +187,8 @@ static Derived derived_layout(const gcb_model_cfg& c, void* base) {
   add(d.bpq, 2 * D * 4); add(d.bat, D * 4);
   // pre-activated embedding tables act(emb)[vocab, D] in the activation dtype: the forward lookup is a row copy
   add(d.tab_atom, (int64_t)c.atom_vocab * D * es); add(d.tab_bond, (int64_t)c.bond_vocab * D * es);
+  // [P|Q] of every bond token, tab_bond [U;V]^T + [b|0]: message step 1 reads it instead of a [rows, 2D] matrix
+  add(d.tab_pq, (int64_t)c.bond_vocab * 2 * D * es);
   d.total = o;
   return d;
 }
@@ -252,6 +254,43 @@ __global__ void finalize_conv_grads_kernel(const float* __restrict__ accWpq, con
   }
 }
 
+// Backward of message step 1 through the bond-token table.  tok[t][n] = sum over the bond rows with token t of
+// [dP|dQ]_1 (per-token sums in bucket order, embed_bwd_partial + ordered reduction).  With B_0[r] = tab_bond[tok r]:
+//   dW_pq   += tok^T tab_bond                    (what gemm_tn([dP|dQ]_1, B_0) sums row by row)
+//   db_pq   += column sums of the dP half
+//   d emb_bond[t] = (tok[t] W_pq) * act'(tab_bond[t])   (what the dB GEMM + embedding backward produce row by row)
+// All sums run over t or n in index order: deterministic.
+template <typename T>
+__global__ void bond_table_bwd_kernel(const float* __restrict__ tok, const T* __restrict__ tab_bond,
+                                      const T* __restrict__ wpq, float* __restrict__ accWpq, float* __restrict__ accBpq,
+                                      float* __restrict__ g_emb_bond, int bv, int D, int act, int acc_first, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int D2 = 2 * D;
+  if (idx < D2 * D) {
+    const int n = idx / D, k = idx % D;
+    float s = 0.f;
+#pragma unroll 16
+    for (int t = 0; t < bv; ++t) s = fmaf(__ldg(tok + (size_t)t * D2 + n), to_float(tab_bond[(size_t)t * D + k]), s);
+    accWpq[idx] = acc_first ? s : accWpq[idx] + s;
+  }
+  if (idx < D2) {
+    float s = 0.f;
+    if (idx < D) {
+#pragma unroll 16
+      for (int t = 0; t < bv; ++t) s += __ldg(tok + (size_t)t * D2 + idx);
+    }
+    accBpq[idx] = acc_first ? s : accBpq[idx] + s;
+  }
+  if (idx < bv * D) {
+    const int t = idx / D, k = idx % D;
+    float s = 0.f;
+#pragma unroll 16
+    for (int n = 0; n < D2; ++n) s = fmaf(__ldg(tok + (size_t)t * D2 + n), to_float(wpq[(size_t)n * D + k]), s);
+    s *= act_grad_t<T>(to_float(tab_bond[idx]), act);
+    g_emb_bond[idx] = accumulate ? g_emb_bond[idx] + s : s;
+  }
+}
+
 // ---- workspace plan -----------------------------------------------------------------------------
 constexpr int kMaxLayers = 256;
 
@@ -281,6 +320,7 @@ struct Plan {
   float* partial = nullptr;
   float *partialAt = nullptr, *partialPq = nullptr;  // per-CTA partials of the two conv weight gradients, summed over layers
   float *accWpq = nullptr, *accBpq = nullptr, *accWat = nullptr, *accBat = nullptr;
+  float* tokPQ = nullptr;  // [bond_vocab][2D] per-token sums of step 1's [dP|dQ]
 };
 
 static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, int64_t E, int64_t G, int64_t M,
@@ -336,6 +376,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
     }
     const int64_t vmax = c.atom_vocab > c.bond_vocab ? c.atom_vocab : c.bond_vocab;
     if (kEmbedSplits * vmax * D > pf) pf = kEmbedSplits * vmax * D;
+    if ((int64_t)kEmbedSplits * c.bond_vocab * 2 * D > pf) pf = (int64_t)kEmbedSplits * c.bond_vocab * 2 * D;
     p.partial = (float*)take(pf * 4);
     p.partialAt = (float*)take((int64_t)tc::kTnMaxCtas * (2 * D * D + 2 * D) * 4);
     p.partialPq = (float*)take((int64_t)tc::kTnMaxCtas * (2 * D * D + 2 * D) * 4);
@@ -344,6 +385,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
     p.accBpq = p.accWpq + 2 * D * D;
     p.accWat = (float*)take((2 * D * D + D) * 4);
     p.accBat = p.accWat + 2 * D * D;
+    p.tokPQ = (float*)take((int64_t)c.bond_vocab * 2 * D * 4);
   }
   p.total = o;
   return GCB_OK;
@@ -455,6 +497,21 @@ static bool tiles_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
          !((flags & GCB_TRAINING) && c.p_dropout > 0.f);
 }
 
+// Message step 1 straight from the bond-token table (tile::bond_update_tok_kernel and, in the backward pass, the
+// per-token sums of [dP|dQ]): the tile preconditions plus a table that fits shared memory.  GCB_NO_TOK1=1 switches
+// it off (A/B switch; the bit-for-bit comparisons with the plain row kernels use it, because summing [dP|dQ] per
+// token BEFORE the transform rounds differently from transforming every row).
+static bool tok1_enabled() {
+  const char* e = std::getenv("GCB_NO_TOK1");
+  return !(e && e[0] == '1');
+}
+template <typename T>
+static bool tok1_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
+  if constexpr (sizeof(T) != 2) return false;
+  return tok1_enabled() && tc::tc_enabled() && c.L >= 1 && tiles_ok<T>(c, g, flags) && tile::bond_tok_ok(c.D, c.bond_vocab) &&
+         !fused_ok<T>(c, g, flags, 0);
+}
+
 // ---- forward ------------------------------------------------------------------------------------
 template <typename T>
 static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Graph& g, const float* params,
@@ -470,7 +527,8 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
   if (N > 0) {
     GCB_KERNEL("embed_rows_kernel", s, embed_rows_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((const T*)(dv.base + dv.tab_atom), g.x_tok, (T*)p.A[0], N, D / V));
   }
-  if (M > 0) {
+  const bool tok1 = tok1_ok<T>(c, g, flags);  // B_0 is then never materialised: step 1 reads the token table
+  if (M > 0 && !tok1) {
     GCB_KERNEL("embed_rows_kernel", s, embed_rows_kernel<T><<<row_chunk_blocks(M, D, V), 256, 0, s>>>((const T*)(dv.base + dv.tab_bond), g.e_tok, (T*)p.B[0], M, D / V));
   }
   // Boustrophedon traversal: every large kernel walks its rows in the direction opposite to the
@@ -498,6 +556,15 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
                         : fr::launch_rows<fr::BOND_FWD, false, false>("fused_bond_fwd_kernel", (const bf16*)p.B[l - 1], (const bf16*)wpq, nullptr, ra, s);
         if (rc == GCB_OK) bond_done = true;
         else if (rc != GCB_ERR_UNSUPPORTED) return rc;
+      }
+    }
+    if constexpr (sizeof(T) == 2) {
+      if (M > 0 && !bond_done && l == 1 && tok1) {
+        const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
+        const tile::TileCommon cm{g.tile_ptr, M, g.in_ptr, g.in_src, (const int4*)g.in_src4, nullptr, nullptr};
+        GCB_TRY(tile::launch_bond_update_tok(D, cm, g.n_tiles, (const bf16*)(dv.base + dv.tab_pq), g.e_tok, c.bond_vocab,
+                                             (bf16*)p.B[l], save ? p.tiemask[l] : nullptr, save ? p.tiecnt[l] : nullptr, c.act, s));
+        bond_done = true;
       }
     }
     if (M > 0 && !bond_done) {
@@ -687,6 +754,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   // they run on a side stream next to the latency-bound row kernels of the same / the next layer:
   //   W_at(l) = dZA_l^T S_l        may start when layer l starts; dZA_l is overwritten by atom_bwd(l-1)
   //   W_pq(l) = [dP|dQ]_l^T B_l-1  may start after scatter(l);   dPQ[l&1] is overwritten by tie(l-2)
+  const bool tok1 = tok1_ok<T>(c, g, flags);
   SideStream* ss = tc::overlap_enabled() ? side_stream() : nullptr;
   const bool overlap = ss != nullptr;
   cudaStream_t sw = overlap ? ss->stream : s;
@@ -790,6 +858,10 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       GCB_TRY(launch_bond_bwd_scatter<T>((const T*)p.PQ[l], (const T*)p.mx, (const T*)p.gsplit, g.out_ptr, g.out_dst, g.out_inpos, g.out_dst4, g.out_inpos4,
                                          p.tiemask[l], dPQ_l, M, D, flip(), s));
     }
+    if (l == 1 && tok1) {  // step 1 read the token table: its weight / embedding gradients go through per-token sums below
+      cur ^= 1;
+      continue;
+    }
     GCB_TRY(fork());
     GCB_TRY(gemm_tn_auto<T>((const T*)dPQ_l, 2 * D, (const T*)p.B[l - 1], D, M, 2 * D, D, p.partial, p.accWpq,
                               p.accBpq, nullptr, GCB_AGGR_ADD, acc_w, sw, 0, p.partialPq, &grid_pq, l == L));
@@ -817,12 +889,25 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dZA[cur], nullptr, g.atok_ptr, g.atok_node, p.partial, av, D, c.act, s));
     }
     GCB_TRY(launch_reduce_partials(p.partial, N > 0 ? kEmbedSplits : 0, (int64_t)av * D, grad + pl.emb_atom, accumulate, s));
-    const T* dB0 = L >= 1 ? dBnext : d_out_bond;
-    const bool have = dB0 != nullptr && M > 0;
-    if (have) {
-      GCB_TRY(launch_embed_bwd_partial<T>(dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, p.partial, bv, D, c.act, s));
+    if (tok1 && M > 0) {
+      // per-token sums of step 1's [dP|dQ] (buckets in row order, ordered split reduction), then the three small
+      // products of bond_table_bwd_kernel
+      if constexpr (sizeof(T) == 2) {
+        GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dPQ2[1], nullptr, g.btok_ptr, g.btok_row, p.partial, bv, 2 * D, c.act, s));
+        GCB_TRY(launch_reduce_partials(p.partial, kEmbedSplits, (int64_t)bv * 2 * D, p.tokPQ, 0, s));
+        const int most = 2 * D * D > bv * D ? 2 * D * D : bv * D;
+        GCB_KERNEL("bond_table_bwd_kernel", s, bond_table_bwd_kernel<T><<<(unsigned)ceil_div(most, 256), 256, 0, s>>>(
+            p.tokPQ, (const T*)(dv.base + dv.tab_bond), (const T*)(dv.base + dv.wpq), p.accWpq, p.accBpq, grad + pl.emb_bond, bv, D,
+            c.act, L == 1, accumulate));
+      }
+    } else {
+      const T* dB0 = L >= 1 ? dBnext : d_out_bond;
+      const bool have = dB0 != nullptr && M > 0;
+      if (have) {
+        GCB_TRY(launch_embed_bwd_partial<T>(dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, p.partial, bv, D, c.act, s));
+      }
+      GCB_TRY(launch_reduce_partials(p.partial, have ? kEmbedSplits : 0, (int64_t)bv * D, grad + pl.emb_bond, accumulate, s));
     }
-    GCB_TRY(launch_reduce_partials(p.partial, have ? kEmbedSplits : 0, (int64_t)bv * D, grad + pl.emb_bond, accumulate, s));
   }
   // ---- conv parameters ----
   GCB_KERNEL("finalize_conv_grads_kernel", s, finalize_conv_grads_kernel<<<(unsigned)ceil_div(2 * D * D, 256), 256, 0, s>>>(
@@ -875,6 +960,14 @@ extern "C" int gcb_prepare_weights(const gcb_model_cfg* cfg, const float* params
         params + pl.b_bond, (bf16*)(d.base + d.wpq), (bf16*)(d.base + d.wat), (bf16*)(d.base + d.watT),
         (bf16*)(d.base + d.wpqT), (float*)(d.base + d.bpq), (float*)(d.base + d.bat), D, params + pl.emb_atom,
         params + pl.emb_bond, (bf16*)(d.base + d.tab_atom), (bf16*)(d.base + d.tab_bond), n_atom, n_bond, cfg->act));
+    if (cfg->L >= 1 && tok1_enabled() && tc::tc_enabled() && tile::bond_tok_ok(D, cfg->bond_vocab)) {
+      // [P|Q] of every bond token through the SAME tcgen05 GEMM that transforms bond rows (bit-identical rows);
+      // prepare_weights_kernel is a normal launch, so it is complete before this GEMM's weight loads start
+      Epilogue ep;
+      ep.bias = (const float*)(d.base + d.bpq);
+      GCB_TRY(gemm_nt_auto<bf16>((const bf16*)(d.base + d.tab_bond), D, (const bf16*)(d.base + d.wpq), D, false,
+                                 (bf16*)(d.base + d.tab_pq), 2 * D, cfg->bond_vocab, 2 * D, D, ep, s));
+    }
   } else {
     GCB_KERNEL("prepare_weights_kernel", s, prepare_weights_kernel<float><<<blocks, 256, 0, s>>>(
         params + pl.w_msg, params + pl.b_msg, params + pl.w_edge, params + pl.b_edge, params + pl.w_bond,

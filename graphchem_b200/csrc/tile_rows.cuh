@@ -180,6 +180,91 @@ bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, cons
   }
 }
 
+// ---- first bond update straight from the token table (embedding lookup fused with the first message step) ----
+// In message step 1 the bond matrix is a row copy out of the pre-activated table, B_0[r] = tab_bond[tok r] (reference
+// gcn.py:156-157), so [P|Q]_1[r] = tabPQ[tok r] with tabPQ = tab_bond [U;V]^T + [b|0]: a [bond_vocab x 2D] table that
+// the step's tcgen05 GEMM produces once per weight refresh (gcb_prepare_weights).  The kernel stages the table
+// (<= 64 KB) and the tile's tokens instead of a [128 x 2D] tile of a [rows x 2D] matrix that then never exists:
+// B_0, the first [P|Q] GEMM and their 5 N D s bytes of HBM traffic disappear.  Same arithmetic, same rounding
+// points and the same tie bookkeeping as bond_update_kernel.
+template <int CH, bool TIES>
+__global__ void __launch_bounds__(kThreads, 3)
+bond_update_tok_kernel(TileCommon cm, const bf16* __restrict__ tabPQ, const int32_t* __restrict__ tok, int vocab,
+                       bf16* __restrict__ Bout, uint8_t* __restrict__ tiemask, uint8_t* __restrict__ tiecnt, int act) {
+  constexpr int kD = Cfg<CH>::D, kSlots = Cfg<CH>::kSlots, kPasses = Cfg<CH>::kPasses;
+  constexpr int kRowBytes = 2 * Cfg<CH>::kRowBytes;  // one table row: [P | Q]
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u;  // table [vocab][2 D] bf16
+  const uint32_t s_n4 = smem + vocab * kRowBytes, s_tok = s_n4 + kRows * 16, s_ptr = s_tok + kRows * 4;
+  const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
+  const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
+  pdl_launch_dependents();
+  // indices and tokens are immutable batch data; the table was written by the weight refresh at the end of the
+  // previous step (a normally launched kernel: complete and visible before this one starts)
+  for (int i = threadIdx.x; i <= kRows; i += kThreads) {
+    const int r = r0 + i;
+    if (i < kRows) {
+      int4 v = make_int4(-1, -1, -1, -1);
+      int t = 0;
+      if (r < r1) { v = __ldg(cm.nbr4 + r); t = __ldg(tok + r); }
+      gcb::tc::sts128(s_n4 + i * 16, make_uint4(v.x, v.y, v.z, v.w));
+      sts32(s_tok + i * 4, t);
+    }
+    sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);
+  }
+  pdl_wait();
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(tabPQ);
+    const int n16 = vocab * (kRowBytes / 16);
+    for (int i = threadIdx.x; i < n16; i += kThreads) gcb::tc::sts128(smem + i * 16, __ldg(src + i));
+  }
+  const int grp = threadIdx.x / CH, lig = threadIdx.x % CH, c = lig * 8;
+  __syncthreads();
+  auto qrow = [&](int nbr_row) -> uint32_t {  // shared address of this lane's Q chunk of a tile-local neighbour row
+    return smem + lds32(s_tok + ((nbr_row - r0) & 127) * 4) * kRowBytes + Cfg<CH>::kRowBytes + lig * 16;
+  };
+#pragma unroll 2
+  for (int ps = 0; ps < kPasses; ++ps) {
+    GCB_TILE_ROW(ps)
+    const uint4 praw = lds16(smem + lds32(s_tok + rr * 4) * kRowBytes + lig * 16);
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) q[u] = lds16(qrow(nidx[u]));
+    uint4 mraw = R::neg_inf();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nidx[u] >= 0) mraw = R::vmax(mraw, q[u]);
+    for (int e = e0 + 4; e < e1; ++e) mraw = R::vmax(mraw, lds16(qrow(__ldg(cm.nbr + e))));
+    if (TIES && e1 > e0) {
+      uint32_t cnt_lo = 0u, cnt_hi = 0u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (nidx[u] >= 0) tiemask[(size_t)(e0 + u) * CH + lig] = (uint8_t)tie_bits(q[u], mraw, cnt_lo, cnt_hi);
+      }
+      for (int e = e0 + 4; e < e1; ++e) {
+        const uint4 qe = lds16(qrow(__ldg(cm.nbr + e)));
+        tiemask[(size_t)e * CH + lig] = (uint8_t)tie_bits(qe, mraw, cnt_lo, cnt_hi);
+      }
+      *reinterpret_cast<uint2*>(tiecnt + (size_t)r * kD + c) = make_uint2(cnt_lo, cnt_hi);
+    }
+    float o[8];
+    if (e0 == e1) {
+      const float z = act_fwd_t<bf16>(0.f, act);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = z;
+    } else {
+      float p[8], mx[8];
+      R::to_float(praw, p);
+      R::to_float(mraw, mx);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = p[i] + mx[i];
+      act_fwd_vec<bf16, 8>(o, act);
+    }
+    store_vec(Bout + (size_t)r * kD + c, o);
+  }
+}
+
 // ---- atom aggregation: S[i] = [ sum_{e->i} A[src e] | sum_{e->i} Bnew[eid e] ]  (Bnew[e >= M] = act(0)) ----
 // staged: A rows of the tile (neighbours are tile-local); the bond rows are addressed by EDGE id and
 // live in other tiles, so they are gathered from global memory, issued before the shared-memory half.
@@ -491,6 +576,30 @@ inline int launch_bond_update(int D, const bf16* PQ, const TileCommon& cm, int n
                               uint8_t* tiecnt, int act, cudaStream_t s) {
   return D == 128 ? launch_bond_update_w<16>(PQ, cm, n_tiles, Bout, tiemask, tiecnt, act, s)
                   : launch_bond_update_w<32>(PQ, cm, n_tiles, Bout, tiemask, tiecnt, act, s);
+}
+
+// Shared memory of bond_update_tok_kernel; the caller falls back to GEMM + bond_update when the table does not fit.
+inline int bond_tok_smem(int D, int vocab) { return vocab * 4 * D + kRows * 16 + kRows * 4 + 544 + 128; }
+inline bool bond_tok_ok(int D, int vocab) { return width_ok(D) && bond_tok_smem(D, vocab) <= 72 * 1024; }
+
+template <int CH>
+inline int launch_bond_update_tok_w(const TileCommon& cm, int n_tiles, const bf16* tabPQ, const int32_t* tok, int vocab,
+                                    bf16* Bout, uint8_t* tiemask, uint8_t* tiecnt, int act, cudaStream_t s) {
+  const int smem = bond_tok_smem(Cfg<CH>::D, vocab);
+  static bool attr = false;
+  if (!attr) {
+    GCB_TRY(set_smem(bond_update_tok_kernel<CH, true>, 72 * 1024));
+    GCB_TRY(set_smem(bond_update_tok_kernel<CH, false>, 72 * 1024));
+    attr = true;
+  }
+  if (tiemask) GCB_KERNEL("tile_bond_update_tok_kernel", s, launch_pdl(bond_update_tok_kernel<CH, true>, n_tiles, kThreads, smem, s, cm, tabPQ, tok, vocab, Bout, tiemask, tiecnt, act));
+  else GCB_KERNEL("tile_bond_update_tok_kernel", s, launch_pdl(bond_update_tok_kernel<CH, false>, n_tiles, kThreads, smem, s, cm, tabPQ, tok, vocab, Bout, tiemask, tiecnt, act));
+  return GCB_OK;
+}
+inline int launch_bond_update_tok(int D, const TileCommon& cm, int n_tiles, const bf16* tabPQ, const int32_t* tok, int vocab,
+                                  bf16* Bout, uint8_t* tiemask, uint8_t* tiecnt, int act, cudaStream_t s) {
+  return D == 128 ? launch_bond_update_tok_w<16>(cm, n_tiles, tabPQ, tok, vocab, Bout, tiemask, tiecnt, act, s)
+                  : launch_bond_update_tok_w<32>(cm, n_tiles, tabPQ, tok, vocab, Bout, tiemask, tiecnt, act, s);
 }
 
 template <int CH>

@@ -26,7 +26,7 @@ def _dev(data):
                 batch=data.batch.cuda(), num_graphs=int(data.batch.max()) + 1)
 
 
-ENV = {"tile": {"GCB_NO_FUSED": "1"}, "tile_split": {"GCB_NO_BOND_MERGE": "1"},
+ENV = {"tile": {"GCB_NO_FUSED": "1", "GCB_NO_TOK1": "1"}, "tile_split": {"GCB_NO_BOND_MERGE": "1", "GCB_NO_TOK1": "1"}, "tok1": {},
        "fused_exact": {"GCB_FUSED": "1", "GCB_FUSED_EXACT": "1", "GCB_NO_FUSED_ATOM": "1"}, "fused": {"GCB_FUSED": "1"}, "v2": {"GCB_NO_TILE": "1"}}
 
 
@@ -70,6 +70,31 @@ def test_fused_equals_unfused_bitwise(n_graphs, max_atoms, L, D, act, mode):
         if train:
             for (name, _), a, b in zip(model.named_parameters(), grad_f, grad_u):
                 assert torch.equal(a, b), f"grad {name} differs: {nerr(a, b)}"
+
+
+@pytest.mark.parametrize("n_graphs,max_atoms,L,D", [(1, 12, 1, 128), (7, 12, 2, 128), (64, 30, 3, 128), (700, 40, 4, 128),
+                                                      (3000, 30, 1, 128), (300, 30, 2, 256)])
+@pytest.mark.parametrize("act", [F.softplus, F.relu])
+def test_first_step_from_the_token_table(n_graphs, max_atoms, L, D, act):
+    """Default path: message step 1 reads [P|Q] of every bond TOKEN (tile::bond_update_tok_kernel; the table comes out
+    of the same tcgen05 GEMM, so its rows are bit-identical to the [rows, 2D] matrix they replace) and the backward
+    pass sums [dP|dQ] per token before the small table products.  Forward: bit-identical to the tile kernels with the
+    table switched off.  Gradients: identical except the three tensors step 1's bond transform feeds, which round
+    differently (sum-then-transform) and must agree to a few bf16 ulps of the largest entry."""
+    data, _ = random_batch(seed=40 + n_graphs, n_graphs=n_graphs, max_atoms=max_atoms)
+    _, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=D, n_messages=L, act_fn=act)
+    dev = _dev(data)
+    for train in (False, True):
+        out_t, grad_t = _run(model, dev, train, "tok1")
+        out_u, grad_u = _run(model, dev, train, "tile")
+        for k, (a, b) in enumerate(zip(out_t, out_u)):
+            assert torch.equal(a, b), f"output {k} differs (train={train}): max diff {float((a.float() - b.float()).abs().max())}"
+        if train:
+            for (name, _), a, b in zip(model.named_parameters(), grad_t, grad_u):
+                if name in ("emb_bond.weight", "bond_conv.nn.0.weight", "bond_conv.nn.0.bias"):
+                    assert nerr(a, b) <= 2e-2, (name, nerr(a, b))
+                else:
+                    assert torch.equal(a, b), f"grad {name} differs: {nerr(a, b)}"
 
 
 @pytest.mark.parametrize("n_graphs,max_atoms,L", [(1, 12, 1), (7, 12, 2), (64, 30, 3), (700, 40, 4), (3000, 30, 4)])
@@ -124,8 +149,9 @@ def test_fused_kernels_are_launched_and_relu_ties_match():
         assert k in names, (k, names)
     for k in ("tile_bond_update_kernel", "tile_atom_gather_kernel", "tile_atom_bwd_kernel"):
         assert k not in names, (k, names)
-    names = kernels_of_a_step({})  # the default: tile kernels + stand-alone tcgen05 GEMMs
-    for k in ("tile_bond_update_kernel", "tile_atom_gather_kernel", "tile_atom_bwd_kernel", "tile_bond_bwd_kernel"):
+    names = kernels_of_a_step({})  # the default: tile kernels + stand-alone tcgen05 GEMMs, step 1 from the token table
+    for k in ("tile_bond_update_tok_kernel", "tile_bond_update_kernel", "tile_atom_gather_kernel", "tile_atom_bwd_kernel",
+              "tile_bond_bwd_kernel", "bond_table_bwd_kernel"):
         assert k in names, (k, names)
     for k in ('"bond_update_kernel"', '"atom_gather_kernel"', "atom_bwd_gather_kernel", "bond_bwd_scatter_kernel", "bond_bwd_tie_kernel"):
         assert k not in names, (k, names)
