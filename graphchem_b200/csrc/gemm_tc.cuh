@@ -10,6 +10,8 @@
 // one CTA per SM, static round-robin over row tiles.  The kernel is HBM-bound by design
 // (arithmetic intensity 50-100 flop/B); the tensor pipe only has to stay out of the way.
 #pragma once
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace gcb {
@@ -56,7 +58,7 @@ struct NtShape {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-template <int K, int N, bool RES>
+template <int K, int N, bool RES, bool COALQ = false>
 __global__ void __launch_bounds__(NtShape<K, N, RES>::THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmC, int rows, TcEpilogue ep) {
@@ -159,13 +161,13 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint4 res_raw[RES ? NCHUNK : 1][4];
     int rp_lo = 0, rp_hi = 0;  // row pointers of the NEXT tile's row: subtracted when used, a tile later
     const int res_col0 = half * COLS_PER_WARP;
-    // COAL (the forward atom transform, N = 128): the residual tile is fetched with COALESCED loads -- the group's
+    // COAL (opt-in, see the launcher; the forward atom transform, N = 128): the residual tile is fetched with COALESCED loads -- the group's
     // 256 threads walk its [128 rows x 128 B] slab 16 bytes per lane, a warp covering four full 128-byte row
     // segments -- one tile ahead into registers, parked in the group's (idle) staging slab in the swizzled layout,
     // and every thread then picks up its own row's 64 bytes from shared memory and overwrites them in place with the
     // result.  The thread = TMEM lane = row mapping made the direct loads a 256-byte-stride gather (32 lines per
     // instruction, half of every sector unused): 39 us instead of 25 us for the plain GEMM (profiles/r2_gemm_epilogue.jsonl).
-    constexpr bool COAL = RES && N == 128 && S::GROUP_THREADS == 256 && S::SLABS_PER_GROUP == 1;
+    constexpr bool COAL = COALQ && RES && N == 128 && S::GROUP_THREADS == 256 && S::SLABS_PER_GROUP == 1;
     const int gtid = ep_tid - group * S::GROUP_THREADS;  // thread index inside the store group
     auto coal_prefetch = [&](int tile_row0) {
       if constexpr (COAL) {
@@ -330,6 +332,21 @@ inline int launch_gemm_nt_tc_res(const bf16* A, int lda, const bf16* W, bf16* C,
                                        : (K == 256 && N == 128) ? (RES ? "gemm_nt_tc_k256n128_res" : "gemm_nt_tc_k256n128")
                                        : (K == 64 && N == 128) ? (RES ? "gemm_nt_tc_k64n128_res" : "gemm_nt_tc_k64n128")
                                                                 : (RES ? "gemm_nt_tc_k128n64_res" : "gemm_nt_tc_k128n64");
+  if constexpr (RES && N == 128 && K == 256) {
+    // A/B switch: GCB_RES_COAL=1 fetches the residual tile with coalesced loads through the staging slab.  Measured
+    // SLOWER on B200 (forward atom GEMM 48.7 vs 42.5 us, train step 1.689 vs 1.658 ms, profiles/r2_fused_ab.jsonl: the
+    // extra barrier and shared-memory round trip cost more than the 256-byte-stride loads), so it stays opt-in.
+    const char* e = std::getenv("GCB_RES_COAL");
+    if (e && e[0] == '1') {
+      static bool attr2 = false;
+      if (!attr2) {
+        GCB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<K, N, RES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+        attr2 = true;
+      }
+      GCB_KERNEL(kName, s, launch_pdl(gemm_nt_tc_kernel<K, N, RES, true>, grid, S::THREADS, S::SMEM_BYTES, s, tmA, tmW, tmC, rows, ep));
+      return GCB_OK;
+    }
+  }
   GCB_KERNEL(kName, s, launch_pdl(gemm_nt_tc_kernel<K, N, RES>, grid, S::THREADS, S::SMEM_BYTES, s, tmA, tmW, tmC, rows, ep));
   return GCB_OK;
 }

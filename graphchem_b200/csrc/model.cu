@@ -15,6 +15,7 @@
 #include "gemm_tc.cuh"
 #include "tile_rows.cuh"
 #include "fused_rows.cuh"
+#include "fused_cm.cuh"
 #include "kernels.cuh"
 #include "readout.cuh"
 #include "rowops.cuh"
@@ -49,7 +50,7 @@ void KernelTimer::stop() {
 }
 
 // ---- GEMM dispatch: tcgen05 kernel for bf16 hot shapes, CUDA-core kernel otherwise ---------------
-namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(int which); bool fused_exact(); bool tile_enabled(); bool bond_bwd_merged_enabled(); }
+namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(int which); bool fused_exact(); bool tile_enabled(); bool bond_bwd_merged_enabled(); bool fused_cm_enabled(); }
 template <typename T>
 static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                         const Epilogue& ep, cudaStream_t s) {
@@ -261,33 +262,49 @@ __global__ void finalize_conv_grads_kernel(const float* __restrict__ accWpq, con
 //   d emb_bond[t] = (tok[t] W_pq) * act'(tab_bond[t])   (what the dB GEMM + embedding backward produce row by row)
 // All sums run over t or n in index order: deterministic.
 template <typename T>
-__global__ void bond_table_bwd_kernel(const float* __restrict__ tok, const T* __restrict__ tab_bond,
-                                      const T* __restrict__ wpq, float* __restrict__ accWpq, float* __restrict__ accBpq,
-                                      float* __restrict__ g_emb_bond, int bv, int D, int act, int acc_first, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+bond_table_bwd_kernel(const float* __restrict__ tok, const T* __restrict__ tab_bond, const T* __restrict__ wpq,
+                      float* __restrict__ accWpq, float* __restrict__ accBpq, float* __restrict__ g_emb_bond, int bv, int D,
+                      int act, int acc_first, int accumulate, int nb1) {
   const int D2 = 2 * D;
-  if (idx < D2 * D) {
-    const int n = idx / D, k = idx % D;
-    float s = 0.f;
-#pragma unroll 16
-    for (int t = 0; t < bv; ++t) s = fmaf(__ldg(tok + (size_t)t * D2 + n), to_float(tab_bond[(size_t)t * D + k]), s);
-    accWpq[idx] = acc_first ? s : accWpq[idx] + s;
-  }
-  if (idx < D2) {
-    float s = 0.f;
-    if (idx < D) {
-#pragma unroll 16
-      for (int t = 0; t < bv; ++t) s += __ldg(tok + (size_t)t * D2 + idx);
+  if ((int)blockIdx.x < nb1) {
+    // dW_pq and db_pq: one output per thread, bv terms each (coalesced over k)
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < D2 * D) {
+      const int n = idx / D, k = idx % D;
+      float s = 0.f;
+#pragma unroll 8
+      for (int t = 0; t < bv; ++t) s = fmaf(__ldg(tok + (size_t)t * D2 + n), to_float(tab_bond[(size_t)t * D + k]), s);
+      accWpq[idx] = acc_first ? s : accWpq[idx] + s;
     }
-    accBpq[idx] = acc_first ? s : accBpq[idx] + s;
+    if (idx < D2) {
+      float s = 0.f;
+      if (idx < D) {
+#pragma unroll 8
+        for (int t = 0; t < bv; ++t) s += __ldg(tok + (size_t)t * D2 + idx);
+      }
+      accBpq[idx] = acc_first ? s : accBpq[idx] + s;
+    }
+    return;
   }
-  if (idx < bv * D) {
-    const int t = idx / D, k = idx % D;
-    float s = 0.f;
-#pragma unroll 16
-    for (int n = 0; n < D2; ++n) s = fmaf(__ldg(tok + (size_t)t * D2 + n), to_float(wpq[(size_t)n * D + k]), s);
-    s *= act_grad_t<T>(to_float(tab_bond[idx]), act);
-    g_emb_bond[idx] = accumulate ? g_emb_bond[idx] + s : s;
+  // d emb_bond: one CTA per (token, 32 output columns); the 2D terms of every output are split over 8 thread rows
+  // (32 consecutive n each) and combined in row order: a fixed summation tree
+  __shared__ float red[8][33];
+  const int b = blockIdx.x - nb1, kgroups = D / 32;
+  const int t = b / kgroups, k = (b % kgroups) * 32 + (threadIdx.x & 31), sub = threadIdx.x >> 5;
+  const int per = D2 / 8;
+  float s = 0.f;
+#pragma unroll 8
+  for (int n = sub * per; n < (sub + 1) * per; ++n) s = fmaf(__ldg(tok + (size_t)t * D2 + n), to_float(wpq[(size_t)n * D + k]), s);
+  red[sub][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (sub == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += red[j][threadIdx.x];
+    const int idx = t * D + k;
+    tot *= act_grad_t<T>(to_float(tab_bond[idx]), act);
+    g_emb_bond[idx] = accumulate ? g_emb_bond[idx] + tot : tot;
   }
 }
 
@@ -497,6 +514,16 @@ static bool tiles_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
          !((flags & GCB_TRAINING) && c.p_dropout > 0.f);
 }
 
+// Channel-major fused bond update (fused_cm.cuh): bf16, D = 128, closed row tiles, every atom row a live bond row, no
+// active dropout.  It keeps P and Q in fp32 (never rounded to bf16), so it agrees with the tile kernels to a few bf16
+// ulps, not bit for bit; GCB_NO_FUSED_CM=1 switches it off.
+template <typename T>
+static bool cm_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
+  if constexpr (sizeof(T) != 2) return false;
+  return tc::fused_cm_enabled() && tc::tc_enabled() && c.D == 128 && tiles_ok<T>(c, g, flags) && tc::bond_bwd_merged_enabled() &&
+         !fused_ok<T>(c, g, flags, 0);
+}
+
 // Message step 1 straight from the bond-token table (tile::bond_update_tok_kernel and, in the backward pass, the
 // per-token sums of [dP|dQ]): the tile preconditions plus a table that fits shared memory.  GCB_NO_TOK1=1 switches
 // it off (A/B switch; the bit-for-bit comparisons with the plain row kernels use it, because summing [dP|dQ] per
@@ -565,6 +592,21 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
         GCB_TRY(tile::launch_bond_update_tok(D, cm, g.n_tiles, (const bf16*)(dv.base + dv.tab_pq), g.e_tok, c.bond_vocab,
                                              (bf16*)p.B[l], save ? p.tiemask[l] : nullptr, save ? p.tiecnt[l] : nullptr, c.act, s));
         bond_done = true;
+      }
+    }
+    if constexpr (sizeof(T) == 2) {
+      if (M > 0 && !bond_done && cm_ok<T>(c, g, flags)) {
+        const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
+        cm::Args ca;
+        ca.tile_ptr = g.tile_ptr; ca.n_tiles = g.n_tiles; ca.rows = M; ca.act = c.act;
+        ca.ptr = g.in_ptr; ca.nbr = g.in_src; ca.nbr4 = (const int4*)g.in_src4;
+        ca.bias = bpq; ca.out = (bf16*)p.B[l];
+        ca.tiemask = save ? reinterpret_cast<uint32_t*>(p.tiemask[l]) : nullptr;
+        ca.tiecnt = save ? p.tiecnt[l] : nullptr;
+        const int rc = save ? cm::launch_bond_fwd<true>((const bf16*)p.B[l - 1], (const bf16*)wpq, ca, s)
+                            : cm::launch_bond_fwd<false>((const bf16*)p.B[l - 1], (const bf16*)wpq, ca, s);
+        if (rc == GCB_OK) bond_done = true;
+        else if (rc != GCB_ERR_UNSUPPORTED) return rc;
       }
     }
     if (M > 0 && !bond_done) {
@@ -895,10 +937,10 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       if constexpr (sizeof(T) == 2) {
         GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dPQ2[1], nullptr, g.btok_ptr, g.btok_row, p.partial, bv, 2 * D, c.act, s));
         GCB_TRY(launch_reduce_partials(p.partial, kEmbedSplits, (int64_t)bv * 2 * D, p.tokPQ, 0, s));
-        const int most = 2 * D * D > bv * D ? 2 * D * D : bv * D;
-        GCB_KERNEL("bond_table_bwd_kernel", s, bond_table_bwd_kernel<T><<<(unsigned)ceil_div(most, 256), 256, 0, s>>>(
+        const int nb1 = (int)ceil_div(2 * D * D, 256);
+        GCB_KERNEL("bond_table_bwd_kernel", s, bond_table_bwd_kernel<T><<<(unsigned)(nb1 + bv * (D / 32)), 256, 0, s>>>(
             p.tokPQ, (const T*)(dv.base + dv.tab_bond), (const T*)(dv.base + dv.wpq), p.accWpq, p.accBpq, grad + pl.emb_bond, bv, D,
-            c.act, L == 1, accumulate));
+            c.act, L == 1, accumulate, nb1));
       }
     } else {
       const T* dB0 = L >= 1 ? dBnext : d_out_bond;

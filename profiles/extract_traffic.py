@@ -1,4 +1,4 @@
-"""ncu --set full report(s) -> profiles/r1_traffic.json (names as bench.py / gcb_timing_report use them): per kernel class the average DRAM traffic
+"""ncu --set full report(s) -> profiles/rN_traffic.json (names as bench.py / gcb_timing_report use them): per kernel class the average DRAM traffic
 (dram__bytes_read.sum + dram__bytes_write.sum) and duration per launch.
 usage: python profiles/extract_traffic.py out.json rep1.ncu-rep|raw1.csv [...]"""
 import csv
@@ -23,6 +23,15 @@ for rep in sys.argv[2:]:
         name = full.split("<")[0].split("(")[0].replace("void ", "").split("::")[-1].strip()
         if "TileCommon" in full:  # gcb::tile kernels are timed under a tile_ prefix (bench.py / gcb_timing_report)
             name = "tile_" + name
+        elif name in ("gemm_nt_tc_kernel", "gemm_tn_tc_kernel"):  # one timing name per template instance
+            import re
+            m = re.search(r"<\(?(?:int\))?\s*(\d+),\s*(?:\(int\))?\s*(\d+)(?:,\s*(?:\(bool\))?\s*(\w+))?", full)
+            a, b, res = m.group(1), m.group(2), m.group(3)
+            name = (f"gemm_nt_tc_k{a}n{b}" + ("_res" if res in ("1", "true") else "")) if name.startswith("gemm_nt") else f"gemm_tn_tc_n{a}k{b}"
+        elif name == "readout2_fwd_kernel":
+            name = "readout_fwd_kernel"
+        elif name == "readout2_bwd_kernel":
+            name = "readout_bwd_kernel"
         elif name == "fused_rows_tc_kernel":
             name = "fused_bond_fwd_kernel" if "<0" in full else "fused_atom_bwd_kernel"
         b = float(r[ri]) * UNIT[units[ri]] + float(r[wi]) * UNIT[units[wi]]

@@ -1,5 +1,6 @@
-"""Profiling driver: N un-graphed train steps of the bench workload (batch 8192, D=128, L=4, bf16)
-so that ncu sees one kernel launch per line.  88 launches per step in round 1 (v1 kernels)."""
+"""Profiling driver: N un-graphed train steps of the bench workload (batch 8192, D=128, L=4, bf16) so that ncu
+sees one kernel launch per line; the LAST step runs between cudaProfilerStart / Stop, so
+`ncu --profile-from-start off ...` captures exactly one warm step."""
 import os
 import sys
 
@@ -7,7 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from bench import CFG
+from bench import CFGS
+
+CFG = CFGS["train"]
 from graphchem_b200.nn import MoleculeGCN
 from graphchem_b200.synthetic import make_molecules
 from graphchem_b200.train import TrainStep
@@ -22,6 +25,10 @@ store = make_molecules(2 * B, seed=1234)
 batches = [store.collate_pack(np.arange(i * B, (i + 1) * B), CFG["L"], 64, 32).to(dev) for i in range(2)]
 step = TrainStep(model, use_cuda_graph=False)
 for i in range(steps):
+    if i == steps - 1:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     loss = step(batches[i % 2])
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("loss", float(loss))
