@@ -106,12 +106,42 @@ template <> struct Raw<bf16> {
     return make_uint4(max2(a.x, b.x), max2(a.y, b.y), max2(a.z, b.z), max2(a.w, b.w));
   }
 };
+// acc_lo += bf16 low half of w, acc_hi += bf16 high half: Blackwell's mixed-precision add (PTX add.f32.bf16, SASS
+// FHADD.BF16 with an .H1 operand selector) takes the packed halves as they are -- ONE instruction per element
+// instead of unpack (shift / mask) + FADD, and the same fp32 result bit for bit (fp32(bf16) + fp32, round to nearest).
+__device__ __forceinline__ void add_bf16x2(float& lo, float& hi, uint32_t w) {
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tadd.f32.bf16 %0, l, %0;\n\tadd.f32.bf16 %1, h, %1;\n\t}"
+      : "+f"(lo), "+f"(hi)
+      : "r"(w));
+}
+__device__ __forceinline__ void add_bf16_lo(float& acc, uint32_t w) {
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tadd.f32.bf16 %0, l, %0;\n\t}" : "+f"(acc) : "r"(w));
+}
+__device__ __forceinline__ void add_bf16_hi(float& acc, uint32_t w) {
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tadd.f32.bf16 %0, h, %0;\n\t}" : "+f"(acc) : "r"(w));
+}
+// acc[i] += channel i of the bf16 chunk r where bit i of `bits` is set (the amax backward routes a gradient only
+// to the in-edges that attained the maximum): a predicate per bit and a predicated mixed-precision add
+__device__ __forceinline__ void raw_add_masked(const uint4& r, uint32_t bits, float (&acc)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (bits & (1u << (2 * i))) add_bf16_lo(acc[2 * i], w[i]);
+    if (bits & (2u << (2 * i))) add_bf16_hi(acc[2 * i + 1], w[i]);
+  }
+}
 template <typename T, int V>
 __device__ __forceinline__ void raw_add(const uint4& r, float (&acc)[V]) {
-  float v[V];
-  Raw<T>::to_float(r, v);
+  if constexpr (sizeof(T) == 2) {
+    static_assert(sizeof(T) != 2 || V == 8, "bf16 chunks hold eight channels");
+    add_bf16x2(acc[0], acc[1], r.x); add_bf16x2(acc[2], acc[3], r.y);
+    add_bf16x2(acc[4], acc[5], r.z); add_bf16x2(acc[6], acc[7], r.w);
+  } else {
+    float v[V];
+    Raw<T>::to_float(r, v);
 #pragma unroll
-  for (int i = 0; i < V; ++i) acc[i] += v[i];
+    for (int i = 0; i < V; ++i) acc[i] += v[i];
+  }
 }
 template <typename T, int V>
 __device__ __forceinline__ void raw_fma(float w, const uint4& r, float (&acc)[V]) {

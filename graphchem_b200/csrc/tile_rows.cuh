@@ -30,7 +30,8 @@ namespace tile {
 
 constexpr int kRows = GCB_TILE_ROWS;              // 128
 constexpr int kThreads = 256;
-constexpr int kIdxBytes = 2 * kRows * 16 + 544;   // two ELL-4 arrays + 129 row pointers (padded)
+constexpr int kIdxBytes = 2 * kRows * 16 + 544 + 1024;   // two ELL-4 arrays + 129 row pointers (padded) + pad row
+constexpr int kPadBytes = 1024;                          // >= the widest staged row ([P|Q] at D = 256 is staged Q-only: 512 B)
 
 // CH = 16-byte chunks (= lanes) per row: 16 for D = 128, 32 for D = 256.
 template <int CH>
@@ -65,13 +66,21 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
 
 // Tile prologue: [r0, r1) of this CTA's tile; one thread issues the TMA boxes (ISSUE, BOX_BYTES in
 // total, 0 = none) while all threads stage the indices; ends with everything visible.
-#define GCB_TILE_PROLOGUE(BOX_BYTES, ISSUE)                                                         \
+//
+// Branch-free neighbours: the ELL-4 view is staged as BYTE OFFSETS of the neighbours' staged rows
+// ((nbr - r0) * STRIDE), and a missing slot (-1) points at a PAD ROW behind the index arrays that holds the
+// identity of the reduction (PADWORD: -inf for max, 0 for sums).  The row loops then load and reduce all four
+// slots unconditionally -- the `if (nidx[u] >= 0)` tests cost a quarter of the instructions of these
+// issue-bound kernels (BSSY / BSYNC / BRA / ISETP per slot).
+#define GCB_TILE_PROLOGUE(BOX_BYTES, ISSUE, STRIDE, PADWORD)                                        \
   constexpr int kD = Cfg<CH>::D, kSlots = Cfg<CH>::kSlots, kPasses = Cfg<CH>::kPasses;              \
   constexpr int kRowBytes = Cfg<CH>::kRowBytes, kBoxBytes = Cfg<CH>::kBoxBytes;                     \
   (void)kD; (void)kSlots; (void)kPasses; (void)kRowBytes; (void)kBoxBytes;                          \
   extern __shared__ uint8_t smem_raw[];                                                             \
   const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u; /* 32-bit shared address */   \
   const uint32_t s_n4 = smem + (BOX_BYTES), s_a4 = s_n4 + kRows * 16, s_ptr = s_a4 + kRows * 16;    \
+  const uint32_t s_pad = s_ptr + 544; /* one staged row of PADWORD (kPadBytes) */                   \
+  constexpr uint32_t kPadOff = (uint32_t)(BOX_BYTES) + kRows * 32 + 544;                            \
   __shared__ uint64_t bar;                                                                          \
   const int r0 = __ldg(cm.tile_ptr + blockIdx.x);                                                   \
   const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);                                 \
@@ -83,6 +92,8 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
     gcb::tc::mbar_arrive_expect_tx(&bar, (BOX_BYTES));                                              \
     ISSUE;                                                                                          \
   }                                                                                                 \
+  for (int i = threadIdx.x; i < kPadBytes / 16; i += kThreads)                                      \
+    gcb::tc::sts128(s_pad + i * 16, make_uint4((PADWORD), (PADWORD), (PADWORD), (PADWORD)));        \
   for (int i = threadIdx.x; i <= kRows; i += kThreads) {                                            \
     const int r = r0 + i;                                                                           \
     if (i < kRows) {                                                                                \
@@ -91,7 +102,11 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
         v = __ldg(cm.nbr4 + r);                                                                     \
         if (cm.aux4) w = __ldg(cm.aux4 + r);                                                        \
       }                                                                                             \
-      gcb::tc::sts128(s_n4 + i * 16, make_uint4(v.x, v.y, v.z, v.w));                               \
+      const uint32_t o0 = v.x >= 0 ? (uint32_t)(v.x - r0) * (STRIDE) : kPadOff;                      \
+      const uint32_t o1 = v.y >= 0 ? (uint32_t)(v.y - r0) * (STRIDE) : kPadOff;                      \
+      const uint32_t o2 = v.z >= 0 ? (uint32_t)(v.z - r0) * (STRIDE) : kPadOff;                      \
+      const uint32_t o3 = v.w >= 0 ? (uint32_t)(v.w - r0) * (STRIDE) : kPadOff;                      \
+      gcb::tc::sts128(s_n4 + i * 16, make_uint4(o0, o1, o2, o3));                                   \
       gcb::tc::sts128(s_a4 + i * 16, make_uint4(w.x, w.y, w.z, w.w));                               \
     }                                                                                               \
     sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);                                          \
@@ -102,12 +117,13 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
   __syncthreads(); /* indices staged, barrier initialised */                                        \
   if ((BOX_BYTES) > 0) gcb::tc::mbar_wait(&bar, 0);
 
+// noff[u]: byte offset (from `smem`) of the staged row of ELL slot u, or of the pad row
 #define GCB_TILE_ROW(PS)                                                                            \
   const int rr = (PS) * kSlots + grp;                                                               \
   const int r = r0 + rr;                                                                            \
   if (r >= r1) continue;                                                                            \
   const uint4 n4_ = lds16(s_n4 + rr * 16);                                                          \
-  const int nidx[4] = {(int)n4_.x, (int)n4_.y, (int)n4_.z, (int)n4_.w};                             \
+  const uint32_t noff[4] = {n4_.x, n4_.y, n4_.z, n4_.w};                                            \
   const int e0 = lds32(s_ptr + rr * 4), e1 = lds32(s_ptr + rr * 4 + 4);
 
 // Tie bookkeeping of the max aggregation on packed words.  q, m: 8 bf16 channels (channel 2i = low
@@ -135,27 +151,27 @@ bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, cons
                    bf16* __restrict__ Bout, uint8_t* __restrict__ tiemask, uint8_t* __restrict__ tiecnt, int act) {
   constexpr int kQRow = QONLY ? Cfg<CH>::kRowBytes : 2 * Cfg<CH>::kRowBytes;  // bytes per staged row
   constexpr int kQOff = QONLY ? 0 : Cfg<CH>::kRowBytes;                        // offset of the Q half inside a staged row
-  GCB_TILE_PROLOGUE((QONLY ? 1 : 2) * Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmPQ, &bar, QONLY ? Cfg<CH>::D : 0, r0))
+  GCB_TILE_PROLOGUE((QONLY ? 1 : 2) * Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmPQ, &bar, QONLY ? Cfg<CH>::D : 0, r0),
+                    kQRow, 0xFF80FF80u)
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
     const uint4 praw = QONLY ? R::load(PQ + (size_t)r * (2 * kD) + c) : lds16(smem + rr * kQRow + lig * 16);
     uint4 q[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) q[u] = lds16(smem + ((nidx[u] - r0) & 127) * kQRow + kQOff + lig * 16);
-    uint4 mraw = R::neg_inf();
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) mraw = R::vmax(mraw, q[u]);
+    for (int u = 0; u < 4; ++u) q[u] = lds16(smem + noff[u] + kQOff + lig * 16);  // pad row: -inf
+    uint4 mraw = R::vmax(R::vmax(q[0], q[1]), R::vmax(q[2], q[3]));
     for (int e = e0 + 4; e < e1; ++e)
       mraw = R::vmax(mraw, lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kQRow + kQOff + lig * 16));
     if (TIES && e1 > e0) {
       // per in-edge: which of the 8 channels attain the max (one byte); per channel: how many edges tie
+      // (a pad slot is -inf and never equals the max of a row that has an in-edge)
       uint32_t cnt_lo = 0u, cnt_hi = 0u;  // four byte counters each: channels 0-3 / 4-7
+      const int deg = e1 - e0;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (nidx[u] >= 0) tiemask[(size_t)(e0 + u) * CH + lig] = (uint8_t)tie_bits(q[u], mraw, cnt_lo, cnt_hi);
+        const uint32_t b = tie_bits(q[u], mraw, cnt_lo, cnt_hi);
+        if (u < deg) tiemask[(size_t)(e0 + u) * CH + lig] = (uint8_t)b;
       }
       for (int e = e0 + 4; e < e1; ++e) {
         const uint4 qe = lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kQRow + kQOff + lig * 16);
@@ -195,20 +211,25 @@ bond_update_tok_kernel(TileCommon cm, const bf16* __restrict__ tabPQ, const int3
   constexpr int kRowBytes = 2 * Cfg<CH>::kRowBytes;  // one table row: [P | Q]
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u;  // table [vocab][2 D] bf16
-  const uint32_t s_n4 = smem + vocab * kRowBytes, s_tok = s_n4 + kRows * 16, s_ptr = s_tok + kRows * 4;
+  // table rows [0, vocab) + one pad row of -inf (what a missing ELL slot reads), then per row: the byte offsets of its
+  // four neighbours' TABLE rows (token looked up once, here), its own table-row offset, its CSR range
+  const uint32_t s_n4 = smem + (vocab + 1) * kRowBytes, s_tok = s_n4 + kRows * 16, s_ptr = s_tok + kRows * 4;
+  const uint32_t pad_off = (uint32_t)vocab * kRowBytes;
   const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
   const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
   pdl_launch_dependents();
   // indices and tokens are immutable batch data; the table was written by the weight refresh at the end of the
-  // previous step (a normally launched kernel: complete and visible before this one starts)
+  // previous step (complete and visible before this kernel's pdl_wait returns)
   for (int i = threadIdx.x; i <= kRows; i += kThreads) {
     const int r = r0 + i;
     if (i < kRows) {
       int4 v = make_int4(-1, -1, -1, -1);
       int t = 0;
       if (r < r1) { v = __ldg(cm.nbr4 + r); t = __ldg(tok + r); }
-      gcb::tc::sts128(s_n4 + i * 16, make_uint4(v.x, v.y, v.z, v.w));
-      sts32(s_tok + i * 4, t);
+      const uint32_t o0 = v.x >= 0 ? (uint32_t)__ldg(tok + v.x) * kRowBytes : pad_off, o1 = v.y >= 0 ? (uint32_t)__ldg(tok + v.y) * kRowBytes : pad_off;
+      const uint32_t o2 = v.z >= 0 ? (uint32_t)__ldg(tok + v.z) * kRowBytes : pad_off, o3 = v.w >= 0 ? (uint32_t)__ldg(tok + v.w) * kRowBytes : pad_off;
+      gcb::tc::sts128(s_n4 + i * 16, make_uint4(o0, o1, o2, o3));
+      sts32(s_tok + i * 4, t * kRowBytes);
     }
     sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);
   }
@@ -217,33 +238,34 @@ bond_update_tok_kernel(TileCommon cm, const bf16* __restrict__ tabPQ, const int3
     const uint4* src = reinterpret_cast<const uint4*>(tabPQ);
     const int n16 = vocab * (kRowBytes / 16);
     for (int i = threadIdx.x; i < n16; i += kThreads) gcb::tc::sts128(smem + i * 16, __ldg(src + i));
+    for (int i = threadIdx.x; i < kRowBytes / 16; i += kThreads)
+      gcb::tc::sts128(smem + pad_off + i * 16, make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u));
   }
   const int grp = threadIdx.x / CH, lig = threadIdx.x % CH, c = lig * 8;
   __syncthreads();
-  auto qrow = [&](int nbr_row) -> uint32_t {  // shared address of this lane's Q chunk of a tile-local neighbour row
-    return smem + lds32(s_tok + ((nbr_row - r0) & 127) * 4) * kRowBytes + Cfg<CH>::kRowBytes + lig * 16;
+  constexpr int kQOff = Cfg<CH>::kRowBytes;
+  auto qtail = [&](int nbr_row) -> uint32_t {  // CSR tail (more than four in-edges): token of a tile-local neighbour row
+    return smem + (uint32_t)__ldg(tok + nbr_row) * kRowBytes + kQOff + lig * 16;
   };
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
-    const uint4 praw = lds16(smem + lds32(s_tok + rr * 4) * kRowBytes + lig * 16);
+    const uint4 praw = lds16(smem + lds32(s_tok + rr * 4) + lig * 16);
     uint4 q[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) q[u] = lds16(qrow(nidx[u]));
-    uint4 mraw = R::neg_inf();
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) mraw = R::vmax(mraw, q[u]);
-    for (int e = e0 + 4; e < e1; ++e) mraw = R::vmax(mraw, lds16(qrow(__ldg(cm.nbr + e))));
+    for (int u = 0; u < 4; ++u) q[u] = lds16(smem + noff[u] + kQOff + lig * 16);
+    uint4 mraw = R::vmax(R::vmax(q[0], q[1]), R::vmax(q[2], q[3]));
+    for (int e = e0 + 4; e < e1; ++e) mraw = R::vmax(mraw, lds16(qtail(__ldg(cm.nbr + e))));
     if (TIES && e1 > e0) {
       uint32_t cnt_lo = 0u, cnt_hi = 0u;
+      const int deg = e1 - e0;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (nidx[u] >= 0) tiemask[(size_t)(e0 + u) * CH + lig] = (uint8_t)tie_bits(q[u], mraw, cnt_lo, cnt_hi);
+        const uint32_t bm = tie_bits(q[u], mraw, cnt_lo, cnt_hi);
+        if (u < deg) tiemask[(size_t)(e0 + u) * CH + lig] = (uint8_t)bm;
       }
       for (int e = e0 + 4; e < e1; ++e) {
-        const uint4 qe = lds16(qrow(__ldg(cm.nbr + e)));
+        const uint4 qe = lds16(qtail(__ldg(cm.nbr + e)));
         tiemask[(size_t)e * CH + lig] = (uint8_t)tie_bits(qe, mraw, cnt_lo, cnt_hi);
       }
       *reinterpret_cast<uint2*>(tiecnt + (size_t)r * kD + c) = make_uint2(cnt_lo, cnt_hi);
@@ -272,44 +294,48 @@ template <int CH>
 __global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 atom_gather_kernel(const __grid_constant__ CUtensorMap tmA, TileCommon cm, const bf16* __restrict__ Bnew, int M,
                    bf16* __restrict__ S, int act) {
-  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmA, &bar, 0, r0))
+  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmA, &bar, 0, r0), kRowBytes, 0u)
   const float cst = round_to(act_fwd_t<bf16>(0.f, act), (const bf16*)nullptr);
+  // act(0) as a packed bf16 pair: what a dead bond row (edge id >= M) contributes to every channel
+  const uint32_t cst2 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(cst)) * 0x00010001u;
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
     const uint4 e4_ = lds16(s_a4 + rr * 16);
     const int eidx[4] = {(int)e4_.x, (int)e4_.y, (int)e4_.z, (int)e4_.w};
+    // bond rows by EDGE id live in other tiles: global gathers, issued first.  Branch-free: a missing slot (-1) or
+    // a dead row (>= M) reads row 0 and is replaced by 0 / act(0) afterwards (same values, same order of addition)
     uint4 b[4], a[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (eidx[u] >= 0 && eidx[u] < M) b[u] = R::load(Bnew + (size_t)eidx[u] * kD + c);
+    for (int u = 0; u < 4; ++u) {
+      const bool live = (unsigned)eidx[u] < (unsigned)M;
+      b[u] = R::load(Bnew + (size_t)(live ? eidx[u] : 0) * kD + c);
+    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) a[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
+    for (int u = 0; u < 4; ++u) a[u] = lds16(smem + noff[u] + lig * 16);  // pad row: zeros
     float sa[8], sb[8];
     v2::vzero<bf16, 8>(sa);
     v2::vzero<bf16, 8>(sb);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) v2::raw_add<bf16, 8>(a[u], sa);
+    for (int u = 0; u < 4; ++u) v2::raw_add<bf16, 8>(a[u], sa);
     for (int e = e0 + 4; e < e1; ++e)
       v2::raw_add<bf16, 8>(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16), sa);
     store_vec(S + (size_t)r * (2 * kD) + c, sa);
-    auto add_const = [&]() {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sb[i] += cst;
-    };
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (eidx[u] >= 0) {
-        if (eidx[u] < M) v2::raw_add<bf16, 8>(b[u], sb);
-        else add_const();
-      }
+      const bool live = (unsigned)eidx[u] < (unsigned)M;
+      const uint32_t fill = eidx[u] < 0 ? 0u : cst2;
+      uint4 t = b[u];
+      t.x = live ? t.x : fill; t.y = live ? t.y : fill; t.z = live ? t.z : fill; t.w = live ? t.w : fill;
+      v2::raw_add<bf16, 8>(t, sb);
     }
     for (int e = e0 + 4; e < e1; ++e) {
       const int eid = __ldg(cm.aux + e);
       if (eid < M) v2::raw_add<bf16, 8>(R::load(Bnew + (size_t)eid * kD + c), sb);
-      else add_const();
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sb[i] += cst;
+      }
     }
     store_vec(S + (size_t)r * (2 * kD) + kD + c, sb);
   }
@@ -321,7 +347,7 @@ template <int CH>
 __global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 atom_bwd_kernel(const __grid_constant__ CUtensorMap tmdS, TileCommon cm, const bf16* __restrict__ dZA,
                 const bf16* __restrict__ A_prev, bf16* __restrict__ dZA_prev, int act) {
-  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmdS, &bar, 0, r0))
+  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmdS, &bar, 0, r0), kRowBytes, 0u)
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
@@ -329,16 +355,14 @@ atom_bwd_kernel(const __grid_constant__ CUtensorMap tmdS, TileCommon cm, const b
     const uint4 yraw = R::load(A_prev + (size_t)r * kD + c);
     uint4 g[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) g[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
+    for (int u = 0; u < 4; ++u) g[u] = lds16(smem + noff[u] + lig * 16);  // pad row: zeros
     float d[8], y[8];
     R::to_float(draw, d);
     R::to_float(yraw, y);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) v2::raw_add<bf16, 8>(g[u], d);
+    for (int u = 0; u < 4; ++u) v2::raw_add<bf16, 8>(g[u], d);
     for (int e = e0 + 4; e < e1; ++e)
-      v2::raw_fma<bf16, 8>(1.f, lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16), d);
+      v2::raw_add<bf16, 8>(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16), d);
     act_grad_mul_vec<bf16, 8>(d, y, act);
     store_vec(dZA_prev + (size_t)r * kD + c, d);
   }
@@ -350,7 +374,7 @@ template <int CH>
 __global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 bond_scatter_kernel(const __grid_constant__ CUtensorMap tmG, TileCommon cm, const uint8_t* __restrict__ tiemask,
                     bf16* __restrict__ dPQ) {
-  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmG, &bar, 0, r0))
+  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmG, &bar, 0, r0), kRowBytes, 0u)
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
@@ -360,25 +384,16 @@ bond_scatter_kernel(const __grid_constant__ CUtensorMap tmG, TileCommon cm, cons
     uint32_t bits[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (nidx[u] >= 0) {
-        bits[u] = __ldg(tiemask + (size_t)oidx[u] * CH + lig);
-        g[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
-      }
+      bits[u] = __ldg(tiemask + (size_t)max(oidx[u], 0) * CH + lig);  // a missing slot reads the zero pad row: its bits do not matter
+      g[u] = lds16(smem + noff[u] + lig * 16);
     }
     float acc[8];
     v2::vzero<bf16, 8>(acc);
-    auto consume = [&](const uint4& gr, uint32_t b) {
-      float gf[8];
-      R::to_float(gr, gf);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += ((b >> i) & 1u) ? gf[i] : 0.f;
-    };
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) consume(g[u], bits[u]);
+    for (int u = 0; u < 4; ++u) v2::raw_add_masked(g[u], bits[u], acc);
     for (int e = e0 + 4; e < e1; ++e)
-      consume(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16),
-              __ldg(tiemask + (size_t)__ldg(cm.aux + e) * CH + lig));
+      v2::raw_add_masked(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16),
+                         __ldg(tiemask + (size_t)__ldg(cm.aux + e) * CH + lig), acc);
     store_vec(dPQ + (size_t)r * (2 * kD) + kD + c, acc);
   }
 }
@@ -408,6 +423,9 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   const uint32_t s_dst = s_ptr + 544;  // [128] destination atom of bond row r, or -1 when r has no in-edge
   const uint32_t s_inv = s_dst + kRows * 4;  // [256] 1 / tie count (1 for counts 0 and 1), the factor of the even tie split
   const uint32_t s_ie = s_inv + 256 * 4;     // [129] dst-CSR row pointers of the tile's rows (tie bits of a row's in-edges)
+  const uint32_t s_pad = s_ie + 544;         // one zero row: what a missing ELL slot gathers
+  const uint32_t kPadOff = s_pad - smem;
+  for (int i = threadIdx.x; i < kRowBytes / 16; i += kThreads) gcb::tc::sts128(s_pad + i * 16, make_uint4(0u, 0u, 0u, 0u));
   const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
   const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
   pdl_launch_dependents();
@@ -423,7 +441,10 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
         w = __ldg(cm.aux4 + r);
         if (__ldg(in_ptr + r + 1) > __ldg(in_ptr + r)) t = __ldg(dst + r);
       }
-      gcb::tc::sts128(s_n4 + i * 16, make_uint4(v.x, v.y, v.z, v.w));
+      // neighbours as byte offsets of their split-gradient rows; a missing slot points at the zero pad row
+      const uint32_t o0 = v.x >= 0 ? (uint32_t)(v.x - r0) * kRowBytes : kPadOff, o1 = v.y >= 0 ? (uint32_t)(v.y - r0) * kRowBytes : kPadOff;
+      const uint32_t o2 = v.z >= 0 ? (uint32_t)(v.z - r0) * kRowBytes : kPadOff, o3 = v.w >= 0 ? (uint32_t)(v.w - r0) * kRowBytes : kPadOff;
+      gcb::tc::sts128(s_n4 + i * 16, make_uint4(o0, o1, o2, o3));
       gcb::tc::sts128(s_a4 + i * 16, make_uint4(w.x, w.y, w.z, w.w));
       sts32(s_dst + i * 4, t);
     }
@@ -501,32 +522,28 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   // ---- phase 2 ----
 #pragma unroll 2
   for (int ps = 0; ps < kPasses; ++ps) {
-    GCB_TILE_ROW(ps)
+    const int rr = ps * kSlots + grp;
+    const int r = r0 + rr;
+    if (r >= r1) continue;
+    const uint4 n4_ = lds16(s_n4 + rr * 16);
+    const uint32_t noff[4] = {n4_.x, n4_.y, n4_.z, n4_.w};
+    const int e0 = lds32(s_ptr + rr * 4), e1 = lds32(s_ptr + rr * 4 + 4);
     const uint4 o4_ = lds16(s_a4 + rr * 16);
     const int oidx[4] = {(int)o4_.x, (int)o4_.y, (int)o4_.z, (int)o4_.w};
     uint4 gq[4];
     uint32_t bits[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (nidx[u] >= 0) {
-        bits[u] = __ldg(tiemask + (size_t)oidx[u] * CH + lig);
-        gq[u] = lds16(smem + ((nidx[u] - r0) & 127) * kRowBytes + lig * 16);
-      }
+      bits[u] = __ldg(tiemask + (size_t)max(oidx[u], 0) * CH + lig);  // a missing slot gathers the zero pad row
+      gq[u] = lds16(smem + noff[u] + lig * 16);
     }
     float acc[8];
     v2::vzero<bf16, 8>(acc);
-    auto consume = [&](const uint4& gr, uint32_t b) {
-      float gf[8];
-      R::to_float(gr, gf);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += ((b >> i) & 1u) ? gf[i] : 0.f;
-    };
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (nidx[u] >= 0) consume(gq[u], bits[u]);
+    for (int u = 0; u < 4; ++u) v2::raw_add_masked(gq[u], bits[u], acc);
     for (int e = e0 + 4; e < e1; ++e)
-      consume(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16),
-              __ldg(tiemask + (size_t)__ldg(cm.aux + e) * CH + lig));
+      v2::raw_add_masked(lds16(smem + ((__ldg(cm.nbr + e) - r0) & 127) * kRowBytes + lig * 16),
+                         __ldg(tiemask + (size_t)__ldg(cm.aux + e) * CH + lig), acc);
     store_vec(dPQ + (size_t)r * (2 * kD) + kD + c, acc);
   }
 }
@@ -579,7 +596,7 @@ inline int launch_bond_update(int D, const bf16* PQ, const TileCommon& cm, int n
 }
 
 // Shared memory of bond_update_tok_kernel; the caller falls back to GEMM + bond_update when the table does not fit.
-inline int bond_tok_smem(int D, int vocab) { return vocab * 4 * D + kRows * 16 + kRows * 4 + 544 + 128; }
+inline int bond_tok_smem(int D, int vocab) { return (vocab + 1) * 4 * D + kRows * 16 + kRows * 4 + 544 + 128; }
 inline bool bond_tok_ok(int D, int vocab) { return width_ok(D) && bond_tok_smem(D, vocab) <= 72 * 1024; }
 
 template <int CH>
@@ -660,7 +677,7 @@ template <int CH>
 inline int launch_bond_bwd_w(const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
                              const bf16* dBnext, const bf16* d_out_bond, const bf16* B_l, const uint8_t* tiecnt,
                              const uint8_t* tiemask, bf16* dPQ, int act, int ds_plane_rows, cudaStream_t s) {
-  const int smem = smem_for<CH>(1) + kRows * 4 + 256 * 4 + 544;
+  const int smem = smem_for<CH>(1) + kRows * 4 + 256 * 4 + 544 + Cfg<CH>::kRowBytes;
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel<CH>, smem)); attr = true; }
   GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
