@@ -203,8 +203,8 @@ bond_update_kernel(const __grid_constant__ CUtensorMap tmPQ, TileCommon cm, cons
 // (<= 64 KB) and the tile's tokens instead of a [128 x 2D] tile of a [rows x 2D] matrix that then never exists:
 // B_0, the first [P|Q] GEMM and their 5 N D s bytes of HBM traffic disappear.  Same arithmetic, same rounding
 // points and the same tie bookkeeping as bond_update_kernel.
-template <int CH, bool TIES>
-__global__ void __launch_bounds__(kThreads, 3)
+template <int CH, bool TIES, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 bond_update_tok_kernel(TileCommon cm, const bf16* __restrict__ tabPQ, const int32_t* __restrict__ tok, int vocab,
                        bf16* __restrict__ Bout, uint8_t* __restrict__ tiemask, uint8_t* __restrict__ tiecnt, int act) {
   constexpr int kD = Cfg<CH>::D, kSlots = Cfg<CH>::kSlots, kPasses = Cfg<CH>::kPasses;
@@ -290,7 +290,7 @@ bond_update_tok_kernel(TileCommon cm, const bf16* __restrict__ tabPQ, const int3
 // ---- atom aggregation: S[i] = [ sum_{e->i} A[src e] | sum_{e->i} Bnew[eid e] ]  (Bnew[e >= M] = act(0)) ----
 // staged: A rows of the tile (neighbours are tile-local); the bond rows are addressed by EDGE id and
 // live in other tiles, so they are gathered from global memory, issued before the shared-memory half.
-template <int CH>
+template <int CH, int UN>
 __global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 atom_gather_kernel(const __grid_constant__ CUtensorMap tmA, TileCommon cm, const bf16* __restrict__ Bnew, int M,
                    bf16* __restrict__ S, int act) {
@@ -298,7 +298,7 @@ atom_gather_kernel(const __grid_constant__ CUtensorMap tmA, TileCommon cm, const
   const float cst = round_to(act_fwd_t<bf16>(0.f, act), (const bf16*)nullptr);
   // act(0) as a packed bf16 pair: what a dead bond row (edge id >= M) contributes to every channel
   const uint32_t cst2 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(cst)) * 0x00010001u;
-#pragma unroll 2
+#pragma unroll (UN)
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
     const uint4 e4_ = lds16(s_a4 + rr * 16);
@@ -343,12 +343,12 @@ atom_gather_kernel(const __grid_constant__ CUtensorMap tmA, TileCommon cm, const
 
 // ---- atom backward: dZA_prev[j] = (dZA[j] + sum_{e: src e = j} dS[dst e, :D]) * act'(A_prev[j]) ----
 // staged: dS[:, :D] rows of the tile (neighbours); the row's own dZA / A_prev chunks stream from global.
-template <int CH>
+template <int CH, int UN>
 __global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 atom_bwd_kernel(const __grid_constant__ CUtensorMap tmdS, TileCommon cm, const bf16* __restrict__ dZA,
                 const bf16* __restrict__ A_prev, bf16* __restrict__ dZA_prev, int act) {
   GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmdS, &bar, 0, r0), kRowBytes, 0u)
-#pragma unroll 2
+#pragma unroll (UN)
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
     const uint4 draw = R::load(dZA + (size_t)r * kD + c);
@@ -406,7 +406,7 @@ bond_scatter_kernel(const __grid_constant__ CUtensorMap tmG, TileCommon cm, cons
 //       dPQ[j, D:] = sum_{e: src e = j} tie(e) * g[dst e]          (dst e is tile-local)
 // The split gradient never goes to HBM.  `dst` is the edge list's destination array: bond row r is
 // EDGE r, and it collects the gradient of the atom it points to (gcn.py:163 quirk).
-template <int CH>
+template <int CH, int UN>
 __global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ dst,
                 const bf16* __restrict__ dS, const bf16* __restrict__ dBnext, const bf16* __restrict__ d_out_bond,
@@ -455,7 +455,7 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   pdl_wait();
   __syncthreads();
   // ---- phase 1 ----
-#pragma unroll 2
+#pragma unroll (UN)
   for (int ps = 0; ps < kPasses; ++ps) {
     const int rr = ps * kSlots + grp;
     const int r = r0 + rr;
@@ -520,7 +520,7 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   }
   __syncthreads();
   // ---- phase 2 ----
-#pragma unroll 2
+#pragma unroll (UN)
   for (int ps = 0; ps < kPasses; ++ps) {
     const int rr = ps * kSlots + grp;
     const int r = r0 + rr;
@@ -550,6 +550,11 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
 
 // ---- launchers (D = 128 -> CH 16, D = 256 -> CH 32) ------------------------------------------------
 inline bool width_ok(int D) { return D == 128 || D == 256; }
+// A/B switch (GCB_TILE_UNROLL=4): passes unrolled four deep in the latency-bound kernels (twice the loads in flight per thread)
+inline int tile_unroll() {
+  const char* e = std::getenv("GCB_TILE_UNROLL");
+  return (e && e[0] == '4') ? 4 : 2;
+}
 
 template <int CH>
 inline int smem_for(int boxes) { return boxes * Cfg<CH>::kBoxBytes + kIdxBytes + 128; }
@@ -605,12 +610,12 @@ inline int launch_bond_update_tok_w(const TileCommon& cm, int n_tiles, const bf1
   const int smem = bond_tok_smem(Cfg<CH>::D, vocab);
   static bool attr = false;
   if (!attr) {
-    GCB_TRY(set_smem(bond_update_tok_kernel<CH, true>, 72 * 1024));
-    GCB_TRY(set_smem(bond_update_tok_kernel<CH, false>, 72 * 1024));
+    GCB_TRY(set_smem(bond_update_tok_kernel<CH, true, 4>, 72 * 1024)); GCB_TRY(set_smem(bond_update_tok_kernel<CH, false, 4>, 72 * 1024));
     attr = true;
   }
-  if (tiemask) GCB_KERNEL("tile_bond_update_tok_kernel", s, launch_pdl(bond_update_tok_kernel<CH, true>, n_tiles, kThreads, smem, s, cm, tabPQ, tok, vocab, Bout, tiemask, tiecnt, act));
-  else GCB_KERNEL("tile_bond_update_tok_kernel", s, launch_pdl(bond_update_tok_kernel<CH, false>, n_tiles, kThreads, smem, s, cm, tabPQ, tok, vocab, Bout, tiemask, tiecnt, act));
+  // four resident CTAs (<= 64 registers): 42.5 vs 46.5 us with three (profiles/r2_fused_ab.jsonl)
+  if (tiemask) GCB_KERNEL("tile_bond_update_tok_kernel", s, launch_pdl(bond_update_tok_kernel<CH, true, 4>, n_tiles, kThreads, smem, s, cm, tabPQ, tok, vocab, Bout, tiemask, tiecnt, act));
+  else GCB_KERNEL("tile_bond_update_tok_kernel", s, launch_pdl(bond_update_tok_kernel<CH, false, 4>, n_tiles, kThreads, smem, s, cm, tabPQ, tok, vocab, Bout, tiemask, tiecnt, act));
   return GCB_OK;
 }
 inline int launch_bond_update_tok(int D, const TileCommon& cm, int n_tiles, const bf16* tabPQ, const int32_t* tok, int vocab,
@@ -627,8 +632,9 @@ inline int launch_atom_gather_w(const bf16* A, const bf16* Bnew, int M, const Ti
   if (gcb::tc::make_tmap_bf16_plain(&tm, A, cm.rows, D, D, kRows, D)) return GCB_ERR_CUDA;
   const int smem = smem_for<CH>(1);
   static bool attr = false;
-  if (!attr) { GCB_TRY(set_smem(atom_gather_kernel<CH>, smem)); attr = true; }
-  GCB_KERNEL("tile_atom_gather_kernel", s, launch_pdl(atom_gather_kernel<CH>, n_tiles, kThreads, smem, s, tm, cm, Bnew, M, S, act));
+  if (!attr) { GCB_TRY(set_smem(atom_gather_kernel<CH, 2>, smem)); GCB_TRY(set_smem(atom_gather_kernel<CH, 4>, smem)); attr = true; }
+  if (tile_unroll() == 4) GCB_KERNEL("tile_atom_gather_kernel", s, launch_pdl(atom_gather_kernel<CH, 4>, n_tiles, kThreads, smem, s, tm, cm, Bnew, M, S, act));
+  else GCB_KERNEL("tile_atom_gather_kernel", s, launch_pdl(atom_gather_kernel<CH, 2>, n_tiles, kThreads, smem, s, tm, cm, Bnew, M, S, act));
   return GCB_OK;
 }
 inline int launch_atom_gather(int D, const bf16* A, const bf16* Bnew, int M, const TileCommon& cm, int n_tiles, bf16* S, int act,
@@ -645,8 +651,9 @@ inline int launch_atom_bwd_w(const bf16* dS, const bf16* dZA, const bf16* A_prev
   if (gcb::tc::make_tmap_bf16_plain(&tmS, dS, cm.rows, D, 2 * D, kRows, D)) return GCB_ERR_CUDA;
   const int smem = smem_for<CH>(1);
   static bool attr = false;
-  if (!attr) { GCB_TRY(set_smem(atom_bwd_kernel<CH>, smem)); attr = true; }
-  GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, dZA_prev, act));
+  if (!attr) { GCB_TRY(set_smem(atom_bwd_kernel<CH, 2>, smem)); GCB_TRY(set_smem(atom_bwd_kernel<CH, 4>, smem)); attr = true; }
+  if (tile_unroll() == 4) GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 4>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, dZA_prev, act));
+  else GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 2>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, dZA_prev, act));
   return GCB_OK;
 }
 inline int launch_atom_bwd(int D, const bf16* dS, const bf16* dZA, const bf16* A_prev, const TileCommon& cm, int n_tiles,
@@ -679,9 +686,11 @@ inline int launch_bond_bwd_w(const TileCommon& cm, int n_tiles, const int32_t* i
                              const uint8_t* tiemask, bf16* dPQ, int act, int ds_plane_rows, cudaStream_t s) {
   const int smem = smem_for<CH>(1) + kRows * 4 + 256 * 4 + 544 + Cfg<CH>::kRowBytes;
   static bool attr = false;
-  if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel<CH>, smem)); attr = true; }
-  GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
-                                                     tiecnt, tiemask, dPQ, act, ds_plane_rows));
+  if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel<CH, 2>, smem)); GCB_TRY(set_smem(bond_bwd_kernel<CH, 4>, smem)); attr = true; }
+  if (tile_unroll() == 4) GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH, 4>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
+                                                                        tiecnt, tiemask, dPQ, act, ds_plane_rows));
+  else GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH, 2>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
+                                                          tiecnt, tiemask, dPQ, act, ds_plane_rows));
   return GCB_OK;
 }
 inline int launch_bond_bwd(int D, const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
