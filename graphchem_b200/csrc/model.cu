@@ -919,26 +919,40 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   }
   if (grid_at > 0) GCB_TRY(launch_reduce_partials(p.partialAt, grid_at, (int64_t)2 * D * D + D, p.accWat, 0, sw, (int64_t)2 * D * D + D));
   if (grid_pq > 0) GCB_TRY(launch_reduce_partials(p.partialPq, grid_pq, (int64_t)2 * D * D + 2 * D, p.accWpq, 0, sw, (int64_t)2 * D * D + 2 * D));
-  if (overlap && L >= 1) {  // everything on the side stream must be done before its results are used
-    cudaEvent_t last = nullptr;
-    GCB_TRY(mark(last));
-    GCB_TRY(join(last));
-  }
   // ---- embeddings ----
+  // The two embedding gradients are independent, low-occupancy bucket walks: the bond one runs on the internal stream
+  // behind the last weight-gradient GEMM (it needs the summed conv accumulators anyway), the atom one on the caller's
+  // stream, each with its own partial-sum scratch; the streams meet again in front of finalize_conv_grads_kernel.
   {
-    const int av = c.atom_vocab, bv = c.bond_vocab, CH = D / V;
-    if (N > 0) {
-      GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dZA[cur], nullptr, g.atok_ptr, g.atok_node, p.partial, av, D, c.act, s));
+    const int av = c.atom_vocab, bv = c.bond_vocab;
+    const int64_t scratch_cap = (int64_t)tc::kTnMaxCtas * (2 * D * D + 2 * D);
+    const bool split = overlap && L >= 1 && grid_at == 0 && grid_pq == 0 && (int64_t)kEmbedSplits * av * D <= scratch_cap &&
+                       (int64_t)kEmbedSplits * bv * 2 * D <= scratch_cap;
+    cudaStream_t se = split ? sw : s;             // stream of the bond half
+    float* part_a = split ? p.partialAt : p.partial;
+    float* part_b = split ? p.partialPq : p.partial;
+    if (split) {  // the bond half reads what the caller's stream produced last ([dP|dQ]_1 or dB_0)
+      cudaEvent_t e = ss->event(evi++);
+      if (!e) return GCB_ERR_CUDA;
+      GCB_CUDA(cudaEventRecord(e, s));
+      GCB_CUDA(cudaStreamWaitEvent(sw, e, 0));
+    } else if (overlap && L >= 1) {  // everything on the side stream must be done before its results are used
+      cudaEvent_t last = nullptr;
+      GCB_TRY(mark(last));
+      GCB_TRY(join(last));
     }
-    GCB_TRY(launch_reduce_partials(p.partial, N > 0 ? kEmbedSplits : 0, (int64_t)av * D, grad + pl.emb_atom, accumulate, s));
+    if (N > 0) {
+      GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dZA[cur], nullptr, g.atok_ptr, g.atok_node, part_a, av, D, c.act, s));
+    }
+    GCB_TRY(launch_reduce_partials(part_a, N > 0 ? kEmbedSplits : 0, (int64_t)av * D, grad + pl.emb_atom, accumulate, s));
     if (tok1 && M > 0) {
       // per-token sums of step 1's [dP|dQ] (buckets in row order, ordered split reduction), then the three small
       // products of bond_table_bwd_kernel
       if constexpr (sizeof(T) == 2) {
-        GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dPQ2[1], nullptr, g.btok_ptr, g.btok_row, p.partial, bv, 2 * D, c.act, s));
-        GCB_TRY(launch_reduce_partials(p.partial, kEmbedSplits, (int64_t)bv * 2 * D, p.tokPQ, 0, s));
+        GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dPQ2[1], nullptr, g.btok_ptr, g.btok_row, part_b, bv, 2 * D, c.act, se));
+        GCB_TRY(launch_reduce_partials(part_b, kEmbedSplits, (int64_t)bv * 2 * D, p.tokPQ, 0, se));
         const int nb1 = (int)ceil_div(2 * D * D, 256);
-        GCB_KERNEL("bond_table_bwd_kernel", s, bond_table_bwd_kernel<T><<<(unsigned)(nb1 + bv * (D / 32)), 256, 0, s>>>(
+        GCB_KERNEL("bond_table_bwd_kernel", se, bond_table_bwd_kernel<T><<<(unsigned)(nb1 + bv * (D / 32)), 256, 0, se>>>(
             p.tokPQ, (const T*)(dv.base + dv.tab_bond), (const T*)(dv.base + dv.wpq), p.accWpq, p.accBpq, grad + pl.emb_bond, bv, D,
             c.act, L == 1, accumulate, nb1));
       }
@@ -946,9 +960,14 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       const T* dB0 = L >= 1 ? dBnext : d_out_bond;
       const bool have = dB0 != nullptr && M > 0;
       if (have) {
-        GCB_TRY(launch_embed_bwd_partial<T>(dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, p.partial, bv, D, c.act, s));
+        GCB_TRY(launch_embed_bwd_partial<T>(dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, part_b, bv, D, c.act, se));
       }
-      GCB_TRY(launch_reduce_partials(p.partial, have ? kEmbedSplits : 0, (int64_t)bv * D, grad + pl.emb_bond, accumulate, s));
+      GCB_TRY(launch_reduce_partials(part_b, have ? kEmbedSplits : 0, (int64_t)bv * D, grad + pl.emb_bond, accumulate, se));
+    }
+    if (split) {
+      cudaEvent_t last = nullptr;
+      GCB_TRY(mark(last));
+      GCB_TRY(join(last));
     }
   }
   // ---- conv parameters ----

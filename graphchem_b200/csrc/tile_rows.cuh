@@ -31,6 +31,7 @@ namespace tile {
 constexpr int kRows = GCB_TILE_ROWS;              // 128
 constexpr int kThreads = 256;
 constexpr int kIdxBytes = 2 * kRows * 16 + 544 + 1024;   // two ELL-4 arrays + 129 row pointers (padded) + pad row
+constexpr int kTieEdges = 640;                           // in-edges of a tile whose tie bits bond_bwd stages (5 per row)
 constexpr int kPadBytes = 1024;                          // >= the widest staged row ([P|Q] at D = 256 is staged Q-only: 512 B)
 
 // CH = 16-byte chunks (= lanes) per row: 16 for D = 128, 32 for D = 256.
@@ -60,6 +61,11 @@ __device__ __forceinline__ uint4 lds16(uint32_t saddr) { return gcb::tc::lds128(
 __device__ __forceinline__ int lds32(uint32_t saddr) {
   int v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
   return v;
 }
 __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
@@ -424,11 +430,22 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   const uint32_t s_inv = s_dst + kRows * 4;  // [256] 1 / tie count (1 for counts 0 and 1), the factor of the even tie split
   const uint32_t s_ie = s_inv + 256 * 4;     // [129] dst-CSR row pointers of the tile's rows (tie bits of a row's in-edges)
   const uint32_t s_pad = s_ie + 544;         // one zero row: what a missing ELL slot gathers
+  const uint32_t s_tm = s_pad + kRowBytes;   // tie bits of the tile's in-edges (CH bytes per edge, at most kTieEdges edges)
   const uint32_t kPadOff = s_pad - smem;
   for (int i = threadIdx.x; i < kRowBytes / 16; i += kThreads) gcb::tc::sts128(s_pad + i * 16, make_uint4(0u, 0u, 0u, 0u));
   const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
   const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
   pdl_launch_dependents();
+  // The out-edges of a closed tile's rows are in-edges of rows of the SAME tile, and those are contiguous in the
+  // dst-sorted CSR: [ie_lo, ie_hi).  Their tie bits (written by the forward pass) are staged with coalesced loads, so
+  // phase 2 reads them from shared memory instead of four dependent one-byte global loads per row chunk.
+  const int ie_lo = __ldg(in_ptr + r0), ie_hi = __ldg(in_ptr + max(r1, r0));
+  const bool tm_staged = ie_hi - ie_lo <= kTieEdges;
+  if (tm_staged) {
+    const uint4* src = reinterpret_cast<const uint4*>(tiemask + (size_t)ie_lo * CH);
+    const int n16 = (ie_hi - ie_lo) * (CH / 16);
+    for (int i = threadIdx.x; i < n16; i += kThreads) gcb::tc::sts128(s_tm + i * 16, __ldg(src + i));
+  }
   // x / cnt of the tie split as x * (1 / cnt): the same MUFU reciprocal __fdividef() uses, looked up instead of recomputed
   for (int i = threadIdx.x; i < 256; i += kThreads) sts32(s_inv + i * 4, __float_as_int(i <= 1 ? 1.f : __fdividef(1.f, (float)i)));
   for (int i = threadIdx.x; i <= kRows; i += kThreads) {
@@ -534,7 +551,9 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
     uint32_t bits[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      bits[u] = __ldg(tiemask + (size_t)max(oidx[u], 0) * CH + lig);  // a missing slot gathers the zero pad row
+      // a missing slot (-1) gathers the zero pad row: whatever bits it reads do not matter
+      if (tm_staged) bits[u] = lds8(s_tm + (uint32_t)max(oidx[u] - ie_lo, 0) * CH + lig);
+      else bits[u] = __ldg(tiemask + (size_t)max(oidx[u], 0) * CH + lig);
       gq[u] = lds16(smem + noff[u] + lig * 16);
     }
     float acc[8];
@@ -684,7 +703,7 @@ template <int CH>
 inline int launch_bond_bwd_w(const TileCommon& cm, int n_tiles, const int32_t* in_ptr, const int32_t* dst, const bf16* dS,
                              const bf16* dBnext, const bf16* d_out_bond, const bf16* B_l, const uint8_t* tiecnt,
                              const uint8_t* tiemask, bf16* dPQ, int act, int ds_plane_rows, cudaStream_t s) {
-  const int smem = smem_for<CH>(1) + kRows * 4 + 256 * 4 + 544 + Cfg<CH>::kRowBytes;
+  const int smem = smem_for<CH>(1) + kRows * 4 + 256 * 4 + 544 + Cfg<CH>::kRowBytes + kTieEdges * CH;
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel<CH, 2>, smem)); GCB_TRY(set_smem(bond_bwd_kernel<CH, 4>, smem)); attr = true; }
   if (tile_unroll() == 4) GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH, 4>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
