@@ -588,7 +588,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
     if constexpr (sizeof(T) == 2) {
       if (M > 0 && !bond_done && l == 1 && tok1) {
         const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
-        const tile::TileCommon cm{g.tile_ptr, M, g.in_ptr, g.in_src, (const int4*)g.in_src4, nullptr, nullptr};
+        const tile::TileCommon cm{g.tile_ptr, M, g.in_ptr, g.in_src, (const int4*)g.in_src4, nullptr, nullptr, flip()};
         GCB_TRY(tile::launch_bond_update_tok(D, cm, g.n_tiles, (const bf16*)(dv.base + dv.tab_pq), g.e_tok, c.bond_vocab,
                                              (bf16*)p.B[l], save ? p.tiemask[l] : nullptr, save ? p.tiecnt[l] : nullptr, c.act, s));
         bond_done = true;
@@ -617,7 +617,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       if constexpr (sizeof(T) == 2) {
         if (tiles_ok<T>(c, g, flags)) {
           const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
-          const tile::TileCommon cm{g.tile_ptr, M, g.in_ptr, g.in_src, (const int4*)g.in_src4, nullptr, nullptr};
+          const tile::TileCommon cm{g.tile_ptr, M, g.in_ptr, g.in_src, (const int4*)g.in_src4, nullptr, nullptr, flip()};
           GCB_TRY(tile::launch_bond_update(D, (const bf16*)p.PQ[l], cm, g.n_tiles, (bf16*)p.B[l], save ? p.tiemask[l] : nullptr,
                                            save ? p.tiecnt[l] : nullptr, c.act, s));
           tiled = true;
@@ -647,7 +647,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       bool a_tiled = false;
       if constexpr (sizeof(T) == 2) {
         if (c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags)) {
-          const tile::TileCommon cm{g.tile_ptr, N, g.in_ptr, g.in_src, (const int4*)g.in_src4, (const int4*)g.in_eid4, g.in_eid};
+          const tile::TileCommon cm{g.tile_ptr, N, g.in_ptr, g.in_src, (const int4*)g.in_src4, (const int4*)g.in_eid4, g.in_eid, flip()};
           GCB_TRY(tile::launch_atom_gather(D, (const bf16*)p.A[l - 1], (const bf16*)p.B[l], M, cm, g.n_tiles, (bf16*)p.S[l], c.act, s));
           a_tiled = true;
         }
@@ -859,7 +859,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       bool tiled = false;
       if constexpr (sizeof(T) == 2) {
         if (N > 0 && c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags)) {
-          const tile::TileCommon cm{g.tile_ptr, N, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, nullptr, nullptr};
+          const tile::TileCommon cm{g.tile_ptr, N, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, nullptr, nullptr, flip()};
           GCB_TRY(tile::launch_atom_bwd(D, (const bf16*)p.dS, (const bf16*)p.dZA[cur], (const bf16*)p.A[l - 1], cm, g.n_tiles,
                                         (bf16*)p.dZA[cur ^ 1], c.act, s));
           tiled = true;
@@ -875,7 +875,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     bool bond_tiled = false;
     if constexpr (sizeof(T) == 2) {
       if (M > 0 && c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags) && tc::bond_bwd_merged_enabled()) {
-        const tile::TileCommon cm{g.tile_ptr, M, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, (const int4*)g.out_inpos4, g.out_inpos};
+        const tile::TileCommon cm{g.tile_ptr, M, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, (const int4*)g.out_inpos4, g.out_inpos, flip()};
         GCB_TRY(tile::launch_bond_bwd(D, cm, g.n_tiles, g.in_ptr, g.dst, (const bf16*)p.dS, (const bf16*)dBnext,
                                       l == L ? (const bf16*)d_out_bond : nullptr, (const bf16*)p.B[l],
                                       fused_ok<T>(c, g, flags, 0) ? nullptr : p.tiecnt[l], p.tiemask[l],
@@ -891,7 +891,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       bool tiled = false;
       if constexpr (sizeof(T) == 2) {
         if (tiles_ok<T>(c, g, flags)) {
-          const tile::TileCommon cm{g.tile_ptr, M, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, (const int4*)g.out_inpos4, g.out_inpos};
+          const tile::TileCommon cm{g.tile_ptr, M, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, (const int4*)g.out_inpos4, g.out_inpos, flip()};
           GCB_TRY(tile::launch_bond_scatter(D, (const bf16*)p.gsplit, cm, g.n_tiles, p.tiemask[l], (bf16*)dPQ_l, s));
           tiled = true;
         }

@@ -55,7 +55,14 @@ struct TileCommon {
   const int4* nbr4;         // ELL-4 view of nbr
   const int4* aux4;         // second ELL-4 view walked with the same CSR (edge ids / dst-CSR positions) or null
   const int32_t* aux;       // CSR form of aux4 (rows with more than four entries) or null
+  int rev = 0;              // walk the tiles last-to-first: start on the rows the producer kernel wrote last (L2 resident)
 };
+
+// Tile of this CTA.  CTAs are dispatched in blockIdx order, so `rev` makes the kernel's first wave read the END of
+// its operand -- which is what the previous kernel of the chain (walking the other way) produced last.
+__device__ __forceinline__ int tile_of_cta(const TileCommon& cm) {
+  return cm.rev ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+}
 
 __device__ __forceinline__ uint4 lds16(uint32_t saddr) { return gcb::tc::lds128(saddr); }
 __device__ __forceinline__ int lds32(uint32_t saddr) {
@@ -88,8 +95,9 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
   const uint32_t s_pad = s_ptr + 544; /* one staged row of PADWORD (kPadBytes) */                   \
   constexpr uint32_t kPadOff = (uint32_t)(BOX_BYTES) + kRows * 32 + 544;                            \
   __shared__ uint64_t bar;                                                                          \
-  const int r0 = __ldg(cm.tile_ptr + blockIdx.x);                                                   \
-  const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);                                 \
+  const int tb_ = tile_of_cta(cm);                                                                  \
+  const int r0 = __ldg(cm.tile_ptr + tb_);                                                          \
+  const int r1 = min(__ldg(cm.tile_ptr + tb_ + 1), cm.rows);                                        \
   pdl_launch_dependents();                                                                          \
   if ((BOX_BYTES) > 0 && threadIdx.x == 0) {                                                        \
     gcb::tc::mbar_init(&bar, 1);                                                                    \
@@ -221,8 +229,9 @@ bond_update_tok_kernel(TileCommon cm, const bf16* __restrict__ tabPQ, const int3
   // four neighbours' TABLE rows (token looked up once, here), its own table-row offset, its CSR range
   const uint32_t s_n4 = smem + (vocab + 1) * kRowBytes, s_tok = s_n4 + kRows * 16, s_ptr = s_tok + kRows * 4;
   const uint32_t pad_off = (uint32_t)vocab * kRowBytes;
-  const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
-  const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
+  const int tb_ = tile_of_cta(cm);
+  const int r0 = __ldg(cm.tile_ptr + tb_);
+  const int r1 = min(__ldg(cm.tile_ptr + tb_ + 1), cm.rows);
   pdl_launch_dependents();
   // indices and tokens are immutable batch data; the table was written by the weight refresh at the end of the
   // previous step (complete and visible before this kernel's pdl_wait returns)
@@ -433,8 +442,9 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   const uint32_t s_tm = s_pad + kRowBytes;   // tie bits of the tile's in-edges (CH bytes per edge, at most kTieEdges edges)
   const uint32_t kPadOff = s_pad - smem;
   for (int i = threadIdx.x; i < kRowBytes / 16; i += kThreads) gcb::tc::sts128(s_pad + i * 16, make_uint4(0u, 0u, 0u, 0u));
-  const int r0 = __ldg(cm.tile_ptr + blockIdx.x);
-  const int r1 = min(__ldg(cm.tile_ptr + blockIdx.x + 1), cm.rows);
+  const int tb_ = tile_of_cta(cm);
+  const int r0 = __ldg(cm.tile_ptr + tb_);
+  const int r1 = min(__ldg(cm.tile_ptr + tb_ + 1), cm.rows);
   pdl_launch_dependents();
   // The out-edges of a closed tile's rows are in-edges of rows of the SAME tile, and those are contiguous in the
   // dst-sorted CSR: [ie_lo, ie_hi).  Their tie bits (written by the forward pass) are staged with coalesced loads, so

@@ -4,6 +4,11 @@ Replaces `torch.optim.Adam(model.parameters(), lr=1e-3)` + `optimizer.step()` of
 (reference examples/predict_cn.ipynb:230-232, 251).  `param_groups[0]["lr"]` stays mutable, as the
 per-epoch rewrite of predict_cn.ipynb:241-242 requires; `torch.optim.Adam` itself also keeps
 working on `model.parameters()` (the parameters are ordinary nn.Parameters).
+
+Differences from `torch.optim.Adam`, by design of the flat update: a parameter whose `.grad` is None is treated as
+having a zero gradient (its moments still decay and move it), where torch skips it; the moments live in three flat
+buffers (`exp_avg`, `exp_avg_sq`, `step_count`) that `state_dict()` / `load_state_dict()` carry under the key
+"fused" next to the usual `param_groups`, so a checkpoint / resume keeps them.
 """
 from __future__ import annotations
 
@@ -44,6 +49,28 @@ class FusedAdam(torch.optim.Optimizer):
         if contiguous and grads[0]._base is not None and grads[0]._base.numel() >= off and grads[0]._base.data_ptr() == base:
             return grads[0]._base
         return torch.cat([g.reshape(-1).float() for g in grads])
+
+    def state_dict(self):
+        sd = super().state_dict()
+        if self._state_ready:
+            sd["fused"] = {"exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                           "step_count": int(self.step_count.item())}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        fused = state_dict.pop("fused", None)
+        super().load_state_dict(state_dict)
+        if fused is None:
+            self._state_ready = False  # a checkpoint taken before the first step: moments start from zero again
+            return
+        flat = self.model.flat_parameters()
+        if fused["exp_avg"].numel() != flat.numel():
+            raise ValueError(f"optimizer state holds {fused['exp_avg'].numel()} elements, the model has {flat.numel()}")
+        self._init_state(flat)
+        self.exp_avg.copy_(fused["exp_avg"].to(flat.device))
+        self.exp_avg_sq.copy_(fused["exp_avg_sq"].to(flat.device))
+        self.step_count.fill_(int(fused["step_count"]))
 
     @torch.no_grad()
     def step(self, closure=None):
