@@ -21,6 +21,7 @@ struct Epilogue {
   int aggr = GCB_AGGR_ADD;
   const void* res = nullptr;  // same dtype as C, leading dimension ld_res
   int ld_res = 0;
+  const int32_t* res_idx = nullptr;  // when set: row r adds res[res_idx[r]] (a lookup table: the pre-activated embedding rows)
   int act = -1;
   const void* actgrad_y = nullptr;  // same dtype as C, leading dimension ld_y
   int ld_y = 0;
@@ -169,7 +170,7 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
         v = v * f * act_grad_t<T>(y, ep.act);
       } else {
         if (ep.bias) v = fmaf(wrow, ep.bias[n], v);
-        if (res) v += to_float(res[(size_t)r * ep.ld_res + n]);
+        if (res) v += to_float(res[(size_t)(ep.res_idx ? ep.res_idx[r] : r) * ep.ld_res + n]);
         if (ep.act >= 0) v = act_fwd_t<T>(v, ep.act);
       }
       C[(size_t)r * ldc + n] = from_float<T>(v);

@@ -23,6 +23,7 @@ struct TcEpilogue {
   int aggr = GCB_AGGR_ADD;
   const bf16* res = nullptr;        // residual [rows, ld_res] or null
   int ld_res = 0;
+  const int32_t* res_idx = nullptr; // when set: row r adds res[res_idx[r]] (a lookup table, e.g. the pre-activated embedding rows)
   int act = -1;                     // enum gcb_act or -1
   int rev = 0;                      // walk the row tiles last-to-first (L2 reuse of a just-written operand)
 };
@@ -175,7 +176,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int k = 0; k < 4; ++k) {
           const int qd = gtid + 256 * k, rr = qd >> 3, cc = qd & 7;  // 16-byte chunk cc of slab row rr
           const int gr = tile_row0 + rr;
-          res_raw[0][k] = gr < rows ? __ldg(reinterpret_cast<const uint4*>(ep.res + (size_t)gr * ep.ld_res + group * 64 + cc * 8))
+          res_raw[0][k] = gr < rows ? __ldg(reinterpret_cast<const uint4*>(ep.res + (size_t)(ep.res_idx ? __ldg(ep.res_idx + gr) : gr) * ep.ld_res + group * 64 + cc * 8))
                                     : make_uint4(0u, 0u, 0u, 0u);
         }
       }
@@ -185,7 +186,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (r0 < rows) {
         if (ep.rowptr) { rp_hi = __ldg(ep.rowptr + r0 + 1); rp_lo = __ldg(ep.rowptr + r0); }
         if constexpr (RES && !COAL) {
-          const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r0 * ep.ld_res + res_col0);
+          const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)(ep.res_idx ? __ldg(ep.res_idx + r0) : r0) * ep.ld_res + res_col0);
 #pragma unroll
           for (int ci = 0; ci < NCHUNK; ++ci)
 #pragma unroll
@@ -208,7 +209,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         wrow = ep.aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
         if (next_valid) { rp_hi = __ldg(ep.rowptr + r_next + 1); rp_lo = __ldg(ep.rowptr + r_next); }
       }
-      const uint4* rp_next = RES ? reinterpret_cast<const uint4*>(ep.res + (size_t)(next_valid ? r_next : 0) * ep.ld_res + res_col0) : nullptr;
+      const int rr_next = next_valid ? (RES && ep.res_idx ? __ldg(ep.res_idx + r_next) : r_next) : 0;
+      const uint4* rp_next = RES ? reinterpret_cast<const uint4*>(ep.res + (size_t)rr_next * ep.ld_res + res_col0) : nullptr;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       // this group's previous TMA store must have finished reading the group's staging slabs
@@ -476,6 +478,7 @@ gemm_nt_tcs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int m0 = (tile / num_n) * S::BM, n0 = (tile % num_n) * S::BN;
       const int r = m0 + row_in_tile;
       const bool valid = r < rows;
+      const int rres = (ep.res_idx && valid) ? __ldg(ep.res_idx + r) : r;  // residual row (identity or table lookup)
       float wrow = 1.f;
       if (ep.rowptr) {
         const int deg = valid ? __ldg(ep.rowptr + r + 1) - __ldg(ep.rowptr + r) : 0;
@@ -490,7 +493,7 @@ gemm_nt_tcs_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int c0 = half * COLS_PER_WARP + ci * 32;  // column inside the tile
         uint4 res_raw[4];
         if (ep.res && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)r * ep.ld_res + n0 + c0);
+          const uint4* rp = reinterpret_cast<const uint4*>(ep.res + (size_t)rres * ep.ld_res + n0 + c0);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) res_raw[j4] = __ldg(rp + j4);
         }
@@ -804,7 +807,14 @@ inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb
   CUtensorMap tmA, tmB;
   if (make_tmap_bf16(&tmA, A, rows, NN, lda, S::BR) || make_tmap_bf16(&tmB, B, rows, KK, ldb, S::BR)) return GCB_ERR_CUDA;
   const int num_tiles = (rows + S::BR - 1) / S::BR;
-  int grid = num_tiles < kTnMaxCtas ? num_tiles : kTnMaxCtas;
+  // A/B switch GCB_TN_CTAS: fewer weight-gradient CTAs leave whole SMs to the kernels of the main chain they overlap
+  // (40-56 of 148 CTAs measured best on B200 at batch 8192: train step 1.547 -> 1.504 ms; 32 makes the side stream the critical path; gpurun_out/r2_ab_s.jsonl, r2_ab_t.jsonl)
+  static const int tn_cap = [] {
+    const char* e = std::getenv("GCB_TN_CTAS");
+    const int n = e ? std::atoi(e) : 48;
+    return n < 1 ? 1 : (n > kTnMaxCtas ? kTnMaxCtas : n);
+  }();
+  int grid = num_tiles < tn_cap ? num_tiles : tn_cap;
   const int per = (num_tiles + grid - 1) / grid;
   grid = (num_tiles + per - 1) / per;  // every CTA owns at least one tile
   *grid_out = grid;

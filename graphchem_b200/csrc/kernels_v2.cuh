@@ -458,13 +458,14 @@ pool_bwd_kernel(const float* __restrict__ dPool, const T* __restrict__ d_out_ato
 
 // Embedding gradient: one CTA per (token, split); 256 threads = (256/CH) row lanes x CH chunks.  Row
 // lane k sums rows k, k+RL, k+2RL, ... of its slice, then the row lanes are combined in lane order.
-template <typename T, int CH>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, int CH, bool HAS_Y>
+__global__ void __launch_bounds__(kThreads, 4)
 embed_bwd_partial_kernel(const T* __restrict__ dZ, const T* __restrict__ Y, const int32_t* __restrict__ tok_ptr,
                          const int32_t* __restrict__ tok_row, float* __restrict__ partial, int vocab, int splits, int act) {
   constexpr int V = Vec<T>::N;
   constexpr int D = CH * V;
   constexpr int RL = kThreads / CH;  // row lanes
+  constexpr int UN = HAS_Y ? 4 : 8;  // rows in flight per thread
   __shared__ float red[RL][D + 4];
   const int t = blockIdx.x / splits, s = blockIdx.x % splits;
   const int lig = threadIdx.x % CH, rl = threadIdx.x / CH, c = lig * V;
@@ -474,31 +475,37 @@ embed_bwd_partial_kernel(const T* __restrict__ dZ, const T* __restrict__ Y, cons
   float acc[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
-  // four rows in flight per thread (index loads first, then the row loads): the walk is a dependent
-  // index -> row chain and was latency bound with one row at a time; the summation order is unchanged
+  // UN rows in flight per thread (index loads first, then the row loads, kept as raw 16-byte words until they are
+  // added): the walk is a dependent index -> row chain and is latency bound; the summation order is unchanged
   int k = lo + rl;
-  for (; k + 3 * RL < hi; k += 4 * RL) {
-    int row[4];
+  for (; k + (UN - 1) * RL < hi; k += UN * RL) {
+    int row[UN];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) row[j] = __ldg(tok_row + k + j * RL);
-    float d[4][V], y[4][V];
+    for (int j = 0; j < UN; ++j) row[j] = __ldg(tok_row + k + j * RL);
+    uint4 d[UN], y[HAS_Y ? UN : 1];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      load_vec(dZ + (size_t)row[j] * D + c, d[j]);
-      if (Y) load_vec(Y + (size_t)row[j] * D + c, y[j]);
+    for (int j = 0; j < UN; ++j) {
+      d[j] = Raw<T>::load(dZ + (size_t)row[j] * D + c);
+      if constexpr (HAS_Y) y[j] = Raw<T>::load(Y + (size_t)row[j] * D + c);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (Y) act_grad_mul_vec<T, V>(d[j], y[j], act);
+    for (int j = 0; j < UN; ++j) {
+      float df[V];
+      Raw<T>::to_float(d[j], df);
+      if constexpr (HAS_Y) {
+        float yf[V];
+        Raw<T>::to_float(y[j], yf);
+        act_grad_mul_vec<T, V>(df, yf, act);
+      }
 #pragma unroll
-      for (int i = 0; i < V; ++i) acc[i] += d[j][i];
+      for (int i = 0; i < V; ++i) acc[i] += df[i];
     }
   }
   for (; k < hi; k += RL) {
     const int row = __ldg(tok_row + k);
     float d[V];
     load_vec(dZ + (size_t)row * D + c, d);
-    if (Y) {
+    if constexpr (HAS_Y) {
       float y[V];
       load_vec(Y + (size_t)row * D + c, y);
       act_grad_mul_vec<T, V>(d, y, act);

@@ -58,7 +58,7 @@ static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* 
     if (!w_kn && ldw == K && !ep.actgrad_y && tc::tc_enabled()) {
       tc::TcEpilogue te;
       te.bias = ep.bias; te.rowptr = ep.rowptr; te.aggr = ep.aggr;
-      te.res = (const bf16*)ep.res; te.ld_res = ep.ld_res; te.act = ep.act; te.rev = ep.rev;
+      te.res = (const bf16*)ep.res; te.ld_res = ep.ld_res; te.res_idx = ep.res_idx; te.act = ep.act; te.rev = ep.rev;
       const int rc = tc::launch_gemm_nt_tc(A, lda, W, C, ldc, M, N, K, te, s);
       if (rc != GCB_ERR_UNSUPPORTED) return rc;
     }
@@ -539,6 +539,18 @@ static bool tok1_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
          !fused_ok<T>(c, g, flags, 0);
 }
 
+// Atom side of the same fusion (reference gcn.py:152-153 -> 172-173): A_0 is never materialised, step 1 gathers the
+// neighbours' rows out of the pre-activated atom table, and the residual of its transform GEMM and act' of its backward
+// read the table through the token.  bf16 tile path with add aggregation only; GCB_NO_ATOK1=1 switches it off.
+template <typename T>
+static bool atok1_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
+  if constexpr (sizeof(T) != 2) return false;
+  const char* e = std::getenv("GCB_NO_ATOK1");
+  const bool off = e && e[0] == '1';
+  return !off && tok1_enabled() && tc::tc_enabled() && c.L >= 1 && c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags) &&
+         tile::atom_tok_ok(c.D, c.atom_vocab) && !fused_ok<T>(c, g, flags, 1) && !fused_ok<T>(c, g, flags, 2);
+}
+
 // ---- forward ------------------------------------------------------------------------------------
 template <typename T>
 static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Graph& g, const float* params,
@@ -551,7 +563,8 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
   const float* bpq = (const float*)(dv.base + dv.bpq);
   const float* bat = (const float*)(dv.base + dv.bat);
 
-  if (N > 0) {
+  const bool atok1 = atok1_ok<T>(c, g, flags);  // A_0 is then never materialised: step 1 reads the atom token table
+  if (N > 0 && !atok1) {
     GCB_KERNEL("embed_rows_kernel", s, embed_rows_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((const T*)(dv.base + dv.tab_atom), g.x_tok, (T*)p.A[0], N, D / V));
   }
   const bool tok1 = tok1_ok<T>(c, g, flags);  // B_0 is then never materialised: step 1 reads the token table
@@ -648,7 +661,11 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       if constexpr (sizeof(T) == 2) {
         if (c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags)) {
           const tile::TileCommon cm{g.tile_ptr, N, g.in_ptr, g.in_src, (const int4*)g.in_src4, (const int4*)g.in_eid4, g.in_eid, flip()};
-          GCB_TRY(tile::launch_atom_gather(D, (const bf16*)p.A[l - 1], (const bf16*)p.B[l], M, cm, g.n_tiles, (bf16*)p.S[l], c.act, s));
+          if (l == 1 && atok1)
+            GCB_TRY(tile::launch_atom_gather_tok(D, cm, g.n_tiles, (const bf16*)(dv.base + dv.tab_atom), g.x_tok, c.atom_vocab, (const bf16*)p.B[l], M,
+                                                 (bf16*)p.S[l], c.act, s));
+          else
+            GCB_TRY(tile::launch_atom_gather(D, (const bf16*)p.A[l - 1], (const bf16*)p.B[l], M, cm, g.n_tiles, (bf16*)p.S[l], c.act, s));
           a_tiled = true;
         }
       }
@@ -658,6 +675,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       Epilogue ep;
       ep.bias = bat; ep.rowptr = g.in_ptr; ep.aggr = c.aggr;
       ep.res = p.A[l - 1]; ep.ld_res = D; ep.act = c.act; ep.rev = flip();
+      if (l == 1 && atok1) { ep.res = dv.base + dv.tab_atom; ep.res_idx = g.x_tok; }  // residual A_0[i] = tab_atom[tok i]
       GCB_TRY(gemm_nt_auto<T>((const T*)p.S[l], 2 * D, wat, 2 * D, false, (T*)p.A[l], D, N, D, 2 * D, ep, s));
       if (da.p > 0.f) {
         GCB_KERNEL("dropout_inplace_kernel", s, dropout_inplace_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((T*)p.A[l], N, D, da));
@@ -726,6 +744,36 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   const T* watT = (const T*)(dv.base + dv.watT);
   const T* wpqT = (const T*)(dv.base + dv.wpqT);
 
+  // Weight-gradient GEMMs (and their partial reductions) feed nothing until the optimiser step, so
+  // they run on a side stream next to the latency-bound row kernels of the same / the next layer:
+  //   W_at(l) = dZA_l^T S_l        may start when layer l starts; dZA_l is overwritten by atom_bwd(l-1)
+  //   W_pq(l) = [dP|dQ]_l^T B_l-1  may start after scatter(l);   dPQ[l&1] is overwritten by tie(l-2)
+  const bool tok1 = tok1_ok<T>(c, g, flags);
+  SideStream* ss = tc::overlap_enabled() ? side_stream() : nullptr;
+  const bool overlap = ss != nullptr;
+  cudaStream_t sw = overlap ? ss->stream : s;
+  size_t evi = 0;
+  cudaEvent_t done_at[kMaxLayers + 2], done_pq[kMaxLayers + 2];
+  for (int i = 0; i < kMaxLayers + 2; ++i) done_at[i] = done_pq[i] = nullptr;
+  auto fork = [&]() -> int {  // side stream continues from the caller stream's current point
+    if (!overlap) return GCB_OK;
+    cudaEvent_t e = ss->event(evi++);
+    if (!e) return GCB_ERR_CUDA;
+    GCB_CUDA(cudaEventRecord(e, s));
+    GCB_CUDA(cudaStreamWaitEvent(sw, e, 0));
+    return GCB_OK;
+  };
+  auto mark = [&](cudaEvent_t& slot) -> int {  // remember "side stream reached this point"
+    if (!overlap) return GCB_OK;
+    slot = ss->event(evi++);
+    if (!slot) return GCB_ERR_CUDA;
+    GCB_CUDA(cudaEventRecord(slot, sw));
+    return GCB_OK;
+  };
+  auto join = [&](cudaEvent_t e) -> int {
+    if (overlap && e) GCB_CUDA(cudaStreamWaitEvent(s, e, 0));
+    return GCB_OK;
+  };
   // ---- readout ----
   const float* dPool = nullptr;
   if (d_out && G > 0) {
@@ -739,7 +787,11 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       const int blocks = (int)ceil_div(G, kReadoutGB2);
       Drop drb = make_drop(c, flags, seed, tag_readout(0));
       GCB_KERNEL("readout_bwd_kernel", s, readout2_bwd_kernel<<<blocks, kReadout2Threads, readout2_bwd_smem(rd2), s>>>(rd2, params, hp, d_out, p.partial, p.dPool, G, c.act, drb));
-      GCB_TRY(launch_reduce_partials(p.partial, blocks, pl.total - pl.r_w[0], grad + pl.r_w[0], accumulate, s, rd2.partial_stride));
+      // the ordered sum of the per-CTA readout weight gradients feeds nothing before the optimiser: on the side stream
+      // (in front of the weight-gradient GEMMs, which reuse p.partial after it) pool_bwd does not wait for it
+      const bool red_side = overlap && L >= 1;
+      if (red_side) GCB_TRY(fork());
+      GCB_TRY(launch_reduce_partials(p.partial, blocks, pl.total - pl.r_w[0], grad + pl.r_w[0], accumulate, red_side ? sw : s, rd2.partial_stride));
       dPool = p.dPool;
     } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
       ReadoutPtrs hp;
@@ -792,36 +844,6 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   int rev = 0;
   const bool pingpong = tc::pingpong_enabled();
   auto flip = [&]() { if (pingpong) rev ^= 1; return rev; };
-  // Weight-gradient GEMMs (and their partial reductions) feed nothing until the optimiser step, so
-  // they run on a side stream next to the latency-bound row kernels of the same / the next layer:
-  //   W_at(l) = dZA_l^T S_l        may start when layer l starts; dZA_l is overwritten by atom_bwd(l-1)
-  //   W_pq(l) = [dP|dQ]_l^T B_l-1  may start after scatter(l);   dPQ[l&1] is overwritten by tie(l-2)
-  const bool tok1 = tok1_ok<T>(c, g, flags);
-  SideStream* ss = tc::overlap_enabled() ? side_stream() : nullptr;
-  const bool overlap = ss != nullptr;
-  cudaStream_t sw = overlap ? ss->stream : s;
-  size_t evi = 0;
-  cudaEvent_t done_at[kMaxLayers + 2], done_pq[kMaxLayers + 2];
-  for (int i = 0; i < kMaxLayers + 2; ++i) done_at[i] = done_pq[i] = nullptr;
-  auto fork = [&]() -> int {  // side stream continues from the caller stream's current point
-    if (!overlap) return GCB_OK;
-    cudaEvent_t e = ss->event(evi++);
-    if (!e) return GCB_ERR_CUDA;
-    GCB_CUDA(cudaEventRecord(e, s));
-    GCB_CUDA(cudaStreamWaitEvent(sw, e, 0));
-    return GCB_OK;
-  };
-  auto mark = [&](cudaEvent_t& slot) -> int {  // remember "side stream reached this point"
-    if (!overlap) return GCB_OK;
-    slot = ss->event(evi++);
-    if (!slot) return GCB_ERR_CUDA;
-    GCB_CUDA(cudaEventRecord(slot, sw));
-    return GCB_OK;
-  };
-  auto join = [&](cudaEvent_t e) -> int {
-    if (overlap && e) GCB_CUDA(cudaStreamWaitEvent(s, e, 0));
-    return GCB_OK;
-  };
   int grid_at = 0, grid_pq = 0;  // > 0: partials deferred in p.partialAt / p.partialPq
   for (int l = L; l >= 1; --l) {
     const int acc_w = l != L;
@@ -860,8 +882,10 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       if constexpr (sizeof(T) == 2) {
         if (N > 0 && c.aggr == GCB_AGGR_ADD && tiles_ok<T>(c, g, flags)) {
           const tile::TileCommon cm{g.tile_ptr, N, g.out_ptr, g.out_dst, (const int4*)g.out_dst4, nullptr, nullptr, flip()};
-          GCB_TRY(tile::launch_atom_bwd(D, (const bf16*)p.dS, (const bf16*)p.dZA[cur], (const bf16*)p.A[l - 1], cm, g.n_tiles,
-                                        (bf16*)p.dZA[cur ^ 1], c.act, s));
+          const bool from_tab = l == 1 && atok1_ok<T>(c, g, flags);  // A_0 lives in the token table
+          GCB_TRY(tile::launch_atom_bwd(D, (const bf16*)p.dS, (const bf16*)p.dZA[cur],
+                                        from_tab ? (const bf16*)(dv.base + dv.tab_atom) : (const bf16*)p.A[l - 1], from_tab ? g.x_tok : nullptr, cm,
+                                        g.n_tiles, (bf16*)p.dZA[cur ^ 1], c.act, s));
           tiled = true;
         }
       }
@@ -944,13 +968,13 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     if (N > 0) {
       GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dZA[cur], nullptr, g.atok_ptr, g.atok_node, part_a, av, D, c.act, s));
     }
-    GCB_TRY(launch_reduce_partials(part_a, N > 0 ? kEmbedSplits : 0, (int64_t)av * D, grad + pl.emb_atom, accumulate, s));
+    GCB_TRY(launch_reduce_partials(part_a, N > 0 ? embed_splits() : 0, (int64_t)av * D, grad + pl.emb_atom, accumulate, s));
     if (tok1 && M > 0) {
       // per-token sums of step 1's [dP|dQ] (buckets in row order, ordered split reduction), then the three small
       // products of bond_table_bwd_kernel
       if constexpr (sizeof(T) == 2) {
         GCB_TRY(launch_embed_bwd_partial<T>((const T*)p.dPQ2[1], nullptr, g.btok_ptr, g.btok_row, part_b, bv, 2 * D, c.act, se));
-        GCB_TRY(launch_reduce_partials(part_b, kEmbedSplits, (int64_t)bv * 2 * D, p.tokPQ, 0, se));
+        GCB_TRY(launch_reduce_partials(part_b, embed_splits(), (int64_t)bv * 2 * D, p.tokPQ, 0, se));
         const int nb1 = (int)ceil_div(2 * D * D, 256);
         GCB_KERNEL("bond_table_bwd_kernel", se, bond_table_bwd_kernel<T><<<(unsigned)(nb1 + bv * (D / 32)), 256, 0, se>>>(
             p.tokPQ, (const T*)(dv.base + dv.tab_bond), (const T*)(dv.base + dv.wpq), p.accWpq, p.accBpq, grad + pl.emb_bond, bv, D,
@@ -962,7 +986,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       if (have) {
         GCB_TRY(launch_embed_bwd_partial<T>(dB0, (const T*)p.B[0], g.btok_ptr, g.btok_row, part_b, bv, D, c.act, se));
       }
-      GCB_TRY(launch_reduce_partials(part_b, have ? kEmbedSplits : 0, (int64_t)bv * D, grad + pl.emb_bond, accumulate, se));
+      GCB_TRY(launch_reduce_partials(part_b, have ? embed_splits() : 0, (int64_t)bv * D, grad + pl.emb_bond, accumulate, se));
     }
     if (split) {
       cudaEvent_t last = nullptr;

@@ -2,6 +2,7 @@
 // the row width is 8, 16 or 32 sixteen-byte chunks (D = 64/128/256 in bf16, 32/64/128 in fp32) and the
 // generic kernels of kernels.cuh otherwise.
 #pragma once
+#include <cstdlib>
 #include "kernels_v2.cuh"
 
 namespace gcb {
@@ -107,7 +108,16 @@ int launch_pool_bwd(const float* dPool, const T* d_out_atom, const T* A_last, co
                    (pool_bwd_kernel<T><<<GCB_V1_GRID(G, D)>>>(dPool, d_out_atom, A_last, graph_ptr, graph_node, dZA, G, D, act, dr)));
 }
 
-constexpr int kEmbedSplits = 32;
+constexpr int kEmbedSplits = 32;  // capacity of the partial-sum scratch
+// splits actually used (A/B switch GCB_EMBED_SPLITS, 1..kEmbedSplits)
+inline int embed_splits() {
+  static const int v = [] {
+    const char* e = std::getenv("GCB_EMBED_SPLITS");
+    const int n = e ? std::atoi(e) : 16;  // 16 measured best on B200 (gpurun_out/r2_ab_q.jsonl)
+    return n < 1 ? 1 : (n > kEmbedSplits ? kEmbedSplits : n);
+  }();
+  return v;
+}
 
 // partial[split][token][D]; the caller reduces over the kEmbedSplits splits in order.
 template <typename T>
@@ -116,11 +126,20 @@ int launch_embed_bwd_partial(const T* dZ, const T* Y, const int32_t* tok_ptr, co
   if (vocab <= 0) return GCB_OK;
   constexpr int V = Vec<T>::N;
   switch (D / V) {
-    case 8: GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 8><<<vocab * kEmbedSplits, v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, kEmbedSplits, act))); break;
-    case 16: GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 16><<<vocab * kEmbedSplits, v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, kEmbedSplits, act))); break;
-    case 32: GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 32><<<vocab * kEmbedSplits, v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, kEmbedSplits, act))); break;
+    case 8:
+      if (Y) GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 8, true><<<vocab * embed_splits(), v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, embed_splits(), act)));
+      else GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 8, false><<<vocab * embed_splits(), v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, embed_splits(), act)));
+      break;
+    case 16:
+      if (Y) GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 16, true><<<vocab * embed_splits(), v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, embed_splits(), act)));
+      else GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 16, false><<<vocab * embed_splits(), v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, embed_splits(), act)));
+      break;
+    case 32:
+      if (Y) GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 32, true><<<vocab * embed_splits(), v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, embed_splits(), act)));
+      else GCB_KERNEL("embed_bwd_partial_kernel", s, (v2::embed_bwd_partial_kernel<T, 32, false><<<vocab * embed_splits(), v2::kThreads, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, embed_splits(), act)));
+      break;
     default:
-      GCB_KERNEL("embed_bwd_partial_kernel", s, (embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)vocab * kEmbedSplits * (D / V), 256), 256, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, kEmbedSplits, D, act)));
+      GCB_KERNEL("embed_bwd_partial_kernel", s, (embed_bwd_partial_kernel<T><<<(unsigned)ceil_div((int64_t)vocab * embed_splits() * (D / V), 256), 256, 0, s>>>(dZ, Y, tok_ptr, tok_row, partial, vocab, embed_splits(), D, act)));
   }
   return GCB_OK;
 }

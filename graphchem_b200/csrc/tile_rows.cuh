@@ -356,18 +356,104 @@ atom_gather_kernel(const __grid_constant__ CUtensorMap tmA, TileCommon cm, const
   }
 }
 
+// ---- first atom aggregation straight from the token table (embedding lookup fused with the first message step) ----
+// In message step 1 the atom matrix is a row copy out of the pre-activated table, A_0[i] = tab_atom[tok i] (reference
+// gcn.py:152-153), so S_1[i] = [ sum_{e->i} tab_atom[tok(src e)] | sum_{e->i} B_1[eid e] ].  The kernel stages the table
+// (vocab x D bf16, 16 KB at 64 tokens) and looks the neighbours' tokens up while it stages the indices; A_0 is never
+// written, and the residual of the step's transform GEMM and act' in the backward pass read the table through the token
+// as well (TcEpilogue::res_idx, atom_bwd_kernel's prev_idx).  Same arithmetic and order of addition as atom_gather_kernel.
+template <int CH, int UN>
+__global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
+atom_gather_tok_kernel(TileCommon cm, const bf16* __restrict__ tabA, const int32_t* __restrict__ tok, int vocab,
+                       const bf16* __restrict__ Bnew, int M, bf16* __restrict__ S, int act) {
+  constexpr int kD = Cfg<CH>::D, kSlots = Cfg<CH>::kSlots, kPasses = Cfg<CH>::kPasses, kRowBytes = Cfg<CH>::kRowBytes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (gcb::tc::smem_u32(smem_raw) + 127u) & ~127u;  // table [vocab][D] bf16, then one zero pad row
+  const uint32_t s_n4 = smem + (vocab + 1) * kRowBytes, s_a4 = s_n4 + kRows * 16, s_ptr = s_a4 + kRows * 16;
+  const uint32_t pad_off = (uint32_t)vocab * kRowBytes;
+  const int tb_ = tile_of_cta(cm);
+  const int r0 = __ldg(cm.tile_ptr + tb_);
+  const int r1 = min(__ldg(cm.tile_ptr + tb_ + 1), cm.rows);
+  pdl_launch_dependents();
+  // indices and tokens are immutable batch data; the table was written by the weight refresh of the previous step
+  for (int i = threadIdx.x; i <= kRows; i += kThreads) {
+    const int r = r0 + i;
+    if (i < kRows) {
+      int4 v = make_int4(-1, -1, -1, -1), w = v;
+      if (r < r1) { v = __ldg(cm.nbr4 + r); w = __ldg(cm.aux4 + r); }
+      const uint32_t o0 = v.x >= 0 ? (uint32_t)__ldg(tok + v.x) * kRowBytes : pad_off, o1 = v.y >= 0 ? (uint32_t)__ldg(tok + v.y) * kRowBytes : pad_off;
+      const uint32_t o2 = v.z >= 0 ? (uint32_t)__ldg(tok + v.z) * kRowBytes : pad_off, o3 = v.w >= 0 ? (uint32_t)__ldg(tok + v.w) * kRowBytes : pad_off;
+      gcb::tc::sts128(s_n4 + i * 16, make_uint4(o0, o1, o2, o3));
+      gcb::tc::sts128(s_a4 + i * 16, make_uint4(w.x, w.y, w.z, w.w));
+    }
+    sts32(s_ptr + i * 4, r <= r1 ? __ldg(cm.ptr + r) : 0);
+  }
+  pdl_wait();
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(tabA);
+    const int n16 = vocab * (kRowBytes / 16);
+    for (int i = threadIdx.x; i < n16; i += kThreads) gcb::tc::sts128(smem + i * 16, __ldg(src + i));
+    for (int i = threadIdx.x; i < kRowBytes / 16; i += kThreads) gcb::tc::sts128(smem + pad_off + i * 16, make_uint4(0u, 0u, 0u, 0u));
+  }
+  const int grp = threadIdx.x / CH, lig = threadIdx.x % CH, c = lig * 8;
+  __syncthreads();
+  const float cst = round_to(act_fwd_t<bf16>(0.f, act), (const bf16*)nullptr);
+  const uint32_t cst2 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(cst)) * 0x00010001u;
+#pragma unroll (UN)
+  for (int ps = 0; ps < kPasses; ++ps) {
+    GCB_TILE_ROW(ps)
+    const uint4 e4_ = lds16(s_a4 + rr * 16);
+    const int eidx[4] = {(int)e4_.x, (int)e4_.y, (int)e4_.z, (int)e4_.w};
+    uint4 b[4], a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool live = (unsigned)eidx[u] < (unsigned)M;
+      b[u] = R::load(Bnew + (size_t)(live ? eidx[u] : 0) * kD + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = lds16(smem + noff[u] + lig * 16);  // pad row: zeros
+    float sa[8], sb[8];
+    v2::vzero<bf16, 8>(sa);
+    v2::vzero<bf16, 8>(sb);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v2::raw_add<bf16, 8>(a[u], sa);
+    for (int e = e0 + 4; e < e1; ++e)
+      v2::raw_add<bf16, 8>(lds16(smem + (uint32_t)__ldg(tok + __ldg(cm.nbr + e)) * kRowBytes + lig * 16), sa);
+    store_vec(S + (size_t)r * (2 * kD) + c, sa);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool live = (unsigned)eidx[u] < (unsigned)M;
+      const uint32_t fill = eidx[u] < 0 ? 0u : cst2;
+      uint4 t = b[u];
+      t.x = live ? t.x : fill; t.y = live ? t.y : fill; t.z = live ? t.z : fill; t.w = live ? t.w : fill;
+      v2::raw_add<bf16, 8>(t, sb);
+    }
+    for (int e = e0 + 4; e < e1; ++e) {
+      const int eid = __ldg(cm.aux + e);
+      if (eid < M) v2::raw_add<bf16, 8>(R::load(Bnew + (size_t)eid * kD + c), sb);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sb[i] += cst;
+      }
+    }
+    store_vec(S + (size_t)r * (2 * kD) + kD + c, sb);
+  }
+}
+
 // ---- atom backward: dZA_prev[j] = (dZA[j] + sum_{e: src e = j} dS[dst e, :D]) * act'(A_prev[j]) ----
 // staged: dS[:, :D] rows of the tile (neighbours); the row's own dZA / A_prev chunks stream from global.
 template <int CH, int UN>
 __global__ void __launch_bounds__(kThreads, Cfg<CH>::kCtas)
 atom_bwd_kernel(const __grid_constant__ CUtensorMap tmdS, TileCommon cm, const bf16* __restrict__ dZA,
-                const bf16* __restrict__ A_prev, bf16* __restrict__ dZA_prev, int act) {
+                const bf16* __restrict__ A_prev, const int32_t* __restrict__ prev_idx, bf16* __restrict__ dZA_prev, int act) {
+  // prev_idx (message step 1 with the embedding lookup fused in): A_prev is the pre-activated token table and row r
+  // reads A_prev[prev_idx[r]] -- A_0 is never materialised
   GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmdS, &bar, 0, r0), kRowBytes, 0u)
 #pragma unroll (UN)
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
     const uint4 draw = R::load(dZA + (size_t)r * kD + c);
-    const uint4 yraw = R::load(A_prev + (size_t)r * kD + c);
+    const uint4 yraw = R::load(A_prev + (size_t)(prev_idx ? __ldg(prev_idx + r) : r) * kD + c);
     uint4 g[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) g[u] = lds16(smem + noff[u] + lig * 16);  // pad row: zeros
@@ -672,8 +758,27 @@ inline int launch_atom_gather(int D, const bf16* A, const bf16* Bnew, int M, con
                   : launch_atom_gather_w<32>(A, Bnew, M, cm, n_tiles, S, act, s);
 }
 
+// Shared memory of atom_gather_tok_kernel; the caller materialises A_0 when the table does not fit.
+inline int atom_tok_smem(int D, int vocab) { return (vocab + 1) * 2 * D + 2 * kRows * 16 + 544 + 128; }
+inline bool atom_tok_ok(int D, int vocab) { return width_ok(D) && atom_tok_smem(D, vocab) <= 48 * 1024; }
+
 template <int CH>
-inline int launch_atom_bwd_w(const bf16* dS, const bf16* dZA, const bf16* A_prev, const TileCommon& cm, int n_tiles,
+inline int launch_atom_gather_tok_w(const TileCommon& cm, int n_tiles, const bf16* tabA, const int32_t* tok, int vocab, const bf16* Bnew,
+                                    int M, bf16* S, int act, cudaStream_t s) {
+  const int smem = atom_tok_smem(Cfg<CH>::D, vocab);
+  static bool attr = false;
+  if (!attr) { GCB_TRY(set_smem(atom_gather_tok_kernel<CH, 2>, 48 * 1024)); attr = true; }
+  GCB_KERNEL("tile_atom_gather_tok_kernel", s, launch_pdl(atom_gather_tok_kernel<CH, 2>, n_tiles, kThreads, smem, s, cm, tabA, tok, vocab, Bnew, M, S, act));
+  return GCB_OK;
+}
+inline int launch_atom_gather_tok(int D, const TileCommon& cm, int n_tiles, const bf16* tabA, const int32_t* tok, int vocab, const bf16* Bnew,
+                                  int M, bf16* S, int act, cudaStream_t s) {
+  return D == 128 ? launch_atom_gather_tok_w<16>(cm, n_tiles, tabA, tok, vocab, Bnew, M, S, act, s)
+                  : launch_atom_gather_tok_w<32>(cm, n_tiles, tabA, tok, vocab, Bnew, M, S, act, s);
+}
+
+template <int CH>
+inline int launch_atom_bwd_w(const bf16* dS, const bf16* dZA, const bf16* A_prev, const int32_t* prev_idx, const TileCommon& cm, int n_tiles,
                              bf16* dZA_prev, int act, cudaStream_t s) {
   constexpr int D = Cfg<CH>::D;
   CUtensorMap tmS;
@@ -681,14 +786,14 @@ inline int launch_atom_bwd_w(const bf16* dS, const bf16* dZA, const bf16* A_prev
   const int smem = smem_for<CH>(1);
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(atom_bwd_kernel<CH, 2>, smem)); GCB_TRY(set_smem(atom_bwd_kernel<CH, 4>, smem)); attr = true; }
-  if (tile_unroll() == 4) GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 4>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, dZA_prev, act));
-  else GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 2>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, dZA_prev, act));
+  if (tile_unroll() == 4) GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 4>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, prev_idx, dZA_prev, act));
+  else GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 2>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, prev_idx, dZA_prev, act));
   return GCB_OK;
 }
-inline int launch_atom_bwd(int D, const bf16* dS, const bf16* dZA, const bf16* A_prev, const TileCommon& cm, int n_tiles,
+inline int launch_atom_bwd(int D, const bf16* dS, const bf16* dZA, const bf16* A_prev, const int32_t* prev_idx, const TileCommon& cm, int n_tiles,
                            bf16* dZA_prev, int act, cudaStream_t s) {
-  return D == 128 ? launch_atom_bwd_w<16>(dS, dZA, A_prev, cm, n_tiles, dZA_prev, act, s)
-                  : launch_atom_bwd_w<32>(dS, dZA, A_prev, cm, n_tiles, dZA_prev, act, s);
+  return D == 128 ? launch_atom_bwd_w<16>(dS, dZA, A_prev, prev_idx, cm, n_tiles, dZA_prev, act, s)
+                  : launch_atom_bwd_w<32>(dS, dZA, A_prev, prev_idx, cm, n_tiles, dZA_prev, act, s);
 }
 
 template <int CH>
