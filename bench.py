@@ -375,7 +375,7 @@ def run_ours(args):
             hb, slot = host_batches[i % n_host], i % 2
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[slot])
-                stage[slot][0].copy_(hb.ints, non_blocking=True)
+                hb.upload_into(stage[slot][0])  # compact prefix over PCIe; gcb_pack_expand_ell rebuilds the ELL-4 views
                 stage[slot][1].copy_(hb.y, non_blocking=True)
                 ready[slot].record(copy_stream)
 
@@ -402,9 +402,10 @@ def run_ours(args):
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
         e2e_steps = K
-        h2d = host_batches[0].ints.numel() * 4 + B * 4
+        h2d = host_batches[0].compact_ints * 4 + B * 4
         d2h = 4
-        e2e_api = "pinned pre-packed PackedBatch -> HBM (copy stream, double buffered) -> TrainStep -> loss to pinned host, every step"
+        e2e_api = ("pinned pre-packed PackedBatch -> HBM (PackedBatch.upload_into on a copy stream, double buffered: compact prefix over "
+                   "PCIe, ELL-4 views rebuilt by gcb_pack_expand_ell) -> TrainStep -> loss to pinned host, every step")
     else:
         # host molecules -> screen(): raw collate on host threads -> H2D -> gcb_pack_device -> forward -> predictions
         # gathered on the device and copied back once (B * out floats per step)

@@ -31,7 +31,7 @@ PACK_HEADER_INTS = 48
 (H_MAGIC, H_N, H_E, H_G, H_M, H_AV, H_BV, H_TOTAL_INTS, H_X_TOK, H_E_TOK, H_SRC, H_DST, H_IN_PTR, H_IN_EID,
  H_IN_SRC, H_OUT_PTR, H_OUT_EID, H_OUT_DST, H_GRAPH_PTR, H_GRAPH_NODE, H_ATOK_PTR, H_ATOK_NODE, H_BTOK_PTR,
  H_BTOK_ROW, H_NODE_GRAPH, H_IN_SRC4, H_IN_EID4, H_OUT_DST4, H_OUT_INPOS4, H_OUT_INPOS, H_TILE_PTR,
- H_NTILES, H_FLAGS, H_BOND_POS) = range(34)
+ H_NTILES, H_FLAGS, H_BOND_POS, H_COMPACT_INTS) = range(35)
 PACK_EACH = 1
 TILE_ROWS = 128
 PACK_MAGIC = 0x47434232
@@ -79,6 +79,7 @@ SIGNATURES = {
     "gcb_collate_raw_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
     "gcb_pack_device_scratch_ints": (_i64, [_vp]),
     "gcb_pack_device": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "gcb_pack_expand_ell": (C.c_int, [_vp, _vp, _vp]),
     "gcb_debug_pack_emulate_host": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i32]),
     "gcb_param_layout": (C.c_int, [_cfgp, _vp]),
     "gcb_derived_bytes": (_i64, [_cfgp]),

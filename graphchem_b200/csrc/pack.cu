@@ -28,11 +28,12 @@ static int section_table(int32_t N, int32_t E, int32_t G, int32_t av, int32_t bv
   put(GCB_H_ATOK_PTR, (int64_t)av + 1); put(GCB_H_ATOK_NODE, N);
   put(GCB_H_BTOK_PTR, (int64_t)bv + 1); put(GCB_H_BTOK_ROW, E);
   put(GCB_H_NODE_GRAPH, N);
-  put(GCB_H_IN_SRC4, 4 * (int64_t)N); put(GCB_H_IN_EID4, 4 * (int64_t)N); put(GCB_H_OUT_DST4, 4 * (int64_t)N);
-  put(GCB_H_OUT_INPOS4, 4 * (int64_t)N);
   put(GCB_H_OUT_INPOS, E);
   put(GCB_H_TILE_PTR, (int64_t)N + 1);
   if (flags & GCB_PACK_EACH) put(GCB_H_BOND_POS, E);
+  // derived tail (GCB_H_COMPACT_INTS = offset of the first of them): a function of the CSRs above, see gcb_pack_expand_ell
+  put(GCB_H_IN_SRC4, 4 * (int64_t)N); put(GCB_H_IN_EID4, 4 * (int64_t)N); put(GCB_H_OUT_DST4, 4 * (int64_t)N);
+  put(GCB_H_OUT_INPOS4, 4 * (int64_t)N);
   return k;
 }
 
@@ -51,7 +52,7 @@ static int64_t layout(int32_t N, int32_t E, int32_t G, int32_t M, int32_t av, in
     off += pad4(t[i].n);
   }
   if (off > INT32_MAX) return -1;
-  if (h) h[GCB_H_TOTAL_INTS] = (int32_t)off;
+  if (h) { h[GCB_H_TOTAL_INTS] = (int32_t)off; h[GCB_H_COMPACT_INTS] = h[GCB_H_IN_SRC4]; }
   return off;
 }
 
@@ -1037,6 +1038,45 @@ extern "C" int64_t gcb_pack_device_scratch_ints(const int32_t* packed_header) {
   if (!packed_header || packed_header[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
   const int32_t* h = packed_header;
   return scratch_layout(h[GCB_H_N], h[GCB_H_E], h[GCB_H_G], h[GCB_H_M], h[GCB_H_AV], h[GCB_H_BV]).total;
+}
+
+// ---- ELL-4 views on the device (gcb_pack_expand_ell) ------------------------------------------------------
+// One thread per (row, view): the first four entries of the row's CSR range, -1 padded -- what finish_pack and
+// collate_pack write on the host, so a batch that crossed PCIe without its derived tail equals one that carried it.
+namespace gcb {
+__global__ void expand_ell_kernel(const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src, const int32_t* __restrict__ in_eid,
+                                  const int32_t* __restrict__ out_ptr, const int32_t* __restrict__ out_dst,
+                                  const int32_t* __restrict__ out_inpos, int4* __restrict__ s4, int4* __restrict__ e4,
+                                  int4* __restrict__ d4, int4* __restrict__ o4, int32_t N) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * (int64_t)N) return;
+  const int32_t i = (int32_t)(t >> 2), view = (int32_t)(t & 3);
+  const int32_t* ptr = view < 2 ? in_ptr : out_ptr;
+  const int32_t* val = view == 0 ? in_src : view == 1 ? in_eid : view == 2 ? out_dst : out_inpos;
+  int4* dst = view == 0 ? s4 : view == 1 ? e4 : view == 2 ? d4 : o4;
+  const int32_t k0 = __ldg(ptr + i), k1 = __ldg(ptr + i + 1);
+  int4 v;
+  v.x = k0 + 0 < k1 ? __ldg(val + k0 + 0) : -1;
+  v.y = k0 + 1 < k1 ? __ldg(val + k0 + 1) : -1;
+  v.z = k0 + 2 < k1 ? __ldg(val + k0 + 2) : -1;
+  v.w = k0 + 3 < k1 ? __ldg(val + k0 + 3) : -1;
+  dst[i] = v;
+}
+}  // namespace gcb
+
+extern "C" int gcb_pack_expand_ell(int32_t* packed_dev, const int32_t* h, void* stream) {
+  using namespace gcb;
+  if (!packed_dev || !h || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
+  const int32_t N = h[GCB_H_N];
+  if (N <= 0) return GCB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t threads = 4 * (int64_t)N;
+  GCB_KERNEL("expand_ell_kernel", s, expand_ell_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+      packed_dev + h[GCB_H_IN_PTR], packed_dev + h[GCB_H_IN_SRC], packed_dev + h[GCB_H_IN_EID], packed_dev + h[GCB_H_OUT_PTR],
+      packed_dev + h[GCB_H_OUT_DST], packed_dev + h[GCB_H_OUT_INPOS], reinterpret_cast<int4*>(packed_dev + h[GCB_H_IN_SRC4]),
+      reinterpret_cast<int4*>(packed_dev + h[GCB_H_IN_EID4]), reinterpret_cast<int4*>(packed_dev + h[GCB_H_OUT_DST4]),
+      reinterpret_cast<int4*>(packed_dev + h[GCB_H_OUT_INPOS4]), N));
+  return GCB_OK;
 }
 
 extern "C" int gcb_pack_device(const int32_t* raw_dev, const int32_t* raw_header_host, const int32_t* packed_header_host,

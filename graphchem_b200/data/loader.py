@@ -196,7 +196,7 @@ class PackedLoader:
                                                    y), d_ints)
                                 else:
                                     n = hb.ints.numel()
-                                    d_ints[:n].copy_(hb.ints, non_blocking=True)
+                                    hb.upload_into(d_ints)  # compact prefix over PCIe, ELL-4 views rebuilt on the device
                                     db = PackedBatch(d_ints[:n], hb.header, y)
                             else:
                                 db = hb.to(self.device, non_blocking=True)

@@ -50,8 +50,30 @@ class PackedBatch:
     def nbytes(self) -> int:
         return self.ints.numel() * 4 + (0 if self.y is None else self.y.numel() * self.y.element_size())
 
+    @property
+    def compact_ints(self) -> int:
+        """Leading ints that have to cross PCIe: the ELL-4 views behind them are derived on the device."""
+        return int(self.header[_lib.H_COMPACT_INTS])
+
+    def upload_into(self, dst: Tensor, non_blocking: bool = True) -> None:
+        """Host -> device into a preallocated int32 buffer of at least `ints.numel()` elements, on the current stream:
+        copies the compact prefix and lets `gcb_pack_expand_ell` rebuild the ELL-4 views (bit-identical to the host's)."""
+        n, total = self.compact_ints, self.ints.numel()
+        if dst.device.type != "cuda" or self.ints.device.type != "cpu" or n <= 0 or n >= total:
+            dst[:total].copy_(self.ints, non_blocking=non_blocking)
+            return
+        dst[:n].copy_(self.ints[:n], non_blocking=non_blocking)
+        with torch.cuda.device(dst.device):
+            _lib.check(_lib.lib().gcb_pack_expand_ell(dst.data_ptr(), self.header.ctypes.data,
+                                                      torch.cuda.current_stream(dst.device).cuda_stream), "gcb_pack_expand_ell")
+
     def to(self, device, non_blocking: bool = False) -> "PackedBatch":
+        device = torch.device(device)
         y = None if self.y is None else self.y.to(device, non_blocking=non_blocking)
+        if device.type == "cuda" and self.ints.device.type == "cpu":
+            ints = torch.empty(self.ints.numel(), dtype=torch.int32, device=device)
+            self.upload_into(ints, non_blocking=non_blocking)
+            return PackedBatch(ints, self.header, y)
         return PackedBatch(self.ints.to(device, non_blocking=non_blocking), self.header, y)
 
     def section(self, field: int, count: int) -> Tensor:

@@ -9,9 +9,13 @@
  *
  * Conventions: plain pointers and sizes only (no torch types); every function returns GCB_OK or a
  * negative error code and never throws; all device buffers are caller-allocated, 16-byte
- * aligned; no hidden allocation, no hidden host synchronisation, no global mutable state; all
- * kernels are deterministic (no floating-point atomics).  `stream` is a cudaStream_t passed as
- * void* (0 = legacy default stream).
+ * aligned; no hidden device allocation, no hidden host synchronisation; all kernels are deterministic
+ * (no floating-point atomics).  `stream` is a cudaStream_t passed as void* (0 = legacy default
+ * stream).  State the library keeps (per host thread, created lazily): one internal non-blocking
+ * side stream + events on which gcb_backward overlaps its weight-gradient GEMMs (it forks from and
+ * rejoins `stream`, so a CUDA-graph capture of `stream` captures it too), the opt-in launch counter /
+ * CUDA-event timing facility (gcb_timing_*), and per-kernel "shared-memory attribute set" flags.
+ * Behaviour switches (GCB_* environment variables) are read-only A/B knobs for profiling.
  */
 #ifndef GRAPHCHEM_B200_H
 #define GRAPHCHEM_B200_H
@@ -23,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 2
+#define GCB_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define GCB_OK 0
@@ -86,6 +90,10 @@ enum gcb_pack_field {
   GCB_H_TILE_PTR, GCB_H_NTILES,
   GCB_H_FLAGS,    /* GCB_PACK_* bits */
   GCB_H_BOND_POS, /* GCB_PACK_EACH only: [E] bond-matrix row that holds edge e, or -1 (constant row) */
+  /* The four ELL-4 views are the LAST sections of the buffer and a pure function of the CSRs in front of them:
+   * ints [0, header[GCB_H_COMPACT_INTS]) are enough to move over PCIe, gcb_pack_expand_ell() derives the rest on
+   * the device (37 % fewer H2D bytes at the benchmark shape). */
+  GCB_H_COMPACT_INTS,
   GCB_H_FIELDS
 };
 
@@ -136,6 +144,13 @@ int gcb_collate_pack_each_host(const int32_t* const* atoms, const int32_t* n_ato
                                const int64_t* const* conn, const int32_t* n_edges, const float* const* y,
                                int32_t n_targets, int32_t n_graphs, int32_t n_messages, int32_t atom_vocab,
                                int32_t bond_vocab, int32_t* packed, int64_t packed_ints, float* y_out);
+
+/* Derives the ELL-4 views (GCB_H_IN_SRC4 .. GCB_H_OUT_INPOS4) of a packed batch ON THE DEVICE from its CSR sections:
+ * the host copies only the first header[GCB_H_COMPACT_INTS] ints of a host-packed batch into a full-size device
+ * buffer and calls this on the copy's stream.  Bit-identical to the views the host packers write
+ * (tests/test_pack_device.py).  Replaces nothing in the reference (PyG's Collater ships index tensors as they are,
+ * examples/predict_cn.ipynb:245); it exists for the end-to-end path's PCIe budget. */
+int gcb_pack_expand_ell(int32_t* packed_dev, const int32_t* packed_header_host, void* stream);
 
 /* ---- device-side packer (SURVEY.md 8 d config 5 "packed on device"; 8 f1) ------------------- */
 /* The host gathers a batch into a RAW buffer (0.7 kB per molecule instead of 3.9 kB): header, molecule

@@ -25,7 +25,7 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_layout():
     lib = _lib.lib()
-    assert lib.gcb_abi_version() == 2
+    assert lib.gcb_abi_version() == 3
     assert b"sm_100a" in lib.gcb_build_info()
     cfg = _lib.ModelCfg(42, 29, 1, 128, 3, 3, 128, 0, 0, 0, 0.0, 0)
     offs = (ctypes.c_int64 * 65)()

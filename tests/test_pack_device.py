@@ -143,6 +143,30 @@ def test_device_pack_equals_host_pack(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_compact_upload_rebuilds_the_ell_views_on_the_device(name):
+    """`PackedBatch.to('cuda')` / `upload_into` move only header[H_COMPACT_INTS] ints over PCIe; gcb_pack_expand_ell derives
+    the four ELL-4 views from the CSRs on the device.  The device buffer must equal the host-packed one bit for bit
+    (plain and each-molecule-alone layouts, L = 0 included), and nothing may be written past it."""
+    store = CASES[name]
+    for L, each in ((2, False), (0, False), (2, True)):
+        for idx in _orders(store):
+            try:
+                ref = store.collate_pack(idx, L, AV, BV, each=each) if each else store.collate_pack(idx, L, AV, BV)
+            except (NotImplementedError, IndexError):
+                continue  # each=True needs at least as many edges as atoms
+            total, compact = ref.ints.numel(), ref.compact_ints
+            assert 0 < compact <= total and compact == int(ref.header[_lib.H_IN_SRC4])
+            assert total - compact == 4 * ((4 * ref.N + 3) // 4 * 4)
+            dst = torch.full((total + 8,), -7, dtype=torch.int32, device="cuda")
+            ref.upload_into(dst)
+            torch.cuda.synchronize()
+            assert torch.equal(dst[:total].cpu(), ref.ints), f"{name}: first difference at int {int((dst[:total].cpu() != ref.ints).nonzero()[0])}"
+            assert bool((dst[total:] == -7).all()), "wrote past the packed batch"
+            assert torch.equal(ref.to("cuda").ints.cpu(), ref.ints)
+
+
+@pytest.mark.gpu
 def test_device_pack_bench_shape_and_train_step_on_top():
     """The bench shape (8192 fixed-shape molecules) packed on the device: identical buffer, identical step."""
     from graphchem_b200.nn.gcn import MoleculeGCN
