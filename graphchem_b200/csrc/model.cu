@@ -15,7 +15,6 @@
 #include "gemm_tc.cuh"
 #include "tile_rows.cuh"
 #include "fused_rows.cuh"
-#include "fused_cm.cuh"
 #include "kernels.cuh"
 #include "readout.cuh"
 #include "rowops.cuh"
@@ -50,7 +49,7 @@ void KernelTimer::stop() {
 }
 
 // ---- GEMM dispatch: tcgen05 kernel for bf16 hot shapes, CUDA-core kernel otherwise ---------------
-namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(int which); bool fused_exact(); bool tile_enabled(); bool bond_bwd_merged_enabled(); bool fused_cm_enabled(); }
+namespace tc { bool tc_enabled(); bool pingpong_enabled(); bool overlap_enabled(); bool fused_enabled(int which); bool fused_exact(); bool tile_enabled(); bool bond_bwd_merged_enabled(); }
 template <typename T>
 static int gemm_nt_auto(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                         const Epilogue& ep, cudaStream_t s) {
@@ -514,16 +513,6 @@ static bool tiles_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
          !((flags & GCB_TRAINING) && c.p_dropout > 0.f);
 }
 
-// Channel-major fused bond update (fused_cm.cuh): bf16, D = 128, closed row tiles, every atom row a live bond row, no
-// active dropout.  It keeps P and Q in fp32 (never rounded to bf16), so it agrees with the tile kernels to a few bf16
-// ulps, not bit for bit; GCB_NO_FUSED_CM=1 switches it off.
-template <typename T>
-static bool cm_ok(const gcb_model_cfg& c, const Graph& g, int flags) {
-  if constexpr (sizeof(T) != 2) return false;
-  return tc::fused_cm_enabled() && tc::tc_enabled() && c.D == 128 && tiles_ok<T>(c, g, flags) && tc::bond_bwd_merged_enabled() &&
-         !fused_ok<T>(c, g, flags, 0);
-}
-
 // Message step 1 straight from the bond-token table (tile::bond_update_tok_kernel and, in the backward pass, the
 // per-token sums of [dP|dQ]): the tile preconditions plus a table that fits shared memory.  GCB_NO_TOK1=1 switches
 // it off (A/B switch; the bit-for-bit comparisons with the plain row kernels use it, because summing [dP|dQ] per
@@ -605,21 +594,6 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
         GCB_TRY(tile::launch_bond_update_tok(D, cm, g.n_tiles, (const bf16*)(dv.base + dv.tab_pq), g.e_tok, c.bond_vocab,
                                              (bf16*)p.B[l], save ? p.tiemask[l] : nullptr, save ? p.tiecnt[l] : nullptr, c.act, s));
         bond_done = true;
-      }
-    }
-    if constexpr (sizeof(T) == 2) {
-      if (M > 0 && !bond_done && cm_ok<T>(c, g, flags)) {
-        const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
-        cm::Args ca;
-        ca.tile_ptr = g.tile_ptr; ca.n_tiles = g.n_tiles; ca.rows = M; ca.act = c.act;
-        ca.ptr = g.in_ptr; ca.nbr = g.in_src; ca.nbr4 = (const int4*)g.in_src4;
-        ca.bias = bpq; ca.out = (bf16*)p.B[l];
-        ca.tiemask = save ? reinterpret_cast<uint32_t*>(p.tiemask[l]) : nullptr;
-        ca.tiecnt = save ? p.tiecnt[l] : nullptr;
-        const int rc = save ? cm::launch_bond_fwd<true>((const bf16*)p.B[l - 1], (const bf16*)wpq, ca, s)
-                            : cm::launch_bond_fwd<false>((const bf16*)p.B[l - 1], (const bf16*)wpq, ca, s);
-        if (rc == GCB_OK) bond_done = true;
-        else if (rc != GCB_ERR_UNSUPPORTED) return rc;
       }
     }
     if (M > 0 && !bond_done) {

@@ -577,7 +577,7 @@ __host__ __device__ inline void pack_one_molecule(const PackPtrs& p, int32_t g, 
 // The same molecule packed by the 32 lanes of a warp, as a sequence of phases that only communicate through memory:
 // the kernel runs phase, __syncwarp(), phase, ...; the emulation hook runs every phase for lanes 0..31 in turn, which is
 // equivalent.  w: per-warp work area of kWarpWork ints (pin | pout | pos | local src | local dst); the molecule must
-// satisfy na <= kPackMaxA and ne <= kPackMaxE.  Results are identical to pack_one_molecule (experimental, GCB_PACK_WARP=1).
+// satisfy na <= kPackMaxA and ne <= kPackMaxE.  Results are identical to pack_one_molecule (the default device packer).
 constexpr int kPackMaxA = 64, kPackMaxE = 160;  // molecules up to this size use thread-local / per-warp arrays, larger ones scratch
 constexpr int kWarpWork = 2 * (kPackMaxA + 1) + 3 * kPackMaxE;
 constexpr int kWarpPhases = 6;
@@ -754,7 +754,7 @@ __global__ void pack_molecules_kernel(const PackPtrs p, const int32_t* __restric
     pack_one_molecule(p, g, a0, na, e0, ne, scr_pin + a0 + g, scr_pout + a0 + g, scr_pos + e0);
   }
 }
-// Warp per molecule (experimental, GCB_PACK_WARP=1): the phases of pack_warp_phase with a __syncwarp() between them, the
+// Warp per molecule (default; GCB_PACK_WARP=0 selects the thread-per-molecule kernel above): the phases of pack_warp_phase with a __syncwarp() between them, the
 // work area in shared memory; a molecule beyond the per-warp limits is packed by lane 0 alone out of global scratch.
 constexpr int kPackWarps = 8;
 __global__ void __launch_bounds__(kPackWarps * 32)
@@ -846,7 +846,7 @@ static int bucket_device(const int32_t* key, int64_t n, int32_t nb, int32_t* ptr
   return GCB_OK;
 }
 
-// Experimental (GCB_PACK_WARP=1): the atom and the bond token sort share their launches (blockIdx.y / the upper half of
+// With the warp-per-molecule kernel (default): the atom and the bond token sort share their launches (blockIdx.y / the upper half of
 // the scan grid selects the job), 4 launches instead of 8; the per-chunk / per-bucket routines are the same.
 struct BucketJob { const int32_t* key; int64_t n; int32_t nb; int64_t chunks; int32_t *ptr, *perm, *hist; };
 __global__ void bucket_hist2_kernel(const BucketJob j0, const BucketJob j1) {
@@ -1097,7 +1097,9 @@ extern "C" int gcb_pack_device(const int32_t* raw_dev, const int32_t* raw_header
   int gx = (maxc + 256 * 4 - 1) / (256 * 4);
   gx = gx < 1 ? 1 : (gx > 4 * kNumSMs ? 4 * kNumSMs : gx);
   GCB_KERNEL("pack_segments_kernel", s, pack_segments_kernel<<<dim3((unsigned)gx, (unsigned)sg.n + 1), 256, 0, s>>>(sg, raw_dev, packed_dev));
-  static const bool warp_path = [] { const char* e = getenv("GCB_PACK_WARP"); return e && e[0] == '1'; }();
+  // warp-per-molecule kernel + token sorts that share their launches: 0.169 vs 0.269 ms per 8192-molecule batch on B200
+  // (profiles/r2_device_pack_time.json); GCB_PACK_WARP=0 selects the thread-per-molecule kernels
+  static const bool warp_path = [] { const char* e = getenv("GCB_PACK_WARP"); return !(e && e[0] == '0'); }();
   if (G > 0) {
     const PackPtrs p = pack_ptrs(packed_dev, h);
     if (warp_path) {

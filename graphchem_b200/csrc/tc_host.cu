@@ -96,14 +96,6 @@ bool fused_exact() {
   return e && e[0] == '1';
 }
 
-// Channel-major fused bond update (fused_cm.cuh): opt-in with GCB_FUSED_CM=1 until it has been measured; GCB_NO_FUSED_CM=1 vetoes.
-bool fused_cm_enabled() {
-  const char* off = std::getenv("GCB_NO_FUSED_CM");
-  if (off && off[0] == '1') return false;
-  const char* on = std::getenv("GCB_FUSED_CM");
-  return on && on[0] == '1';
-}
-
 // Tile-staged row kernels (tile_rows.cuh); on unless GCB_NO_TILE=1.
 bool tile_enabled() {
   const char* e = std::getenv("GCB_NO_TILE");

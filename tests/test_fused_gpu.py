@@ -26,9 +26,8 @@ def _dev(data):
                 batch=data.batch.cuda(), num_graphs=int(data.batch.max()) + 1)
 
 
-ENV = {"tile": {"GCB_NO_FUSED": "1", "GCB_NO_TOK1": "1", "GCB_NO_FUSED_CM": "1"},
-       "tile_split": {"GCB_NO_BOND_MERGE": "1", "GCB_NO_TOK1": "1", "GCB_NO_FUSED_CM": "1"}, "tok1": {"GCB_NO_FUSED_CM": "1"},
-       "cm": {"GCB_FUSED_CM": "1"}, "cm_only": {"GCB_FUSED_CM": "1", "GCB_NO_TOK1": "1"},
+ENV = {"tile": {"GCB_NO_FUSED": "1", "GCB_NO_TOK1": "1"},
+       "tile_split": {"GCB_NO_BOND_MERGE": "1", "GCB_NO_TOK1": "1"}, "tok1": {},
        "fused_exact": {"GCB_FUSED": "1", "GCB_FUSED_EXACT": "1", "GCB_NO_FUSED_ATOM": "1"}, "fused": {"GCB_FUSED": "1"}, "v2": {"GCB_NO_TILE": "1"}}
 
 
@@ -97,55 +96,6 @@ def test_first_step_from_the_token_table(n_graphs, max_atoms, L, D, act):
                     assert nerr(a, b) <= 2e-2, (name, nerr(a, b))
                 else:
                     assert torch.equal(a, b), f"grad {name} differs: {nerr(a, b)}"
-
-
-@pytest.mark.parametrize("mode", ["cm", "cm_only"])
-@pytest.mark.parametrize("n_graphs,max_atoms,L", [(1, 12, 1), (7, 12, 2), (64, 30, 3), (700, 40, 4), (3000, 30, 4)])
-@pytest.mark.parametrize("act", [F.softplus, F.tanh])
-def test_channel_major_fused_bond_update_close_to_tile_kernels(n_graphs, max_atoms, L, act, mode):
-    """fused_cm.cuh (GEMM issued transposed, neighbours read as TMEM columns, P and Q never rounded to bf16) against
-    the tile kernels + stand-alone GEMM: two bf16 paths with different rounding points."""
-    data, _ = random_batch(seed=200 + n_graphs, n_graphs=n_graphs, max_atoms=max_atoms)
-    _, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=L, act_fn=act)
-    dev = _dev(data)
-    for train in (False, True):
-        out_f, grad_f = _run(model, dev, train, mode)
-        out_u, grad_u = _run(model, dev, train, "tile")
-        for k, (a, b) in enumerate(zip(out_f, out_u)):
-            assert nerr(a.float(), b.float()) <= 4e-2 or float((a.float() - b.float()).abs().max()) <= 2e-2, (k, train, nerr(a.float(), b.float()))
-        if train:
-            for (name, _), a, b in zip(model.named_parameters(), grad_f, grad_u):
-                if float(b.abs().max()) > 0:
-                    assert nerr(a, b) <= 1.5e-1, (name, nerr(a, b))
-
-
-def test_channel_major_kernel_matches_the_oracle_and_counts_ties():
-    """Oracle parity of the channel-major path at the bf16 bar, and exact ties (relu, shared bond tokens) split as
-    torch's scatter_reduce(amax) backward does."""
-    import os
-    os.environ["GCB_FUSED_CM"] = "1"
-    os.environ["GCB_NO_TOK1"] = "1"
-    try:
-        for act, n in ((F.softplus, 300), (F.relu, 64)):
-            data, _ = random_batch(seed=17, n_graphs=n, max_atoms=25)
-            oracle, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=3, act_fn=act)
-            dev = _dev(data)
-            oracle.eval(); model.eval()
-            with torch.no_grad():
-                ro, rm = oracle(data), model(dev)
-            for a, b in zip(rm, ro):
-                assert nerr(a.float(), b) <= 1e-2, nerr(a.float(), b)
-            oracle.train(); model.train()
-            lo = F.mse_loss(oracle(data)[0], data.y)
-            oracle.zero_grad(); lo.backward()
-            lm = F.mse_loss(model(dev)[0], dev.y)
-            model.zero_grad(); lm.backward()
-            for (name, po), (_, pm) in zip(oracle.named_parameters(), model.named_parameters()):
-                if po.grad is not None and float(po.grad.abs().max()) > 0:
-                    assert nerr(pm.grad, po.grad) <= 6e-2, (name, nerr(pm.grad, po.grad))
-    finally:
-        os.environ.pop("GCB_FUSED_CM", None)
-        os.environ.pop("GCB_NO_TOK1", None)
 
 
 @pytest.mark.parametrize("n_graphs,max_atoms,L", [(1, 12, 1), (7, 12, 2), (64, 30, 3), (700, 40, 4), (3000, 30, 4)])

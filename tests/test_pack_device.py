@@ -215,10 +215,10 @@ def test_loader_device_pack_argument_checks():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("GCB_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental warp-per-molecule pack kernel (GCB_PACK_WARP=1): pinned on the CPU lane by lane "
-                           "(force_scratch=2 above), not yet run on a GPU; set GCB_TEST_EXPERIMENTAL=1 to include it")
-def test_warp_per_molecule_kernel_in_a_subprocess():
+def test_thread_per_molecule_kernels_in_a_subprocess():
+    """The default device packer is the warp-per-molecule kernel (every other GPU test here runs it); the
+    thread-per-molecule kernels it replaced stay selectable (GCB_PACK_WARP=0, read once per process) and must keep
+    producing the same buffers."""
     import os
     import subprocess
     import sys
@@ -230,8 +230,8 @@ def test_warp_per_molecule_kernel_in_a_subprocess():
         "        ref = store.collate_pack(idx, 2, AV, BV)\n"
         "        got = store.collate_raw(idx, 2, AV, BV).to('cuda').pack().ints.cpu()\n"
         "        assert torch.equal(got, ref.ints), name\n"
-        "print('warp pack ok')\n")
-    env = dict(os.environ, GCB_PACK_WARP="1")
+        "print('thread pack ok')\n")
+    env = dict(os.environ, GCB_PACK_WARP="0")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0 and "warp pack ok" in res.stdout, res.stdout + res.stderr
+    assert res.returncode == 0 and "thread pack ok" in res.stdout, res.stdout + res.stderr
