@@ -23,7 +23,8 @@ GCB_ERR_CUDA = -4
 GCB_ERR_WORKSPACE = -5
 
 ACT_SOFTPLUS, ACT_SIGMOID, ACT_RELU, ACT_TANH, ACT_LEAKY_RELU = range(5)
-AGGR_ADD, AGGR_MEAN = 0, 1
+AGGR_ADD, AGGR_MEAN, AGGR_MAX = 0, 1, 2
+POOL_ADD, POOL_MEAN = 0, 1
 F32, BF16 = 0, 1
 TRAINING, SAVE_FOR_BWD = 1, 2
 
@@ -43,7 +44,7 @@ class ModelCfg(C.Structure):
     """Mirror of `gcb_model_cfg` (constructor arguments of MoleculeGCN, reference gcn.py:35-42)."""
     _fields_ = [("atom_vocab", C.c_int32), ("bond_vocab", C.c_int32), ("out_dim", C.c_int32), ("D", C.c_int32),
                 ("L", C.c_int32), ("n_readout", C.c_int32), ("R", C.c_int32), ("act", C.c_int32),
-                ("aggr", C.c_int32), ("dtype", C.c_int32), ("p_dropout", C.c_float), ("reserved", C.c_int32)]
+                ("aggr", C.c_int32), ("dtype", C.c_int32), ("p_dropout", C.c_float), ("pool", C.c_int32)]
 
 
 class GcbError(RuntimeError):
@@ -131,7 +132,7 @@ def check(rc: int, what: str = "") -> int:
         raise ValueError(f"{what}: invalid argument")
     if rc == GCB_ERR_UNSUPPORTED:
         raise NotImplementedError(f"{what}: configuration not supported by the sm_100a kernels "
-                                  "(embedding_dim must be a multiple of 8; aggr in {'add','mean'})")
+                                  "(embedding_dim must be a multiple of 8; aggr in {'add','mean','max'})")
     if rc == GCB_ERR_CUDA:
         raise GcbError(f"{what}: CUDA error: {lib().gcb_last_cuda_error().decode()}")
     if rc == GCB_ERR_WORKSPACE:

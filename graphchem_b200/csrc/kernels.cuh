@@ -193,7 +193,7 @@ __global__ void gather_bond_rows_kernel(const T* __restrict__ B, const int32_t* 
 // global_add_pool (gcn.py:181): out[g,:] = sum_{i in graph g} A[i,:], in node order.
 template <typename T>
 __global__ void pool_kernel(const T* __restrict__ A, const int32_t* __restrict__ graph_ptr,
-                            const int32_t* __restrict__ graph_node, float* __restrict__ out, int G, int D) {
+                            const int32_t* __restrict__ graph_node, float* __restrict__ out, int G, int D, int mean) {
   GCB_ROW_CHUNK_PROLOGUE(G)
   const int k0 = graph_ptr[r], k1 = graph_ptr[r + 1];
   float acc[V];
@@ -205,6 +205,11 @@ __global__ void pool_kernel(const T* __restrict__ A, const int32_t* __restrict__
     load_vec(A + (size_t)n * D + c, a);
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] += a[i];
+  }
+  if (mean && k1 > k0) {  // global_mean_pool: sum / max(count, 1)
+    const float inv = 1.f / (float)(k1 - k0);
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] *= inv;
   }
   float* o = out + (size_t)r * D + c;
 #pragma unroll
@@ -219,17 +224,18 @@ template <typename T>
 __global__ void pool_bwd_kernel(const float* __restrict__ dPool, const T* __restrict__ d_out_atom,
                                 const T* __restrict__ A_last, const int32_t* __restrict__ graph_ptr,
                                 const int32_t* __restrict__ graph_node, T* __restrict__ dZA, int G, int D, int act,
-                                Drop dr) {
+                                Drop dr, int mean) {
   GCB_ROW_CHUNK_PROLOGUE(G)
   const int k0 = graph_ptr[r], k1 = graph_ptr[r + 1];
   float dp[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) dp[i] = 0.f;
   if (dPool) {
+    const float w = mean && k1 > k0 ? 1.f / (float)(k1 - k0) : 1.f;
 #pragma unroll
     for (int i = 0; i < V; i += 4) {
       float4 t = __ldg(reinterpret_cast<const float4*>(dPool + (size_t)r * D + c + i));
-      dp[i] = t.x; dp[i + 1] = t.y; dp[i + 2] = t.z; dp[i + 3] = t.w;
+      dp[i] = w * t.x; dp[i + 1] = w * t.y; dp[i + 2] = w * t.z; dp[i + 3] = w * t.w;
     }
   }
   for (int k = k0; k < k1; ++k) {

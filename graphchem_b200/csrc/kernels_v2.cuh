@@ -429,7 +429,9 @@ bond_bwd_scatter_kernel(const T* __restrict__ gsplit, const uint8_t* __restrict_
 template <typename T, int CH, bool DROP>
 __global__ void __launch_bounds__(kThreads)
 pool_bwd_kernel(const float* __restrict__ dPool, const T* __restrict__ d_out_atom, const T* __restrict__ A_last,
-                const int32_t* __restrict__ node_graph, T* __restrict__ dZA, int N, int act, Drop dr, int rev) {
+                const int32_t* __restrict__ node_graph, T* __restrict__ dZA, int N, int act, Drop dr, int rev,
+                const int32_t* __restrict__ mean_ptr) {
+  // mean_ptr: graph_ptr when the pooling is a mean (every node gets dPool / node count of its graph), else null
   GCB_V2_PROLOGUE(N)
   float d[V], y[V];
   vzero<T, V>(d);
@@ -439,6 +441,11 @@ pool_bwd_kernel(const float* __restrict__ dPool, const T* __restrict__ d_out_ato
     for (int i = 0; i < V; i += 4) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(dPool + (size_t)g * D + c + i));
       d[i] = t.x; d[i + 1] = t.y; d[i + 2] = t.z; d[i + 3] = t.w;
+    }
+    if (mean_ptr) {
+      const float w = 1.f / (float)max(__ldg(mean_ptr + g + 1) - __ldg(mean_ptr + g), 1);
+#pragma unroll
+      for (int i = 0; i < V; ++i) d[i] *= w;
     }
   }
   if (d_out_atom) {

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "readout.cuh"
 #include "rowops.cuh"
+#include "aggr_max.cuh"
 
 namespace gcb {
 
@@ -165,7 +166,8 @@ static int make_layout(const gcb_model_cfg& c, ParamLayout& p) {
 static int check_cfg(const gcb_model_cfg& c) {
   if (c.dtype != GCB_F32 && c.dtype != GCB_BF16) return GCB_ERR_INVALID_ARG;
   if (c.act < 0 || c.act > GCB_ACT_LEAKY_RELU) return GCB_ERR_INVALID_ARG;
-  if (c.aggr != GCB_AGGR_ADD && c.aggr != GCB_AGGR_MEAN) return GCB_ERR_UNSUPPORTED;
+  if (c.aggr != GCB_AGGR_ADD && c.aggr != GCB_AGGR_MEAN && c.aggr != GCB_AGGR_MAX) return GCB_ERR_UNSUPPORTED;
+  if (c.pool != GCB_POOL_ADD && c.pool != GCB_POOL_MEAN) return GCB_ERR_INVALID_ARG;
   if (c.D % 8 != 0) return GCB_ERR_UNSUPPORTED;  // 16-byte channel chunks in both dtypes
   if (!(c.p_dropout >= 0.f && c.p_dropout < 1.f)) return GCB_ERR_UNSUPPORTED;
   if (c.L > 250) return GCB_ERR_UNSUPPORTED;
@@ -337,6 +339,12 @@ struct Plan {
   float *partialAt = nullptr, *partialPq = nullptr;  // per-CTA partials of the two conv weight gradients, summed over layers
   float *accWpq = nullptr, *accBpq = nullptr, *accWat = nullptr, *accBat = nullptr;
   float* tokPQ = nullptr;  // [bond_vocab][2D] per-token sums of step 1's [dP|dQ]
+  // aggr = "max" (aggr_max.cuh): per-edge rows in dst-CSR order
+  void* Msg[kMaxLayers];    // [E, D] messages of every layer (saved for the amax backward)
+  void* Zrow = nullptr;     // [E, 2D] [A[src] | B'[eid]] (recomputed in backward)
+  void* dMsg = nullptr;     // [E, D]
+  void* dZrow = nullptr;    // [E, 2D]
+  int32_t* einpos = nullptr;  // [E] dst-CSR position of edge e
 };
 
 static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, int64_t E, int64_t G, int64_t M,
@@ -345,6 +353,8 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
   const bool save = (flags & GCB_SAVE_FOR_BWD) != 0;
   const int L = c.L;
   if (L + 1 > kMaxLayers) return GCB_ERR_UNSUPPORTED;
+  const bool amax = c.aggr == GCB_AGGR_MAX;  // per-edge messages instead of the aggregated [N, 2D] operands
+  const int64_t NS = amax ? 0 : N;           // rows of S / dS
   int64_t o = 0;
   auto take = [&](int64_t bytes) -> void* {
     void* ptr = base ? (char*)base + o : nullptr;
@@ -356,21 +366,29 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
     for (int l = 0; l <= L; ++l) p.A[l] = take(N * D * es);
     for (int l = 0; l <= L; ++l) p.B[l] = take(M * D * es);
     for (int l = 1; l <= L; ++l) p.PQ[l] = take(M * 2 * D * es);
-    for (int l = 1; l <= L; ++l) p.S[l] = take(N * 2 * D * es);
+    for (int l = 1; l <= L; ++l) p.S[l] = take(NS * 2 * D * es);
+    if (amax) for (int l = 1; l <= L; ++l) p.Msg[l] = take(E * D * es);
   } else {
     void* a2[2] = {take(N * D * es), take(N * D * es)};
     void* b2[2] = {take(M * D * es), take(M * D * es)};
     void* pq = take(M * 2 * D * es);
-    void* s = take(N * 2 * D * es);
-    for (int l = 0; l <= L; ++l) { p.A[l] = a2[l & 1]; p.B[l] = b2[l & 1]; p.PQ[l] = pq; p.S[l] = s; }
+    void* s = take(NS * 2 * D * es);
+    void* msg = amax ? take(E * D * es) : nullptr;
+    for (int l = 0; l <= L; ++l) { p.A[l] = a2[l & 1]; p.B[l] = b2[l & 1]; p.PQ[l] = pq; p.S[l] = s; p.Msg[l] = msg; }
   }
+  if (amax) p.Zrow = take(E * 2 * D * es);
   p.pooled = (float*)take(G * D * 4);
   const int64_t R = c.n_readout > 0 ? c.R : 0;
   p.H[0] = p.pooled;
   for (int k = 1; k <= c.n_readout; ++k) p.H[k] = (float*)take(G * R * 4);
   if (save) {
     p.dZA[0] = take(N * D * es); p.dZA[1] = take(N * D * es);
-    p.dS = take(N * 2 * D * es);
+    p.dS = take(NS * 2 * D * es);
+    if (amax) {
+      p.dMsg = take(E * D * es);
+      p.dZrow = take(E * 2 * D * es);
+      p.einpos = (int32_t*)take(E * 4);
+    }
     p.dBn[0] = take(M * D * es); p.dBn[1] = take(M * D * es);
     p.dPQ2[0] = take(M * 2 * D * es); p.dPQ2[1] = take(M * 2 * D * es);
     p.dPQ = p.dPQ2[0];
@@ -630,6 +648,20 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
         else if (rc != GCB_ERR_UNSUPPORTED) return rc;
       }
     }
+    if (N > 0 && !atom_done && c.aggr == GCB_AGGR_MAX) {
+      // transform-then-aggregate (aggr_max.cuh): per-edge rows -> messages -> segmented max + residual + act
+      GCB_TRY(launch_edge_rows<T>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_src, g.in_eid, (T*)p.Zrow, E, M, D, c.act, db, s));
+      if (E > 0) {
+        Epilogue ep;
+        ep.bias = bat;
+        GCB_TRY(gemm_nt_auto<T>((const T*)p.Zrow, 2 * D, wat, 2 * D, false, (T*)p.Msg[l], D, E, D, 2 * D, ep, s));
+      }
+      GCB_TRY(launch_atom_max_update<T>((const T*)p.Msg[l], g.in_ptr, (const T*)p.A[l - 1], (T*)p.A[l], N, D, c.act, s));
+      if (da.p > 0.f) {
+        GCB_KERNEL("dropout_inplace_kernel", s, dropout_inplace_kernel<T><<<row_chunk_blocks(N, D, V), 256, 0, s>>>((T*)p.A[l], N, D, da));
+      }
+      atom_done = true;
+    }
     if (N > 0 && !atom_done) {
       bool a_tiled = false;
       if constexpr (sizeof(T) == 2) {
@@ -658,7 +690,7 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
   }
   // pooling + readout (fp32)
   if (G > 0) {
-    GCB_KERNEL("pool_kernel", s, pool_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>((const T*)p.A[L], g.graph_ptr, g.graph_node, p.pooled, G, D));
+    GCB_KERNEL("pool_kernel", s, pool_kernel<T><<<row_chunk_blocks(G, D, V), 256, 0, s>>>((const T*)p.A[L], g.graph_ptr, g.graph_node, p.pooled, G, D, c.pool == GCB_POOL_MEAN ? 1 : 0));
     if (pl.n_lin == 0) {
       if (out) GCB_CUDA(cudaMemcpyAsync(out, p.pooled, (size_t)G * D * 4, cudaMemcpyDeviceToDevice, s));
     } else if (ReadoutDesc rd2; readout2_ok(pl, rd2, G)) {
@@ -807,7 +839,7 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
   if (N > 0) {
     if (G > 0) {
       GCB_TRY(launch_pool_bwd<T>(dPool, d_out_atom, (const T*)p.A[L], g.graph_ptr, g.graph_node, g.node_graph, (T*)p.dZA[cur],
-                                 N, G, D, c.act, L >= 1 ? make_drop(c, flags, seed, tag_atom(L)) : Drop(), s));
+                                 N, G, D, c.act, L >= 1 ? make_drop(c, flags, seed, tag_atom(L)) : Drop(), c.pool == GCB_POOL_MEAN ? 1 : 0, s));
     } else {
       GCB_CUDA(cudaMemsetAsync(p.dZA[cur], 0, (size_t)N * D * sizeof(T), s));
     }
@@ -836,7 +868,29 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
         else if (rc != GCB_ERR_UNSUPPORTED) return rc;
       }
     }
-    if (atom_done) {
+    const bool amax = c.aggr == GCB_AGGR_MAX;
+    if (amax) {
+      // aggr = "max": the gradient goes to the in-edges that attained the maximum (even tie split), then through the
+      // per-edge linear maps; dZrow [E, 2D] takes the place of dS for the source-side kernels (aggr_max.cuh)
+      GCB_TRY(join(done_at[l + 1]));  // W_at(l+1) read Zrow / dMsg / dZA[cur ^ 1]
+      if (l == L) GCB_TRY(launch_edge_inpos<T>(g.in_eid, p.einpos, g.E, s));
+      GCB_TRY(launch_edge_rows<T>((const T*)p.A[l - 1], (const T*)p.B[l], g.in_src, g.in_eid, (T*)p.Zrow, g.E, M, D, c.act,
+                                  make_drop(c, flags, seed, tag_bond(l)), s));
+      GCB_TRY(launch_atom_max_bwd<T>((const T*)p.Msg[l], g.in_ptr, (const T*)p.dZA[cur], (T*)p.dMsg, N, D, s));
+      if (g.E > 0) {
+        Epilogue ep;
+        GCB_TRY(gemm_nt_auto<T>((const T*)p.dMsg, D, watT, D, false, (T*)p.dZrow, 2 * D, g.E, 2 * D, D, ep, s));
+      }
+      GCB_TRY(fork());
+      GCB_TRY(gemm_tn_auto<T>((const T*)p.dMsg, D, (const T*)p.Zrow, 2 * D, g.E, D, 2 * D, p.partial, p.accWat,
+                                p.accBat, nullptr, GCB_AGGR_ADD, acc_w, sw));
+      GCB_TRY(mark(done_at[l]));
+      if (N > 0) {
+        GCB_TRY(launch_atom_bwd_gather<T>((const T*)p.dZA[cur], (const T*)p.dZrow, g.out_ptr, g.out_inpos, g.out_inpos4, g.in_ptr,
+                                          (const T*)p.A[l - 1], (T*)p.dZA[cur ^ 1], N, D, c.act, GCB_AGGR_ADD,
+                                          l - 1 >= 1 ? make_drop(c, flags, seed, tag_atom(l - 1)) : Drop(), flip(), s));
+      }
+    } else if (atom_done) {
       GCB_TRY(fork());
       GCB_TRY(gemm_tn_auto<T>((const T*)p.dZA[cur], D, (const T*)p.S[l], 2 * D, N, D, 2 * D, p.partial, p.accWat,
                                 p.accBat, g.in_ptr, c.aggr, acc_w, sw, 0, p.partialAt, &grid_at, l == L));
@@ -882,9 +936,10 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       }
     }
     if (M > 0 && !bond_tiled) {
-      GCB_TRY(launch_bond_bwd_tie<T>((const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l],
-                                     g.dst, g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, dPQ_l, (T*)p.mx, (T*)p.gsplit,
-                                     p.tiemask[l], p.tiecnt[l], M, D, c.act, c.aggr,
+      // bond row r = edge r feeds the atom it points to: dS[dst r, D:] (add / mean), its own message row (max)
+      GCB_TRY(launch_bond_bwd_tie<T>(amax ? (const T*)p.dZrow : (const T*)p.dS, dBnext, l == L ? d_out_bond : nullptr, (const T*)p.B[l], (const T*)p.PQ[l],
+                                     amax ? p.einpos : g.dst, g.in_ptr, g.in_src, g.in_eid, g.in_src4, g.in_eid4, dPQ_l, (T*)p.mx, (T*)p.gsplit,
+                                     p.tiemask[l], p.tiecnt[l], M, D, c.act, amax ? (int)GCB_AGGR_ADD : c.aggr,
                                      make_drop(c, flags, seed, tag_bond(l)), flip(), s));
       bool tiled = false;
       if constexpr (sizeof(T) == 2) {

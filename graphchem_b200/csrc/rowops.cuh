@@ -102,10 +102,10 @@ int launch_bond_bwd_scatter(const T* PQ, const T* mx, const T* gsplit, const int
 template <typename T>
 int launch_pool_bwd(const float* dPool, const T* d_out_atom, const T* A_last, const int32_t* graph_ptr,
                     const int32_t* graph_node, const int32_t* node_graph, T* dZA, int N, int G, int D, int act, Drop dr,
-                    cudaStream_t s) {
+                    int mean, cudaStream_t s) {
   GCB_ROW_DISPATCH("pool_bwd_kernel", N, D, dr.p > 0.f,
-                   (v2::pool_bwd_kernel<T, CH, DROP><<<GCB_V2_GRID_FLAT(N)>>>(dPool, d_out_atom, A_last, node_graph, dZA, N, act, dr, 0)),
-                   (pool_bwd_kernel<T><<<GCB_V1_GRID(G, D)>>>(dPool, d_out_atom, A_last, graph_ptr, graph_node, dZA, G, D, act, dr)));
+                   (v2::pool_bwd_kernel<T, CH, DROP><<<GCB_V2_GRID_FLAT(N)>>>(dPool, d_out_atom, A_last, node_graph, dZA, N, act, dr, 0, mean ? graph_ptr : nullptr)),
+                   (pool_bwd_kernel<T><<<GCB_V1_GRID(G, D)>>>(dPool, d_out_atom, A_last, graph_ptr, graph_node, dZA, G, D, act, dr, mean)));
 }
 
 constexpr int kEmbedSplits = 32;  // capacity of the partial-sum scratch

@@ -54,7 +54,7 @@ def _act_id(act_fn) -> Optional[int]:
 
 
 _POISON = os.environ.get("GCB_DEBUG_POISON", "0") == "1"
-_AGGR_IDS = {"add": _lib.AGGR_ADD, "sum": _lib.AGGR_ADD, "mean": _lib.AGGR_MEAN}
+_AGGR_IDS = {"add": _lib.AGGR_ADD, "sum": _lib.AGGR_ADD, "mean": _lib.AGGR_MEAN, "max": _lib.AGGR_MAX}
 
 
 class _Linear(nn.Linear):
@@ -117,14 +117,16 @@ class _GCNFunction(torch.autograd.Function):
 
 
 class MoleculeGCN(nn.Module):
-    """See module docstring.  Extra keyword (not in the reference): `compute_dtype`
-    (torch.float32 = parity mode, default; torch.bfloat16 = bf16 storage / fp32 accumulate)."""
+    """See module docstring.  Extra keywords (not in the reference): `compute_dtype`
+    (torch.float32 = parity mode, default; torch.bfloat16 = bf16 storage / fp32 accumulate) and `pool`
+    ("add" = the reference's global_add_pool, gcn.py:181; "mean" = PyG's global_mean_pool)."""
 
     def __init__(self, atom_vocab_size: int, bond_vocab_size: int, output_dim: Optional[int],
                  embedding_dim: Optional[int] = 128, n_messages: Optional[int] = 2,
                  n_readout: Optional[int] = 2, readout_dim: Optional[int] = 64,
                  p_dropout: Optional[float] = 0.0, aggr: Optional[str] = "add",
-                 act_fn: Optional[Callable] = F.softplus, *, compute_dtype: torch.dtype = torch.float32):
+                 act_fn: Optional[Callable] = F.softplus, *, compute_dtype: torch.dtype = torch.float32,
+                 pool: str = "add"):
         super().__init__()
         self._p_dropout = p_dropout
         self._n_messages = n_messages
@@ -135,7 +137,10 @@ class MoleculeGCN(nn.Module):
                              "(or the nn.Module of the same function with default arguments): "
                              "the activation is fused into the CUDA kernels")
         if aggr not in _AGGR_IDS:
-            raise NotImplementedError(f"aggr={aggr!r} is not implemented by the CUDA kernels (use 'add' or 'mean')")
+            raise NotImplementedError(f"aggr={aggr!r} is not implemented by the CUDA kernels (use 'add', 'mean' or 'max')")
+        if pool not in ("add", "sum", "mean"):
+            raise ValueError("pool must be 'add' (global_add_pool, the reference) or 'mean' (global_mean_pool)")
+        self._pool = _lib.POOL_MEAN if pool == "mean" else _lib.POOL_ADD
         if compute_dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("compute_dtype must be torch.float32 or torch.bfloat16")
         self._aggr = aggr
@@ -168,7 +173,7 @@ class MoleculeGCN(nn.Module):
             cfg = _lib.ModelCfg(av, bv, int(out_dim) if (n_readout > 0 and out_dim is not None) else 0, D,
                                 int(self._n_messages), n_readout, R, self._act_id, _AGGR_IDS[self._aggr],
                                 _lib.BF16 if self._compute_dtype == torch.bfloat16 else _lib.F32,
-                                float(self._p_dropout), 0)
+                                float(self._p_dropout), self._pool)
             offs = (C.c_int64 * (_lib.MAX_PARAM_TENSORS + 1))()
             n = _lib.check(_lib.lib().gcb_param_layout(C.byref(cfg), offs), "gcb_param_layout")
             self._cfg_cache = (key, cfg, [int(offs[i]) for i in range(n + 1)])

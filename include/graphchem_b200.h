@@ -41,7 +41,10 @@ extern "C" {
 /* act_fn of graphchem/nn/gcn.py:42,75 -- the five callables tests/test_gcn.py:107-113 exercise */
 enum gcb_act { GCB_ACT_SOFTPLUS = 0, GCB_ACT_SIGMOID = 1, GCB_ACT_RELU = 2, GCB_ACT_TANH = 3, GCB_ACT_LEAKY_RELU = 4 };
 /* aggr of GeneralConv, graphchem/nn/gcn.py:41,84-86 */
-enum gcb_aggr { GCB_AGGR_ADD = 0, GCB_AGGR_MEAN = 1 };
+enum gcb_aggr { GCB_AGGR_ADD = 0, GCB_AGGR_MEAN = 1, GCB_AGGR_MAX = 2 };
+/* graph pooling, graphchem/nn/gcn.py:181 (the reference calls global_add_pool; mean = PyG global_mean_pool:
+   segment sum / max(count, 1), BASELINE north_star item 4) */
+enum gcb_pool { GCB_POOL_ADD = 0, GCB_POOL_MEAN = 1 };
 /* storage type of activations (accumulation is always fp32) */
 enum gcb_dtype { GCB_F32 = 0, GCB_BF16 = 1 };
 
@@ -58,7 +61,7 @@ typedef struct gcb_model_cfg {
   int32_t aggr;        /* enum gcb_aggr                                    */
   int32_t dtype;       /* enum gcb_dtype                                   */
   float p_dropout;     /* p_dropout (applied only when flags & GCB_TRAINING) */
-  int32_t reserved;
+  int32_t pool;        /* enum gcb_pool: graph pooling of gcn.py:181 (0 = the reference's global_add_pool) */
 } gcb_model_cfg;
 
 /* ---- packed batch ------------------------------------------------------------------------ */

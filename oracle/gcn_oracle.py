@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .pyg_restated import EdgeConv, GeneralConv, global_add_pool
+from .pyg_restated import EdgeConv, GeneralConv, global_add_pool, global_mean_pool
 
 
 class OracleMoleculeGCN(nn.Module):
@@ -29,8 +29,9 @@ class OracleMoleculeGCN(nn.Module):
     def __init__(self, atom_vocab_size: int, bond_vocab_size: int, output_dim: Optional[int],
                  embedding_dim: int = 128, n_messages: int = 2, n_readout: int = 2,
                  readout_dim: int = 64, p_dropout: float = 0.0, aggr: str = "add",
-                 act_fn: Callable = F.softplus):
+                 act_fn: Callable = F.softplus, *, pool: str = "add"):
         super().__init__()
+        self._pool = pool                    # not in the reference (always global_add_pool); checks the product's `pool="mean"`
         self._p_dropout = p_dropout          # gcn.py:73
         self._n_messages = n_messages        # gcn.py:74
         self.act_fn = act_fn                 # gcn.py:75
@@ -60,7 +61,7 @@ class OracleMoleculeGCN(nn.Module):
             out_atom = self.act_fn(self.atom_conv(out_atom, edge_index, out_bond))     # :172-173
             out_atom = F.dropout(out_atom, p=self._p_dropout, training=self.training)  # :176-178
             layers.append((out_atom, out_bond))
-        out = global_add_pool(out_atom, batch)                # gcn.py:181
+        out = (global_mean_pool if self._pool == "mean" else global_add_pool)(out_atom, batch)  # gcn.py:181
         if self.readout is not None:                          # gcn.py:184
             for layer in self.readout[:-1]:                   # gcn.py:187-196
                 out = self.act_fn(layer(out))

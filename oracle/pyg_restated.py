@@ -182,6 +182,14 @@ def global_add_pool(x: Tensor, batch: Optional[Tensor], size: Optional[int] = No
     return scatter(x, batch, dim=dim, dim_size=size, reduce="sum")
 
 
+# nn/pool/glob.py::global_mean_pool (not called by graphchem; the product offers it as `pool="mean"`)
+def global_mean_pool(x: Tensor, batch: Optional[Tensor], size: Optional[int] = None) -> Tensor:
+    dim = -1 if x.dim() == 1 else -2
+    if batch is None:
+        return x.mean(dim=dim, keepdim=x.dim() <= 2)
+    return scatter(x, batch, dim=dim, dim_size=size, reduce="mean")
+
+
 # ----------------------------------------------------------------------------------------------
 # data/data.py, data/batch.py, data/collate.py -- the subset MoleculeGraph uses
 # ----------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ def test_constructor_signature_matches_reference():
     sig = inspect.signature(MoleculeGCN.__init__)
     ref = inspect.signature(OracleMoleculeGCN.__init__)
     names = [n for n, p in sig.parameters.items() if p.kind is not inspect.Parameter.KEYWORD_ONLY]
-    assert names == list(ref.parameters)
+    assert names == [n for n, p in ref.parameters.items() if p.kind is not inspect.Parameter.KEYWORD_ONLY]
     for n in names[1:]:
         assert sig.parameters[n].default == ref.parameters[n].default
 
@@ -68,10 +68,19 @@ def test_unfused_activation_is_refused_not_approximated(fn):
         MoleculeGCN(8, 4, 1, embedding_dim=16, act_fn=fn)
 
 
-def test_unsupported_aggregation_is_refused():
+def test_pool_keyword():
+    assert MoleculeGCN(8, 4, 1, embedding_dim=16)._cfg().pool == 0
+    assert MoleculeGCN(8, 4, 1, embedding_dim=16, pool="mean")._cfg().pool == 1
+    with pytest.raises(ValueError):
+        MoleculeGCN(8, 4, 1, embedding_dim=16, pool="max")
+
+
+def test_aggregations():
+    """gcn.py:84-86 hands `aggr` to GeneralConv: add (default), mean and max are built, anything else is refused."""
     with pytest.raises(NotImplementedError):
-        MoleculeGCN(8, 4, 1, embedding_dim=16, aggr="max")
-    assert MoleculeGCN(8, 4, 1, embedding_dim=16, aggr="mean").atom_conv.aggr == "mean"
+        MoleculeGCN(8, 4, 1, embedding_dim=16, aggr="min")
+    for aggr in ("add", "mean", "max"):
+        assert MoleculeGCN(8, 4, 1, embedding_dim=16, aggr=aggr).atom_conv.aggr == aggr
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour of a box without a GPU")

@@ -171,3 +171,27 @@ def test_fp32_oracle_is_within_its_noise_floor_of_the_fp64_oracle(act):
     F.mse_loss(r64[0], data.y.double().expand_as(r64[0])).backward()
     for (name, p), q in zip(o32.named_parameters(), o64.parameters()):
         assert nerr(p.grad, q.grad) <= 2e-5, name
+
+
+def test_global_mean_pool_restated():
+    """nn/pool/glob.py::global_mean_pool: segment sum / max(count, 1); batch=None averages all rows"""
+    from oracle.pyg_restated import global_mean_pool
+    x = torch.arange(12.0).view(6, 2)
+    batch = torch.tensor([0, 0, 2, 2, 2, 3])
+    out = global_mean_pool(x, batch, size=5)
+    want = torch.stack([x[:2].mean(0), torch.zeros(2), x[2:5].mean(0), x[5], torch.zeros(2)])
+    assert torch.equal(out, want)
+    assert torch.equal(global_mean_pool(x, None), x.mean(0, keepdim=True))
+
+
+def test_general_conv_max_restated():
+    """GeneralConv(aggr="max"): per-edge messages, zero-initialised amax (rows without in-edges stay 0) + x"""
+    from oracle.pyg_restated import GeneralConv
+    torch.manual_seed(0)
+    conv = GeneralConv(4, 4, 4, aggr="max")
+    x, ea = torch.randn(3, 4), torch.randn(4, 4)
+    ei = torch.tensor([[0, 1, 1, 2], [1, 0, 0, 0]])
+    out = conv(x, ei, ea)
+    msg = conv.lin_msg(x[ei[0]]) + conv.lin_edge(ea)
+    want = torch.stack([msg[1:4].max(0).values, msg[0], torch.zeros(4)]) + x
+    assert torch.allclose(out, want, atol=1e-6)

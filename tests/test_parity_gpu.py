@@ -109,6 +109,44 @@ def test_aggr_mean_fp32():
     _check_backward(oracle, model, data, GRAD_F32)
 
 
+@pytest.mark.parametrize("dtype,ftol,gtol", [(torch.float32, FWD_F32, GRAD_F32), (torch.bfloat16, FWD_BF16, GRAD_BF16)])
+def test_global_mean_pool(dtype, ftol, gtol):
+    """pool="mean" (BASELINE north_star item 4; PyG global_mean_pool = segment sum / max(count, 1)), batched and bare"""
+    data, graphs = random_batch(seed=23, n_graphs=64 if dtype == torch.bfloat16 else 8, max_atoms=30)
+    oracle, model = make_pair(12, 7, 2, dtype=dtype, embedding_dim=128 if dtype == torch.bfloat16 else 64, n_messages=2, pool="mean")
+    _check_forward(oracle, model, data, ftol)
+    _check_backward(oracle, model, data, gtol)
+    if dtype == torch.float32:
+        _check_forward(oracle, model, graphs[0], ftol)
+
+
+@pytest.mark.parametrize("act", [F.softplus, F.relu])
+def test_aggr_max_fp32(act):
+    """GeneralConv(aggr="max"), gcn.py:84-86: transform-then-aggregate per edge, amax with even tie split in
+    backward (relu makes exact ties -- several in-edges at 0 -- common)."""
+    data, _ = random_batch(seed=17, n_graphs=8)
+    oracle, model = make_pair(12, 7, 1, embedding_dim=64, n_messages=3, aggr="max", act_fn=act)
+    _check_forward(oracle, model, data, FWD_F32)
+    _check_backward(oracle, model, data, GRAD_F32 * (3 if act is F.relu else 1))
+
+
+@pytest.mark.parametrize("N,E,G", [(3, 5, 1), (40, 40, 1), (50, 200, 4), (64, 70, 3)])
+def test_aggr_max_random_graphs_fp32(N, E, G):
+    """the reference's own test inputs (tests/test_gcn.py:51-56): duplicate edges, isolated atoms (empty max = 0), E == N,
+    bond rows >= N that stay act(0)"""
+    data = random_graph_batch(seed=N + E + 1, N=N, E=E, av=10, bv=5, G=G)
+    oracle, model = make_pair(10, 5, 2, embedding_dim=40, n_messages=2, n_readout=1, readout_dim=32, aggr="max")
+    _check_forward(oracle, model, data, FWD_F32)
+    _check_backward(oracle, model, data, GRAD_F32)
+
+
+def test_aggr_max_bf16():
+    data, _ = random_batch(seed=19, n_graphs=64, max_atoms=30)
+    oracle, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=2, aggr="max")
+    _check_forward(oracle, model, data, FWD_BF16)
+    _check_backward(oracle, model, data, GRAD_BF16)
+
+
 @pytest.mark.parametrize("N,E,G", [(3, 5, 1), (40, 40, 1), (50, 200, 4), (64, 70, 3)])
 def test_random_graphs_duplicates_isolated_fp32(N, E, G):
     """The reference's own test inputs (tests/test_gcn.py:51-56): random edge_index with duplicate
@@ -217,11 +255,12 @@ def test_dropout_semantics():
     _check_forward(oracle, model, big, FWD_F32)
 
 
-def test_dropout_gradient_matches_masked_oracle():
+@pytest.mark.parametrize("aggr", ["add", "max"])
+def test_dropout_gradient_matches_masked_oracle(aggr):
     """Recover the kernel's keep-mask from a train-mode forward (n_messages=1, n_readout=0), replay
     it in the oracle and compare gradients: checks the backward's regenerated masks."""
     data, _ = random_batch(seed=4, n_graphs=8)
-    oracle, model = make_pair(12, 7, None, embedding_dim=64, n_messages=1, n_readout=0, p_dropout=0.25)
+    oracle, model = make_pair(12, 7, None, embedding_dim=64, n_messages=1, n_readout=0, p_dropout=0.25, aggr=aggr)
     model.train()
     torch.manual_seed(123)
     out, out_atom, out_bond = model(_to_dev(data))
