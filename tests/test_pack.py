@@ -214,3 +214,33 @@ def test_packed_loader_host_side_logic_on_cpu():
     each = next(iter(PackedLoader(store, 8, 3, av, bv, device="cpu", each=True)))
     ref = store.collate_pack(np.arange(8), 3, av, bv, pin=False, each=True)
     assert torch.equal(each.ints, ref.ints) and each.M == each.N
+
+
+def test_packed_loader_lookahead_across_epochs():
+    """The persistent worker pool packs the head of epoch e+1 while epoch e drains (`lookahead`): same batches in the
+    same order as without it, over several shuffled epochs; a loader left mid-epoch or re-targeted in between still
+    yields exactly what a fresh loader would."""
+    from graphchem_b200.data import PackedLoader
+    from graphchem_b200.synthetic import make_molecules
+    store = make_molecules(200, seed=7, variable=True)
+    kw = dict(device="cpu", shuffle=True, seed=11, workers=3, prefetch=2)
+    a = PackedLoader(store, 32, 2, 64, 32, lookahead=True, **kw)
+    b = PackedLoader(store, 32, 2, 64, 32, lookahead=False, **kw)
+    for _ in range(3):
+        ea, eb = list(a), list(b)
+        assert len(ea) == len(eb) == 7
+        assert all(torch.equal(x.ints, y.ints) and torch.equal(x.y, y.y) for x, y in zip(ea, eb))
+        assert a._ahead_epoch == a.epoch + 1 and 1 <= len(a._ahead) <= 5   # the next epoch is already being packed
+        assert not b._ahead
+    # leave an epoch early, then a full epoch: still the reference order of that epoch
+    it = iter(a)
+    next(it); it.close()
+    next(iter(b))
+    ea, eb = list(a), list(b)
+    assert all(torch.equal(x.ints, y.ints) for x, y in zip(ea, eb))
+    # re-target the loader between epochs: what was packed ahead is discarded, not served
+    a.indices = np.arange(0, 200, 2); b.indices = np.arange(0, 200, 2)
+    ea, eb = list(a), list(b)
+    assert sum(x.G for x in ea) == 100 and all(torch.equal(x.ints, y.ints) for x, y in zip(ea, eb))
+    a.close(); b.close()
+    assert [x.G for x in a] == [x.G for x in b]   # usable again after close()
