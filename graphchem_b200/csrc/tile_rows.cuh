@@ -56,7 +56,27 @@ struct TileCommon {
   const int4* aux4;         // second ELL-4 view walked with the same CSR (edge ids / dst-CSR positions) or null
   const int32_t* aux;       // CSR form of aux4 (rows with more than four entries) or null
   int rev = 0;              // walk the tiles last-to-first: start on the rows the producer kernel wrote last (L2 resident)
+  int pf = 0;               // set by the launchers (tile_prefetch()): bulk L2 prefetch of the tile's row-streamed operands
 };
+
+// A/B switch GCB_TILE_PREFETCH (bit mask; 0 = off): 1 bond backward's row operands (B_l, dBnext, tie counts), 2 its gathered
+// dS rows, 4 / 8 atom backward's A_prev / dZA rows.  Measured on B200 (profiles/r2_ab_v_prefetch.jsonl): 3 takes the bond
+// backward from 91 to 86 us (train step 1.506 -> 1.484 ms); 4 and 8 make the atom backward 1-2 us SLOWER, a prefetch one
+// wave of CTAs ahead costs 4-7 us, and prefetching the by-edge-id bond rows of the atom aggregation gains 0.15 %.
+inline int tile_prefetch() {
+  static const int v = [] { const char* e = std::getenv("GCB_TILE_PREFETCH"); return e ? std::atoi(e) : 3; }();
+  return v;
+}
+
+// One instruction asks L2 for a contiguous run of rows (the tile's [r0, r1) x row bytes, a multiple of 16): the row
+// phase then finds in L2 what it would otherwise fetch from DRAM two 16-byte chunks per thread at a time behind a
+// long-scoreboard stall.  L2 is the coherence point, so a prefetch is safe at any time (also before griddepcontrol.wait).
+__device__ __forceinline__ void prefetch_l2_rows(const void* p, int bytes) {
+  if (bytes > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_line(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
+}
 
 // Tile of this CTA.  CTAs are dispatched in blockIdx order, so `rev` makes the kernel's first wave read the END of
 // its operand -- which is what the previous kernel of the chain (walking the other way) produced last.
@@ -85,7 +105,8 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
 // identity of the reduction (PADWORD: -inf for max, 0 for sums).  The row loops then load and reduce all four
 // slots unconditionally -- the `if (nidx[u] >= 0)` tests cost a quarter of the instructions of these
 // issue-bound kernels (BSSY / BSYNC / BRA / ISETP per slot).
-#define GCB_TILE_PROLOGUE(BOX_BYTES, ISSUE, STRIDE, PADWORD)                                        \
+#define GCB_TILE_PROLOGUE(BOX_BYTES, ISSUE, STRIDE, PADWORD) GCB_TILE_PROLOGUE_PF(BOX_BYTES, ISSUE, STRIDE, PADWORD, (void)0)
+#define GCB_TILE_PROLOGUE_PF(BOX_BYTES, ISSUE, STRIDE, PADWORD, PREFETCH)                           \
   constexpr int kD = Cfg<CH>::D, kSlots = Cfg<CH>::kSlots, kPasses = Cfg<CH>::kPasses;              \
   constexpr int kRowBytes = Cfg<CH>::kRowBytes, kBoxBytes = Cfg<CH>::kBoxBytes;                     \
   (void)kD; (void)kSlots; (void)kPasses; (void)kRowBytes; (void)kBoxBytes;                          \
@@ -99,6 +120,7 @@ __device__ __forceinline__ void sts32(uint32_t saddr, int v) { asm volatile("st.
   const int r0 = __ldg(cm.tile_ptr + tb_);                                                          \
   const int r1 = min(__ldg(cm.tile_ptr + tb_ + 1), cm.rows);                                        \
   pdl_launch_dependents();                                                                          \
+  if (threadIdx.x == 32 && cm.pf) { PREFETCH; } /* another warp than the TMA issuer */              \
   if ((BOX_BYTES) > 0 && threadIdx.x == 0) {                                                        \
     gcb::tc::mbar_init(&bar, 1);                                                                    \
     gcb::tc::fence_barrier_init();                                                                  \
@@ -448,7 +470,9 @@ atom_bwd_kernel(const __grid_constant__ CUtensorMap tmdS, TileCommon cm, const b
                 const bf16* __restrict__ A_prev, const int32_t* __restrict__ prev_idx, bf16* __restrict__ dZA_prev, int act) {
   // prev_idx (message step 1 with the embedding lookup fused in): A_prev is the pre-activated token table and row r
   // reads A_prev[prev_idx[r]] -- A_0 is never materialised
-  GCB_TILE_PROLOGUE(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmdS, &bar, 0, r0), kRowBytes, 0u)
+  GCB_TILE_PROLOGUE_PF(Cfg<CH>::kBoxBytes, gcb::tc::tma_load_2d_s(smem, &tmdS, &bar, 0, r0), kRowBytes, 0u,
+                       (prefetch_l2_rows(prev_idx ? nullptr : A_prev + (size_t)r0 * Cfg<CH>::D, prev_idx || !(cm.pf & 4) ? 0 : (r1 - r0) * Cfg<CH>::kRowBytes),
+                        prefetch_l2_rows(dZA + (size_t)r0 * Cfg<CH>::D, (cm.pf & 8) ? (r1 - r0) * Cfg<CH>::kRowBytes : 0)))
 #pragma unroll (UN)
   for (int ps = 0; ps < kPasses; ++ps) {
     GCB_TILE_ROW(ps)
@@ -532,6 +556,12 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
   const int r0 = __ldg(cm.tile_ptr + tb_);
   const int r1 = min(__ldg(cm.tile_ptr + tb_ + 1), cm.rows);
   pdl_launch_dependents();
+  if ((cm.pf & 1) && threadIdx.x == 32 && r1 > r0) {  // phase 1 streams these rows of the tile: ask L2 for them now
+    prefetch_l2_rows(B_l + (size_t)r0 * kD, (r1 - r0) * kRowBytes);
+    if (dBnext) prefetch_l2_rows(dBnext + (size_t)r0 * kD, (r1 - r0) * kRowBytes);
+    if (d_out_bond) prefetch_l2_rows(d_out_bond + (size_t)r0 * kD, (r1 - r0) * kRowBytes);
+    if (tiecnt) prefetch_l2_rows(tiecnt + (size_t)r0 * kD, (r1 - r0) * kD);
+  }
   // The out-edges of a closed tile's rows are in-edges of rows of the SAME tile, and those are contiguous in the
   // dst-sorted CSR: [ie_lo, ie_hi).  Their tie bits (written by the forward pass) are staged with coalesced loads, so
   // phase 2 reads them from shared memory instead of four dependent one-byte global loads per row chunk.
@@ -553,6 +583,12 @@ bond_bwd_kernel(TileCommon cm, const int32_t* __restrict__ in_ptr, const int32_t
         v = __ldg(cm.nbr4 + r);
         w = __ldg(cm.aux4 + r);
         if (__ldg(in_ptr + r + 1) > __ldg(in_ptr + r)) t = __ldg(dst + r);
+        if ((cm.pf & 2) && t >= 0 && ds_plane_rows <= 0) {  // the row of another molecule this bond row collects its gradient from
+          const bf16* q = dS + (size_t)t * (2 * kD) + kD;
+          prefetch_l2_line(q);
+          if (kRowBytes > 128) prefetch_l2_line(q + 64);
+          if (kRowBytes > 256) { prefetch_l2_line(q + 128); prefetch_l2_line(q + 192); }
+        }
       }
       // neighbours as byte offsets of their split-gradient rows; a missing slot points at the zero pad row
       const uint32_t o0 = v.x >= 0 ? (uint32_t)(v.x - r0) * kRowBytes : kPadOff, o1 = v.y >= 0 ? (uint32_t)(v.y - r0) * kRowBytes : kPadOff;
@@ -786,8 +822,10 @@ inline int launch_atom_bwd_w(const bf16* dS, const bf16* dZA, const bf16* A_prev
   const int smem = smem_for<CH>(1);
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(atom_bwd_kernel<CH, 2>, smem)); GCB_TRY(set_smem(atom_bwd_kernel<CH, 4>, smem)); attr = true; }
-  if (tile_unroll() == 4) GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 4>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, prev_idx, dZA_prev, act));
-  else GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 2>, n_tiles, kThreads, smem, s, tmS, cm, dZA, A_prev, prev_idx, dZA_prev, act));
+  TileCommon cp = cm;
+  cp.pf = tile_prefetch();
+  if (tile_unroll() == 4) GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 4>, n_tiles, kThreads, smem, s, tmS, cp, dZA, A_prev, prev_idx, dZA_prev, act));
+  else GCB_KERNEL("tile_atom_bwd_kernel", s, launch_pdl(atom_bwd_kernel<CH, 2>, n_tiles, kThreads, smem, s, tmS, cp, dZA, A_prev, prev_idx, dZA_prev, act));
   return GCB_OK;
 }
 inline int launch_atom_bwd(int D, const bf16* dS, const bf16* dZA, const bf16* A_prev, const int32_t* prev_idx, const TileCommon& cm, int n_tiles,
@@ -821,9 +859,11 @@ inline int launch_bond_bwd_w(const TileCommon& cm, int n_tiles, const int32_t* i
   const int smem = smem_for<CH>(1) + kRows * 4 + 256 * 4 + 544 + Cfg<CH>::kRowBytes + kTieEdges * CH;
   static bool attr = false;
   if (!attr) { GCB_TRY(set_smem(bond_bwd_kernel<CH, 2>, smem)); GCB_TRY(set_smem(bond_bwd_kernel<CH, 4>, smem)); attr = true; }
-  if (tile_unroll() == 4) GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH, 4>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
+  TileCommon cp = cm;
+  cp.pf = tile_prefetch();
+  if (tile_unroll() == 4) GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH, 4>, n_tiles, kThreads, smem, s, cp, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
                                                                         tiecnt, tiemask, dPQ, act, ds_plane_rows));
-  else GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH, 2>, n_tiles, kThreads, smem, s, cm, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
+  else GCB_KERNEL("tile_bond_bwd_kernel", s, launch_pdl(bond_bwd_kernel<CH, 2>, n_tiles, kThreads, smem, s, cp, in_ptr, dst, dS, dBnext, d_out_bond, B_l,
                                                           tiecnt, tiemask, dPQ, act, ds_plane_rows));
   return GCB_OK;
 }

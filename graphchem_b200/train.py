@@ -387,7 +387,7 @@ class Screener:
             graphed = bool((na == na[0]).all() and (ne == ne[0]).all()) and n >= self.batch_size
         loader = PackedLoader(store, self.batch_size, L, av, bv, device=dev, workers=self.workers, prefetch=self.prefetch,
                               indices=idx, device_slots=3 if graphed else 0, device_pack=self.device_pack,
-                              buffers=self._buffers.get(graphed))
+                              buffers=self._buffers.get(graphed), lookahead=False)  # one epoch per loader
         if graphed and self._step is None:
             self._step = InferStep(model, use_cuda_graph=True)
         step = self._step if graphed else None
