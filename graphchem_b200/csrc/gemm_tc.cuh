@@ -623,12 +623,25 @@ struct TnShape {
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns must be a power of two");
 };
 
-template <int NN, int KK>
+// Column-blocked form (BLK; wide models, embedding_dim 256: dW is [256 x 512] / [512 x 256] and does not fit the 512
+// TMEM columns): the grid is (row ranges) x (blocks_m x blocks_n) CTAs, CTA (ci, mb, nb) owns the [128 x 256] block
+// (mb, nb) of its row range's partial dW -- the same kernel on column windows of A and B (TMA coordinates), written into
+// a [NN_total x KK_total] partial with that row stride.  The CTAs of one row range walk the same row tiles, so the
+// windows they re-read (A blocks_n times, B blocks_m times) meet in L2.  Bias sums: the nb == 0 blocks whose A window
+// lies inside the first `bias_cols` columns.
+struct TnBlocks {
+  int blocks_m = 1, blocks_n = 1;  // dW blocks of 128 rows x 256 columns
+  int nn_total = 0, kk_total = 0;  // full dW extent (row stride of the partial = kk_total)
+  int bias_cols = 0;               // leading columns of A that carry a bias gradient
+};
+
+template <int NN, int KK, bool BLK = false>
 __global__ void __launch_bounds__(192, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int rows,
                   float* __restrict__ partial, int want_bias_i, const int32_t* __restrict__ rowptr,
-                  int aggr, int rev, int acc_partial) {
+                  int aggr, int rev, int acc_partial, TnBlocks blk) {
   using S = TnShape<NN, KK>;
+  static_assert(!BLK || (NN == 128 && KK == 256), "the blocked form runs on [128 x 256] blocks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sT = smem;  // [STAGES][A tile | B tile]
@@ -642,12 +655,22 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (rows + S::BR - 1) / S::BR;
   // contiguous tile range of this CTA (fixed partition -> fixed summation order)
-  const int per = (num_tiles + gridDim.x - 1) / gridDim.x;
-  const int t_begin = blockIdx.x * per;
+  const int nblk = BLK ? blk.blocks_m * blk.blocks_n : 1;
+  const int ci = BLK ? (int)blockIdx.x / nblk : (int)blockIdx.x;      // row range
+  const int bi = BLK ? (int)blockIdx.x % nblk : 0;
+  const int mb_blk = BLK ? bi / blk.blocks_n : 0, nb_blk = BLK ? bi % blk.blocks_n : 0;
+  const int a_col0 = mb_blk * 128, b_col0 = nb_blk * 256;              // column windows of A and B
+  const int n_ranges = BLK ? (int)gridDim.x / nblk : (int)gridDim.x;
+  const int per = (num_tiles + n_ranges - 1) / n_ranges;
+  const int t_begin = ci * per;
   const int t_end = min(num_tiles, t_begin + per);
-  const bool want_bias = want_bias_i != 0;
-  // per-CTA partial block: [NN*KK weight-gradient partial | NN bias sums]
-  float* const cta_partial = partial + (size_t)blockIdx.x * (NN * KK + (want_bias ? NN : 0));
+  // blocked: every row range's partial carries NN_total bias slots; a block computes the 128 of its A window when it is an
+  // nb == 0 block inside the bias columns, writes zeros when it is an nb == 0 block outside them, and nothing otherwise
+  const bool bias_owner = !BLK || nb_blk == 0;
+  const bool want_bias = want_bias_i != 0 && bias_owner && (!BLK || a_col0 < blk.bias_cols);
+  const int out_nn = BLK ? blk.nn_total : NN, out_kk = BLK ? blk.kk_total : KK;
+  // per-CTA (row range) partial block: [NN*KK weight-gradient partial | NN bias sums]
+  float* const cta_partial = partial + (size_t)ci * ((size_t)out_nn * out_kk + (want_bias_i != 0 ? out_nn : 0));
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -674,8 +697,8 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint8_t* a = sT + stage * S::STAGE_BYTES;
         uint8_t* b = a + S::A_BYTES;
         const int ptile = rev ? num_tiles - 1 - tile : tile;
-        for (int k = 0; k < S::AS; ++k) tma_load_2d(a + k * (S::BR * 128), &tmA, &full[stage], k * 64, ptile * S::BR);
-        for (int k = 0; k < S::BS; ++k) tma_load_2d(b + k * (S::BR * 128), &tmB, &full[stage], k * 64, ptile * S::BR);
+        for (int k = 0; k < S::AS; ++k) tma_load_2d(a + k * (S::BR * 128), &tmA, &full[stage], a_col0 + k * 64, ptile * S::BR);
+        for (int k = 0; k < S::BS; ++k) tma_load_2d(b + k * (S::BR * 128), &tmB, &full[stage], b_col0 + k * 64, ptile * S::BR);
         if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -754,14 +777,19 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float tot = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) tot += red_s[k * 128 + t];
-      cta_partial[NN * KK + t] = acc_partial ? cta_partial[NN * KK + t] + tot : tot;
+      float* bslot = cta_partial + (size_t)out_nn * out_kk + a_col0;
+      bslot[t] = acc_partial ? bslot[t] + tot : tot;
+      if constexpr (!BLK) {
 #pragma unroll
-      for (int i = 1; i < NN / 128; ++i) cta_partial[NN * KK + i * 128 + t] = 0.f;
+        for (int i = 1; i < NN / 128; ++i) bslot[i * 128 + t] = 0.f;
+      }
+    } else if (BLK && want_bias_i != 0 && bias_owner) {
+      cta_partial[(size_t)out_nn * out_kk + a_col0 + t] = 0.f;  // an A window without a bias gradient (the dQ half)
     }
     mbar_wait(done, 0);
     tc_fence_after();
     const int q = warp & 3;
-    float* out = cta_partial;
+    float* out = cta_partial + (size_t)a_col0 * out_kk + b_col0;
 #pragma unroll 1
     for (int mb = 0; mb < S::MB; ++mb) {
       const int m = mb * 128 + q * 32 + lane;
@@ -770,7 +798,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + mb * KK + c0, v);
         tmem_ld_wait();
-        float4* o = reinterpret_cast<float4*>(out + (size_t)m * KK + c0);
+        float4* o = reinterpret_cast<float4*>(out + (size_t)m * out_kk + c0);
         if (acc_partial) {  // keep summing this CTA's partial across launches (layers); one reduction at the end
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -819,7 +847,40 @@ inline int launch_gemm_tn_tc_impl(const bf16* A, int lda, const bf16* B, int ldb
   grid = (num_tiles + per - 1) / per;  // every CTA owns at least one tile
   *grid_out = grid;
   GCB_KERNEL(NN == 128 ? "gemm_tn_tc_n128k256" : "gemm_tn_tc_n256k128", s, launch_pdl(gemm_tn_tc_kernel<NN, KK>, grid, S::THREADS, S::SMEM_BYTES, s,
-      tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr, rev, acc_partial));
+      tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr, rev, acc_partial, TnBlocks()));
+  return GCB_OK;
+}
+
+// Wide shapes (NN a multiple of 128, KK a multiple of 256, beyond one [128 x 256] block): the column-blocked form.
+// *grid_out = number of ROW RANGES (= partial blocks the caller reduces, each [NN*KK (+ NN)] floats).
+inline int launch_gemm_tn_tc_blocked(const bf16* A, int lda, const bf16* B, int ldb, int rows, int NN, int KK, float* partial,
+                                     bool want_bias, int bias_cols, const int32_t* rowptr, int aggr, int rev, int* grid_out,
+                                     cudaStream_t s) {
+  using S = TnShape<128, 256>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCB_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel<128, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (make_tmap_bf16(&tmA, A, rows, NN, lda, S::BR) || make_tmap_bf16(&tmB, B, rows, KK, ldb, S::BR)) return GCB_ERR_CUDA;
+  TnBlocks blk;
+  blk.blocks_m = NN / 128; blk.blocks_n = KK / 256; blk.nn_total = NN; blk.kk_total = KK; blk.bias_cols = bias_cols;
+  const int nblk = blk.blocks_m * blk.blocks_n;
+  const int num_tiles = (rows + S::BR - 1) / S::BR;
+  static const int tn_cap = [] {
+    const char* e = std::getenv("GCB_TN_CTAS_WIDE");
+    const int n = e ? std::atoi(e) : 144;
+    return n < 1 ? 1 : (n > kTnMaxCtas ? kTnMaxCtas : n);
+  }();
+  int ranges = tn_cap / nblk;
+  if (ranges < 1) ranges = 1;
+  if (ranges > num_tiles) ranges = num_tiles;
+  const int per = (num_tiles + ranges - 1) / ranges;
+  ranges = (num_tiles + per - 1) / per;  // every row range owns at least one tile
+  *grid_out = ranges;
+  GCB_KERNEL("gemm_tn_tc_blocked", s, launch_pdl(gemm_tn_tc_kernel<128, 256, true>, ranges * nblk, S::THREADS, S::SMEM_BYTES, s,
+      tmA, tmB, rows, partial, want_bias ? 1 : 0, rowptr, aggr, rev, 0, blk));
   return GCB_OK;
 }
 
@@ -832,6 +893,11 @@ inline int launch_gemm_tn_tc(const bf16* A, int lda, const bf16* B, int ldb, int
   if (lda % 8 || ldb % 8) return GCB_ERR_UNSUPPORTED;
   if (NN == 128 && KK == 256) return launch_gemm_tn_tc_impl<128, 256>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, rev, grid_out, s, acc_partial);
   if (NN == 256 && KK == 128) return launch_gemm_tn_tc_impl<256, 128>(A, lda, B, ldb, rows, partial, want_bias, rowptr, aggr, rev, grid_out, s, acc_partial);
+  // wide models (embedding_dim 256: [256 x 512] and [512 x 256]); the bias gradient lives in the first min(NN, KK) columns
+  // of A (all of dZA, the dP half of [dP|dQ]) -- the same convention as the two shapes above
+  static const bool wide_off = std::getenv("GCB_NO_TN_WIDE") && std::getenv("GCB_NO_TN_WIDE")[0] == '1';  // A/B: CUDA-core fallback
+  if (!wide_off && !acc_partial && NN % 128 == 0 && KK % 256 == 0 && (NN / 128) * (KK / 256) <= kTnMaxCtas && (int64_t)NN * KK <= 512 * 512)
+    return launch_gemm_tn_tc_blocked(A, lda, B, ldb, rows, NN, KK, partial, want_bias, NN < KK ? NN : KK, rowptr, aggr, rev, grid_out, s);
   return GCB_ERR_UNSUPPORTED;
 }
 

@@ -115,3 +115,39 @@ def test_tc_gemm_tn_weight_grad(rows, Nn, Kk):
     # bias sums cover the first 128 columns only (all of dZA; the dP half of [dP|dQ]); the rest is zero
     assert float((db[:128].double() - refb[:128]).abs().max() / refb[:128].abs().max()) < 1e-4
     assert float(db[128:].abs().max()) == 0.0 if Nn > 128 else True
+
+
+@pytest.mark.parametrize("Nn,Kk", [(256, 512), (512, 256)])
+@pytest.mark.parametrize("rows", [128, 1000, 70001])
+def test_tc_gemm_tn_weight_grad_wide(rows, Nn, Kk):
+    """embedding_dim 256: dW is [256 x 512] / [512 x 256] -- the column-blocked tcgen05 kernel ([128 x 256] blocks, row ranges
+    x blocks CTAs); bias sums over the first min(Nn, Kk) columns of A (all of dZA, the dP half of [dP|dQ])."""
+    g = torch.Generator().manual_seed(rows + Nn)
+    A = (torch.randn(rows, Nn, generator=g) * 0.3).bfloat16().cuda()
+    B = torch.randn(rows, Kk, generator=g).bfloat16().cuda()
+    d = torch.randint(0, 4, (rows,), generator=g)
+    rp = torch.cat([torch.zeros(1, dtype=torch.long), d.cumsum(0)]).int().cuda()
+    partial = torch.empty(148 * (Nn * Kk + Nn), device="cuda")
+    lib = _lib.lib()
+    lib.gcb_timing_enable(1)
+    outs = []
+    for _ in range(2):
+        dW = torch.full((Nn, Kk), float("nan"), device="cuda")
+        db = torch.full((Nn,), float("nan"), device="cuda")
+        rc = lib.gcb_debug_gemm_tn_bf16(A.data_ptr(), B.data_ptr(), rows, Nn, Kk, partial.data_ptr(), dW.data_ptr(),
+                                        db.data_ptr(), rp.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        outs.append((dW.clone(), db.clone()))
+    import ctypes as C
+    buf = C.create_string_buffer(1 << 16)
+    lib.gcb_timing_report(buf, len(buf))
+    lib.gcb_timing_enable(0)
+    assert b"gemm_tn_tc_blocked" in buf.value, "the wide shapes must run on the tcgen05 kernel"
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), "must be deterministic"
+    ref = A.double().t() @ B.double()
+    refb = (A.double() * d.double().cuda()[:, None]).sum(0)
+    assert float((dW.double() - ref).abs().max() / ref.abs().max()) < 1e-4
+    nb = min(Nn, Kk)
+    assert float((db[:nb].double() - refb[:nb]).abs().max() / refb[:nb].abs().max()) < 1e-4
+    assert Nn == nb or float(db[nb:].abs().max()) == 0.0

@@ -88,3 +88,15 @@ def test_screening_shape_bf16_forward():
     data, pb, oracle, model = synthetic_case(4096, 256, 6)
     errs = forward_errors(data, pb, oracle, model)
     assert max(errs) <= FWD_BF16_L6, errs
+
+
+def test_wide_model_bf16_training_gradients():
+    """D = 256 training (2048 molecules, 4 message steps): the [256 x 512] / [512 x 256] weight gradients come from the
+    column-blocked tcgen05 TN kernel; all gradients against the CPU oracle."""
+    data, pb, oracle, model = synthetic_case(2048, 256, 4)
+    errs = forward_errors(data, pb, oracle, model)
+    assert max(errs) <= FWD_BF16_L4, errs
+    gerrs, loss_err = gradient_errors(data, pb, oracle, model)
+    assert loss_err <= 2e-2, loss_err
+    bad = {k: v for k, v in gerrs.items() if v > GRAD_BF16}
+    assert not bad, (bad, gerrs)
