@@ -411,7 +411,10 @@ def run_ours(args):
         # gathered on the device and copied back once (B * out floats per step)
         n_stream = max(8, min(K, 24))
         sub = make_molecules(n_stream * B, seed=4321 + rank, atom_vocab=cfg["atom_vocab"], bond_vocab=cfg["bond_vocab"])
-        workers = max(2, min(16, (os.cpu_count() or 2) // max(1, world)))
+        # half of the host threads: with one worker per core the main thread (H2D, graph launches) gets descheduled for
+        # milliseconds at a time and the call time doubles at random (profiles/micro/screener_diag.py: 4-8 workers are
+        # steady at 8.1 ms per 32768-molecule batch, 16 workers swing between 8.2 and 13-18 ms on a 16-thread box)
+        workers = max(2, min(8, (os.cpu_count() or 2) // (2 * max(1, world))))
         screener = Screener(model, batch_size=B, workers=workers)
         screener(sub)  # warm-up: pinned pool, device slot ring, one CUDA graph per slot (kept by the Screener)
         barrier()

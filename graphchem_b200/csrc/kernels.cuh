@@ -199,7 +199,20 @@ __global__ void pool_kernel(const T* __restrict__ A, const int32_t* __restrict__
   float acc[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) acc[i] = 0.f;
-  for (int k = k0; k < k1; ++k) {
+  int k = k0;
+  for (; k + 4 <= k1; k += 4) {  // four node ids, then four rows in flight; same order of addition
+    int n[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) n[u] = __ldg(graph_node + k + u);
+    float a[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load_vec(A + (size_t)n[u] * D + c, a[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += a[u][i];
+  }
+  for (; k < k1; ++k) {
     const int n = __ldg(graph_node + k);
     float a[V];
     load_vec(A + (size_t)n * D + c, a);

@@ -405,7 +405,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
       if (need > pf) pf = need;
     }
     if (pl.n_lin > 0) {
-      const int64_t need = ceil_div(G, kReadoutGB) * (pl.total - pl.r_w[0]);
+      const int64_t need = ceil_div(G, kReadoutGB) * ((pl.total - pl.r_w[0] + 3) & ~int64_t(3));  // 16-byte aligned per-CTA blocks
       if (need > pf) pf = need;
     }
     const int64_t vmax = c.atom_vocab > c.bond_vocab ? c.atom_vocab : c.bond_vocab;
@@ -449,6 +449,17 @@ static bool make_readout_desc(const ParamLayout& pl, ReadoutDesc& rd, int G) {
   return (3 * kReadoutGB * (rd.max_dim + 1) + rd.max_w) * 4 <= 200 * 1024;
 }
 
+// Graphs per CTA of the register-tiled readout: 64.  32 (two CTAs per SM at 8192 graphs, twice the resident warps) measured
+// SLOWER on B200 -- forward 31 vs 26 us, backward 66 vs 48 us, train step 1.506 vs 1.482 ms (profiles/r2_ab_x_readout.jsonl):
+// every CTA stages the layer's weights again, and that, not the per-graph chain, is what the kernel waits for.
+// GCB_READOUT_GB=32 keeps the variant reachable for tests / other shapes.
+static int readout2_gb(int G) {
+  const char* e = std::getenv("GCB_READOUT_GB");  // read per call: the tests switch it inside one process
+  const int forced = e ? std::atoi(e) : 0;
+  if (forced == 32 || forced == 64) return forced;
+  (void)G;
+  return 64;
+}
 // Register-tiled readout (readout.cuh, second half): large batches, every layer input a multiple of 4 wide.
 static bool readout2_ok(const ParamLayout& pl, ReadoutDesc& rd, int G) {
   const char* e = std::getenv("GCB_NO_READOUT2");
@@ -697,9 +708,16 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
       ReadoutPtrs hp;
       for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
       static bool attr2 = false;
-      if (!attr2) { GCB_CUDA(cudaFuncSetAttribute(readout2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr2 = true; }
+      if (!attr2) {
+        GCB_CUDA(cudaFuncSetAttribute(readout2_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        GCB_CUDA(cudaFuncSetAttribute(readout2_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr2 = true;
+      }
       Drop drb = make_drop(c, flags, seed, tag_readout(0));
-      GCB_KERNEL("readout_fwd_kernel", s, readout2_fwd_kernel<<<(unsigned)ceil_div(G, kReadoutGB2), kReadout2Threads, readout2_fwd_smem(rd2), s>>>(rd2, params, hp, out, G, c.act, drb));
+      if (readout2_gb(G) == 32)
+        GCB_KERNEL("readout_fwd_kernel", s, readout2_fwd_kernel<32><<<(unsigned)ceil_div(G, 32), kReadout2Threads, readout2_fwd_smem(rd2, 32), s>>>(rd2, params, hp, out, G, c.act, drb));
+      else
+        GCB_KERNEL("readout_fwd_kernel", s, readout2_fwd_kernel<64><<<(unsigned)ceil_div(G, 64), kReadout2Threads, readout2_fwd_smem(rd2, 64), s>>>(rd2, params, hp, out, G, c.act, drb));
     } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
       ReadoutPtrs hp;
       for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
@@ -789,10 +807,18 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
       ReadoutPtrs hp;
       for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
       static bool attr2 = false;
-      if (!attr2) { GCB_CUDA(cudaFuncSetAttribute(readout2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr2 = true; }
-      const int blocks = (int)ceil_div(G, kReadoutGB2);
+      if (!attr2) {
+        GCB_CUDA(cudaFuncSetAttribute(readout2_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        GCB_CUDA(cudaFuncSetAttribute(readout2_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr2 = true;
+      }
+      const int gb = readout2_gb(G);
+      const int blocks = (int)ceil_div(G, gb);
       Drop drb = make_drop(c, flags, seed, tag_readout(0));
-      GCB_KERNEL("readout_bwd_kernel", s, readout2_bwd_kernel<<<blocks, kReadout2Threads, readout2_bwd_smem(rd2), s>>>(rd2, params, hp, d_out, p.partial, p.dPool, G, c.act, drb));
+      if (gb == 32)
+        GCB_KERNEL("readout_bwd_kernel", s, readout2_bwd_kernel<32><<<blocks, kReadout2Threads, readout2_bwd_smem(rd2, 32), s>>>(rd2, params, hp, d_out, p.partial, p.dPool, G, c.act, drb));
+      else
+        GCB_KERNEL("readout_bwd_kernel", s, readout2_bwd_kernel<64><<<blocks, kReadout2Threads, readout2_bwd_smem(rd2, 64), s>>>(rd2, params, hp, d_out, p.partial, p.dPool, G, c.act, drb));
       // the ordered sum of the per-CTA readout weight gradients feeds nothing before the optimiser: on the side stream
       // (in front of the weight-gradient GEMMs, which reuse p.partial after it) pool_bwd does not wait for it
       const bool red_side = overlap && L >= 1;

@@ -157,32 +157,33 @@ readout_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs
 // issue two shared loads per FFMA).  Weights are kept [out][in + 4] in shared memory: with in % 32 == 0
 // the row stride is 4 banks and the 16 output lanes of a warp hit disjoint banks.  Needs every
 // layer's input width to be a multiple of 4.
-constexpr int kReadoutGB2 = 64;
+constexpr int kReadoutGB2 = 64;  // graphs per CTA (GB below): 64, or 32 when that puts two CTAs on every SM
 
 __host__ __device__ inline int readout2_ld(const ReadoutDesc& rd) { return rd.max_dim + 4; }
-inline size_t readout2_fwd_smem(const ReadoutDesc& rd) {
-  return (size_t)(2 * kReadoutGB2 * readout2_ld(rd) + rd.max_dim * readout2_ld(rd)) * sizeof(float);
+inline size_t readout2_fwd_smem(const ReadoutDesc& rd, int gb = kReadoutGB2) {
+  return (size_t)(2 * gb * readout2_ld(rd) + rd.max_dim * readout2_ld(rd)) * sizeof(float);
 }
-inline size_t readout2_bwd_smem(const ReadoutDesc& rd) {
-  return (size_t)(3 * kReadoutGB2 * readout2_ld(rd) + rd.max_dim * readout2_ld(rd)) * sizeof(float);
+inline size_t readout2_bwd_smem(const ReadoutDesc& rd, int gb = kReadoutGB2) {
+  return (size_t)(3 * gb * readout2_ld(rd) + rd.max_dim * readout2_ld(rd)) * sizeof(float);
 }
 
 constexpr int kReadout2Threads = 512;  // 16 output lanes x 32 graph lanes
 
+template <int GB>
 __global__ void __launch_bounds__(kReadout2Threads)
 readout2_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs hp, float* __restrict__ out, int G,
                     int act, Drop dr_base) {
   extern __shared__ __align__(16) float rs2[];
   const int ld = readout2_ld(rd);
   float* cur = rs2;
-  float* nxt = rs2 + kReadoutGB2 * ld;
-  float* Ws = rs2 + 2 * kReadoutGB2 * ld;  // [on][ld]
-  const int g0 = blockIdx.x * kReadoutGB2;
-  const int ng = min(kReadoutGB2, G - g0);
+  float* nxt = rs2 + GB * ld;
+  float* Ws = rs2 + 2 * GB * ld;  // [on][ld]
+  const int g0 = blockIdx.x * GB;
+  const int ng = min(GB, G - g0);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   {
     const int in4 = rd.in_dim[0] >> 2;
-    for (int i = threadIdx.x; i < kReadoutGB2 * in4; i += kReadout2Threads) {
+    for (int i = threadIdx.x; i < GB * in4; i += kReadout2Threads) {
       const int g = i / in4, j4 = i % in4;
       const float4 v = g < ng ? __ldg(reinterpret_cast<const float4*>(hp.h[0] + (size_t)(g0 + g) * rd.in_dim[0]) + j4)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -201,7 +202,7 @@ readout2_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
     }
     __syncthreads();
     for (int ob = 0; ob < on; ob += 64) {
-      constexpr int GA = 2;  // graphs per thread: g = ty + 32 a
+      constexpr int GA = GB / 32;  // graphs per thread: g = ty + 32 a
       float acc[GA][4];
 #pragma unroll
       for (int a = 0; a < GA; ++a)
@@ -256,28 +257,29 @@ readout2_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
   }
 }
 
+template <int GB>
 __global__ void __launch_bounds__(kReadout2Threads)
 readout2_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs hp, const float* __restrict__ d_out,
                     float* __restrict__ partial, float* __restrict__ dPool, int G, int act, Drop dr_base) {
   extern __shared__ __align__(16) float rs2[];
   const int ld = readout2_ld(rd);
   float* dz = rs2;                            // [GB][ld] gradient w.r.t. the current layer's output (0 for padded graphs)
-  float* hin = rs2 + kReadoutGB2 * ld;        // [GB][ld] the current layer's input H[k]
-  float* dh = rs2 + 2 * kReadoutGB2 * ld;     // [GB][ld] gradient w.r.t. the current layer's input
-  float* Ws = rs2 + 3 * kReadoutGB2 * ld;     // [on][ld]
-  const int g0 = blockIdx.x * kReadoutGB2;
-  const int ng = min(kReadoutGB2, G - g0);
+  float* hin = rs2 + GB * ld;        // [GB][ld] the current layer's input H[k]
+  float* dh = rs2 + 2 * GB * ld;     // [GB][ld] gradient w.r.t. the current layer's input
+  float* Ws = rs2 + 3 * GB * ld;     // [on][ld]
+  const int g0 = blockIdx.x * GB;
+  const int ng = min(GB, G - g0);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float* my_partial = partial + (size_t)blockIdx.x * rd.partial_stride;
   const int o_last = rd.out_dim[rd.n_lin - 1];
-  for (int i = threadIdx.x; i < kReadoutGB2 * o_last; i += kReadout2Threads) {
+  for (int i = threadIdx.x; i < GB * o_last; i += kReadout2Threads) {
     const int g = i / o_last, o = i % o_last;
     dz[g * ld + o] = g < ng ? d_out[(size_t)(g0 + g) * o_last + o] : 0.f;
   }
   for (int k = rd.n_lin - 1; k >= 0; --k) {
     const int in = rd.in_dim[k], on = rd.out_dim[k], in4 = in >> 2;
     const float* W = params + rd.w_off[k];
-    for (int i = threadIdx.x; i < kReadoutGB2 * in4; i += kReadout2Threads) {
+    for (int i = threadIdx.x; i < GB * in4; i += kReadout2Threads) {
       const int g = i / in4, j4 = i % in4;
       const float4 v = g < ng ? __ldg(reinterpret_cast<const float4*>(hp.h[k] + (size_t)(g0 + g) * in) + j4)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -302,7 +304,7 @@ readout2_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
         for (int c = 0; c < CW; ++c)
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
-        for (int g = 0; g < kReadoutGB2; ++g) {
+        for (int g = 0; g < GB; ++g) {
           const float4 h0 = *reinterpret_cast<const float4*>(hin + g * ld + j);
           const float4 h1 = wide ? *reinterpret_cast<const float4*>(hin + g * ld + j + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
@@ -325,12 +327,12 @@ readout2_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtr
     }
     for (int o = threadIdx.x; o < on; o += kReadout2Threads) {
       float acc = 0.f;
-      for (int g = 0; g < kReadoutGB2; ++g) acc += dz[g * ld + o];
+      for (int g = 0; g < GB; ++g) acc += dz[g * ld + o];
       pw[(size_t)on * in + o] = acc;
     }
     // ---- gradient w.r.t. the layer input: graphs g = ty + 32 a (a < 2), inputs j = jb + 8 tx .. + 7
     for (int jb = 0; jb < in; jb += 128) {
-      constexpr int GA = 2;
+      constexpr int GA = GB / 32;
       const int j = jb + 8 * tx;
       if (j >= in) continue;
       const bool wide = j + 8 <= in;

@@ -371,6 +371,12 @@ def test_large_batch_readout_fp32(n_readout, R, out_dim):
         return out.detach().clone(), [p.grad.clone() for p in model.parameters()]
 
     o1, g1 = grads()
+    os.environ["GCB_READOUT_GB"] = "32"   # 32 graphs per CTA instead of 64
+    try:
+        o3, g3 = grads()
+    finally:
+        os.environ.pop("GCB_READOUT_GB", None)
+    assert nerr(o3, o1) <= 1e-6 and all(nerr(a, b) <= 1e-5 for a, b in zip(g3, g1))
     os.environ["GCB_NO_READOUT2"] = "1"
     try:
         o2, g2 = grads()
