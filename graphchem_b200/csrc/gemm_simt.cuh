@@ -321,46 +321,10 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, int64_t st
   }
 }
 
-// Wide form for large partial sets (>= 16 splits of >= 4096 elements, everything 16-byte aligned): 256 threads = 32 float4
-// lanes x 8 z-groups, 16-byte loads (a warp reads 512 contiguous bytes per split), each group adds its contiguous eighth of
-// the splits in order, the eight group sums are combined as ((g0+g1)+(g2+g3))+((g4+g5)+(g6+g7)): again a fixed tree.
-__global__ void __launch_bounds__(256)
-reduce_partials4_kernel(const float* __restrict__ partial, int splits, int64_t stride, int64_t count4,
-                        float* __restrict__ out, int accumulate) {
-  __shared__ float4 red[8][32];
-  const int e = threadIdx.x & 31, zg = threadIdx.x >> 5;
-  const int64_t i = (int64_t)blockIdx.x * 32 + e;  // float4 index
-  const int per = (splits + 7) / 8;
-  const int z0 = zg * per, z1 = min(splits, z0 + per);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < count4) {
-#pragma unroll 4
-    for (int z = z0; z < z1; ++z) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)z * stride) + i);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-  }
-  red[zg][e] = s;
-  __syncthreads();
-  if (zg == 0 && i < count4) {
-    auto add = [](const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); };
-    float4 t = add(add(add(red[0][e], red[1][e]), add(red[2][e], red[3][e])), add(add(red[4][e], red[5][e]), add(red[6][e], red[7][e])));
-    float4* o = reinterpret_cast<float4*>(out) + i;
-    if (accumulate) t = add(*o, t);
-    *o = t;
-  }
-}
-
 inline int launch_reduce_partials(const float* partial, int splits, int64_t count, float* out, int accumulate,
                                   cudaStream_t s, int64_t stride = -1) {
   if (count <= 0) return GCB_OK;
   if (stride < 0) stride = count;
-  static const bool wide_off = std::getenv("GCB_NO_REDUCE4") && std::getenv("GCB_NO_REDUCE4")[0] == '1';
-  if (!wide_off && splits >= 16 && count >= 4096 && count % 4 == 0 && stride % 4 == 0 &&
-      ((reinterpret_cast<uintptr_t>(partial) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-    GCB_KERNEL("reduce_partials_kernel", s, reduce_partials4_kernel<<<(unsigned)ceil_div(count / 4, 32), 256, 0, s>>>(partial, splits, stride, count / 4, out, accumulate));
-    return GCB_OK;
-  }
   GCB_KERNEL("reduce_partials_kernel", s, reduce_partials_kernel<<<(unsigned)ceil_div(count, 64), 256, 0, s>>>(partial, splits, stride, count, out, accumulate));
   return GCB_OK;
 }

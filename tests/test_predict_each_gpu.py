@@ -37,6 +37,21 @@ def test_predict_each_equals_per_molecule_loop(dtype, tol):
     assert nerr(batched, out.float()) > 1e-3
 
 
+@pytest.mark.parametrize("kw", [dict(aggr="max"), dict(aggr="mean"), dict(pool="mean")])
+def test_predict_each_other_aggregations_and_pooling(kw):
+    """max / mean aggregation and mean pooling through the each-molecule layout: equal to the oracle one molecule at a time"""
+    from graphchem_b200.data import MoleculeGraph
+    _, graphs = random_batch(seed=6, n_graphs=40, max_atoms=12)
+    mgs = [MoleculeGraph(g.x, g.edge_attr, g.edge_index, g.y) for g in graphs]
+    oracle, model = make_pair(12, 7, 2, embedding_dim=64, n_messages=2, n_readout=1, readout_dim=32, **kw)
+    oracle.eval(); model.eval()
+    out, atoms, bonds = model.predict_each(mgs, batch_size=16, return_all=True)
+    with torch.no_grad():
+        for i in (0, 15, 16, 39):
+            po, ao, bo = oracle(graphs[i])
+            assert nerr(out[i:i + 1], po) <= 1e-5 and nerr(atoms[i], ao) <= 1e-5 and nerr(bonds[i], bo) <= 1e-5
+
+
 def test_each_batches_are_inference_only():
     from graphchem_b200.data import MoleculeGraph, MoleculeStore
     _, graphs = random_batch(seed=5, n_graphs=8)
