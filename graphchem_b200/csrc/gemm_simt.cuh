@@ -179,10 +179,125 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
   }
 }
 
+// Small-problem form (the notebooks' 16-molecule batches: a few hundred rows, K <= 256): the step is a chain of launch
+// latencies there, and the tiled kernel above spends K/16 global-load latencies + barriers per launch (19 us for
+// [170 x 256] x [256 x 128]).  Here a CTA owns a [32 x 32] output tile and fetches the WHOLE K extent of its A rows and W
+// rows in one go (all loads in flight at once, one barrier), then every thread accumulates a 2 x 2 block with 16-byte
+// shared-memory loads.  Same accumulation order (k ascending, one fmaf per term) as the tiled kernel: bit-identical results.
+template <typename T, bool W_KN>
+__global__ void __launch_bounds__(256)
+gemm_nt_small_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw, T* __restrict__ C, int ldc,
+                     int M, int N, int K, Epilogue ep) {
+  constexpr int BM = 32, BN = 32;
+  extern __shared__ __align__(16) float sm_small[];
+  const int ld = K + 4;                 // row stride: 16-byte aligned, 4 banks off per row
+  float* As = sm_small;                 // [BM][ld]
+  float* Ws = sm_small + BM * ld;       // [BN][ld]
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int k4n = K >> 2;
+  const bool a_vec = (lda % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool w_vec = (ldw % 8 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  for (int i = tid; i < BM * k4n; i += 256) {
+    const int r = i / k4n, k = (i - r * k4n) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m0 + r < M) load_seg<T, 4>(A + (size_t)(m0 + r) * lda, k, K, a_vec, v);
+    *reinterpret_cast<float4*>(As + r * ld + k) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  if (W_KN) {  // W[k][n]: a thread reads 4 consecutive n of one k and scatters them over 4 staged rows
+    for (int i = tid; i < K * (BN / 4); i += 256) {
+      const int k = i / (BN / 4), n = (i - k * (BN / 4)) * 4;
+      float v[4];
+      load_seg<T, 4>(W + (size_t)k * ldw, n0 + n, N, w_vec, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ws[(n + j) * ld + k] = v[j];
+    }
+  } else {
+    for (int i = tid; i < BN * k4n; i += 256) {
+      const int n = i / k4n, k = (i - n * k4n) * 4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (n0 + n < N) load_seg<T, 4>(W + (size_t)(n0 + n) * ldw, k, K, w_vec, v);
+      *reinterpret_cast<float4*>(Ws + n * ld + k) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;  // rows ty*2 + i, columns tx + 16 j
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  const float* a0 = As + (ty * 2) * ld;
+  const float* a1 = a0 + ld;
+  const float* w0 = Ws + tx * ld;
+  const float* w1 = Ws + (tx + 16) * ld;
+  for (int k = 0; k < K; k += 4) {
+    const float4 x0 = *reinterpret_cast<const float4*>(a0 + k), x1 = *reinterpret_cast<const float4*>(a1 + k);
+    const float4 y0 = *reinterpret_cast<const float4*>(w0 + k), y1 = *reinterpret_cast<const float4*>(w1 + k);
+    const float xa[2][4] = {{x0.x, x0.y, x0.z, x0.w}, {x1.x, x1.y, x1.z, x1.w}};
+    const float yb[2][4] = {{y0.x, y0.y, y0.z, y0.w}, {y1.x, y1.y, y1.z, y1.w}};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j] = fmaf(xa[i][q], yb[j][q], acc[i][j]);
+  }
+  const T* res = reinterpret_cast<const T*>(ep.res);
+  const T* ygrad = reinterpret_cast<const T*>(ep.actgrad_y);
+  const float keep_scale = ep.p_drop > 0.f ? 1.f / (1.f - ep.p_drop) : 1.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = m0 + ty * 2 + i;
+    if (r >= M) continue;
+    float wrow = 1.f;
+    if (ep.rowptr) {
+      const int deg = ep.rowptr[r + 1] - ep.rowptr[r];
+      wrow = ep.aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (ygrad) {
+        float y = to_float(ygrad[(size_t)r * ep.ld_y + n]);
+        float f = 1.f;
+        if (ep.p_drop > 0.f) {
+          const bool keep = dropout_keep(ep.seed, ep.drop_tag, (uint64_t)r * (uint64_t)N + n, ep.p_drop);
+          f = keep ? keep_scale : 0.f;
+          y = y * (1.f - ep.p_drop);
+        }
+        v = v * f * act_grad_t<T>(y, ep.act);
+      } else {
+        if (ep.bias) v = fmaf(wrow, ep.bias[n], v);
+        if (res) v += to_float(res[(size_t)(ep.res_idx ? ep.res_idx[r] : r) * ep.ld_res + n]);
+        if (ep.act >= 0) v = act_fwd_t<T>(v, ep.act);
+      }
+      C[(size_t)r * ldc + n] = from_float<T>(v);
+    }
+  }
+}
+
+constexpr int kSmallGemmRows = 2048, kSmallGemmK = 256;
+
 template <typename T>
 inline int launch_gemm_nt(const T* A, int lda, const T* W, int ldw, bool w_kn, T* C, int ldc, int M, int N, int K,
                           const Epilogue& ep, cudaStream_t s) {
   if (M <= 0 || N <= 0) return GCB_OK;
+  static const bool small_off = std::getenv("GCB_NO_SMALL_GEMM") && std::getenv("GCB_NO_SMALL_GEMM")[0] == '1';
+  if (!small_off && M <= kSmallGemmRows && K <= kSmallGemmK && K % 4 == 0 && K > 0) {
+    const int smem = 64 * (K + 4) * (int)sizeof(float);  // <= 66.6 KB
+    static bool attr = false;
+    if (!attr) {
+      GCB_CUDA(cudaFuncSetAttribute(gemm_nt_small_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * (kSmallGemmK + 4) * 4));
+      GCB_CUDA(cudaFuncSetAttribute(gemm_nt_small_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * (kSmallGemmK + 4) * 4));
+      attr = true;
+    }
+    dim3 grid((unsigned)ceil_div(M, 32), (unsigned)ceil_div(N, 32));
+    if (w_kn) {
+      GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_small_kernel<T, true><<<grid, 256, smem, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+    } else {
+      GCB_KERNEL("gemm_nt_kernel", s, gemm_nt_small_kernel<T, false><<<grid, 256, smem, s>>>(A, lda, W, ldw, C, ldc, M, N, K, ep));
+    }
+    return GCB_OK;
+  }
   if (M > 16384) {
     dim3 grid((unsigned)ceil_div(M, 128), (unsigned)ceil_div(N, 64));
     if (w_kn) {
@@ -209,7 +324,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gemm_tn_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, float* __restrict__ partial,
                float* __restrict__ bias_partial, const int32_t* __restrict__ rowptr, int aggr, int rows, int Nn,
-               int Kk, int rows_per_split) {
+               int Kk, int rows_per_split, int direct_accumulate = -1) {
+  // direct_accumulate >= 0 (single split): `partial` / `bias_partial` ARE dW / db, written (0) or added to (1) here --
+  // the same values the one-split reduction would produce, without its two launches
   constexpr int BT = 64, BR = 16;
   __shared__ __align__(16) float As[2][BR][BT + 4];
   __shared__ __align__(16) float Bs[2][BR][BT + 4];
@@ -291,9 +408,9 @@ gemm_tn_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ld
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = k0 + tx * 4 + j;
-      if (k < Kk) out[(size_t)n * Kk + k] = acc[i][j];
+      if (k < Kk) out[(size_t)n * Kk + k] = direct_accumulate == 1 ? out[(size_t)n * Kk + k] + acc[i][j] : acc[i][j];
     }
-    if (want_bias && tx == 0) bias_partial[(size_t)z * Nn + n] = bacc[i];
+    if (want_bias && tx == 0) bias_partial[(size_t)z * Nn + n] = direct_accumulate == 1 ? bias_partial[(size_t)z * Nn + n] + bacc[i] : bacc[i];
   }
 }
 
@@ -329,8 +446,12 @@ inline int launch_reduce_partials(const float* partial, int splits, int64_t coun
   return GCB_OK;
 }
 
+// One split up to kTnDirectRows rows: in the small-batch regime (the notebooks' 16-molecule batches, ~200 rows) a step is a
+// chain of ~60 launch latencies, and the two ordered reductions behind every weight-gradient GEMM are a fifth of them.
+constexpr int kTnDirectRows = 512;
 inline int tn_splits(int rows) {
   if (rows <= 0) return 0;
+  if (rows <= kTnDirectRows) return 1;
   int s = (int)ceil_div(rows, 128);
   if (s > 64) s = 64;
   return s;
@@ -343,6 +464,12 @@ inline int launch_gemm_tn(const T* A, int lda, const T* B, int ldb, int rows, in
                           float* dW, float* db, const int32_t* rowptr, int aggr, int accumulate, cudaStream_t s) {
   if (Nn <= 0 || Kk <= 0) return GCB_OK;
   const int splits = tn_splits(rows);
+  if (splits == 1) {  // direct: no partials, no reductions
+    dim3 grid((unsigned)ceil_div(Kk, 64), (unsigned)ceil_div(Nn, 64), 1);
+    GCB_KERNEL("gemm_tn_kernel", s, gemm_tn_kernel<T><<<grid, 256, 0, s>>>(A, lda, B, ldb, dW, db, rowptr, aggr, rows, Nn, Kk,
+                                                                            (int)align_up(rows, 16), accumulate ? 1 : 0));
+    return GCB_OK;
+  }
   float* bias_partial = db ? partial + (size_t)splits * Nn * Kk : nullptr;
   if (splits > 0) {
     const int rps = (int)align_up(ceil_div(rows, splits), 16);

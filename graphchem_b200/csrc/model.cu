@@ -405,7 +405,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
       if (need > pf) pf = need;
     }
     if (pl.n_lin > 0) {
-      const int64_t need = ceil_div(G, kReadoutGB) * ((pl.total - pl.r_w[0] + 3) & ~int64_t(3));  // 16-byte aligned per-CTA blocks
+      const int64_t need = ceil_div(G, G > 1024 ? kReadoutGB : readout_gb((int)G)) * ((pl.total - pl.r_w[0] + 3) & ~int64_t(3));  // 16-byte aligned per-CTA blocks
       if (need > pf) pf = need;
     }
     const int64_t vmax = c.atom_vocab > c.bond_vocab ? c.atom_vocab : c.bond_vocab;
@@ -464,7 +464,8 @@ static int readout2_gb(int G) {
 static bool readout2_ok(const ParamLayout& pl, ReadoutDesc& rd, int G) {
   const char* e = std::getenv("GCB_NO_READOUT2");
   const bool off = e && e[0] == '1';
-  if (off || pl.n_lin <= 0 || pl.n_lin > kReadoutMaxLin || G <= 1024) return false;
+  static const int min_g = std::getenv("GCB_READOUT2_MIN_G") ? std::atoi(std::getenv("GCB_READOUT2_MIN_G")) : 1024;
+  if (off || pl.n_lin <= 0 || pl.n_lin > kReadoutMaxLin || G <= min_g) return false;
   rd.n_lin = pl.n_lin;
   rd.max_dim = 0;
   for (int k = 0; k < pl.n_lin; ++k) {
@@ -721,11 +722,12 @@ static int forward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gra
     } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
       ReadoutPtrs hp;
       for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
-      const int smem = (2 * kReadoutGB * (rd.max_dim + 1) + rd.max_w) * (int)sizeof(float);
+      const int gb = readout_gb(G);
+      const int smem = (2 * gb * (rd.max_dim + 1) + rd.max_w) * (int)sizeof(float);
       static bool attr = false;
       if (!attr) { GCB_CUDA(cudaFuncSetAttribute(readout_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
       Drop drb = make_drop(c, flags, seed, tag_readout(0));
-      GCB_KERNEL("readout_fwd_kernel", s, readout_fwd_kernel<<<(unsigned)ceil_div(G, kReadoutGB), 256, smem, s>>>(rd, params, hp, out, G, c.act, drb));
+      GCB_KERNEL("readout_fwd_kernel", s, readout_fwd_kernel<<<(unsigned)ceil_div(G, gb), kReadoutThreads, smem, s>>>(rd, params, hp, out, G, c.act, drb, gb));
     } else {
       for (int k = 0; k < pl.n_lin; ++k) {
         const bool last = k == pl.n_lin - 1;
@@ -828,13 +830,16 @@ static int backward_impl(const gcb_model_cfg& c, const ParamLayout& pl, const Gr
     } else if (ReadoutDesc rd; make_readout_desc(pl, rd, G)) {
       ReadoutPtrs hp;
       for (int k = 0; k <= pl.n_lin; ++k) hp.h[k] = k < pl.n_lin ? p.H[k] : nullptr;
-      const int smem = (3 * kReadoutGB * (rd.max_dim + 1) + rd.max_w) * (int)sizeof(float);
+      const int gb = readout_gb(G);
+      const int smem = (3 * gb * (rd.max_dim + 1) + rd.max_w) * (int)sizeof(float);
       static bool attr = false;
       if (!attr) { GCB_CUDA(cudaFuncSetAttribute(readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-      const int blocks = (int)ceil_div(G, kReadoutGB);
+      const int blocks = (int)ceil_div(G, gb);
       Drop drb = make_drop(c, flags, seed, tag_readout(0));
-      GCB_KERNEL("readout_bwd_kernel", s, readout_bwd_kernel<<<blocks, 256, smem, s>>>(rd, params, hp, d_out, p.partial, p.dPool, G, c.act, drb));
-      GCB_TRY(launch_reduce_partials(p.partial, blocks, rd.partial_stride, grad + pl.r_w[0], accumulate, s));
+      // a single CTA's partial block IS the readout gradient (same layout as the flat parameters): no reduction launch
+      const bool direct = blocks == 1 && !accumulate;
+      GCB_KERNEL("readout_bwd_kernel", s, readout_bwd_kernel<<<blocks, kReadoutThreads, smem, s>>>(rd, params, hp, d_out, direct ? grad + pl.r_w[0] : p.partial, p.dPool, G, c.act, drb, gb));
+      if (!direct) GCB_TRY(launch_reduce_partials(p.partial, blocks, rd.partial_stride, grad + pl.r_w[0], accumulate, s));
       dPool = p.dPool;
     } else {
       const float* dcur = d_out;

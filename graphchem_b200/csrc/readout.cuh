@@ -4,11 +4,25 @@
 // forward and ten launches backward; the arithmetic is tiny (<= 0.1 GF at 8192 graphs), so the point is
 // launch count and latency, not FLOP/s.  Each CTA owns GB consecutive graphs.
 #pragma once
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace gcb {
 
-constexpr int kReadoutGB = 32;       // graphs per CTA
+constexpr int kReadoutGB = 32;       // graphs per CTA, at most
+// Graphs per CTA for a batch of G graphs: the chain is bound by the warp instructions ONE SM can issue, so a small batch is
+// spread over several SMs (every CTA stages the layer's weights again, in parallel): 4 graphs per CTA up to ~600 graphs
+// (148 SMs), then more.  A/B: GCB_READOUT_GB_SMALL=32 restores one CTA per 32 graphs.
+inline int readout_gb(int G) {
+  const char* e = std::getenv("GCB_READOUT_GB_SMALL");
+  if (e && std::atoi(e) >= 1 && std::atoi(e) <= kReadoutGB) return std::atoi(e);
+  int gb = (G + 147) / 148;
+  gb = gb < 4 ? 4 : gb;
+  return gb > kReadoutGB ? kReadoutGB : gb;
+}
+// 1024 threads: a 16-graph batch (the notebooks') is ONE CTA on one SM, 200 k / 510 k warp instructions forward / backward at
+// two warps per scheduler (IPC 1.2-1.9, 85 / 142 us under ncu); 32 warps hide the shared-memory and index-math latencies
+constexpr int kReadoutThreads = 1024;
 constexpr int kReadoutMaxLin = 32;   // Linear layers (n_readout + 1)
 
 struct ReadoutPtrs { float* h[kReadoutMaxLin + 1]; };  // H[0] = pooled, H[k] = input of Linear k
@@ -24,17 +38,17 @@ struct ReadoutDesc {
 };
 
 // H[0] = pooled [G, D]; H[k+1] = dropout(act(H[k] W_k^T + b_k)) for k < n_lin-1; out = H[n_lin-1] W^T + b.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kReadoutThreads)
 readout_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs hp, float* __restrict__ out,
-                   int G, int act, Drop dr_base) {
+                   int G, int act, Drop dr_base, int gb) {
   extern __shared__ float rs[];
   const int ld = rd.max_dim + 1;
   float* cur = rs;
-  float* nxt = rs + kReadoutGB * ld;
-  float* Wt = rs + 2 * kReadoutGB * ld;  // current layer's weights, transposed: Wt[j * (on + 1) + o]
-  const int g0 = blockIdx.x * kReadoutGB;
-  const int ng = min(kReadoutGB, G - g0);
-  for (int i = threadIdx.x; i < ng * rd.in_dim[0]; i += 256) {
+  float* nxt = rs + gb * ld;
+  float* Wt = rs + 2 * gb * ld;  // current layer's weights, transposed: Wt[j * (on + 1) + o]
+  const int g0 = blockIdx.x * gb;
+  const int ng = min(gb, G - g0);
+  for (int i = threadIdx.x; i < ng * rd.in_dim[0]; i += kReadoutThreads) {
     const int g = i / rd.in_dim[0], j = i % rd.in_dim[0];
     cur[g * ld + j] = hp.h[0][(size_t)(g0 + g) * rd.in_dim[0] + j];
   }
@@ -46,9 +60,9 @@ readout_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs
     const float* b = params + rd.b_off[k];
     float* dst = last ? out : hp.h[k + 1];
     const int onp = on + 1;
-    for (int i = threadIdx.x; i < on * in; i += 256) Wt[(i % in) * onp + (i / in)] = __ldg(W + i);
+    for (int i = threadIdx.x; i < on * in; i += kReadoutThreads) Wt[(i % in) * onp + (i / in)] = __ldg(W + i);
     __syncthreads();
-    for (int i = threadIdx.x; i < ng * on; i += 256) {
+    for (int i = threadIdx.x; i < ng * on; i += kReadoutThreads) {
       const int g = i / on, o = i % on;
       const float* h = cur + g * ld;
       float a0 = __ldg(b + o), a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -78,49 +92,49 @@ readout_fwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs
 }
 
 // Backward: d_out [G, out] -> per-CTA partials of every dW_k / db_k, and dPool [G, D].
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kReadoutThreads)
 readout_bwd_kernel(ReadoutDesc rd, const float* __restrict__ params, ReadoutPtrs hp,
                    const float* __restrict__ d_out, float* __restrict__ partial, float* __restrict__ dPool, int G,
-                   int act, Drop dr_base) {
+                   int act, Drop dr_base, int gb) {
   extern __shared__ float rs[];
   const int ld = rd.max_dim + 1;
   float* dz = rs;                           // [GB][ld] gradient w.r.t. the current layer's output
-  float* hin = rs + kReadoutGB * ld;        // [GB][ld] the current layer's input H[k]
-  float* dh = rs + 2 * kReadoutGB * ld;     // [GB][ld] gradient w.r.t. the current layer's input
-  float* Ws = rs + 3 * kReadoutGB * ld;     // current layer's weights: Ws[o * (in + 1) + j]
-  const int g0 = blockIdx.x * kReadoutGB;
-  const int ng = min(kReadoutGB, G - g0);
+  float* hin = rs + gb * ld;        // [GB][ld] the current layer's input H[k]
+  float* dh = rs + 2 * gb * ld;     // [GB][ld] gradient w.r.t. the current layer's input
+  float* Ws = rs + 3 * gb * ld;     // current layer's weights: Ws[o * (in + 1) + j]
+  const int g0 = blockIdx.x * gb;
+  const int ng = min(gb, G - g0);
   float* my_partial = partial + (size_t)blockIdx.x * rd.partial_stride;
   const int o_last = rd.out_dim[rd.n_lin - 1];
-  for (int i = threadIdx.x; i < ng * o_last; i += 256) {
+  for (int i = threadIdx.x; i < ng * o_last; i += kReadoutThreads) {
     const int g = i / o_last, o = i % o_last;
     dz[g * ld + o] = d_out[(size_t)(g0 + g) * o_last + o];
   }
   for (int k = rd.n_lin - 1; k >= 0; --k) {
     const int in = rd.in_dim[k], on = rd.out_dim[k];
     const float* W = params + rd.w_off[k];
-    for (int i = threadIdx.x; i < ng * in; i += 256) {
+    for (int i = threadIdx.x; i < ng * in; i += kReadoutThreads) {
       const int g = i / in, j = i % in;
       hin[g * ld + j] = hp.h[k][(size_t)(g0 + g) * in + j];
     }
     const int inp = in + 1;
-    for (int i = threadIdx.x; i < on * in; i += 256) Ws[(i / in) * inp + (i % in)] = __ldg(W + i);
+    for (int i = threadIdx.x; i < on * in; i += kReadoutThreads) Ws[(i / in) * inp + (i % in)] = __ldg(W + i);
     __syncthreads();
     // weight / bias gradient partials of this CTA's graphs (graph order: deterministic)
     float* pw = my_partial + rd.p_off[k];
-    for (int i = threadIdx.x; i < on * in; i += 256) {
+    for (int i = threadIdx.x; i < on * in; i += kReadoutThreads) {
       const int o = i / in, j = i % in;
       float acc = 0.f;
       for (int g = 0; g < ng; ++g) acc = fmaf(dz[g * ld + o], hin[g * ld + j], acc);
       pw[i] = acc;
     }
-    for (int o = threadIdx.x; o < on; o += 256) {
+    for (int o = threadIdx.x; o < on; o += kReadoutThreads) {
       float acc = 0.f;
       for (int g = 0; g < ng; ++g) acc += dz[g * ld + o];
       pw[(size_t)on * in + o] = acc;
     }
     // gradient w.r.t. the layer input; through activation + dropout of H[k] when k > 0
-    for (int i = threadIdx.x; i < ng * in; i += 256) {
+    for (int i = threadIdx.x; i < ng * in; i += kReadoutThreads) {
       const int g = i / in, j = i % in;
       float a0 = 0.f, a1 = 0.f;
       int o = 0;

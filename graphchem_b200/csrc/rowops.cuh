@@ -49,7 +49,9 @@ int launch_atom_gather(const T* A, const T* Bnew, const int32_t* in_ptr, const i
                        const int32_t* in_src4, const int32_t* in_eid4, T* S, int N, int M, int D, int act, int aggr, Drop dr_bond, int rev, cudaStream_t s) {
   const bool generic = dr_bond.p > 0.f || aggr == GCB_AGGR_MEAN;
   const int ch = D / Vec<T>::N;
-  if (!generic && N > 0 && (ch == 8 || ch == 16 || ch == 32)) {  // lean path: one single-stream pass per half
+  // lean path: one single-stream pass per half -- for batches large enough to be bandwidth-bound; small batches are
+  // launch-latency-bound and take the one-launch kernel below (same arithmetic and order)
+  if (!generic && N >= 2048 && (ch == 8 || ch == 16 || ch == 32)) {
     switch (ch) {
       case 8:
         GCB_KERNEL("atom_gather_kernel", s, (v2::atom_gather_kernel<T, 8, false, 0><<<v2::blocks_for<8>(N), v2::kThreads, 0, s>>>(A, Bnew, in_ptr, in_src, in_eid, (const int4*)in_src4, (const int4*)in_eid4, S, N, M, act, aggr, dr_bond, 0)));
