@@ -59,7 +59,9 @@ class PackedBatch:
         """Host -> device into a preallocated int32 buffer of at least `ints.numel()` elements, on the current stream:
         copies the compact prefix and lets `gcb_pack_expand_ell` rebuild the ELL-4 views (bit-identical to the host's)."""
         n, total = self.compact_ints, self.ints.numel()
-        if dst.device.type != "cuda" or self.ints.device.type != "cpu" or n <= 0 or n >= total:
+        # small batches (the notebooks' 16 molecules: ~40 kB) go over in one copy: the rebuild kernel would cost more
+        # than the bytes it saves
+        if dst.device.type != "cuda" or self.ints.device.type != "cpu" or n <= 0 or n >= total or total < (1 << 18):
             dst[:total].copy_(self.ints, non_blocking=non_blocking)
             return
         dst[:n].copy_(self.ints[:n], non_blocking=non_blocking)

@@ -179,7 +179,15 @@ class MoleculeGCN(nn.Module):
             self._cfg_cache = (key, cfg, [int(offs[i]) for i in range(n + 1)])
         return self._cfg_cache[1]
 
+    def _apply(self, fn, *args, **kwargs):
+        self._params_cache = None  # .to() / .cuda() / .float() may replace the Parameter objects
+        return super()._apply(fn, *args, **kwargs)
+
     def _ordered_params(self) -> List[nn.Parameter]:
+        # cached: walking the module tree costs ~40 us, and the small-batch training loop asks several times per step
+        ps = getattr(self, "_params_cache", None)
+        if ps is not None:
+            return ps
         ps = [self.emb_atom.weight, self.emb_bond.weight,
               self.atom_conv.lin_msg.weight, self.atom_conv.lin_msg.bias,
               self.atom_conv.lin_edge.weight, self.atom_conv.lin_edge.bias,
@@ -187,6 +195,7 @@ class MoleculeGCN(nn.Module):
         if self.readout is not None:
             for layer in self.readout:
                 ps += [layer[0].weight, layer[0].bias]
+        self._params_cache = ps
         return ps
 
     def flat_parameters(self) -> Tensor:

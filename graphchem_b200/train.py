@@ -39,7 +39,7 @@ class TrainStep:
         self.betas, self.eps = betas, eps
         dev = model._ensure_device()
         self.device = dev
-        flat = model.flat_parameters()
+        flat = self._flat_now = model.flat_parameters()
         self._flat_ptr = flat.data_ptr()
         self.grad = torch.zeros_like(flat)
         self.exp_avg = torch.zeros_like(flat)
@@ -120,7 +120,7 @@ class TrainStep:
     def _rebind(self) -> None:
         """The captured graphs hold the address of the flat parameter vector: if the model re-flattened its
         parameters (`.to()`, externally replaced `.data`), drop them."""
-        flat = self.model.flat_parameters()
+        flat = self._flat_now = self.model.flat_parameters()  # verified once per step; the enqueue helpers reuse it
         if flat.data_ptr() != self._flat_ptr:
             self._flat_ptr = flat.data_ptr()
             self._drop_graphs()
@@ -150,7 +150,7 @@ class TrainStep:
         """Forward, MSE and backward of one batch on the current stream: `self.loss`, `self.grad` (this rank's)."""
         lib, model = _lib.lib(), self.model
         cfg = model._cfg()
-        flat = model.flat_parameters()
+        flat = self._flat_now
         flags = _lib.TRAINING | _lib.SAVE_FOR_BWD
         s = torch.cuda.current_stream(self.device).cuda_stream
         seed = 0
@@ -170,7 +170,7 @@ class TrainStep:
         """Data-parallel gradient sum, Adam on the flat parameter vector, refresh of the derived weights."""
         lib, model = _lib.lib(), self.model
         cfg = model._cfg()
-        flat = model.flat_parameters()
+        flat = self._flat_now
         s = torch.cuda.current_stream(self.device).cuda_stream
         if self.world > 1:
             allreduce_sum_(self.grad, group=self.pg)  # 1/world is folded into the Adam kernel (hyper[1])
