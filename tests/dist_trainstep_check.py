@@ -78,7 +78,8 @@ def main() -> int:
         ref.flat_parameters().copy_(init_flat)
         ref.refresh_weights()
         solo = TrainStep(ref, lr=1e-3, use_cuda_graph=False)
-        solo.hyper[1:2].fill_(1.0 / world)
+        solo.world = 1                      # the replay runs on this rank alone: no collective (the other ranks wait below)
+        solo.hyper[1:2].fill_(1.0 / world)  # ... but the same 1/world factor in Adam
         all_batches = [batches_of(r) for r in range(world)]
         for k in range(K):
             solo.lr = 1e-3 - k * 1e-5
