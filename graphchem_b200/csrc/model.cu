@@ -405,7 +405,7 @@ static int make_plan(const gcb_model_cfg& c, const ParamLayout& pl, int64_t N, i
       if (need > pf) pf = need;
     }
     if (pl.n_lin > 0) {
-      const int64_t need = ceil_div(G, G > 1024 ? kReadoutGB : readout_gb((int)G)) * ((pl.total - pl.r_w[0] + 3) & ~int64_t(3));  // 16-byte aligned per-CTA blocks
+      const int64_t need = ceil_div(G, readout_gb((int)G)) * ((pl.total - pl.r_w[0] + 3) & ~int64_t(3));  // 16-byte aligned per-CTA blocks
       if (need > pf) pf = need;
     }
     const int64_t vmax = c.atom_vocab > c.bond_vocab ? c.atom_vocab : c.bond_vocab;
