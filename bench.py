@@ -502,7 +502,8 @@ def run_ours(args):
             # ---- (3b) streaming: host collate + pack on a thread pool INSIDE the timed region ------
             def stream_leg(device_pack):
                 from graphchem_b200.data import PackedLoader
-                workers = min(16, os.cpu_count() or 1)
+                # half of the host threads (see the screening leg: one worker per core starves the launching thread)
+                workers = max(2, min(8, (os.cpu_count() or 2) // 2))
                 loader = PackedLoader(store, B, L, cfg["atom_vocab"], cfg["bond_vocab"], device=dev, workers=workers,
                                       prefetch=4, device_slots=3, device_pack=device_pack)
                 n_stream, done = max(8, min(K, 24)), 0

@@ -200,8 +200,12 @@ class PackedLoader:
             # device, it must not happen in the middle of an epoch
             nt = 0 if self.store.targets is None else int(self.store.targets.size(1))
             with self._pool_lock:
-                # (batches packed ahead during the previous epoch hold one pinned pair each)
-                missing = min(len(batches), self.prefetch + self.workers) - len(self._pool) - len(pending)
+                # (batches packed ahead during the previous epoch hold one pinned pair each; with lookahead the pipeline
+                # stays `prefetch + workers` deep across the epoch boundary, whatever the epoch length -- a worker that
+                # finds the pool empty would call cudaHostAlloc, which synchronises the device and INVALIDATES a CUDA graph
+                # capture running on the consumer's thread)
+                cap = self.prefetch + self.workers
+                missing = (cap if self.lookahead else min(len(batches), cap)) - len(self._pool) - len(pending)
                 if missing > 0:
                     cap = self._capacity_host()
                     for _ in range(missing):
