@@ -20,7 +20,10 @@ def test_cuda_loader_batches_are_exact_and_recycled():
             assert (b.header == ref.header).all()
             n += 1
         assert n == 8
-    assert 1 <= len(loader._pool) <= 4 + 2 + 2 and loader._pool_ready
+    # pinned pairs: free in the pool, or held by the batches already packed ahead for the next epoch -- exactly the
+    # `prefetch + workers` pairs of the first epoch, none added since
+    held = [f.result() for f in loader._ahead]
+    assert len(loader._pool) + len(held) == 4 + 2 and loader._pool_ready
 
 
 def test_trainstep_over_loader_learns():
@@ -157,3 +160,31 @@ def test_screen_streams_the_batched_forward(variable):
     for r in range(2):
         part = screen(model, store, batch_size=128, rank=r, world=2, workers=2, device_pack=bool(r))
         assert torch.equal(part, reference(screening_shard(700, r, 2), 128))
+
+
+def test_lookahead_never_allocates_pinned_buffers_mid_epoch():
+    """The pinned pool is sized for the pipeline that stays `prefetch + workers` deep across epoch boundaries: after the
+    first epoch no worker may find it empty (cudaHostAlloc synchronises the device and invalidates a CUDA graph capture
+    running on the consumer's thread -- seen as cudaErrorStreamCaptureInvalidated in bench.py's streaming leg)."""
+    import time
+    from graphchem_b200.data import PackedLoader
+    from graphchem_b200.synthetic import make_molecules
+    store = make_molecules(3 * 256, seed=5)
+    loader = PackedLoader(store, 256, 2, 64, 32, device="cuda", workers=4, prefetch=2, shuffle=True, seed=1)
+    seen = set()
+
+    def buffers():
+        time.sleep(0.2)  # let the batches packed ahead finish
+        held = [f.result()[1][0].data_ptr() for f in loader._ahead]
+        with loader._pool_lock:
+            return set(held) | {b[0].data_ptr() for b in loader._pool}
+
+    for _ in loader:
+        pass
+    seen = buffers()
+    assert len(seen) == loader.prefetch + loader.workers
+    for _ in range(4):
+        for _ in loader:
+            pass
+        assert buffers() == seen, "a worker allocated a new pinned buffer"
+    loader.close()
