@@ -140,6 +140,20 @@ def test_aggr_max_random_graphs_fp32(N, E, G):
     _check_backward(oracle, model, data, GRAD_F32)
 
 
+def test_aggr_max_without_edges_and_bare_molecules():
+    """aggr="max" on a lone atom (no edges at all: every maximum is the empty one, 0) and on bare molecules (batch=None)"""
+    from oracle.pyg_restated import Data as OData
+    _, graphs = random_batch(seed=3, n_graphs=3, min_atoms=3)
+    oracle, model = make_pair(12, 7, 1, embedding_dim=64, n_messages=2, aggr="max")
+    single = OData(x=torch.tensor([3], dtype=torch.int32), edge_index=torch.zeros(2, 0, dtype=torch.long),
+                   edge_attr=torch.zeros(0, dtype=torch.int32), y=torch.zeros(1, 1))
+    _check_forward(oracle, model, single, FWD_F32)
+    _check_backward(oracle, model, single, GRAD_F32)
+    for gr in graphs:
+        _check_forward(oracle, model, gr, FWD_F32)
+        _check_backward(oracle, model, gr, GRAD_F32)
+
+
 def test_aggr_max_bf16():
     data, _ = random_batch(seed=19, n_graphs=64, max_atoms=30)
     oracle, model = make_pair(12, 7, 1, dtype=torch.bfloat16, embedding_dim=128, n_messages=2, aggr="max")
