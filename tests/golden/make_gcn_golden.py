@@ -16,12 +16,15 @@ from oracle.gcn_oracle import OracleMoleculeGCN, train_step
 from tests.util import random_batch
 
 AV, BV, KW = 12, 7, dict(embedding_dim=64, n_messages=3, n_readout=2, readout_dim=32)  # small: the file is committed
+# second file (round 2): the non-default aggregation and pooling -- GeneralConv(aggr="max"), global_mean_pool
+VARIANTS = {"gcn_small.pt": {}, "gcn_small_max_meanpool.pt": dict(aggr="max", pool="mean")}
 
 
-def build():
+def build(extra=None):
+    extra = dict(extra or {})
     data, _ = random_batch(seed=2024, n_graphs=24, av=AV, bv=BV, max_atoms=14)
     torch.manual_seed(2024)
-    model = OracleMoleculeGCN(AV, BV, 2, **KW)
+    model = OracleMoleculeGCN(AV, BV, 2, **KW, **extra)
     state = {k: v.clone() for k, v in model.state_dict().items()}
     model.train()
     out, out_atom, out_bond = model(data)
@@ -37,10 +40,14 @@ def build():
     after = {k: v.clone() for k, v in model.state_dict().items()}
     return dict(x=data.x, edge_index=data.edge_index, edge_attr=data.edge_attr, batch=data.batch, y=y, state=state,
                 out=out.detach(), out_atom=out_atom.detach(), out_bond=out_bond.detach(), loss=float(loss.detach()), grads=grads,
-                adam_losses=losses, state_after_3_adam_steps=after, dims=dict(av=AV, bv=BV, out=2, **KW))
+                adam_losses=losses, state_after_3_adam_steps=after, dims=dict(av=AV, bv=BV, out=2, **KW), extra=extra)
 
 
 if __name__ == "__main__":
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gcn_small.pt")
-    torch.save(build(), path)
-    print("wrote", path, os.path.getsize(path), "bytes")
+    only = sys.argv[1:]  # file names to (re)generate; default: those that do not exist yet (committed files stay as they are)
+    for name, extra in VARIANTS.items():
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), name)
+        if (only and name not in only) or (not only and os.path.exists(path)):
+            continue
+        torch.save(build(extra), path)
+        print("wrote", path, os.path.getsize(path), "bytes")

@@ -136,12 +136,13 @@ def test_oracle_matches_real_pyg():
     assert torch.equal(global_add_pool(xa, data.batch), R.global_add_pool(xa, data.batch))
 
 
-def test_oracle_reproduces_committed_golden_vectors():
-    """tests/golden/gcn_small.pt (made by tests/golden/make_gcn_golden.py): the oracle must keep producing the
+@pytest.mark.parametrize("name", ["gcn_small.pt", "gcn_small_max_meanpool.pt"])
+def test_oracle_reproduces_committed_golden_vectors(name):
+    """tests/golden/gcn_small*.pt (made by tests/golden/make_gcn_golden.py): the oracle must keep producing the
     committed forward outputs, gradients and Adam trajectory (guards against drift of the checker itself)."""
     from tests.golden.make_gcn_golden import build
-    gold = torch.load(os.path.join(HERE, "golden", "gcn_small.pt"), weights_only=False)
-    now = build()
+    gold = torch.load(os.path.join(HERE, "golden", name), weights_only=False)
+    now = build(gold.get("extra"))
     for k in ("x", "edge_index", "edge_attr", "batch"):
         assert torch.equal(gold[k], now[k]), k
     for k in ("out", "out_atom", "out_bond"):

@@ -401,17 +401,18 @@ def test_large_batch_readout_fp32(n_readout, R, out_dim):
         assert nerr(a, b) <= 1e-5
 
 
-def test_cuda_path_matches_committed_golden_vectors():
-    """The committed oracle outputs (tests/golden/gcn_small.pt): forward, gradients and three Adam steps of the
-    fused TrainStep, fp32, through the C-ABI."""
+@pytest.mark.parametrize("name", ["gcn_small.pt", "gcn_small_max_meanpool.pt"])
+def test_cuda_path_matches_committed_golden_vectors(name):
+    """The committed oracle outputs (tests/golden/gcn_small*.pt): forward, gradients and three Adam steps of the
+    fused TrainStep, fp32, through the C-ABI; the second file is GeneralConv(aggr="max") with mean pooling."""
     import os
     from graphchem_b200.data import Data
     from graphchem_b200.nn import MoleculeGCN
     from graphchem_b200.train import TrainStep
-    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gcn_small.pt"), weights_only=False)
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name), weights_only=False)
     d = gold["dims"]
     model = MoleculeGCN(d["av"], d["bv"], d["out"], embedding_dim=d["embedding_dim"], n_messages=d["n_messages"],
-                        n_readout=d["n_readout"], readout_dim=d["readout_dim"])
+                        n_readout=d["n_readout"], readout_dim=d["readout_dim"], **gold.get("extra", {}))
     model.load_state_dict(gold["state"])
     model = model.cuda().train()
     dev = Data(x=gold["x"].cuda(), edge_index=gold["edge_index"].cuda(), edge_attr=gold["edge_attr"].cuda(),
