@@ -90,6 +90,8 @@ SIGNATURES = {
     "gcb_backward": (C.c_int, [_cfgp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _u64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gcb_mse_loss": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _f32, _vp]),
     "gcb_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _f32, _f32, _f32, _vp]),
+    "gcb_train_steps": (C.c_int, [_cfgp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _f32, _f32, _f32, _vp, _vp]),
     "gcb_debug_gemm_nt_bf16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp]),
     "gcb_debug_gemm_tn_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "gcb_launch_count": (_i64, []),

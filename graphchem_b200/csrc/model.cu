@@ -1199,6 +1199,38 @@ extern "C" int gcb_adam_step(float* params, const float* grad, float* exp_avg, f
   return GCB_OK;
 }
 
+// The notebook training loop over pre-packed device batches in ONE call (examples/predict_cn.ipynb:243-252):
+//   for batch in loader: pred = model(batch); loss = mse_loss(pred, batch.y); loss.backward(); optimizer.step()
+// Per batch exactly what gcb_forward -> gcb_mse_loss -> gcb_backward -> gcb_adam_step -> gcb_prepare_weights enqueue,
+// in that order on `stream` (bit-identical to calling them one by one): the small-batch regime is bound by the host
+// work per step, and this removes the caller's per-step share of it.
+extern "C" int gcb_train_steps(const gcb_model_cfg* cfg, int32_t n_batches, const int32_t* const* packed,
+                               const int32_t* const* packed_header_host, const float* const* y, float* params,
+                               void* derived, void* workspace, int64_t workspace_bytes, uint64_t seed0, float* pred,
+                               float* d_pred, float* grad, float* exp_avg, float* exp_avg_sq, const float* hyper,
+                               int32_t* step_count, float beta1, float beta2, float eps, float* losses, void* stream) {
+  if (!cfg || n_batches < 0 || (n_batches > 0 && (!packed || !packed_header_host || !y)) || !params || !derived ||
+      !workspace || !pred || !d_pred || !grad || !losses)
+    return GCB_ERR_INVALID_ARG;
+  GCB_TRY(check_cfg(*cfg));
+  ParamLayout pl;
+  GCB_TRY(make_layout(*cfg, pl));
+  const int32_t flags = GCB_TRAINING | GCB_SAVE_FOR_BWD;
+  const int64_t cols = cfg->n_readout > 0 ? cfg->out_dim : cfg->D;
+  for (int32_t b = 0; b < n_batches; ++b) {
+    const int32_t* h = packed_header_host[b];
+    if (!packed[b] || !h || !y[b] || h[GCB_H_MAGIC] != GCB_PACK_MAGIC) return GCB_ERR_INVALID_ARG;
+    const uint64_t seed = seed0 + (uint64_t)b;
+    GCB_TRY(gcb_forward(cfg, packed[b], h, params, derived, workspace, workspace_bytes, flags, seed, pred, nullptr, nullptr, stream));
+    GCB_TRY(gcb_mse_loss(pred, y[b], (int64_t)h[GCB_H_G] * cols, losses + b, d_pred, 1.0f, stream));
+    GCB_TRY(gcb_backward(cfg, packed[b], h, params, derived, workspace, workspace_bytes, flags, seed, d_pred, nullptr, nullptr,
+                         grad, 0, stream));
+    GCB_TRY(gcb_adam_step(params, grad, exp_avg, exp_avg_sq, pl.total, hyper, step_count, beta1, beta2, eps, stream));
+    GCB_TRY(gcb_prepare_weights(cfg, params, derived, stream));
+  }
+  return GCB_OK;
+}
+
 // ---- debug entry: one bf16 GEMM through the dispatcher (tests/test_gemm_gpu.py) -------------------
 extern "C" int gcb_debug_gemm_nt_bf16(const void* A, const void* W, void* C, int32_t rows, int32_t N, int32_t K,
                                       const float* bias, const int32_t* rowptr, int32_t aggr, const void* res,

@@ -11,7 +11,7 @@ examples/predict_cn.ipynb:212,245).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -295,6 +295,55 @@ class MoleculeStore:
         _lib.check(rc, "gcb_collate_raw_host")
         raw_header = ints[:_lib.RAW_HEADER_INTS].numpy().copy()
         return RawBatch(ints, raw_header, header, y)
+
+    def collate_pack_epoch(self, batches: Sequence[Sequence[int]], n_messages: int, atom_vocab: int, bond_vocab: int,
+                           device) -> List[PackedBatch]:
+        """All batches of an epoch (index sets, in order) packed into ONE pinned buffer and shipped with ONE host-to-device
+        copy each for the indices and the targets; returns device-resident PackedBatches that are views of one device
+        buffer (valid until the next-but-one call: two pinned / device buffer sets alternate, so the CPU can pack the
+        next epoch while the GPU still trains on this one).  For small data sets trained in small batches -- the
+        notebooks' 368 molecules in batches of 16, ~1 MB per epoch -- together with `TrainStep.run_epoch`."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise ValueError("collate_pack_epoch ships to a CUDA device")
+        nt = 0 if self.targets is None else int(self.targets.size(1))
+        sizes, offs, yoffs, total, ytotal = [], [], [], 0, 0
+        for idx in batches:
+            idx = np.asarray(idx, dtype=np.int64)
+            N, E = int(self.n_atoms[idx].sum()), int(self.n_edges[idx].sum())
+            n_ints = _header(N, E, len(idx), live_bond_rows(N, E, n_messages), atom_vocab, bond_vocab, 0)[1]
+            offs.append(total); sizes.append(n_ints)
+            total += (n_ints + 63) & ~63          # every batch starts 256-byte aligned (the kernels' 16-byte vector loads)
+            yoffs.append(ytotal)
+            ytotal += (len(idx) * nt + 3) & ~3
+        st = getattr(self, "_epoch_state", None)
+        if st is None or st["device"] != device:
+            st = self._epoch_state = {"device": device, "flip": 0, "sets": [None, None]}
+        st["flip"] ^= 1
+        cur = st["sets"][st["flip"]]
+        if cur is None or cur["ints"].numel() < total or cur["y"].numel() < max(1, ytotal):
+            cap, ycap = int(total * 1.25) + 1024, int(max(1, ytotal) * 1.25) + 16
+            cur = st["sets"][st["flip"]] = {
+                "ints": torch.empty(cap, dtype=torch.int32, pin_memory=True), "y": torch.empty(ycap, dtype=torch.float32, pin_memory=True),
+                "d_ints": torch.empty(cap, dtype=torch.int32, device=device), "d_y": torch.empty(ycap, dtype=torch.float32, device=device),
+                "ev": None}
+        if cur["ev"] is not None:
+            cur["ev"].synchronize()  # the copy that last read this pinned pair (two epochs ago) has left the host
+        hosts = []
+        for idx, off, n_ints, yo in zip(batches, offs, sizes, yoffs):
+            hosts.append(self.collate_pack(idx, n_messages, atom_vocab, bond_vocab, pin=False, out=cur["ints"][off:off + n_ints],
+                                           y_out=cur["y"][yo:] if nt else None))
+        with torch.cuda.device(device):
+            cur["d_ints"][:total].copy_(cur["ints"][:total], non_blocking=True)
+            if nt:
+                cur["d_y"][:ytotal].copy_(cur["y"][:ytotal], non_blocking=True)
+            cur["ev"] = torch.cuda.Event()
+            cur["ev"].record(torch.cuda.current_stream(device))
+        out = []
+        for hb, off, n_ints, yo in zip(hosts, offs, sizes, yoffs):
+            y = cur["d_y"][yo:yo + hb.y.numel()].view(hb.y.shape) if hb.y is not None else None
+            out.append(PackedBatch(cur["d_ints"][off:off + n_ints], hb.header, y))
+        return out
 
     def collate_pack(self, idx: Sequence[int], n_messages: int, atom_vocab: int, bond_vocab: int,
                      pin: bool = True, each: bool = False, out: Optional[Tensor] = None,

@@ -195,6 +195,54 @@ class TrainStep:
         self._warm = True
         return self.grad
 
+    def run_epoch(self, batches) -> torch.Tensor:
+        """One optimiser step per batch of `batches` (device-resident PackedBatches, in order), enqueued by ONE library
+        call (`gcb_train_steps`): the notebook loop `for batch in loader: ...` of examples/predict_cn.ipynb:243-252 without
+        the per-step Python / ctypes work, which is what bounds the 16-molecule regime.  Bit-identical to calling the
+        step once per batch.  Returns the per-batch losses [n] as a device tensor (no synchronisation).  Single process
+        only: with a process group the batches are stepped one by one (the all-reduce lives in `__call__`)."""
+        batches = list(batches)
+        if self.world > 1:
+            return torch.stack([self(pb).reshape(()).clone() for pb in batches])
+        n = len(batches)
+        losses = torch.empty(n, dtype=torch.float32, device=self.device)
+        if n == 0:
+            return losses
+        for pb in batches:
+            if pb.device != self.device or pb.y is None:
+                raise ValueError("run_epoch needs device-resident PackedBatches with targets")
+        self._rebind()
+        lib, model = _lib.lib(), self.model
+        cfg = model._cfg()
+        flags = _lib.TRAINING | _lib.SAVE_FOR_BWD
+        need = max(int(_lib.check(int(lib.gcb_workspace_bytes(C.byref(cfg), pb.N, pb.E, pb.G, flags)), "gcb_workspace_bytes"))
+                   for pb in batches)
+        if self._ws is None or self._ws.numel() < need:
+            self._drop_graphs()
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        g_max = max(pb.G for pb in batches)
+        out_cols = model._dims[2] if model._dims[4] > 0 else model._dims[3]
+        if self._pred_buf is None or self._pred_buf.shape[0] < g_max or self._pred_buf.shape[1] != out_cols:
+            self._drop_graphs()
+            self._pred_buf = torch.empty(g_max, out_cols, dtype=torch.float32, device=self.device)
+            self._dpred_buf = torch.empty_like(self._pred_buf)
+        ptrs = (C.c_void_p * n)(*[pb.ints.data_ptr() for pb in batches])
+        hdrs = (C.c_void_p * n)(*[pb.header.ctypes.data for pb in batches])
+        ys = (C.c_void_p * n)(*[pb.y.data_ptr() for pb in batches])
+        seed0 = 0
+        if model._p_dropout > 0:
+            seed0 = int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 62) - 1)
+        flat = self._flat_now
+        b1, b2 = self.betas
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(lib.gcb_train_steps(C.byref(cfg), n, ptrs, hdrs, ys, flat.data_ptr(), model._derived.data_ptr(),
+                                       self._ws.data_ptr(), self._ws.numel(), seed0, self._pred_buf.data_ptr(),
+                                       self._dpred_buf.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), self.hyper.data_ptr(), self.step_count.data_ptr(), b1, b2,
+                                       self.eps, losses.data_ptr(), s), "gcb_train_steps")
+        self._warm = True
+        return losses
+
     def _capture(self, pb: PackedBatch) -> torch.cuda.CUDAGraph:
         if not self._warm:
             # one eager step on a side stream before the first capture (lazy one-time initialisation inside the

@@ -238,6 +238,18 @@ int gcb_adam_step(float* params, const float* grad, float* exp_avg, float* exp_a
                   const float* hyper, int32_t* step_count, float beta1, float beta2, float eps,
                   void* stream);
 
+/* The notebook training loop over n_batches pre-packed device batches in one call (examples/predict_cn.ipynb:243-252:
+ * for batch in loader: model(batch) -> F.mse_loss -> backward -> optimizer.step): per batch b exactly what gcb_forward,
+ * gcb_mse_loss (loss into losses[b]), gcb_backward, gcb_adam_step and gcb_prepare_weights enqueue on `stream`, in that
+ * order, with dropout seed seed0 + b.  packed / packed_header_host / y: host arrays of n_batches pointers (device packed
+ * batch, its host header, device targets [G, out]); pred / d_pred: float scratch for the largest batch's [G, out];
+ * workspace sized for the largest batch with GCB_TRAINING | GCB_SAVE_FOR_BWD; losses: device float[n_batches]. */
+int gcb_train_steps(const gcb_model_cfg* cfg, int32_t n_batches, const int32_t* const* packed,
+                    const int32_t* const* packed_header_host, const float* const* y, float* params, void* derived,
+                    void* workspace, int64_t workspace_bytes, uint64_t seed0, float* pred, float* d_pred, float* grad,
+                    float* exp_avg, float* exp_avg_sq, const float* hyper, int32_t* step_count, float beta1, float beta2,
+                    float eps, float* losses, void* stream);
+
 /* ---- bench / debug facility (thread-local) ------------------------------------------------- */
 /* Number of kernels this thread has launched through the library since load. */
 int64_t gcb_launch_count(void);

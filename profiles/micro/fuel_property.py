@@ -30,6 +30,7 @@ from graphchem_b200.nn import MoleculeGCN
 from graphchem_b200.train import TrainStep
 from tests.util import encoded_fuel_set
 
+EPOCH_RUNNER = True   # --step-by-step: the streamed loader + one TrainStep call per batch instead
 NOTEBOOK = {"cn": (4.83, 0.884), "ysi": (5.65, 0.980), "ron": (5.65, 0.758), "mon": (6.96, 0.611), "lhv": (0.575, 0.911)}
 KW = dict(embedding_dim=128, n_messages=3, n_readout=3, readout_dim=128)
 
@@ -84,9 +85,14 @@ def run(name: str, epochs: int, seed: int = 0, oracle_steps: bool = True, dtype=
     t0 = time.perf_counter()
     for epoch in range(epochs):
         step.lr = max(0.0, 1e-3 - epoch * 1e-8)
-        losses = [step(pb).clone() for pb in loader]
+        if EPOCH_RUNNER:
+            # same batches in the same order as the loader would deliver them, packed and shipped once per epoch,
+            # stepped by one library call
+            losses = step.run_epoch(store.collate_pack_epoch(loader._batches(epoch + 1), KW["n_messages"], av, bv, "cuda"))
+        else:
+            losses = torch.stack([step(pb).reshape(()).clone() for pb in loader])
         if epoch % 25 == 0 or epoch == epochs - 1:
-            curve[epoch] = float(torch.stack(losses).sum().item()) / len(train)   # the notebook's train_loss / len(dataset)
+            curve[epoch] = float(losses.sum().item()) / len(train)   # the notebook's train_loss / len(dataset)
     torch.cuda.synchronize()
     t_train = time.perf_counter() - t0
     model.eval()
@@ -107,9 +113,11 @@ if __name__ == "__main__":
     ap.add_argument("--sets", nargs="+", default=["cn", "ysi"])
     ap.add_argument("--epochs", type=int, default=400)
     ap.add_argument("--seeds", nargs="+", type=int, default=[0])
+    ap.add_argument("--step-by-step", action="store_true", help="PackedLoader + one TrainStep call per batch (default: the epoch runner)")
     ap.add_argument("--no-oracle-steps", action="store_true", help="skip the first-steps comparison with the CPU oracle")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"], help="activation dtype (bf16: tile kernels + tcgen05 GEMMs)")
     a = ap.parse_args()
+    EPOCH_RUNNER = not a.step_by_step
     for s in a.sets:
         for seed in a.seeds:
             print(json.dumps(run(s, a.epochs, seed, not a.no_oracle_steps and a.dtype == "fp32",
