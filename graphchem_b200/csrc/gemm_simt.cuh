@@ -446,6 +446,80 @@ inline int launch_reduce_partials(const float* partial, int splits, int64_t coun
   return GCB_OK;
 }
 
+// Small-row form of the weight-gradient GEMM (rows <= kTnDirectRows: the notebooks' 16-molecule batches): a CTA owns a
+// [32 x 32] block of dW and stages 128 rows of its A / B column windows per barrier (the tiled kernel above: 16 rows per
+// barrier, one global-load latency each -- 11 round trips for 170 rows, ~13 us per launch of a step that is a chain of
+// launch latencies).  Writes dW / db directly.  Same accumulation order (rows ascending, one fmaf per term): bit-identical.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemm_tn_small_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, float* __restrict__ dW,
+                     float* __restrict__ db, const int32_t* __restrict__ rowptr, int aggr, int rows, int Nn, int Kk,
+                     int accumulate) {
+  constexpr int BT = 32, RC = 128;
+  __shared__ __align__(16) float As[RC][BT + 4];
+  __shared__ __align__(16) float Bs[RC][BT + 4];
+  __shared__ float ws[RC];
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * BT, n0 = blockIdx.y * BT;
+  const bool a_vec = (lda % 8 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool b_vec = (ldb % 8 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  const bool want_bias = db != nullptr && blockIdx.x == 0;
+  const int ty = tid >> 4, tx = tid & 15;  // n = n0 + ty*2 + i, k = k0 + tx + 16 j
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float bacc[2] = {0.f, 0.f};
+  for (int r0 = 0; r0 < rows; r0 += RC) {
+    for (int i = tid; i < RC * (BT / 4); i += 256) {
+      const int r = i >> 3, c4 = (i & 7) * 4, row = r0 + r;
+      float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row < rows) {
+        load_seg<T, 4>(A + (size_t)row * lda, n0 + c4, Nn, a_vec, va);
+        load_seg<T, 4>(B + (size_t)row * ldb, k0 + c4, Kk, b_vec, vb);
+      }
+      *reinterpret_cast<float4*>(&As[r][c4]) = make_float4(va[0], va[1], va[2], va[3]);
+      *reinterpret_cast<float4*>(&Bs[r][c4]) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    }
+    if (want_bias && tid < RC) {
+      const int row = r0 + tid;
+      float w = 0.f;
+      if (row < rows) {
+        if (rowptr) {
+          const int deg = rowptr[row + 1] - rowptr[row];
+          w = aggr == GCB_AGGR_MEAN ? (deg > 0 ? 1.f : 0.f) : (float)deg;
+        } else w = 1.f;
+      }
+      ws[tid] = w;
+    }
+    __syncthreads();
+    const int nr = min(RC, rows - r0);
+    for (int r = 0; r < nr; ++r) {
+      const float2 a2 = *reinterpret_cast<const float2*>(&As[r][ty * 2]);
+      const float b0 = Bs[r][tx], b1 = Bs[r][tx + 16];
+      acc[0][0] = fmaf(a2.x, b0, acc[0][0]); acc[0][1] = fmaf(a2.x, b1, acc[0][1]);
+      acc[1][0] = fmaf(a2.y, b0, acc[1][0]); acc[1][1] = fmaf(a2.y, b1, acc[1][1]);
+      if (want_bias && tx == 0) {
+        const float w = ws[r];
+        bacc[0] = fmaf(w, a2.x, bacc[0]);
+        bacc[1] = fmaf(w, a2.y, bacc[1]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int n = n0 + ty * 2 + i;
+    if (n >= Nn) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = k0 + tx + 16 * j;
+      if (k < Kk) {
+        float* o = dW + (size_t)n * Kk + k;
+        *o = accumulate ? *o + acc[i][j] : acc[i][j];
+      }
+    }
+    if (want_bias && tx == 0) db[n] = accumulate ? db[n] + bacc[i] : bacc[i];
+  }
+}
+
 // One split up to kTnDirectRows rows: in the small-batch regime (the notebooks' 16-molecule batches, ~200 rows) a step is a
 // chain of ~60 launch latencies, and the two ordered reductions behind every weight-gradient GEMM are a fifth of them.
 constexpr int kTnDirectRows = 512;
@@ -465,6 +539,12 @@ inline int launch_gemm_tn(const T* A, int lda, const T* B, int ldb, int rows, in
   if (Nn <= 0 || Kk <= 0) return GCB_OK;
   const int splits = tn_splits(rows);
   if (splits == 1) {  // direct: no partials, no reductions
+    static const bool small_off = std::getenv("GCB_NO_SMALL_GEMM") && std::getenv("GCB_NO_SMALL_GEMM")[0] == '1';
+    if (!small_off) {
+      dim3 grid((unsigned)ceil_div(Kk, 32), (unsigned)ceil_div(Nn, 32), 1);
+      GCB_KERNEL("gemm_tn_kernel", s, gemm_tn_small_kernel<T><<<grid, 256, 0, s>>>(A, lda, B, ldb, dW, db, rowptr, aggr, rows, Nn, Kk, accumulate ? 1 : 0));
+      return GCB_OK;
+    }
     dim3 grid((unsigned)ceil_div(Kk, 64), (unsigned)ceil_div(Nn, 64), 1);
     GCB_KERNEL("gemm_tn_kernel", s, gemm_tn_kernel<T><<<grid, 256, 0, s>>>(A, lda, B, ldb, dW, db, rowptr, aggr, rows, Nn, Kk,
                                                                             (int)align_up(rows, 16), accumulate ? 1 : 0));
