@@ -199,7 +199,7 @@ class TrainStep:
         """One optimiser step per batch of `batches` (device-resident PackedBatches, in order), enqueued by ONE library
         call (`gcb_train_steps`): the notebook loop `for batch in loader: ...` of examples/predict_cn.ipynb:243-252 without
         the per-step Python / ctypes work, which is what bounds the 16-molecule regime.  Bit-identical to calling the
-        step once per batch.  Returns the per-batch losses [n] as a device tensor (no synchronisation).  Single process
+        step once per batch (with dropout active the masks differ: batch b is seeded with seed0 + b, one draw per epoch).  Returns the per-batch losses [n] as a device tensor (no synchronisation).  Single process
         only: with a process group the batches are stepped one by one (the all-reduce lives in `__call__`)."""
         batches = list(batches)
         if self.world > 1:
