@@ -38,3 +38,20 @@ def test_abi_version_and_layout():
     assert lib.gcb_workspace_bytes(ctypes.byref(cfg2), 23 * 16, 50 * 16, 16, 3) > 0
     bad = _lib.ModelCfg(64, 32, 1, 100, 4, 2, 64, 0, 0, 1, 0.0, 0)  # D not a multiple of 8
     assert lib.gcb_workspace_bytes(ctypes.byref(bad), 10, 20, 1, 0) == _lib.GCB_ERR_UNSUPPORTED
+
+
+def test_argument_validation_without_a_gpu():
+    """Entry points reject malformed arguments before touching CUDA (status codes, never exceptions): the new config
+    values of round 2 (aggr = max, pool = mean) are accepted by the sizing helpers, unknown ones are refused, and
+    gcb_train_steps refuses missing buffers."""
+    lib = _lib.lib()
+    ok = _lib.ModelCfg(64, 32, 1, 128, 4, 2, 64, 0, _lib.AGGR_MAX, 1, 0.0, _lib.POOL_MEAN)
+    assert lib.gcb_workspace_bytes(ctypes.byref(ok), 230, 500, 10, 3) > 0
+    add = _lib.ModelCfg(64, 32, 1, 128, 4, 2, 64, 0, _lib.AGGR_ADD, 1, 0.0, _lib.POOL_ADD)
+    # max aggregation keeps per-edge messages instead of the aggregated [N, 2D] operands: a different workspace
+    assert lib.gcb_workspace_bytes(ctypes.byref(ok), 230, 500, 10, 3) != lib.gcb_workspace_bytes(ctypes.byref(add), 230, 500, 10, 3)
+    for bad in (_lib.ModelCfg(64, 32, 1, 128, 4, 2, 64, 0, 7, 1, 0.0, 0), _lib.ModelCfg(64, 32, 1, 128, 4, 2, 64, 0, 0, 1, 0.0, 9)):
+        assert lib.gcb_workspace_bytes(ctypes.byref(bad), 230, 500, 10, 3) < 0
+    rc = lib.gcb_train_steps(ctypes.byref(ok), 0, None, None, None, None, None, None, 0, 0, None, None, None, None, None, None,
+                             None, 0.9, 0.999, 1e-8, None, None)
+    assert rc == _lib.GCB_ERR_INVALID_ARG
